@@ -1,0 +1,331 @@
+// collate.cu - K0: batch collate + per-subject CSR, integer-exact.
+//
+// Replaces reference graph.py:143-167 (collate_graphs: concatenation, node-id offsets, `batch`,
+// `ptr`) and hoists the per-layer structure work of models.py:94-108 (self-loop weights, D^,
+// d^-1/2, normalised weights) and models.py:147-148 (w_sum) to once per batch.
+//
+// One CTA per subject.  The CSR is a *stable* counting sort of the subject's COO edges (order
+// inside a row = COO order) so that the sequential fp32 row sums below reproduce the CPU
+// scatter_add_ of the reference bit for bit.
+#include "common.cuh"
+
+namespace cgnn {
+
+// ---- prefix sums of the selected subjects' node / edge counts ---------------------------
+__global__ void __launch_bounds__(1024) k_scan_ptrs(const long long* __restrict__ node_ptr,
+                                                    const long long* __restrict__ edge_ptr,
+                                                    const long long* __restrict__ ids, long long B,
+                                                    long long* __restrict__ ptr, long long* __restrict__ eptr) {
+  __shared__ long long s_wn[32], s_we[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const long long per = (B + nthreads - 1) / nthreads;
+  long long lo = (long long)tid * per; if (lo > B) lo = B;
+  long long hi = lo + per; if (hi > B) hi = B;
+  long long sn = 0, se = 0;
+  for (long long g = lo; g < hi; ++g) {
+    long long s = ids[g];
+    sn += node_ptr[s + 1] - node_ptr[s];
+    se += edge_ptr[s + 1] - edge_ptr[s];
+  }
+  long long in = sn, ie = se;
+  for (int o = 1; o < 32; o <<= 1) {
+    long long vn = __shfl_up_sync(kFull, in, o), ve = __shfl_up_sync(kFull, ie, o);
+    if (lane >= o) { in += vn; ie += ve; }
+  }
+  if (lane == 31) { s_wn[warp] = in; s_we[warp] = ie; }
+  __syncthreads();
+  if (warp == 0) {
+    int nw = nthreads >> 5;
+    long long vn = lane < nw ? s_wn[lane] : 0, ve = lane < nw ? s_we[lane] : 0;
+    long long cn = vn, ce = ve;
+    for (int o = 1; o < 32; o <<= 1) {
+      long long an = __shfl_up_sync(kFull, cn, o), ae = __shfl_up_sync(kFull, ce, o);
+      if (lane >= o) { cn += an; ce += ae; }
+    }
+    s_wn[lane] = cn - vn;
+    s_we[lane] = ce - ve;
+  }
+  __syncthreads();
+  long long rn = s_wn[warp] + in - sn, re = s_we[warp] + ie - se;
+  if (tid == 0) { ptr[0] = 0; eptr[0] = 0; }
+  for (long long g = lo; g < hi; ++g) {
+    long long s = ids[g];
+    rn += node_ptr[s + 1] - node_ptr[s];
+    re += edge_ptr[s + 1] - edge_ptr[s];
+    ptr[g + 1] = rn;
+    eptr[g + 1] = re;
+  }
+}
+
+// Edge ranges of an already collated COO batch: edges are grouped by subject, so
+// eptr[g] = first edge whose source id is >= ptr[g].
+__global__ void __launch_bounds__(256) k_edge_ranges(const long long* __restrict__ src, long long E,
+                                                     const long long* __restrict__ ptr, long long B,
+                                                     long long* __restrict__ eptr) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > B) return;
+  if (g == B) { eptr[B] = E; return; }
+  long long key = ptr[g], lo = 0, hi = E;
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if (src[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  eptr[g] = lo;
+}
+
+struct CollateArgs {
+  // source: subject store (FROM_STORE) or collated COO
+  cgnn_store_t store;
+  const long long* ids;
+  const long long* coo;        // [2, E] global ids (from-COO path)
+  const float* coo_w;
+  long long B, total_rows, total_edges;
+  int max_nodes;               // shared memory was sized for this many nodes per subject
+  // reference-visible outputs (FROM_STORE only)
+  float* x; long long* edge_index; float* edge_weight; long long* batch; long long* labels;
+  const long long* ptr; const long long* eptr;
+  cgnn_csr_out_t csr;
+};
+
+// In-place exclusive scan of a[0..n) in shared memory by the whole CTA.
+__device__ __forceinline__ void block_excl_scan(int* a, int n, int* s_warp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const int per = (n + nthreads - 1) / nthreads;
+  int lo = min(tid * per, n), hi = min(lo + per, n);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += a[i];
+  int inc = s;
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int nw = nthreads >> 5;
+    int v = lane < nw ? s_warp[lane] : 0, c = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(kFull, c, o);
+      if (lane >= o) c += t;
+    }
+    s_warp[lane] = c - v;
+  }
+  __syncthreads();
+  int run = s_warp[warp] + inc - s;
+  for (int i = lo; i < hi; ++i) { int t = a[i]; a[i] = run; run += t; }
+  __syncthreads();
+}
+
+template <bool FROM_STORE>
+__global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
+  CGNN_SMEM_DECL;
+  __shared__ int s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long g = blockIdx.x;
+  const long long nb = p.ptr[g], eb = p.eptr[g];
+  const int n = (int)(p.ptr[g + 1] - nb);
+  const int m = (int)(p.eptr[g + 1] - eb);
+  if (n > p.max_nodes) return;  // host contract violated: never index past the shared arrays
+
+  int* cur_in = reinterpret_cast<int*>(cgnn_smem);   // [n] counts -> row starts -> cursors
+  int* cur_out = cur_in + n;                          // [n]
+  float* s_dinv = reinterpret_cast<float*>(cur_out + n);  // [n]
+
+  const int32_t* lsrc = nullptr; const int32_t* ldst = nullptr; const float* lw = nullptr;
+  const long long* gsrc = nullptr; const long long* gdst = nullptr;
+  if (FROM_STORE) {
+    const long long sid = p.ids[g];
+    const long long sn = p.store.node_ptr[sid], se = p.store.edge_ptr[sid];
+    lsrc = p.store.src + se; ldst = p.store.dst + se; lw = p.store.w + se;
+    const int F = p.store.num_features;
+    const float* sx = p.store.x + sn * F;
+    float* dx = p.x + nb * F;
+    for (int i = tid; i < n * F; i += kThreads) dx[i] = sx[i];
+    for (int i = tid; i < n; i += kThreads) p.batch[nb + i] = g;
+    if (tid == 0 && p.labels && p.store.label) p.labels[g] = p.store.label[sid];
+    for (int e = tid; e < m; e += kThreads) {
+      p.edge_index[eb + e] = (long long)lsrc[e] + nb;
+      p.edge_index[p.total_edges + eb + e] = (long long)ldst[e] + nb;
+      p.edge_weight[eb + e] = lw[e];
+    }
+  } else {
+    gsrc = p.coo + eb; gdst = p.coo + p.total_edges + eb; lw = p.coo_w + eb;
+  }
+  // Local endpoints of edge e.  Endpoints outside the subject (malformed hand-built batches)
+  // are redirected to a zero-weight self edge on node 0 so the CSR stays consistent.
+  auto edge = [&](int e, int& s, int& d, float& w) {
+    if (FROM_STORE) { s = lsrc[e]; d = ldst[e]; }
+    else { s = (int)(gsrc[e] - nb); d = (int)(gdst[e] - nb); }
+    w = lw[e];
+    if ((unsigned)s >= (unsigned)n || (unsigned)d >= (unsigned)n) { s = 0; d = 0; w = 0.0f; }
+  };
+
+  for (int i = tid; i < n; i += kThreads) { cur_in[i] = 0; cur_out[i] = 0; }
+  __syncthreads();
+  if (n > 0)
+    for (int e = tid; e < m; e += kThreads) {
+      int s, d; float w; edge(e, s, d, w);
+      atomicAdd(&cur_in[d], 1);
+      atomicAdd(&cur_out[s], 1);
+    }
+  __syncthreads();
+  block_excl_scan(cur_in, n, s_warp);
+  block_excl_scan(cur_out, n, s_warp);
+  for (int i = tid; i < n; i += kThreads) {
+    p.csr.in_rowptr[nb + i] = (int32_t)(eb + cur_in[i]);
+    p.csr.out_rowptr[nb + i] = (int32_t)(eb + cur_out[i]);
+  }
+  if (g == p.B - 1 && tid == 0) {
+    p.csr.in_rowptr[p.total_rows] = (int32_t)p.total_edges;
+    p.csr.out_rowptr[p.total_rows] = (int32_t)p.total_edges;
+  }
+  __syncthreads();
+
+  // Stable placement: warp 0 builds the by-destination CSR, warp 1 the by-source CSR.  Edges are
+  // visited 32 at a time in COO order; lanes that share a row take consecutive slots in lane order.
+  if (warp < 2 && n > 0) {
+    int* cur = warp == 0 ? cur_in : cur_out;
+    int32_t* col = warp == 0 ? p.csr.in_col : p.csr.out_col;
+    float* wv = warp == 0 ? p.csr.in_w : p.csr.out_w;
+    for (int e0 = 0; e0 < m; e0 += 32) {
+      const int e = e0 + lane;
+      int s = 0, d = 0; float w = 0.0f;
+      const bool live = e < m;
+      if (live) edge(e, s, d, w);
+      const int key = live ? (warp == 0 ? d : s) : -1 - lane;
+      const unsigned peers = __match_any_sync(kFull, key);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      int start = 0;
+      if (live) start = cur[key];
+      __syncwarp();
+      if (live) {
+        const long long pos = eb + start + rank;
+        col[pos] = (int32_t)(nb + (warp == 0 ? s : d));
+        wv[pos] = w;
+        if (rank == 0) cur[key] = start + __popc(peers);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // Row sums in COO order (fp32, sequential): D^ (by source, self-loop weight 1 last) and w_sum.
+  for (int i = tid; i < n; i += kThreads) {
+    const int o0 = i ? cur_out[i - 1] : 0, o1 = cur_out[i];
+    float deg = 0.0f;
+    for (int q = o0; q < o1; ++q) deg = __fadd_rn(deg, p.csr.out_w[eb + q]);
+    deg = __fadd_rn(deg, 1.0f);
+    const int i0 = i ? cur_in[i - 1] : 0, i1 = cur_in[i];
+    float ws = 0.0f;
+    for (int q = i0; q < i1; ++q) ws = __fadd_rn(ws, p.csr.in_w[eb + q]);
+    const float dinv = (float)(1.0 / sqrt((double)__fadd_rn(deg, 1e-8f)));
+    s_dinv[i] = dinv;
+    p.csr.deg[nb + i] = deg;
+    p.csr.dinv[nb + i] = dinv;
+    p.csr.wsum[nb + i] = ws;
+  }
+  __syncthreads();
+  // w^_e = (dinv[src] * w) * dinv[dst]   (reference models.py:108 evaluation order)
+  for (int i = tid; i < n; i += kThreads) {
+    const int i0 = i ? cur_in[i - 1] : 0, i1 = cur_in[i];
+    for (int q = i0; q < i1; ++q) {
+      const int s = (int)(p.csr.in_col[eb + q] - nb);
+      p.csr.in_wn[eb + q] = __fmul_rn(__fmul_rn(s_dinv[s], p.csr.in_w[eb + q]), s_dinv[i]);
+    }
+    const int o0 = i ? cur_out[i - 1] : 0, o1 = cur_out[i];
+    for (int q = o0; q < o1; ++q) {
+      const int d = (int)(p.csr.out_col[eb + q] - nb);
+      p.csr.out_wn[eb + q] = __fmul_rn(__fmul_rn(s_dinv[i], p.csr.out_w[eb + q]), s_dinv[d]);
+    }
+  }
+}
+
+}  // namespace cgnn
+
+using namespace cgnn;
+
+static bool csr_out_ok(const cgnn_csr_out_t* c) {
+  return c && c->in_rowptr && c->in_col && c->in_w && c->in_wn && c->out_rowptr && c->out_col && c->out_w &&
+         c->out_wn && c->deg && c->dinv && c->wsum;
+}
+
+// Dynamic shared memory (two cursor arrays + dinv) is sized for the largest subject of the batch.
+static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaStream_t stream) {
+  const DeviceInfo dev = device_info();
+  if (max_nodes < 1) max_nodes = 1;
+  size_t smem = (size_t)max_nodes * 12 + 16;
+  if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
+  a.max_nodes = max_nodes;
+  if (a.B <= 0) return CGNN_OK;
+  if (from_store) {
+    auto kfn = k_collate_graph<true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CGNN_LAUNCH(kfn, (unsigned)a.B, kThreads, smem, stream, a);
+  } else {
+    auto kfn = k_collate_graph<false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CGNN_LAUNCH(kfn, (unsigned)a.B, kThreads, smem, stream, a);
+  }
+  CGNN_CHECK_LAUNCH();
+  return CGNN_OK;
+}
+
+extern "C" {
+
+int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int64_t num_graphs,
+                     int64_t total_rows, int64_t total_edges, int32_t max_nodes, float* node_features, int64_t* edge_index,
+                     float* edge_weight, int64_t* batch, int64_t* labels, int64_t* ptr, int64_t* eptr,
+                     const cgnn_csr_out_t* csr, cgnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!store || !subject_ids || num_graphs < 0 || total_rows < 0 || total_edges < 0 || !ptr || !eptr ||
+      !csr_out_ok(csr) || !store->node_ptr || !store->edge_ptr || store->num_features <= 0)
+    return CGNN_ERR_INVALID_ARG;
+  if (total_rows > 0 && (!node_features || !batch || !store->x)) return CGNN_ERR_INVALID_ARG;
+  if (total_edges > 0 && (!edge_index || !edge_weight || !store->src || !store->dst || !store->w))
+    return CGNN_ERR_INVALID_ARG;
+  if (total_edges >= ((int64_t)1 << 31) || total_rows >= ((int64_t)1 << 31)) return CGNN_ERR_INVALID_ARG;
+  {
+    auto kfn = k_scan_ptrs;
+    CGNN_LAUNCH(kfn, 1, 1024, 0, stream, (const long long*)store->node_ptr, (const long long*)store->edge_ptr,
+                (const long long*)subject_ids, (long long)num_graphs, (long long*)ptr, (long long*)eptr);
+    CGNN_CHECK_LAUNCH();
+  }
+  CollateArgs a;
+  a.store = *store;
+  a.ids = (const long long*)subject_ids;
+  a.coo = nullptr; a.coo_w = nullptr;
+  a.B = num_graphs; a.total_rows = total_rows; a.total_edges = total_edges;
+  a.x = node_features; a.edge_index = (long long*)edge_index; a.edge_weight = edge_weight;
+  a.batch = (long long*)batch; a.labels = (long long*)labels;
+  a.ptr = (const long long*)ptr; a.eptr = (const long long*)eptr;
+  a.csr = *csr;
+  return collate_launch(a, true, max_nodes, stream);
+}
+
+int cgnn_csr_from_coo(const int64_t* edge_index, const float* edge_weight, const int64_t* ptr,
+                      int64_t num_graphs, int64_t total_rows, int64_t total_edges, int32_t max_nodes,
+                      int64_t* eptr, const cgnn_csr_out_t* csr, cgnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!ptr || !eptr || num_graphs < 0 || total_rows < 0 || total_edges < 0 || !csr_out_ok(csr))
+    return CGNN_ERR_INVALID_ARG;
+  if (total_edges > 0 && (!edge_index || !edge_weight)) return CGNN_ERR_INVALID_ARG;
+  if (total_edges >= ((int64_t)1 << 31) || total_rows >= ((int64_t)1 << 31)) return CGNN_ERR_INVALID_ARG;
+  {
+    auto kfn = k_edge_ranges;
+    long long items = num_graphs + 1;
+    CGNN_LAUNCH(kfn, (unsigned)((items + 255) / 256), 256, 0, stream, (const long long*)edge_index,
+                (long long)total_edges, (const long long*)ptr, (long long)num_graphs, (long long*)eptr);
+    CGNN_CHECK_LAUNCH();
+  }
+  CollateArgs a;
+  a.store = cgnn_store_t{};
+  a.ids = nullptr;
+  a.coo = (const long long*)edge_index; a.coo_w = edge_weight;
+  a.B = num_graphs; a.total_rows = total_rows; a.total_edges = total_edges;
+  a.x = nullptr; a.edge_index = nullptr; a.edge_weight = nullptr; a.batch = nullptr; a.labels = nullptr;
+  a.ptr = (const long long*)ptr; a.eptr = (const long long*)eptr;
+  a.csr = *csr;
+  return collate_launch(a, false, max_nodes, stream);
+}
+
+}  // extern "C"

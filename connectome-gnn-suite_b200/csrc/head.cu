@@ -1,0 +1,348 @@
+// head.cu - K4 / K5: mean-pool readout, MLP head, cross-entropy and their backward passes.
+//
+// Reference: models.py:57-59 (_graph_mean_pool -> _scatter_mean 40-47), models.py:196-201
+// (Linear - ReLU - Dropout - Linear), train.py:39,49,64-66 (CrossEntropyLoss, argmax accuracy).
+// These are O(B*H) - negligible next to the layer kernels - so they are written for
+// clarity and determinism rather than peak throughput.
+#include "tile.cuh"
+
+namespace cgnn {
+
+constexpr int kHeadMaxC = 512;   // pooled width
+constexpr int kHeadMaxM = 256;   // hidden width of the head
+constexpr int kHeadMaxK = 64;    // classes
+constexpr uint32_t kHeadSite = 0x48454144u;
+
+// ---- mean pool ---------------------------------------------------------------------------
+struct PoolArgs {
+  const float* t; Act act; const long long* ptr; long long B; int C, C4; float* emb;
+};
+
+template <int CC>
+__global__ void __launch_bounds__(kThreads) k_pool_fwd(PoolArgs p) {
+  CGNN_SMEM_DECL;
+  float* sm = reinterpret_cast<float*>(cgnn_smem);
+  const int C = p.C, C4 = p.C4;
+  float* s_c = sm;             // [2][C4]
+  float* s_red = sm + 2 * C4;  // [kWarps][C4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool affine = p.act.scale != nullptr;
+  stage_affine(p.act, C, C4, s_c, s_c + C4);
+  __syncthreads();
+  for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
+    const long long nb = p.ptr[g];
+    const int n = (int)(p.ptr[g + 1] - nb);
+    float acc[CC];
+#pragma unroll
+    for (int j = 0; j < CC; ++j) acc[j] = 0.0f;
+    for (int i = warp; i < n; i += kWarps) {
+      const long long grow = nb + i;
+      const uint32_t rh = p.act.drop ? drop_row_hash(p.act, p.act.row_base + grow) : 0u;
+#pragma unroll
+      for (int j = 0; j < CC; ++j) {
+        const int ch = lane + 32 * j;
+        if (ch < C) acc[j] += act_fwd(p.act, affine, p.t[grow * C + ch], s_c[ch], s_c[C4 + ch], rh, ch);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CC; ++j) {
+      const int ch = lane + 32 * j;
+      if (ch < C4) s_red[warp * C4 + ch] = acc[j];
+    }
+    __syncthreads();
+    const float denom = (float)n + 1e-8f;
+    for (int c = tid; c < C; c += kThreads) {
+      float s = 0.0f;
+      for (int w = 0; w < kWarps; ++w) s += s_red[w * C4 + c];
+      p.emb[g * C + c] = s / denom;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- MLP head forward: one warp per graph -------------------------------------------------
+struct HeadArgs {
+  const float* emb; const float* W0; const float* b0; const float* W1; const float* b1;
+  long long B; int C, M, K; Act drop;  // drop: dropout after the hidden ReLU (row id = graph id)
+  float* hidden; float* logits;
+};
+
+__global__ void __launch_bounds__(kThreads) k_head_fwd(HeadArgs p) {
+  __shared__ float s_hid[kWarps][kHeadMaxM];
+  __shared__ float s_emb[kWarps][kHeadMaxC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long g = (long long)blockIdx.x * kWarps + warp;
+  if (g >= p.B) return;
+  const int C = p.C, M = p.M, K = p.K;
+  for (int c = lane; c < C; c += 32) s_emb[warp][c] = p.emb[g * C + c];
+  __syncwarp();
+  const uint32_t rh = p.drop.drop ? drop_row_hash(p.drop, p.drop.row_base + g) : 0u;
+  for (int m = 0; m < M; ++m) {
+    float part = 0.0f;
+    for (int c = lane; c < C; c += 32) part = fmaf(p.W0[m * C + c], s_emb[warp][c], part);
+    float h = warp_sum(part) + p.b0[m];
+    h = fmaxf(h, 0.0f);
+    if (p.drop.drop) h = drop_keep(p.drop, rh, m) ? h * p.drop.keep_scale : 0.0f;
+    if (lane == 0) { s_hid[warp][m] = h; p.hidden[g * M + m] = h; }
+  }
+  __syncwarp();
+  for (int k = 0; k < K; ++k) {
+    float part = 0.0f;
+    for (int m = lane; m < M; m += 32) part = fmaf(p.W1[k * M + m], s_hid[warp][m], part);
+    const float v = warp_sum(part) + p.b1[k];
+    if (lane == 0) p.logits[g * K + k] = v;
+  }
+}
+
+// ---- cross entropy --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ce_fwd(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                long long B, int K, float inv_count, float* __restrict__ nll,
+                                                float* __restrict__ loss, long long* __restrict__ correct) {
+  __shared__ double s_loss[256];
+  __shared__ long long s_corr[256];
+  const int tid = threadIdx.x;
+  double acc = 0.0;
+  long long corr = 0;
+  for (long long g = tid; g < B; g += blockDim.x) {
+    const float* l = logits + g * K;
+    float mx = l[0]; int arg = 0;
+    for (int k = 1; k < K; ++k) if (l[k] > mx) { mx = l[k]; arg = k; }
+    float se = 0.0f;
+    for (int k = 0; k < K; ++k) se += expf(l[k] - mx);
+    const float lse = mx + logf(se);
+    long long y = labels[g];
+    const bool ok = y >= 0 && y < K;
+    const float v = ok ? lse - l[y] : 0.0f;
+    if (nll) nll[g] = v;
+    acc += (double)v;
+    corr += (ok && arg == (int)y) ? 1 : 0;
+  }
+  s_loss[tid] = acc;
+  s_corr[tid] = corr;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0; long long c = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) { s += s_loss[i]; c += s_corr[i]; }
+    if (loss) loss[0] = (float)(s * (double)inv_count);
+    if (correct) correct[0] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ce_bwd(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                long long B, int K, float inv_count, const float* __restrict__ gout,
+                                                float* __restrict__ dlogits) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B) return;
+  const float* l = logits + g * K;
+  float mx = l[0];
+  for (int k = 1; k < K; ++k) mx = fmaxf(mx, l[k]);
+  float se = 0.0f;
+  for (int k = 0; k < K; ++k) se += expf(l[k] - mx);
+  const float scale = inv_count * (gout ? gout[0] : 1.0f);
+  const long long y = labels[g];
+  const bool ok = y >= 0 && y < K;
+  for (int k = 0; k < K; ++k) {
+    const float sm = expf(l[k] - mx) / se;
+    dlogits[g * K + k] = ok ? (sm - (k == (int)y ? 1.0f : 0.0f)) * scale : 0.0f;
+  }
+}
+
+// ---- MLP head backward ------------------------------------------------------------------------
+struct HeadBwdArgs {
+  const float* emb; const float* hidden; const float* dlogits; const float* W0; const float* W1;
+  long long B; int C, M, K; float keep_scale;
+  float* demb; float* partials; int part_stride, o_dw0, o_db0, o_dw1, o_db1;
+  int o_acc, o_dhp, o_emb, o_dl, o_hid;  // smem float offsets
+};
+
+__global__ void __launch_bounds__(kThreads) k_head_bwd(HeadBwdArgs p) {
+  CGNN_SMEM_DECL;
+  float* sm = reinterpret_cast<float*>(cgnn_smem);
+  const int C = p.C, M = p.M, K = p.K;
+  float* s_acc = sm + p.o_acc;  // [part_stride] running sums of this CTA
+  float* s_dhp = sm + p.o_dhp;  // [kWarps][M]  gradient w.r.t. the hidden pre-activation
+  float* s_emb = sm + p.o_emb;  // [kWarps][C]
+  float* s_dl = sm + p.o_dl;    // [kWarps][K]
+  float* s_hid = sm + p.o_hid;  // [kWarps][M]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < p.part_stride; i += kThreads) s_acc[i] = 0.0f;
+  __syncthreads();
+  const long long groups = (p.B + kWarps - 1) / kWarps;
+  for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const long long g = grp * kWarps + warp;
+    const bool live = g < p.B;
+    for (int k = lane; k < K; k += 32) s_dl[warp * K + k] = live ? p.dlogits[g * K + k] : 0.0f;
+    for (int m = lane; m < M; m += 32) s_hid[warp * M + m] = live ? p.hidden[g * M + m] : 0.0f;
+    for (int c = lane; c < C; c += 32) s_emb[warp * C + c] = live ? p.emb[g * C + c] : 0.0f;
+    __syncwarp();
+    for (int m = lane; m < M; m += 32) {
+      float d = 0.0f;
+      for (int k = 0; k < K; ++k) d = fmaf(s_dl[warp * K + k], p.W1[k * M + m], d);
+      s_dhp[warp * M + m] = s_hid[warp * M + m] > 0.0f ? d * p.keep_scale : 0.0f;
+    }
+    __syncwarp();
+    if (live) {
+      for (int c = lane; c < C; c += 32) {
+        float d = 0.0f;
+        for (int m = 0; m < M; ++m) d = fmaf(s_dhp[warp * M + m], p.W0[m * C + c], d);
+        p.demb[g * C + c] = d;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < M * C; idx += kThreads) {
+      const int m = idx / C, c = idx - m * C;
+      float s = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s = fmaf(s_dhp[w * M + m], s_emb[w * C + c], s);
+      s_acc[p.o_dw0 + idx] += s;
+    }
+    for (int m = tid; m < M; m += kThreads) {
+      float s = 0.0f;
+      for (int w = 0; w < kWarps; ++w) s += s_dhp[w * M + m];
+      s_acc[p.o_db0 + m] += s;
+    }
+    for (int idx = tid; idx < K * M; idx += kThreads) {
+      const int k = idx / M, m = idx - k * M;
+      float s = 0.0f;
+      for (int w = 0; w < kWarps; ++w) s = fmaf(s_dl[w * K + k], s_hid[w * M + m], s);
+      s_acc[p.o_dw1 + idx] += s;
+    }
+    for (int k = tid; k < K; k += kThreads) {
+      float s = 0.0f;
+      for (int w = 0; w < kWarps; ++w) s += s_dl[w * K + k];
+      s_acc[p.o_db1 + k] += s;
+    }
+    __syncthreads();
+  }
+  float* part = p.partials + (size_t)blockIdx.x * p.part_stride;
+  for (int i = tid; i < p.part_stride; i += kThreads) part[i] = s_acc[i];
+}
+
+}  // namespace cgnn
+
+using namespace cgnn;
+
+extern "C" {
+
+int cgnn_pool_fwd(const float* t_in, const cgnn_act_t* act, const int64_t* ptr, int64_t num_graphs, int64_t rows,
+                  int32_t C, float* emb, cgnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (num_graphs < 0 || rows < 0 || C <= 0) return CGNN_ERR_INVALID_ARG;
+  if (num_graphs == 0) return CGNN_OK;
+  if (!ptr || !emb || (rows > 0 && !t_in)) return CGNN_ERR_INVALID_ARG;
+  const DeviceInfo dev = device_info();
+  PoolArgs a;
+  a.t = t_in; a.act = make_act(act); a.ptr = (const long long*)ptr; a.B = num_graphs; a.C = C; a.C4 = round_up(C, 4);
+  a.emb = emb;
+  if (a.C4 > 256) return CGNN_ERR_TILE_TOO_LARGE;
+  const size_t smem = (size_t)(2 * a.C4 + kWarps * a.C4) * sizeof(float);
+  const int grid = persistent_grid(num_graphs, smem, dev, kThreads);
+  const int cc = pick_hc(a.C4);
+#define CGNN_POOL(CC_)                                       \
+  {                                                          \
+    auto kfn = k_pool_fwd<CC_>;                              \
+    CGNN_LAUNCH(kfn, grid, kThreads, smem, stream, a);       \
+  }
+  if (cc == 1) CGNN_POOL(1) else if (cc == 2) CGNN_POOL(2) else if (cc == 4) CGNN_POOL(4) else CGNN_POOL(8)
+#undef CGNN_POOL
+  CGNN_CHECK_LAUNCH();
+  return CGNN_OK;
+}
+
+int cgnn_head_fwd(const float* emb, const float* W0, const float* b0, const float* W1, const float* b1,
+                  int64_t num_graphs, int32_t C, int32_t M, int32_t K, float p_drop, uint64_t seed,
+                  int64_t graph_base, float* hidden, float* logits, cgnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (num_graphs < 0 || C <= 0 || M <= 0 || K <= 0) return CGNN_ERR_INVALID_ARG;
+  if (num_graphs == 0) return CGNN_OK;
+  if (!emb || !W0 || !b0 || !W1 || !b1 || !hidden || !logits) return CGNN_ERR_INVALID_ARG;
+  if (C > kHeadMaxC || M > kHeadMaxM || K > kHeadMaxK) return CGNN_ERR_TILE_TOO_LARGE;
+  HeadArgs a;
+  a.emb = emb; a.W0 = W0; a.b0 = b0; a.W1 = W1; a.b1 = b1; a.B = num_graphs; a.C = C; a.M = M; a.K = K;
+  cgnn_act_t d{};
+  d.p_drop = p_drop; d.seed = seed; d.site = kHeadSite; d.row_base = graph_base;
+  a.drop = make_act(&d);
+  a.hidden = hidden; a.logits = logits;
+  auto kfn = k_head_fwd;
+  CGNN_LAUNCH(kfn, (unsigned)((num_graphs + kWarps - 1) / kWarps), kThreads, 0, stream, a);
+  CGNN_CHECK_LAUNCH();
+  return CGNN_OK;
+}
+
+int cgnn_ce_fwd(const float* logits, const int64_t* labels, int64_t num_graphs, int32_t K, float inv_count,
+                float* nll, float* loss, int64_t* correct, cgnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (num_graphs < 0 || K <= 0) return CGNN_ERR_INVALID_ARG;
+  if (num_graphs > 0 && (!logits || !labels)) return CGNN_ERR_INVALID_ARG;
+  auto kfn = k_ce_fwd;
+  CGNN_LAUNCH(kfn, 1, 256, 0, stream, logits, (const long long*)labels, (long long)num_graphs, (int)K, inv_count,
+              nll, loss, (long long*)correct);
+  CGNN_CHECK_LAUNCH();
+  return CGNN_OK;
+}
+
+int cgnn_ce_bwd(const float* logits, const int64_t* labels, int64_t num_graphs, int32_t K, float inv_count,
+                const float* gout, float* dlogits, cgnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (num_graphs < 0 || K <= 0) return CGNN_ERR_INVALID_ARG;
+  if (num_graphs == 0) return CGNN_OK;
+  if (!logits || !labels || !dlogits) return CGNN_ERR_INVALID_ARG;
+  auto kfn = k_ce_bwd;
+  CGNN_LAUNCH(kfn, (unsigned)((num_graphs + 255) / 256), 256, 0, stream, logits, (const long long*)labels,
+              (long long)num_graphs, (int)K, inv_count, gout, dlogits);
+  CGNN_CHECK_LAUNCH();
+  return CGNN_OK;
+}
+
+int cgnn_head_bwd(const float* emb, const float* hidden, const float* dlogits, const float* W0, const float* W1,
+                  int64_t num_graphs, int32_t C, int32_t M, int32_t K, float p_drop, float* demb, float* dW0,
+                  float* db0, float* dW1, float* db1, void* workspace, size_t workspace_bytes,
+                  cgnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (num_graphs < 0 || C <= 0 || M <= 0 || K <= 0 || !dW0 || !db0 || !dW1 || !db1) return CGNN_ERR_INVALID_ARG;
+  if (num_graphs == 0) {
+    cudaMemsetAsync(dW0, 0, (size_t)M * C * sizeof(float), stream);
+    cudaMemsetAsync(db0, 0, (size_t)M * sizeof(float), stream);
+    cudaMemsetAsync(dW1, 0, (size_t)K * M * sizeof(float), stream);
+    cudaMemsetAsync(db1, 0, (size_t)K * sizeof(float), stream);
+    return CGNN_OK;
+  }
+  if (!emb || !hidden || !dlogits || !W0 || !W1 || !demb || !workspace) return CGNN_ERR_INVALID_ARG;
+  if (C > kHeadMaxC || M > kHeadMaxM || K > kHeadMaxK) return CGNN_ERR_TILE_TOO_LARGE;
+  const DeviceInfo dev = device_info();
+  HeadBwdArgs a;
+  a.emb = emb; a.hidden = hidden; a.dlogits = dlogits; a.W0 = W0; a.W1 = W1;
+  a.B = num_graphs; a.C = C; a.M = M; a.K = K;
+  a.keep_scale = p_drop > 0.0f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  a.demb = demb;
+  a.o_dw0 = 0; a.o_db0 = M * C; a.o_dw1 = a.o_db0 + M; a.o_db1 = a.o_dw1 + K * M;
+  a.part_stride = a.o_db1 + K;
+  int off = 0;
+  a.o_acc = off; off += round_up(a.part_stride, 4);
+  a.o_dhp = off; off += kWarps * M;
+  a.o_emb = off; off += kWarps * C;
+  a.o_dl = off; off += kWarps * K;
+  a.o_hid = off; off += kWarps * M;
+  const size_t smem = (size_t)off * sizeof(float);
+  if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
+  const long long groups = (num_graphs + kWarps - 1) / kWarps;
+  int grid = persistent_grid(groups, smem, dev, kThreads);
+  if (grid > 2 * dev.sm_count) grid = 2 * dev.sm_count;
+  const size_t rec = (size_t)a.part_stride * sizeof(float);
+  if (workspace_bytes < rec) return CGNN_ERR_WORKSPACE;
+  if ((size_t)grid * rec > workspace_bytes) grid = (int)(workspace_bytes / rec);
+  a.partials = (float*)workspace;
+  auto kfn = k_head_bwd;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  CGNN_LAUNCH(kfn, grid, kThreads, smem, stream, a);
+  CGNN_CHECK_LAUNCH();
+  int rc = launch_reduce_partials(a.partials + a.o_dw0, grid, a.part_stride, M, C, C, dW0, stream);
+  if (rc) return rc;
+  rc = launch_reduce_partials(a.partials + a.o_db0, grid, a.part_stride, 1, M, M, db0, stream);
+  if (rc) return rc;
+  rc = launch_reduce_partials(a.partials + a.o_dw1, grid, a.part_stride, K, M, M, dW1, stream);
+  if (rc) return rc;
+  return launch_reduce_partials(a.partials + a.o_db1, grid, a.part_stride, 1, K, K, db1, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,595 @@
+// sage.cu - K2 / K7: GraphSAGE layer forward and backward, one persistent CTA per subject graph.
+//
+// Forward (reference models.py:136-152, fused with the previous layer's models.py:260-261):
+//   u = dropout(bn(t_in))                               on load (identity for the first layer)
+//   agg_i = (sum_{e: dst=i} w_e u_src(e)) / (wsum_i + 1e-8)          COO order
+//   z = relu([u || agg] W^T + b)                        + Welford statistics for BatchNorm
+// Backward: kernel A (row-local: dq, dW, db, d[u||agg] = dq W) and kernel B (transposed
+//   neighbour aggregation of the agg-gradient + previous layer's BatchNorm backward sums).
+#include "tile.cuh"
+
+namespace cgnn {
+
+// Weighted-mean neighbourhood rows for a chunk: s_cat[r] = [u_i || agg_i], i = r0 + r.
+template <int CC>
+__device__ __forceinline__ void sage_cat_rows(const float* s_u, int K4, float* s_cat, int ldc, int r0, int rows,
+                                              int n, long long nb, const int32_t* __restrict__ in_rowptr,
+                                              const int32_t* __restrict__ in_col, const float* __restrict__ in_w,
+                                              const float* __restrict__ wsum) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < kChunkRows; r += kWarps) {
+    float acc[CC];
+#pragma unroll
+    for (int j = 0; j < CC; ++j) acc[j] = 0.0f;
+    float denom = 1.0f;
+    if (r < rows) {
+      const int i = r0 + r;
+      const int e0 = in_rowptr[nb + i], e1 = in_rowptr[nb + i + 1];
+      for (int eb = e0; eb < e1; eb += 32) {
+        const int e = eb + lane;
+        int colv = 0; float wv = 0.0f;
+        if (e < e1) { colv = (int)(in_col[e] - nb); wv = in_w[e]; }
+        const int cnt = min(32, e1 - eb);
+        for (int k = 0; k < cnt; ++k) {
+          const int c = __shfl_sync(kFull, colv, k);
+          const float w = __shfl_sync(kFull, wv, k);
+          if ((unsigned)c < (unsigned)n) {
+#pragma unroll
+            for (int j = 0; j < CC; ++j) {
+              const int ch = lane + 32 * j;
+              if (ch < K4) acc[j] = __fadd_rn(acc[j], __fmul_rn(s_u[c * K4 + ch], w));
+            }
+          }
+        }
+      }
+      denom = __fadd_rn(wsum[nb + i], 1e-8f);
+    }
+#pragma unroll
+    for (int j = 0; j < CC; ++j) {
+      const int ch = lane + 32 * j;
+      if (ch < K4) {
+        s_cat[r * ldc + ch] = r < rows ? s_u[(r0 + r) * K4 + ch] : 0.0f;
+        s_cat[r * ldc + K4 + ch] = r < rows ? acc[j] / denom : 0.0f;
+      }
+    }
+  }
+}
+
+struct SageFwdArgs {
+  const float* t_in; Act act; const float* W; const float* bias;
+  const int32_t* in_rowptr; const int32_t* in_col; const float* in_w; const float* wsum;
+  const long long* ptr; long long B;
+  int K, H, K4, H4, ldc, max_nodes, vec_in;
+  float* z; double* partials;
+  int o_wt, o_scale, o_shift, o_bias, o_u, o_cat, o_out, o_st;
+};
+
+template <int CC>
+__global__ void __launch_bounds__(kThreads) k_sage_fwd(SageFwdArgs p) {
+  CGNN_SMEM_DECL;
+  float* sm = reinterpret_cast<float*>(cgnn_smem);
+  float* s_wt = sm + p.o_wt;        // [2*K4][H4]
+  float* s_scale = sm + p.o_scale;
+  float* s_shift = sm + p.o_shift;
+  float* s_bias = sm + p.o_bias;
+  float* s_u = sm + p.o_u;          // [max_nodes][K4]
+  float* s_cat = sm + p.o_cat;      // [kChunkRows][ldc]
+  float* s_out = sm + p.o_out;      // [kChunkRows][H4]
+  float* s_cnt = sm + p.o_st;
+  float* s_mean = s_cnt + kWarps;
+  float* s_m2 = s_mean + kWarps * p.H4;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = p.K, H = p.H, K4 = p.K4, H4 = p.H4, ldc = p.ldc;
+
+  for (int idx = tid; idx < 2 * K4 * H4; idx += kThreads) {
+    const int kk = idx / H4, h = idx - kk * H4;
+    const int half = kk >= K4, k = kk - half * K4;
+    s_wt[idx] = (k < K && h < H) ? p.W[h * 2 * K + half * K + k] : 0.0f;
+  }
+  stage_affine(p.act, K, K4, s_scale, s_shift);
+  for (int h = tid; h < H4; h += kThreads) s_bias[h] = (h < H && p.bias) ? p.bias[h] : 0.0f;
+  __syncthreads();
+
+  WarpStats<CC> st;
+  st.init();
+  const int tiles_x = H4 >> 2;
+  const int ntiles = (kChunkRows >> 2) * tiles_x;
+
+  for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
+    const long long nb = p.ptr[g];
+    int n = (int)(p.ptr[g + 1] - nb);
+    if (n > p.max_nodes) n = p.max_nodes;
+    if (p.vec_in) stage_rows<true>(p.t_in, nb, n, n, K, K4, K4, p.act, s_scale, s_shift, s_u, nullptr);
+    else stage_rows<false>(p.t_in, nb, n, n, K, K4, K4, p.act, s_scale, s_shift, s_u, nullptr);
+    __syncthreads();
+    for (int r0 = 0; r0 < n; r0 += kChunkRows) {
+      const int rows = min(kChunkRows, n - r0);
+      sage_cat_rows<CC>(s_u, K4, s_cat, ldc, r0, rows, n, nb, p.in_rowptr, p.in_col, p.in_w, p.wsum);
+      __syncthreads();
+      for (int t = tid; t < ntiles; t += kThreads) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        if (4 * ty >= rows) continue;
+        float acc[4][4] = {};
+        mma_4x4(s_cat + 4 * ty * ldc, ldc, s_wt + 4 * tx, H4, 2 * K4, acc);
+        const float4 b = *reinterpret_cast<const float4*>(s_bias + 4 * tx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(s_out + (4 * ty + i) * H4 + 4 * tx) =
+              make_float4(fmaxf(acc[i][0] + b.x, 0.f), fmaxf(acc[i][1] + b.y, 0.f), fmaxf(acc[i][2] + b.z, 0.f),
+                          fmaxf(acc[i][3] + b.w, 0.f));
+      }
+      __syncthreads();
+      for (int r = warp; r < rows; r += kWarps) {
+        float inv;
+        st.begin_row(inv);
+#pragma unroll
+        for (int j = 0; j < CC; ++j) {
+          const int ch = lane + 32 * j;
+          if (ch < H) {
+            const float v = s_out[r * H4 + ch];
+            p.z[(nb + r0 + r) * H + ch] = v;
+            st.w[j].push(v, inv);
+          }
+        }
+      }
+    }
+    __syncthreads();  // s_u / s_out are rewritten by the next subject
+  }
+
+  if (p.partials) {
+    st.deposit(s_cnt, s_mean, s_m2, H4, H4);
+    __syncthreads();
+    cta_write_stats(s_cnt, s_mean, s_m2, H4, H, p.partials + (size_t)blockIdx.x * (1 + 2 * H));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct SageBwdArgs {
+  const float* du; const float* demb; const float* z; Act act_out;
+  const float* bn_scale; const float* bn_mean; const float* bn_rstd; const float* bn_s1; const float* bn_s2;
+  float inv_count; int bn_train; int has_bn;
+  const float* t_in; Act act_in; const float* W;
+  const int32_t* in_rowptr; const int32_t* in_col; const float* in_w; const float* wsum;
+  const long long* ptr; long long B;
+  int K, H, K4, H4, ldc, ldq, max_nodes, vec_in, need_du;
+  float* direct; float* nbr;  // scratch [rows, K] each
+  float* partials; int part_stride, o_pdw, o_pdb;
+  int o_w, o_co, o_ci, o_u, o_cat, o_dq, o_red;
+};
+
+enum { SO_SCALE = 0, SO_SHIFT, SO_BSC, SO_MEAN, SO_RSTD, SO_S1N, SO_S2N, SO_ROWS };
+
+template <int CC, int MAXT>
+__global__ void __launch_bounds__(kThreads) k_sage_bwd_a(SageBwdArgs p) {
+  CGNN_SMEM_DECL;
+  float* sm = reinterpret_cast<float*>(cgnn_smem);
+  float* s_w = sm + p.o_w;      // [H4][2*K4] natural layout
+  float* s_co = sm + p.o_co;    // [SO_ROWS][H4]
+  float* s_ci = sm + p.o_ci;    // [2][K4] scale, shift of act_in
+  float* s_u = sm + p.o_u;      // [max_nodes][K4]
+  float* s_cat = sm + p.o_cat;  // [kChunkRows][ldc]
+  float* s_dq = sm + p.o_dq;    // [kChunkRows][ldq]
+  float* s_red = sm + p.o_red;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = p.K, H = p.H, K4 = p.K4, H4 = p.H4, ldc = p.ldc, ldq = p.ldq, K8 = 2 * p.K4;
+  const bool aff_out = p.act_out.scale != nullptr;
+
+  for (int idx = tid; idx < H4 * K8; idx += kThreads) {
+    const int h = idx / K8, kk = idx - h * K8;
+    const int half = kk >= K4, k = kk - half * K4;
+    s_w[idx] = (h < H && k < K) ? p.W[h * 2 * K + half * K + k] : 0.0f;
+  }
+  stage_affine(p.act_out, H, H4, s_co + SO_SCALE * H4, s_co + SO_SHIFT * H4);
+  for (int c = tid; c < H4; c += kThreads) {
+    const bool ok = c < H && p.has_bn;
+    s_co[SO_BSC * H4 + c] = ok ? p.bn_scale[c] : (c < H ? 1.0f : 0.0f);
+    s_co[SO_MEAN * H4 + c] = ok ? p.bn_mean[c] : 0.0f;
+    s_co[SO_RSTD * H4 + c] = ok ? p.bn_rstd[c] : 0.0f;
+    s_co[SO_S1N * H4 + c] = (ok && p.bn_train) ? p.bn_s1[c] * p.inv_count : 0.0f;
+    s_co[SO_S2N * H4 + c] = (ok && p.bn_train) ? p.bn_s2[c] * p.inv_count : 0.0f;
+  }
+  stage_affine(p.act_in, K, K4, s_ci, s_ci + K4);
+  __syncthreads();
+
+  const int tk = K8 >> 2;
+  const int ntiles_w = (H4 >> 2) * tk;
+  const int ntiles_u = (kChunkRows >> 2) * tk;
+
+  float acc_w[MAXT][4][4];
+#pragma unroll
+  for (int it = 0; it < MAXT; ++it)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc_w[it][i][j] = 0.0f;
+  float acc_db[CC];
+#pragma unroll
+  for (int j = 0; j < CC; ++j) acc_db[j] = 0.0f;
+
+  for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
+    const long long nb = p.ptr[g];
+    int n = (int)(p.ptr[g + 1] - nb);
+    if (n > p.max_nodes) n = p.max_nodes;
+    const float inv_n = 1.0f / ((float)n + 1e-8f);
+    if (p.vec_in) stage_rows<true>(p.t_in, nb, n, n, K, K4, K4, p.act_in, s_ci, s_ci + K4, s_u, nullptr);
+    else stage_rows<false>(p.t_in, nb, n, n, K, K4, K4, p.act_in, s_ci, s_ci + K4, s_u, nullptr);
+    __syncthreads();
+
+    for (int r0 = 0; r0 < n; r0 += kChunkRows) {
+      const int rows = min(kChunkRows, n - r0);
+      // (a) [u || agg] rows
+      sage_cat_rows<CC>(s_u, K4, s_cat, ldc, r0, rows, n, nb, p.in_rowptr, p.in_col, p.in_w, p.wsum);
+      // (b) dq = relu'(z) * bn_bwd(dropout_bwd(du))
+      for (int idx = tid; idx < kChunkRows * H4; idx += kThreads) {
+        const int r = idx / H4, c = idx - r * H4;
+        float dq = 0.0f;
+        if (r < rows && c < H) {
+          const long long grow = nb + r0 + r;
+          const float t = p.z[grow * H + c];
+          const float up = p.du ? p.du[grow * H + c] : p.demb[g * H + c] * inv_n;
+          const uint32_t rh = p.act_out.drop ? drop_row_hash(p.act_out, p.act_out.row_base + grow) : 0u;
+          const float dy = act_bwd(p.act_out, aff_out, t, s_co[SO_SCALE * H4 + c], s_co[SO_SHIFT * H4 + c], rh, c, up);
+          float dz = dy;
+          if (p.has_bn) {
+            if (p.bn_train) {
+              const float xh = (t - s_co[SO_MEAN * H4 + c]) * s_co[SO_RSTD * H4 + c];
+              dz = s_co[SO_BSC * H4 + c] * (dy - s_co[SO_S1N * H4 + c] - xh * s_co[SO_S2N * H4 + c]);
+            } else {
+              dz = s_co[SO_BSC * H4 + c] * dy;
+            }
+          }
+          dq = t > 0.0f ? dz : 0.0f;
+        }
+        s_dq[r * ldq + c] = dq;
+      }
+      __syncthreads();
+      for (int r = warp; r < rows; r += kWarps) {
+#pragma unroll
+        for (int j = 0; j < CC; ++j) {
+          const int ch = lane + 32 * j;
+          if (ch < H4) acc_db[j] += s_dq[r * ldq + ch];
+        }
+      }
+      // (c) dW += dq^T [u || agg]
+#pragma unroll
+      for (int it = 0; it < MAXT; ++it) {
+        const int t = tid + it * kThreads;
+        if (t < ntiles_w) {
+          const int th = t / tk, tq = t - th * tk;
+          outer_4x4(s_dq + 4 * th, ldq, s_cat + 4 * tq, ldc, rows, acc_w[it]);
+        }
+      }
+      // (d) d[u || agg] = dq W : direct half and (already mean-normalised) neighbour half
+      if (p.need_du) {
+        for (int t = tid; t < ntiles_u; t += kThreads) {
+          const int ty = t / tk, tx = t - ty * tk;
+          if (4 * ty >= rows) continue;
+          float acc[4][4] = {};
+          mma_4x4(s_dq + 4 * ty * ldq, ldq, s_w + 4 * tx, K8, H4, acc);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 4 * ty + i;
+            if (r >= rows) continue;
+            const long long grow = nb + r0 + r;
+            const bool is_nbr = 4 * tx >= K4;
+            const float sc = is_nbr ? 1.0f / __fadd_rn(p.wsum[grow], 1e-8f) : 1.0f;
+            float* dst = is_nbr ? p.nbr : p.direct;
+            const int kb = 4 * tx - (is_nbr ? K4 : 0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (kb + q < K) dst[grow * K + kb + q] = acc[i][q] * sc;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  float* part = p.partials + (size_t)blockIdx.x * p.part_stride;
+#pragma unroll
+  for (int it = 0; it < MAXT; ++it) {
+    const int t = tid + it * kThreads;
+    if (t < ntiles_w) {
+      const int th = t / tk, tq = t - th * tk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(part + p.o_pdw + (4 * th + i) * K8 + 4 * tq) =
+            make_float4(acc_w[it][i][0], acc_w[it][i][1], acc_w[it][i][2], acc_w[it][i][3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CC; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < H4) s_red[warp * H4 + ch] = acc_db[j];
+  }
+  __syncthreads();
+  for (int c = tid; c < H4; c += kThreads) {
+    float s = 0.0f;
+    for (int w = 0; w < kWarps; ++w) s += s_red[w * H4 + c];
+    part[p.o_pdb + c] = s;
+  }
+}
+
+struct SageBwdBArgs {
+  const float* direct; const float* nbr; const float* t_in; Act act_in;
+  const int32_t* out_rowptr; const int32_t* out_col; const float* out_w;
+  const float* prev_mean; const float* prev_rstd; int want_prev;
+  const long long* ptr; long long B;
+  int K, K4, max_nodes;
+  float* du_in; float* partials;  // [grid][2*K4]
+  int o_g, o_ci, o_red;
+};
+
+// du_in[j] = direct[j] + sum_{e: src=j} w_e * nbr[dst(e)]   (nbr already divided by wsum+1e-8)
+template <int CC>
+__global__ void __launch_bounds__(kThreads) k_sage_bwd_b(SageBwdBArgs p) {
+  CGNN_SMEM_DECL;
+  float* sm = reinterpret_cast<float*>(cgnn_smem);
+  float* s_g = sm + p.o_g;      // [max_nodes][K4]
+  float* s_ci = sm + p.o_ci;    // [4][K4] scale, shift, mean, rstd
+  float* s_red = sm + p.o_red;  // [kWarps][2*K4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = p.K, K4 = p.K4;
+  const bool aff_in = p.act_in.scale != nullptr;
+
+  stage_affine(p.act_in, K, K4, s_ci, s_ci + K4);
+  for (int c = tid; c < K4; c += kThreads) {
+    const bool ok = c < K && p.want_prev;
+    s_ci[2 * K4 + c] = ok ? p.prev_mean[c] : 0.0f;
+    s_ci[3 * K4 + c] = ok ? p.prev_rstd[c] : 0.0f;
+  }
+  __syncthreads();
+
+  float ps1[CC], ps2[CC];
+#pragma unroll
+  for (int j = 0; j < CC; ++j) { ps1[j] = 0.0f; ps2[j] = 0.0f; }
+
+  for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
+    const long long nb = p.ptr[g];
+    int n = (int)(p.ptr[g + 1] - nb);
+    if (n > p.max_nodes) n = p.max_nodes;
+    for (int idx = tid; idx < n * K4; idx += kThreads) {
+      const int i = idx / K4, c = idx - i * K4;
+      s_g[idx] = c < K ? p.nbr[(nb + i) * K + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int jr = warp; jr < n; jr += kWarps) {
+      const long long grow = nb + jr;
+      float acc[CC];
+#pragma unroll
+      for (int j = 0; j < CC; ++j) {
+        const int ch = lane + 32 * j;
+        acc[j] = ch < K ? p.direct[grow * K + ch] : 0.0f;
+      }
+      const int e0 = p.out_rowptr[grow], e1 = p.out_rowptr[grow + 1];
+      for (int eb = e0; eb < e1; eb += 32) {
+        const int e = eb + lane;
+        int colv = 0; float wv = 0.0f;
+        if (e < e1) { colv = (int)(p.out_col[e] - nb); wv = p.out_w[e]; }
+        const int cnt = min(32, e1 - eb);
+        for (int k = 0; k < cnt; ++k) {
+          const int c = __shfl_sync(kFull, colv, k);
+          const float w = __shfl_sync(kFull, wv, k);
+          if ((unsigned)c < (unsigned)n) {
+#pragma unroll
+            for (int j = 0; j < CC; ++j) {
+              const int ch = lane + 32 * j;
+              if (ch < K4) acc[j] = fmaf(s_g[c * K4 + ch], w, acc[j]);
+            }
+          }
+        }
+      }
+      const uint32_t rh = (p.want_prev && p.act_in.drop) ? drop_row_hash(p.act_in, p.act_in.row_base + grow) : 0u;
+#pragma unroll
+      for (int j = 0; j < CC; ++j) {
+        const int ch = lane + 32 * j;
+        if (ch < K) {
+          p.du_in[grow * K + ch] = acc[j];
+          if (p.want_prev) {
+            const float t0 = p.t_in[grow * K + ch];
+            const float dyp = act_bwd(p.act_in, aff_in, t0, s_ci[ch], s_ci[K4 + ch], rh, ch, acc[j]);
+            const float xh = (t0 - s_ci[2 * K4 + ch]) * s_ci[3 * K4 + ch];
+            ps1[j] += dyp;
+            ps2[j] = fmaf(dyp, xh, ps2[j]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  if (p.want_prev) {
+#pragma unroll
+    for (int j = 0; j < CC; ++j) {
+      const int ch = lane + 32 * j;
+      if (ch < K4) { s_red[warp * 2 * K4 + ch] = ps1[j]; s_red[warp * 2 * K4 + K4 + ch] = ps2[j]; }
+    }
+    __syncthreads();
+    float* part = p.partials + (size_t)blockIdx.x * 2 * K4;
+    for (int c = tid; c < 2 * K4; c += kThreads) {
+      float s = 0.0f;
+      for (int w = 0; w < kWarps; ++w) s += s_red[w * 2 * K4 + c];
+      part[c] = s;
+    }
+  }
+}
+
+}  // namespace cgnn
+
+using namespace cgnn;
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+extern "C" {
+
+int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
+                        const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
+                        int32_t d_in, int32_t H, int32_t max_nodes, float* z, double* bn_stats, void* workspace,
+                        size_t workspace_bytes, cgnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0) return CGNN_ERR_INVALID_ARG;
+  if (num_graphs == 0 || rows == 0) {
+    if (bn_stats) cudaMemsetAsync(bn_stats, 0, (size_t)(1 + 2 * H) * sizeof(double), stream);
+    return CGNN_OK;
+  }
+  if (!t_in || !W || !csr || !csr->in_rowptr || !csr->in_col || !csr->in_w || !csr->wsum || !ptr || !z)
+    return CGNN_ERR_INVALID_ARG;
+  const DeviceInfo dev = device_info();
+  SageFwdArgs a;
+  a.t_in = t_in; a.act = make_act(act); a.W = W; a.bias = bias;
+  a.in_rowptr = csr->in_rowptr; a.in_col = csr->in_col; a.in_w = csr->in_w; a.wsum = csr->wsum;
+  a.ptr = (const long long*)ptr; a.B = num_graphs;
+  a.K = d_in; a.H = H; a.K4 = round_up(d_in, 4); a.H4 = round_up(H, 4); a.ldc = 2 * a.K4 + 4;
+  a.max_nodes = max_nodes < 1 ? 1 : max_nodes;
+  a.vec_in = (d_in % 4 == 0) && aligned16(t_in);
+  a.z = z;
+  if (a.H4 > 256 || a.K4 > 256) return CGNN_ERR_TILE_TOO_LARGE;
+  int off = 0;
+  a.o_wt = off; off += 2 * a.K4 * a.H4;
+  a.o_scale = off; off += a.K4;
+  a.o_shift = off; off += a.K4;
+  a.o_bias = off; off += a.H4;
+  a.o_u = off; off += a.max_nodes * a.K4;
+  a.o_cat = off; off += kChunkRows * a.ldc;
+  a.o_out = off; off += kChunkRows * a.H4;
+  a.o_st = off; off += kWarps + 2 * kWarps * a.H4;
+  const size_t smem = (size_t)off * sizeof(float);
+  if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
+  int grid = persistent_grid(num_graphs, smem, dev, kThreads);
+  const size_t rec = (size_t)(1 + 2 * H) * sizeof(double);
+  a.partials = nullptr;
+  if (bn_stats) {
+    if (!workspace || workspace_bytes < rec) return CGNN_ERR_WORKSPACE;
+    if ((size_t)grid * rec > workspace_bytes) grid = (int)(workspace_bytes / rec);
+    a.partials = (double*)workspace;
+  }
+  const int cc = imax(pick_hc(a.H4), pick_hc(a.K4));
+#define CGNN_SAGE_FWD(CC_)                                                                       \
+  {                                                                                              \
+    auto kfn = k_sage_fwd<CC_>;                                                                  \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    CGNN_LAUNCH(kfn, grid, kThreads, smem, stream, a);                                           \
+  }
+  if (cc == 1) CGNN_SAGE_FWD(1) else if (cc == 2) CGNN_SAGE_FWD(2) else if (cc == 4) CGNN_SAGE_FWD(4) else CGNN_SAGE_FWD(8)
+#undef CGNN_SAGE_FWD
+  CGNN_CHECK_LAUNCH();
+  if (bn_stats) return launch_stats_merge(a.partials, grid, H, bn_stats, stream);
+  return CGNN_OK;
+}
+
+int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
+                        const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in, const float* W,
+                        const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
+                        int32_t d_in, int32_t H, int32_t max_nodes, float* dW, float* dbias, float* du_in,
+                        const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
+                        void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!dW || !dbias || num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0) return CGNN_ERR_INVALID_ARG;
+  if (num_graphs == 0 || rows == 0) {
+    cudaMemsetAsync(dW, 0, (size_t)H * 2 * d_in * sizeof(float), stream);
+    cudaMemsetAsync(dbias, 0, (size_t)H * sizeof(float), stream);
+    if (prev_sums) cudaMemsetAsync(prev_sums, 0, (size_t)2 * d_in * sizeof(float), stream);
+    return CGNN_OK;
+  }
+  if ((du == nullptr) == (demb == nullptr)) return CGNN_ERR_INVALID_ARG;
+  if (!z || !t_in || !W || !csr || !csr->in_rowptr || !csr->in_col || !csr->in_w || !csr->wsum || !ptr || !workspace)
+    return CGNN_ERR_INVALID_ARG;
+  if (du_in && (!scratch || !csr->out_rowptr || !csr->out_col || !csr->out_w)) return CGNN_ERR_INVALID_ARG;
+  if (prev_sums && (!du_in || !prev_mean || !prev_rstd)) return CGNN_ERR_INVALID_ARG;
+  if (bn && (!bn->scale || !bn->mean || !bn->rstd || (bn->train && (!bn->s1 || !bn->s2)))) return CGNN_ERR_INVALID_ARG;
+  const DeviceInfo dev = device_info();
+  SageBwdArgs a;
+  a.du = du; a.demb = demb; a.z = z; a.act_out = make_act(act_out);
+  a.has_bn = bn ? 1 : 0;
+  a.bn_scale = bn ? bn->scale : nullptr; a.bn_mean = bn ? bn->mean : nullptr; a.bn_rstd = bn ? bn->rstd : nullptr;
+  a.bn_s1 = bn ? bn->s1 : nullptr; a.bn_s2 = bn ? bn->s2 : nullptr;
+  a.bn_train = bn ? bn->train : 0;
+  a.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
+  a.t_in = t_in; a.act_in = make_act(act_in); a.W = W;
+  a.in_rowptr = csr->in_rowptr; a.in_col = csr->in_col; a.in_w = csr->in_w; a.wsum = csr->wsum;
+  a.ptr = (const long long*)ptr; a.B = num_graphs;
+  a.K = d_in; a.H = H; a.K4 = round_up(d_in, 4); a.H4 = round_up(H, 4);
+  a.ldc = 2 * a.K4 + 4; a.ldq = a.H4 + 4;
+  a.max_nodes = max_nodes < 1 ? 1 : max_nodes;
+  a.vec_in = (d_in % 4 == 0) && aligned16(t_in);
+  a.need_du = du_in ? 1 : 0;
+  a.direct = scratch; a.nbr = scratch ? scratch + (size_t)rows * d_in : nullptr;
+  const int ntiles_w = (a.H4 / 4) * (2 * a.K4 / 4);
+  if (a.H4 > 128 || a.K4 > 128 || ntiles_w > 4 * kThreads) return CGNN_ERR_TILE_TOO_LARGE;
+  int off = 0;
+  a.o_w = off; off += a.H4 * 2 * a.K4;
+  a.o_co = off; off += SO_ROWS * a.H4;
+  a.o_ci = off; off += 2 * a.K4;
+  a.o_u = off; off += a.max_nodes * a.K4;
+  a.o_cat = off; off += kChunkRows * a.ldc;
+  a.o_dq = off; off += kChunkRows * a.ldq;
+  a.o_red = off; off += kWarps * a.H4;
+  const size_t smem = (size_t)off * sizeof(float);
+  if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
+  a.o_pdw = 0; a.o_pdb = a.H4 * 2 * a.K4;
+  a.part_stride = a.o_pdb + a.H4;
+  int grid = persistent_grid(num_graphs, smem, dev, kThreads);
+  const size_t rec = (size_t)a.part_stride * sizeof(float);
+  if (workspace_bytes < rec) return CGNN_ERR_WORKSPACE;
+  if ((size_t)grid * rec > workspace_bytes) grid = (int)(workspace_bytes / rec);
+  a.partials = (float*)workspace;
+  const int cc = imax(pick_hc(a.H4), pick_hc(a.K4));
+  const int maxt = ntiles_w <= kThreads ? 1 : (ntiles_w <= 2 * kThreads ? 2 : 4);
+#define CGNN_SAGE_BWD(CC_, MT_)                                                                  \
+  {                                                                                              \
+    auto kfn = k_sage_bwd_a<CC_, MT_>;                                                           \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    CGNN_LAUNCH(kfn, grid, kThreads, smem, stream, a);                                           \
+  }
+  if (cc == 1) { if (maxt == 1) CGNN_SAGE_BWD(1, 1) else if (maxt == 2) CGNN_SAGE_BWD(1, 2) else CGNN_SAGE_BWD(1, 4) }
+  else if (cc == 2) { if (maxt == 1) CGNN_SAGE_BWD(2, 1) else if (maxt == 2) CGNN_SAGE_BWD(2, 2) else CGNN_SAGE_BWD(2, 4) }
+  else { if (maxt == 1) CGNN_SAGE_BWD(4, 1) else if (maxt == 2) CGNN_SAGE_BWD(4, 2) else CGNN_SAGE_BWD(4, 4) }
+#undef CGNN_SAGE_BWD
+  CGNN_CHECK_LAUNCH();
+  int rc = launch_reduce_partials(a.partials + a.o_pdw, grid, a.part_stride, H, 2 * d_in, 2 * a.K4, dW, stream);
+  if (rc) return rc;
+  rc = launch_reduce_partials(a.partials + a.o_pdb, grid, a.part_stride, 1, H, a.H4, dbias, stream);
+  if (rc) return rc;
+  if (!du_in) return CGNN_OK;
+
+  // kernel B: transposed neighbour aggregation
+  SageBwdBArgs b;
+  b.direct = a.direct; b.nbr = a.nbr; b.t_in = t_in; b.act_in = a.act_in;
+  b.out_rowptr = csr->out_rowptr; b.out_col = csr->out_col; b.out_w = csr->out_w;
+  b.prev_mean = prev_mean; b.prev_rstd = prev_rstd; b.want_prev = prev_sums ? 1 : 0;
+  b.ptr = (const long long*)ptr; b.B = num_graphs; b.K = d_in; b.K4 = a.K4; b.max_nodes = a.max_nodes;
+  b.du_in = du_in;
+  int offb = 0;
+  b.o_g = offb; offb += a.max_nodes * a.K4;
+  b.o_ci = offb; offb += 4 * a.K4;
+  b.o_red = offb; offb += kWarps * 2 * a.K4;
+  const size_t smem_b = (size_t)offb * sizeof(float);
+  if (smem_b > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
+  int grid_b = persistent_grid(num_graphs, smem_b, dev, kThreads);
+  // partials of kernel B live after kernel A's (the reduce kernels above still read those)
+  const size_t used_a = (size_t)grid * rec;
+  const size_t rec_b = (size_t)2 * a.K4 * sizeof(float);
+  if (used_a + rec_b > workspace_bytes) return CGNN_ERR_WORKSPACE;
+  if (used_a + (size_t)grid_b * rec_b > workspace_bytes) grid_b = (int)((workspace_bytes - used_a) / rec_b);
+  b.partials = (float*)((char*)workspace + used_a);
+  const int ccb = pick_hc(a.K4);
+#define CGNN_SAGE_BWDB(CC_)                                                                      \
+  {                                                                                              \
+    auto kfn = k_sage_bwd_b<CC_>;                                                                \
+    if (smem_b > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b); \
+    CGNN_LAUNCH(kfn, grid_b, kThreads, smem_b, stream, b);                                       \
+  }
+  if (ccb == 1) CGNN_SAGE_BWDB(1) else if (ccb == 2) CGNN_SAGE_BWDB(2) else CGNN_SAGE_BWDB(4)
+#undef CGNN_SAGE_BWDB
+  CGNN_CHECK_LAUNCH();
+  if (prev_sums) {
+    rc = launch_reduce_partials(b.partials, grid_b, 2 * a.K4, 2, d_in, a.K4, prev_sums, stream);
+    if (rc) return rc;
+  }
+  return CGNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// util.cu - status strings, device query, deterministic partial reductions.
+#include "common.cuh"
+
+namespace cgnn {
+
+static thread_local int g_last_cuda_error = 0;
+void set_cuda_error(int err) { g_last_cuda_error = err; }
+
+DeviceInfo device_info() {
+  static thread_local int cached_dev = -1;
+  static thread_local DeviceInfo cached = {148, 227 * 1024};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cached;
+  if (dev != cached_dev) {
+    int sms = 148, smem = 227 * 1024;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cached.sm_count = sms;
+    cached.smem_optin = smem;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// out[r*cols + c] = sum_g partials[g*stride + r*ld + c]; one thread per output, fp64, fixed order.
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partials, int G, int stride,
+                                                         int rows, int cols, int ld, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  int r = i / cols, c = i - r * cols;
+  const float* p = partials + (size_t)r * ld + c;
+  double s = 0.0;
+  for (int g = 0; g < G; ++g) s += (double)p[(size_t)g * stride];
+  out[i] = (float)s;
+}
+
+int launch_reduce_partials(const float* partials, int G, int stride, int rows, int cols, int ld, float* out,
+                           cudaStream_t stream) {
+  int n = rows * cols;
+  if (n <= 0) return CGNN_OK;
+  auto kfn = k_reduce_partials;
+  CGNN_LAUNCH(kfn, (n + 255) / 256, 256, 0, stream, partials, G, stride, rows, cols, ld, out);
+  CGNN_CHECK_LAUNCH();
+  return CGNN_OK;
+}
+
+// One warp per channel: merge `parts` records {count, mean[C], M2[C]} (doubles) exactly:
+//   N = sum n_i;  mean = sum n_i mean_i / N;  M2 = sum M2_i + n_i (mean_i - mean)^2
+__global__ void __launch_bounds__(256) k_stats_merge(const double* __restrict__ parts, int parts_n, int C,
+                                                     double* __restrict__ stats) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= C) return;
+  const int rec = 1 + 2 * C;
+  double n = 0.0, s = 0.0;
+  for (int g = lane; g < parts_n; g += 32) {
+    double ng = parts[(size_t)g * rec];
+    n += ng;
+    s += ng * parts[(size_t)g * rec + 1 + warp];
+  }
+  n = warp_sum(n);
+  s = warp_sum(s);
+  double mean = n > 0.0 ? s / n : 0.0;
+  double q = 0.0;
+  for (int g = lane; g < parts_n; g += 32) {
+    double ng = parts[(size_t)g * rec];
+    if (ng > 0.0) {
+      double d = parts[(size_t)g * rec + 1 + warp] - mean;
+      q += parts[(size_t)g * rec + 1 + C + warp] + ng * d * d;
+    }
+  }
+  q = warp_sum(q);
+  if (lane == 0) {
+    stats[1 + warp] = mean;
+    stats[1 + C + warp] = q;
+    if (warp == 0) stats[0] = n;
+  }
+}
+
+int launch_stats_merge(const double* parts, int parts_n, int C, double* stats, cudaStream_t stream) {
+  auto kfn = k_stats_merge;
+  int warps_per_block = 8;
+  CGNN_LAUNCH(kfn, (C + warps_per_block - 1) / warps_per_block, 256, 0, stream, parts, parts_n, C, stats);
+  CGNN_CHECK_LAUNCH();
+  return CGNN_OK;
+}
+
+}  // namespace cgnn
+
+extern "C" {
+
+const char* cgnn_status_string(int status) {
+  switch (status) {
+    case CGNN_OK: return "ok";
+    case CGNN_ERR_INVALID_ARG: return "invalid argument";
+    case CGNN_ERR_TILE_TOO_LARGE: return "subject tile or weight matrix does not fit in shared memory";
+    case CGNN_ERR_WORKSPACE: return "workspace too small";
+    case CGNN_ERR_CUDA: return "CUDA runtime error";
+    default: return "unknown status";
+  }
+}
+
+int cgnn_abi_version(void) { return CGNN_ABI_VERSION; }
+int cgnn_last_cuda_error(void) { return cgnn::g_last_cuda_error; }
+size_t cgnn_workspace_bytes(void) { return (size_t)32 << 20; }
+
+int cgnn_bn_merge_stats(const double* stats_parts, int32_t parts, int32_t C, double* stats, cgnn_stream_t stream) {
+  if (!stats_parts || !stats || parts <= 0 || C <= 0) return CGNN_ERR_INVALID_ARG;
+  return cgnn::launch_stats_merge(stats_parts, parts, C, stats, (cudaStream_t)stream);
+}
+
+}  // extern "C"

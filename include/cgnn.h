@@ -1,0 +1,257 @@
+/*
+ * cgnn.h - C ABI of the B200-native batched message-passing path of connectome-gnn-suite.
+ *
+ * The reference (danieleschmidt/connectome-gnn-suite) is pure Python and has no FFI of its
+ * own: its "operators" are ATen call sequences inside connectome_gnn/graph.py, models.py
+ * and train.py.  Each entry point below replaces one such sequence (cited per function as
+ * reference file:line).  A maintainer binds these with ctypes; the
+ * host package under connectome-gnn-suite_b200/connectome_gnn does exactly that.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name
+ *     ends in _host.  No torch types.  All tensors are dense, row-major, fp32 / int32 /
+ *     int64 exactly as documented.
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *     returns immediately; 0 = CGNN_OK, otherwise a cgnn_status code (never throws).
+ *   - functions are re-entrant; the only state is caller-owned (`workspace`).
+ *   - "rows" are the nodes (brain regions) of all subjects of a batch, packed subject
+ *     after subject; `ptr[B+1]` (int64) delimits subjects, as ConnectomeBatch.ptr does.
+ */
+#ifndef CGNN_H_
+#define CGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGNN_ABI_VERSION 1
+
+typedef void* cgnn_stream_t; /* cudaStream_t */
+
+typedef enum {
+  CGNN_OK = 0,
+  CGNN_ERR_INVALID_ARG = 1,     /* null pointer / negative size / unsupported combination */
+  CGNN_ERR_TILE_TOO_LARGE = 2,  /* one subject's [N_g, C] fp32 tile (or W) exceeds shared memory */
+  CGNN_ERR_WORKSPACE = 3,       /* workspace too small: call cgnn_workspace_bytes()          */
+  CGNN_ERR_CUDA = 4             /* a CUDA runtime call failed: see cgnn_last_cuda_error()     */
+} cgnn_status;
+
+const char* cgnn_status_string(int status);
+int cgnn_abi_version(void);
+int cgnn_last_cuda_error(void);          /* cudaError_t of the last CGNN_ERR_CUDA on this thread */
+/* Upper bound on the scratch a single call needs (partials of BN statistics / weight
+ * gradients).  The caller allocates it once per device+stream and passes it to every call. */
+size_t cgnn_workspace_bytes(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Device CSR of a batch.  Built once per batch by cgnn_collate_csr / cgnn_csr_from_coo and
+ * read by every layer; replaces the per-layer recomputation in reference models.py:94-108
+ * (self-loops, D^, d^-1/2, w^) and models.py:147-148 (w_sum).
+ *
+ *   in_*   rows = destination node, entries in COO order (stable), col = source node id
+ *   out_*  rows = source node,      entries in COO order (stable), col = destination id
+ *   *_w    raw edge weight;  *_wn = (dinv[src] * w) * dinv[dst]   (GCN normalisation)
+ *   deg    D^_i = ((0 + w_e1) + w_e2 ... ) + 1.0f over edges with src == i in COO order
+ *          (bit-exact with the CPU scatter_add_ of models.py:103-104, self-loop last)
+ *   wsum   sum_{e: dst == i} w_e, same sequential order (models.py:147-148)
+ *   dinv   (deg + 1e-8f)^-1/2  (models.py:105)
+ * Self-loops are NOT stored; kernels add (dinv_i*dinv_i) * P_i last, as the reference's
+ * concatenation order implies (models.py:98-100).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const int32_t* in_rowptr;  /* [rows+1] positions into in_col/in_w/in_wn   */
+  const int32_t* in_col;     /* [E] global row id of the source node        */
+  const float*   in_w;       /* [E] */
+  const float*   in_wn;      /* [E] */
+  const int32_t* out_rowptr; /* [rows+1] */
+  const int32_t* out_col;    /* [E] global row id of the destination node   */
+  const float*   out_w;      /* [E] */
+  const float*   out_wn;     /* [E] */
+  const float*   deg;        /* [rows] */
+  const float*   dinv;       /* [rows] */
+  const float*   wsum;       /* [rows] */
+} cgnn_csr_t;
+
+/* How a stored activation tensor t [rows, C] is turned into the layer input u on load:
+ *     u = dropout( relu?( scale * t + shift ) )
+ * This is the previous layer's BatchNorm1d + ReLU + dropout (reference models.py:208-210 for
+ * GCN, :260-261 for SAGE) fused into the consumer.  scale == NULL means identity (first
+ * layer reads node_features as is).  Dropout masks are a pure function of
+ * (seed, site, global row id, channel) so forward and backward regenerate the same mask
+ * and the result does not depend on how subjects are sharded over GPUs. */
+typedef struct {
+  const float* scale;  /* [C] gamma * rstd, or NULL */
+  const float* shift;  /* [C] beta - mean * scale   */
+  int32_t  relu;       /* 1: max(.,0) after the affine map */
+  float    p_drop;     /* drop probability, 0 disables (eval mode or dropout=0) */
+  uint64_t seed;
+  uint32_t site;       /* which dropout site of the network (layer index)  */
+  int64_t  row_base;   /* global row id of local row 0 (rank offset under data parallelism) */
+} cgnn_act_t;
+
+/* BatchNorm1d backward coefficients of one layer (reference: autograd of models.py:208/260):
+ *   dz = scale * (dy - s1/count - xhat * s2/count),  xhat = (z - mean) * rstd   [train]
+ *   dz = scale * dy                                                              [eval]
+ * s1 = sum dy, s2 = sum dy*xhat over all rows of the GLOBAL batch (all ranks). */
+typedef struct {
+  const float* scale;  /* [C] gamma * rstd */
+  const float* mean;   /* [C] */
+  const float* rstd;   /* [C] */
+  const float* s1;     /* [C] (unused when train == 0) */
+  const float* s2;     /* [C] */
+  double  count;       /* rows of the global batch */
+  int32_t train;       /* 1: batch statistics were used in forward */
+} cgnn_bn_bwd_t;
+
+/* ---- K0: collate (reference graph.py:143-167) ---------------------------------------- */
+
+/* Subject store ("arena"): all subjects of a dataset packed once on the device.
+ * Edge endpoints are subject-local int32 ids; node_ptr/edge_ptr are int64 prefix sums. */
+typedef struct {
+  const float*   x;         /* [sum N_s, F] */
+  const int32_t* src;       /* [sum E_s] local source id      (edge_index[0]) */
+  const int32_t* dst;       /* [sum E_s] local destination id (edge_index[1]) */
+  const float*   w;         /* [sum E_s] */
+  const int64_t* node_ptr;  /* [S+1] */
+  const int64_t* edge_ptr;  /* [S+1] */
+  const int64_t* label;     /* [S] or NULL */
+  int32_t num_features;
+} cgnn_store_t;
+
+/* Mutable view of the CSR arrays the collate kernels fill (same layout as cgnn_csr_t). */
+typedef struct {
+  int32_t* in_rowptr;  int32_t* in_col;  float* in_w;  float* in_wn;
+  int32_t* out_rowptr; int32_t* out_col; float* out_w; float* out_wn;
+  float* deg; float* dinv; float* wsum;
+} cgnn_csr_out_t;
+
+/* Gather `num_graphs` subjects (ids into the store, device int64) into one batch.
+ * Writes the six ConnectomeBatch fields (graph.py:117-122) bit-exactly as collate_graphs
+ * does - node_features [rows,F], edge_index [2,E] int64 with node offsets added
+ * (graph.py:152), edge_weight [E], batch [rows] int64 (graph.py:154), labels [B] int64
+ * (NULL to skip), ptr [B+1] int64 (graph.py:158,166) - plus eptr [B+1] int64 (edge prefix
+ * sums) and the device CSR.  total_rows / total_edges are the host-computed sums used to
+ * size the outputs; max_nodes is the largest N_s among the selected subjects (sizes the
+ * per-CTA shared memory). */
+int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int64_t num_graphs,
+                     int64_t total_rows, int64_t total_edges, int32_t max_nodes,
+                     float* node_features, int64_t* edge_index, float* edge_weight,
+                     int64_t* batch, int64_t* labels, int64_t* ptr, int64_t* eptr,
+                     const cgnn_csr_out_t* csr, cgnn_stream_t stream);
+
+/* Same CSR, from an already collated batch (COO with global ids, grouped by subject as
+ * collate_graphs emits it).  Used for ConnectomeBatch objects built by hand / moved from
+ * the host.  eptr [B+1] is an output. */
+int cgnn_csr_from_coo(const int64_t* edge_index, const float* edge_weight, const int64_t* ptr,
+                      int64_t num_graphs, int64_t total_rows, int64_t total_edges, int32_t max_nodes,
+                      int64_t* eptr, const cgnn_csr_out_t* csr, cgnn_stream_t stream);
+
+/* ---- K1/K2: layer forward ------------------------------------------------------------ */
+
+/* GCN layer (reference models.py:84-114):  z = A^ (u W^T) + bias,  u = act(t_in).
+ * t_in [rows, d_in], W [H, d_in], bias [H], z [rows, H].
+ * If bn_stats != NULL also returns the BatchNorm batch statistics of z as doubles
+ * [1 + 2H] = {count, mean[H], M2[H]} (Welford/Chan merged, deterministic). */
+int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
+                       const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
+                       int32_t d_in, int32_t H, int32_t max_nodes, float* z, double* bn_stats,
+                       void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
+
+/* GraphSAGE layer (reference models.py:136-152):
+ *   agg_i = sum_{e: dst=i} w_e u_src / (wsum_i + 1e-8);  z = relu([u || agg] W^T + b)
+ * W [H, 2*d_in], b [H]. */
+int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
+                        const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
+                        int32_t d_in, int32_t H, int32_t max_nodes, float* z, double* bn_stats,
+                        void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
+
+/* ---- K3: BatchNorm1d bookkeeping (reference models.py:191-193, 208, 260) -------------- */
+
+/* Merge `parts` statistic records [parts, 1+2C] (one per rank) into one (Chan, fp64). */
+int cgnn_bn_merge_stats(const double* stats_parts, int32_t parts, int32_t C, double* stats,
+                        cgnn_stream_t stream);
+
+/* Training mode: stats -> scale/shift (+ mean, rstd for backward) and the running-stat
+ * update  r = (1-m) r + m * stat  with the unbiased variance, num_batches_tracked += 1. */
+int cgnn_bn_finalize(const double* stats, const float* gamma, const float* beta, int32_t C,
+                     float eps, float momentum, float* running_mean, float* running_var,
+                     int64_t* num_batches_tracked, float* scale, float* shift, float* mean,
+                     float* rstd, cgnn_stream_t stream);
+
+/* Eval mode: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale. */
+int cgnn_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, int32_t C, float eps, float* scale, float* shift,
+                        float* mean, float* rstd, cgnn_stream_t stream);
+
+/* ---- K4: readout, head, loss (reference models.py:57-59, 196-201; train.py:49,64-66) -- */
+
+/* emb[g] = sum_{i in g} act(t)[i] / (N_g + 1e-8)    -> emb [B, C] */
+int cgnn_pool_fwd(const float* t_in, const cgnn_act_t* act, const int64_t* ptr, int64_t num_graphs,
+                  int64_t rows, int32_t C, float* emb, cgnn_stream_t stream);
+
+/* logits = W1 drop(relu(W0 emb + b0)) + b1.  W0 [M, C], W1 [K, M].  hidden [B, M] receives the
+ * post-ReLU, post-dropout activations (kept for backward). */
+int cgnn_head_fwd(const float* emb, const float* W0, const float* b0, const float* W1, const float* b1,
+                  int64_t num_graphs, int32_t C, int32_t M, int32_t K, float p_drop, uint64_t seed,
+                  int64_t graph_base, float* hidden, float* logits, cgnn_stream_t stream);
+
+/* Cross entropy over graphs: loss_sum[0] = sum_g nll_g * inv_count (inv_count = 1/B_global gives
+ * nn.CrossEntropyLoss()'s mean), correct[0] = #argmax == label (int64), nll [B] per graph. */
+int cgnn_ce_fwd(const float* logits, const int64_t* labels, int64_t num_graphs, int32_t K,
+                float inv_count, float* nll, float* loss, int64_t* correct, cgnn_stream_t stream);
+
+/* ---- K5-K7: backward ------------------------------------------------------------------ */
+
+/* dlogits = (softmax - onehot) * inv_count * gout[0] */
+int cgnn_ce_bwd(const float* logits, const int64_t* labels, int64_t num_graphs, int32_t K,
+                float inv_count, const float* gout, float* dlogits, cgnn_stream_t stream);
+
+/* Head backward: given dlogits [B,K] -> demb [B,C] and parameter grads (overwritten). */
+int cgnn_head_bwd(const float* emb, const float* hidden, const float* dlogits, const float* W0,
+                  const float* W1, int64_t num_graphs, int32_t C, int32_t M, int32_t K,
+                  float p_drop, float* demb, float* dW0, float* db0, float* dW1, float* db1,
+                  void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
+
+/* BatchNorm backward sums of one layer:  s[0:C] = sum dy, s[C:2C] = sum dy * xhat where
+ * dy = dact(du) and du is either a per-row tensor du [rows, C] (demb == NULL) or the pooled
+ * gradient demb [B, C] broadcast as demb[g]/(N_g + 1e-8) (du == NULL).  z is the layer's raw
+ * (pre-BN) output; act describes the BN+ReLU+dropout applied to it; post_relu = 1 when z
+ * itself is a ReLU output (SAGE) - it does not change the sums, only documents the caller. */
+int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, const float* rstd,
+                     const float* du, const float* demb, const int64_t* ptr, int64_t num_graphs,
+                     int64_t rows, int32_t C, float* sums, void* workspace, size_t workspace_bytes,
+                     cgnn_stream_t stream);
+
+/* GCN layer backward (autograd of models.py:84-114 plus the BN/ReLU/dropout that follows).
+ *   upstream: du [rows,H] or pooled demb [B,H] (exactly one non-NULL), w.r.t. act_out(z).
+ *   z [rows,H]       this layer's forward output, act_out / bn its BN+ReLU+dropout
+ *   t_in [rows,d_in] this layer's stored input, act_in how it was transformed on load
+ * Outputs: dW [H,d_in], dbias [H]; du_in [rows,d_in] = gradient w.r.t. act_in(t_in) (NULL for
+ * the first layer); prev_sums [2*d_in] = BN backward sums of the previous layer computed
+ * from du_in on the fly (NULL to skip; needs prev_mean/prev_rstd). */
+int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
+                       const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in,
+                       const float* W, const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs,
+                       int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes,
+                       float* dW, float* dbias, float* du_in,
+                       const float* prev_mean, const float* prev_rstd, float* prev_sums,
+                       void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
+
+/* GraphSAGE layer backward (autograd of models.py:136-152 plus the BN/dropout that follows).
+ * Same contract as cgnn_gcn_layer_bwd; W [H, 2*d_in].  scratch [2, rows, d_in] fp32 holds the
+ * direct and neighbour parts of the input gradient between the two kernels of this call. */
+int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
+                        const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in,
+                        const float* W, const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs,
+                        int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes,
+                        float* dW, float* dbias, float* du_in,
+                        const float* prev_mean, const float* prev_rstd, float* prev_sums,
+                        float* scratch, void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGNN_H_ */
