@@ -1,0 +1,244 @@
+"""Typed host-side wrappers over the C ABI (``include/cgnn.h``): one method per entry point.
+
+PyTorch is plumbing here - it owns device memory (caching allocator), the current stream and
+``torch.distributed``; every bit of arithmetic on the hot path happens inside ``libcgnn.so``.
+There is deliberately no CPU branch: :func:`engine_for` refuses anything that is not a CUDA
+tensor, and :func:`_lib.load` raises when the CUDA library has not been built.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ActT, BnBwdT, CsrT, StoreT
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a tensor (None -> NULL).  Tensors must be contiguous."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "cgnn kernels take dense row-major tensors"
+    return t.data_ptr()
+
+
+@dataclass
+class Act:
+    """Host mirror of ``cgnn_act_t``: how a stored tensor becomes a layer input on load."""
+    scale: Optional[torch.Tensor] = None
+    shift: Optional[torch.Tensor] = None
+    relu: bool = False
+    p_drop: float = 0.0
+    seed: int = 0
+    site: int = 0
+    row_base: int = 0
+
+    def struct(self) -> ActT:
+        return ActT(_p(self.scale), _p(self.shift), int(self.relu), float(self.p_drop),
+                    int(self.seed) & 0xFFFFFFFFFFFFFFFF, int(self.site) & 0xFFFFFFFF, int(self.row_base))
+
+
+@dataclass
+class BnBwd:
+    """Host mirror of ``cgnn_bn_bwd_t``."""
+    scale: torch.Tensor
+    mean: torch.Tensor
+    rstd: torch.Tensor
+    sums: Optional[torch.Tensor]   # [2, C]: sum dy, sum dy*xhat (global batch)
+    count: float
+    train: bool
+
+    def struct(self) -> BnBwdT:
+        s1 = s2 = None
+        if self.sums is not None:
+            c = self.scale.shape[0]
+            base = self.sums.data_ptr()
+            s1, s2 = base, base + 4 * c
+        return BnBwdT(_p(self.scale), _p(self.mean), _p(self.rstd), s1, s2, float(self.count), int(self.train))
+
+
+class Engine:
+    """Binds a loaded ABI library to one device: workspace, stream lookup, call wrappers."""
+
+    def __init__(self, lib: C.CDLL, device: torch.device):
+        self.lib = lib
+        self.device = torch.device(device)
+        self.workspace_bytes = int(lib.cgnn_workspace_bytes())
+        self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+        self.launches = 0  # C-ABI calls issued (each enqueues >= 1 kernel); bench reports kernel counts separately
+
+    # -- plumbing -------------------------------------------------------------------------
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _call(self, name: str, *args) -> None:
+        self.launches += 1
+        _lib.check(self.lib, getattr(self.lib, name)(*args), name)
+
+    def empty(self, shape, dtype=torch.float32) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # -- K0 ---------------------------------------------------------------------------------
+    def new_csr(self, rows: int, edges: int) -> dict:
+        e = self.empty
+        return dict(
+            in_rowptr=e(rows + 1, torch.int32), in_col=e(edges, torch.int32), in_w=e(edges), in_wn=e(edges),
+            out_rowptr=e(rows + 1, torch.int32), out_col=e(edges, torch.int32), out_w=e(edges), out_wn=e(edges),
+            deg=e(rows), dinv=e(rows), wsum=e(rows))
+
+    @staticmethod
+    def csr_struct(c) -> CsrT:
+        g = (lambda k: c[k]) if isinstance(c, dict) else (lambda k: getattr(c, k))
+        return CsrT(*[_p(g(k)) for k in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col",
+                                         "out_w", "out_wn", "deg", "dinv", "wsum")])
+
+    def collate_csr(self, store: StoreT, ids: torch.Tensor, num_graphs: int, rows: int, edges: int, max_nodes: int,
+                    num_features: int, with_labels: bool):
+        e = self.empty
+        out = dict(
+            node_features=e((rows, num_features)), edge_index=e((2, edges), torch.int64), edge_weight=e(edges),
+            batch=e(rows, torch.int64), labels=e(num_graphs, torch.int64) if with_labels else None,
+            ptr=e(num_graphs + 1, torch.int64), eptr=e(num_graphs + 1, torch.int64))
+        csr = self.new_csr(rows, edges)
+        cs = self.csr_struct(csr)
+        self._call("cgnn_collate_csr", C.byref(store), _p(ids), num_graphs, rows, edges, max_nodes,
+                   _p(out["node_features"]), _p(out["edge_index"]), _p(out["edge_weight"]), _p(out["batch"]),
+                   _p(out["labels"]), _p(out["ptr"]), _p(out["eptr"]), C.byref(cs), self.stream())
+        return out, csr
+
+    def csr_from_coo(self, edge_index, edge_weight, ptr, num_graphs: int, rows: int, edges: int, max_nodes: int):
+        csr = self.new_csr(rows, edges)
+        eptr = self.empty(num_graphs + 1, torch.int64)
+        cs = self.csr_struct(csr)
+        self._call("cgnn_csr_from_coo", _p(edge_index), _p(edge_weight), _p(ptr), num_graphs, rows, edges,
+                   max_nodes, _p(eptr), C.byref(cs), self.stream())
+        return csr, eptr
+
+    # -- K1 / K2 ------------------------------------------------------------------------------
+    def layer_fwd(self, kind: str, t_in, act: Act, W, bias, csr, ptr, num_graphs: int, max_nodes: int,
+                  want_stats: bool):
+        rows, d_in = t_in.shape
+        H = W.shape[0]
+        z = self.empty((rows, H))
+        stats = self.empty(1 + 2 * H, torch.float64) if want_stats else None
+        a, cs = act.struct(), self.csr_struct(csr)
+        self._call(f"cgnn_{kind}_layer_fwd", _p(t_in), C.byref(a), _p(W), _p(bias), C.byref(cs), _p(ptr),
+                   num_graphs, rows, d_in, H, max_nodes, _p(z), _p(stats), _p(self.workspace),
+                   self.workspace_bytes, self.stream())
+        return z, stats
+
+    # -- K3 -------------------------------------------------------------------------------------
+    def bn_merge_stats(self, parts: torch.Tensor, C_: int) -> torch.Tensor:
+        out = self.empty(1 + 2 * C_, torch.float64)
+        self._call("cgnn_bn_merge_stats", _p(parts), parts.shape[0], C_, _p(out), self.stream())
+        return out
+
+    def bn_finalize(self, stats, gamma, beta, eps: float, momentum: float, running_mean, running_var, nbt):
+        C_ = gamma.shape[0]
+        scale, shift, mean, rstd = (self.empty(C_) for _ in range(4))
+        self._call("cgnn_bn_finalize", _p(stats), _p(gamma), _p(beta), C_, eps, momentum, _p(running_mean),
+                   _p(running_var), _p(nbt), _p(scale), _p(shift), _p(mean), _p(rstd), self.stream())
+        return scale, shift, mean, rstd
+
+    def bn_eval_affine(self, gamma, beta, running_mean, running_var, eps: float):
+        C_ = gamma.shape[0]
+        scale, shift, mean, rstd = (self.empty(C_) for _ in range(4))
+        self._call("cgnn_bn_eval_affine", _p(gamma), _p(beta), _p(running_mean), _p(running_var), C_, eps,
+                   _p(scale), _p(shift), _p(mean), _p(rstd), self.stream())
+        return scale, shift, mean, rstd
+
+    # -- K4 -------------------------------------------------------------------------------------
+    def pool_fwd(self, t_in, act: Act, ptr, num_graphs: int):
+        rows, C_ = t_in.shape
+        emb = self.empty((num_graphs, C_))
+        a = act.struct()
+        self._call("cgnn_pool_fwd", _p(t_in), C.byref(a), _p(ptr), num_graphs, rows, C_, _p(emb), self.stream())
+        return emb
+
+    def head_fwd(self, emb, W0, b0, W1, b1, p_drop: float, seed: int, graph_base: int):
+        B, C_ = emb.shape
+        M, K = W0.shape[0], W1.shape[0]
+        hidden, logits = self.empty((B, M)), self.empty((B, K))
+        self._call("cgnn_head_fwd", _p(emb), _p(W0), _p(b0), _p(W1), _p(b1), B, C_, M, K, float(p_drop),
+                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(graph_base), _p(hidden), _p(logits), self.stream())
+        return hidden, logits
+
+    def ce_fwd(self, logits, labels, inv_count: float):
+        B, K = logits.shape
+        nll, loss, correct = self.empty(B), self.empty(()), self.empty((), torch.int64)
+        self._call("cgnn_ce_fwd", _p(logits), _p(labels), B, K, float(inv_count), _p(nll), _p(loss), _p(correct),
+                   self.stream())
+        return loss, nll, correct
+
+    # -- K5..K7 -----------------------------------------------------------------------------------
+    def ce_bwd(self, logits, labels, inv_count: float, gout):
+        B, K = logits.shape
+        d = self.empty((B, K))
+        self._call("cgnn_ce_bwd", _p(logits), _p(labels), B, K, float(inv_count), _p(gout), _p(d), self.stream())
+        return d
+
+    def head_bwd(self, emb, hidden, dlogits, W0, W1, p_drop: float):
+        B, C_ = emb.shape
+        M, K = W0.shape[0], W1.shape[0]
+        demb = self.empty((B, C_))
+        dW0, db0, dW1, db1 = self.empty((M, C_)), self.empty(M), self.empty((K, M)), self.empty(K)
+        self._call("cgnn_head_bwd", _p(emb), _p(hidden), _p(dlogits), _p(W0), _p(W1), B, C_, M, K, float(p_drop),
+                   _p(demb), _p(dW0), _p(db0), _p(dW1), _p(db1), _p(self.workspace), self.workspace_bytes,
+                   self.stream())
+        return demb, dW0, db0, dW1, db1
+
+    def bn_bwd_sums(self, z, act: Act, mean, rstd, du, demb, ptr, num_graphs: int):
+        rows, C_ = z.shape
+        sums = self.empty((2, C_))
+        a = act.struct()
+        self._call("cgnn_bn_bwd_sums", _p(z), C.byref(a), _p(mean), _p(rstd), _p(du), _p(demb), _p(ptr),
+                   num_graphs, rows, C_, _p(sums), _p(self.workspace), self.workspace_bytes, self.stream())
+        return sums
+
+    def layer_bwd(self, kind: str, du, demb, z, act_out: Act, bn: Optional[BnBwd], t_in, act_in: Act, W, csr, ptr,
+                  num_graphs: int, max_nodes: int, need_du: bool, prev_mean, prev_rstd):
+        rows, d_in = t_in.shape
+        H = z.shape[1]
+        dW, db = self.empty(W.shape), self.empty(H)
+        du_in = self.empty((rows, d_in)) if need_du else None
+        want_prev = need_du and prev_mean is not None
+        prev_sums = self.empty((2, d_in)) if want_prev else None
+        ao, ai, cs = act_out.struct(), act_in.struct(), self.csr_struct(csr)
+        bs = bn.struct() if bn is not None else None
+        args = [_p(du), _p(demb), _p(z), C.byref(ao), C.byref(bs) if bs is not None else None, _p(t_in),
+                C.byref(ai), _p(W), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, max_nodes, _p(dW), _p(db),
+                _p(du_in), _p(prev_mean) if want_prev else None, _p(prev_rstd) if want_prev else None,
+                _p(prev_sums)]
+        if kind == "sage":
+            scratch = self.empty((2, rows, d_in)) if need_du else None
+            args.append(_p(scratch))
+        args += [_p(self.workspace), self.workspace_bytes, self.stream()]
+        self._call(f"cgnn_{kind}_layer_bwd", *args)
+        return dW, db, du_in, prev_sums
+
+
+_ENGINES: dict = {}
+
+
+def engine_for(t: torch.Tensor) -> Engine:
+    """The engine of the CUDA device `t` lives on.  No CUDA tensor, no engine: there is no CPU path."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(
+            "connectome_gnn (B200 build) computes on CUDA only: got a "
+            f"{'non-tensor' if not isinstance(t, torch.Tensor) else t.device.type} input. "
+            "Move the batch with .to('cuda'); there is no CPU fallback.")
+    dev = t.device
+    eng = _ENGINES.get(dev)
+    if eng is None:
+        eng = _ENGINES[dev] = Engine(_lib.load(), dev)
+    return eng
+
+
+def default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("connectome_gnn (B200 build) needs a CUDA device; none is visible and there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())

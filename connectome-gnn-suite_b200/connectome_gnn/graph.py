@@ -1,0 +1,355 @@
+"""Subject graphs, device-resident subject stores and batch collation.
+
+Host-side mirror of reference ``connectome_gnn/graph.py`` with the same public names and
+signatures (``ConnectomeGraph``, ``ConnectomeBatch``, ``collate_graphs``, ``ConnectomeDataLoader``).
+What changes is where the work happens: subjects are packed once into a device arena
+(:class:`SubjectStore`); a batch is then produced by ONE kernel sequence
+(``cgnn_collate_csr``) that gathers the selected subjects, writes the six reference fields
+bit-exactly as reference ``graph.py:143-167`` would, and builds the per-subject CSR, weighted
+degrees and GCN normalisation that reference ``models.py:94-108,147-148`` recompute in every
+layer.  Nothing here has a CPU compute path; host code only packs, indexes and shards.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _engine
+from ._lib import StoreT
+
+__all__ = ["ConnectomeGraph", "ConnectomeBatch", "BatchCSR", "SubjectStore", "collate_graphs",
+           "ConnectomeDataLoader", "shard_bounds"]
+
+
+# ---------------------------------------------------------------------------
+# One subject
+# ---------------------------------------------------------------------------
+
+@dataclass
+class ConnectomeGraph:
+    """One subject: regions are nodes, weighted connections are directed COO edges (both
+    directions present for an undirected connectome).  Same fields as reference ``graph.py:27-56``."""
+
+    node_features: torch.Tensor            # [N, F] float32
+    edge_index: torch.Tensor               # [2, E] int64, subject-local node ids
+    edge_weight: torch.Tensor              # [E] float32
+    label: Optional[torch.Tensor] = None   # scalar
+    subject_id: str = "unknown"
+
+    @property
+    def num_nodes(self) -> int:
+        return int(self.node_features.shape[0])
+
+    @property
+    def num_edges(self) -> int:
+        return int(self.edge_index.shape[1])
+
+    @property
+    def num_features(self) -> int:
+        return int(self.node_features.shape[1])
+
+    def adjacency_matrix(self) -> torch.Tensor:
+        """Dense ``[N, N]`` weight matrix (later duplicates overwrite earlier ones)."""
+        n = self.num_nodes
+        dense = self.edge_weight.new_zeros((n, n))
+        dense[self.edge_index[0], self.edge_index[1]] = self.edge_weight
+        return dense
+
+    def degree(self) -> torch.Tensor:
+        """Weighted out-degree ``[N]``."""
+        out = self.edge_weight.new_zeros(self.num_nodes)
+        return out.scatter_add_(0, self.edge_index[0], self.edge_weight)
+
+    def to(self, device) -> "ConnectomeGraph":
+        move = lambda t: None if t is None else t.to(device)
+        return ConnectomeGraph(move(self.node_features), move(self.edge_index), move(self.edge_weight),
+                               move(self.label), self.subject_id)
+
+
+# ---------------------------------------------------------------------------
+# Batch
+# ---------------------------------------------------------------------------
+
+@dataclass
+class BatchCSR:
+    """Device CSR of a batch (``cgnn_csr_t``): by-destination and by-source rows in stable COO
+    order, raw and GCN-normalised weights, D^ / d^-1/2 / w_sum.  See include/cgnn.h."""
+
+    in_rowptr: torch.Tensor
+    in_col: torch.Tensor
+    in_w: torch.Tensor
+    in_wn: torch.Tensor
+    out_rowptr: torch.Tensor
+    out_col: torch.Tensor
+    out_w: torch.Tensor
+    out_wn: torch.Tensor
+    deg: torch.Tensor
+    dinv: torch.Tensor
+    wsum: torch.Tensor
+    eptr: torch.Tensor        # [B+1] int64 edge prefix sums
+    max_nodes: int            # largest subject of the batch (sizes shared-memory tiles)
+
+    _FIELDS = ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn",
+               "deg", "dinv", "wsum", "eptr")
+
+    def to(self, device) -> "BatchCSR":
+        return BatchCSR(*[getattr(self, f).to(device) for f in self._FIELDS], max_nodes=self.max_nodes)
+
+
+@dataclass
+class ConnectomeBatch:
+    """Block-diagonal packing of B subjects; the first six fields are exactly the reference's
+    (``graph.py:101-122``).  ``csr`` carries the device CSR the kernels read; ``row_base`` /
+    ``graph_base`` / ``global_num_graphs`` describe this rank's slice of a data-parallel batch."""
+
+    node_features: torch.Tensor            # [sum N, F]
+    edge_index: torch.Tensor               # [2, sum E] int64, node ids offset per subject
+    edge_weight: torch.Tensor              # [sum E]
+    batch: torch.Tensor                    # [sum N] int64 subject index of each node
+    labels: Optional[torch.Tensor]         # [B] int64
+    ptr: torch.Tensor                      # [B+1] int64
+    csr: Optional[BatchCSR] = None
+    row_base: int = 0
+    graph_base: int = 0
+    global_num_graphs: Optional[int] = None
+    global_num_nodes: Optional[int] = None
+
+    @property
+    def num_graphs(self) -> int:
+        return int(self.ptr.shape[0]) - 1
+
+    @property
+    def num_nodes(self) -> int:
+        return int(self.node_features.shape[0])
+
+    @property
+    def device(self) -> torch.device:
+        return self.node_features.device
+
+    def to(self, device) -> "ConnectomeBatch":
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None and self.node_features.is_cuda:
+            return self
+        if device == self.node_features.device:
+            return self
+        move = lambda t: None if t is None else t.to(device)
+        return ConnectomeBatch(
+            move(self.node_features), move(self.edge_index), move(self.edge_weight), move(self.batch),
+            move(self.labels), move(self.ptr), None if self.csr is None else self.csr.to(device),
+            self.row_base, self.graph_base, self.global_num_graphs, self.global_num_nodes)
+
+    def ensure_csr(self) -> BatchCSR:
+        """Build the CSR for a batch that was assembled by hand or moved from the host
+        (COO grouped by subject, as ``collate_graphs`` emits it)."""
+        if self.csr is None:
+            eng = _engine.engine_for(self.node_features)
+            counts = (self.ptr[1:] - self.ptr[:-1])
+            max_nodes = int(counts.max().item()) if counts.numel() else 0
+            ei = self.edge_index.contiguous()
+            csr, eptr = eng.csr_from_coo(ei, self.edge_weight.contiguous(), self.ptr.contiguous(), self.num_graphs,
+                                         self.num_nodes, int(ei.shape[1]), max_nodes)
+            self.csr = BatchCSR(**csr, eptr=eptr, max_nodes=max_nodes)
+        return self.csr
+
+
+# ---------------------------------------------------------------------------
+# Subject store: the dataset packed once
+# ---------------------------------------------------------------------------
+
+def pack_graphs(graphs: Sequence[ConnectomeGraph]) -> dict:
+    """Host packing of a list of subjects into arena arrays (pure indexing, no arithmetic).
+
+    Returns CPU tensors: ``x [sum N, F]`` f32, ``src/dst [sum E]`` int32 subject-local ids,
+    ``w [sum E]`` f32, ``node_ptr/edge_ptr [S+1]`` int64, ``label [S]`` int64 (0 where absent)
+    and ``has_label [S]`` bool.  Raises ``ValueError`` on ragged feature widths or edge
+    endpoints outside ``[0, N_s)`` - the kernels index shared-memory tiles with them."""
+    if len(graphs) == 0:
+        raise ValueError("cannot pack an empty list of ConnectomeGraph")
+    feat = graphs[0].num_features
+    n_nodes = np.fromiter((g.num_nodes for g in graphs), dtype=np.int64, count=len(graphs))
+    n_edges = np.fromiter((g.num_edges for g in graphs), dtype=np.int64, count=len(graphs))
+    if any(g.num_features != feat for g in graphs):
+        raise ValueError("all subjects must have the same number of node features")
+    node_ptr = np.zeros(len(graphs) + 1, dtype=np.int64)
+    edge_ptr = np.zeros(len(graphs) + 1, dtype=np.int64)
+    np.cumsum(n_nodes, out=node_ptr[1:])
+    np.cumsum(n_edges, out=edge_ptr[1:])
+
+    cpu = lambda t: t.detach().to("cpu")
+    x = torch.cat([cpu(g.node_features).to(torch.float32) for g in graphs], dim=0).contiguous()
+    ei = torch.cat([cpu(g.edge_index).to(torch.int64) for g in graphs], dim=1)
+    w = torch.cat([cpu(g.edge_weight).to(torch.float32) for g in graphs], dim=0).contiguous()
+    if ei.numel():
+        bound = torch.from_numpy(np.repeat(n_nodes, n_edges))
+        if int(ei.min()) < 0 or bool((ei >= bound.unsqueeze(0)).any()):
+            raise ValueError("edge_index refers to a node outside its subject")
+    has_label = np.fromiter((g.label is not None for g in graphs), dtype=bool, count=len(graphs))
+    label = torch.zeros(len(graphs), dtype=torch.int64)
+    if has_label.any():
+        vals = torch.stack([cpu(g.label).reshape(()).to(torch.int64) for g in graphs if g.label is not None])
+        label[torch.from_numpy(np.nonzero(has_label)[0])] = vals
+    return dict(
+        x=x, src=ei[0].to(torch.int32).contiguous(), dst=ei[1].to(torch.int32).contiguous(), w=w,
+        node_ptr=torch.from_numpy(node_ptr), edge_ptr=torch.from_numpy(edge_ptr), label=label,
+        has_label=has_label, num_features=feat)
+
+
+class SubjectStore:
+    """All subjects of a dataset, packed once and resident on one GPU (``cgnn_store_t``).
+
+    ``collate(ids)`` turns any selection of subject indices into a :class:`ConnectomeBatch`
+    entirely on the device; the only per-batch host->device traffic is ``ids`` (8 B / subject).
+    """
+
+    def __init__(self, packed: dict, device=None):
+        # default_device() raises when no CUDA device is visible; collate() goes through
+        # engine_for(), which refuses non-CUDA tensors - there is no CPU path.
+        self.device = torch.device(device) if device is not None else _engine.default_device()
+        self.num_features = int(packed["num_features"])
+        self.node_ptr_host = packed["node_ptr"].numpy()
+        self.edge_ptr_host = packed["edge_ptr"].numpy()
+        self.has_label = np.asarray(packed["has_label"], dtype=bool)
+        nb = lambda t: t.to(self.device, non_blocking=True)
+        self.x, self.src, self.dst, self.w = nb(packed["x"]), nb(packed["src"]), nb(packed["dst"]), nb(packed["w"])
+        self.node_ptr, self.edge_ptr = nb(packed["node_ptr"]), nb(packed["edge_ptr"])
+        self.label = nb(packed["label"])
+        self._struct = StoreT(self.x.data_ptr(), self.src.data_ptr(), self.dst.data_ptr(), self.w.data_ptr(),
+                              self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), self.label.data_ptr(),
+                              self.num_features)
+
+    @classmethod
+    def from_graphs(cls, graphs: Sequence[ConnectomeGraph], device=None) -> "SubjectStore":
+        return cls(pack_graphs(graphs), device)
+
+    def __len__(self) -> int:
+        return int(self.node_ptr_host.shape[0]) - 1
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.x, self.src, self.dst, self.w, self.node_ptr,
+                                                          self.edge_ptr, self.label))
+
+    def collate(self, ids, *, row_base: int = 0, graph_base: int = 0, global_num_graphs: Optional[int] = None,
+                global_num_nodes: Optional[int] = None, ids_device: Optional[torch.Tensor] = None) -> ConnectomeBatch:
+        """Device collate of subjects ``ids`` (host int sequence / array, in batch order)."""
+        ids_np = np.asarray(ids, dtype=np.int64).reshape(-1)
+        n_sel = self.node_ptr_host[ids_np + 1] - self.node_ptr_host[ids_np]
+        e_sel = self.edge_ptr_host[ids_np + 1] - self.edge_ptr_host[ids_np]
+        rows, edges = int(n_sel.sum()), int(e_sel.sum())
+        max_nodes = int(n_sel.max()) if ids_np.size else 0
+        labelled = self.has_label[ids_np]
+        all_labelled = bool(labelled.all()) and ids_np.size > 0
+        if ids_device is None:
+            ids_device = torch.from_numpy(ids_np).to(self.device, non_blocking=True)
+        eng = _engine.engine_for(self.x)
+        out, csr = eng.collate_csr(self._struct, ids_device, int(ids_np.size), rows, edges, max_nodes,
+                                   self.num_features, all_labelled)
+        labels = out["labels"]
+        if not all_labelled and labelled.any():
+            # reference quirk (graph.py:155-156,165): only labelled subjects contribute, so the
+            # stack is shorter than B
+            labels = self.label[torch.from_numpy(ids_np[labelled]).to(self.device)]
+        return ConnectomeBatch(
+            out["node_features"], out["edge_index"], out["edge_weight"], out["batch"], labels, out["ptr"],
+            BatchCSR(**csr, eptr=out["eptr"], max_nodes=max_nodes), row_base, graph_base,
+            global_num_graphs, global_num_nodes)
+
+
+def collate_graphs(graphs: list) -> ConnectomeBatch:
+    """Collate a list of :class:`ConnectomeGraph` into a device-resident :class:`ConnectomeBatch`
+    (same signature as reference ``graph.py:143``).  The list is packed on the host, shipped in one
+    copy per array and collated by the device kernel; results live on the current CUDA device."""
+    store = SubjectStore.from_graphs(graphs)
+    return store.collate(np.arange(len(graphs), dtype=np.int64))
+
+
+# ---------------------------------------------------------------------------
+# Loader
+# ---------------------------------------------------------------------------
+
+def shard_bounds(count: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous slice ``[lo, hi)`` of a chunk of ``count`` subjects owned by ``rank``.
+    Slices differ by at most one subject; ranks past the end of a short chunk get an empty slice."""
+    base, extra = divmod(count, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class ConnectomeDataLoader:
+    """Batches of subjects, same contract as reference ``graph.py:174-197``: ``len`` is
+    ``ceil(n / batch_size)``, each epoch draws ``torch.randperm`` from the global CPU generator
+    (so batch membership matches the reference under the same seed) and the last batch may be
+    ragged.  The dataset is packed into a :class:`SubjectStore` on first use.
+
+    Under data parallelism (``world_size > 1``) every rank draws the same permutation and takes
+    its contiguous slice of every global chunk, so the union over ranks is exactly the
+    single-process batch."""
+
+    def __init__(self, dataset, batch_size: int = 16, shuffle: bool = True, *, rank: Optional[int] = None,
+                 world_size: Optional[int] = None, device=None):
+        self.dataset = dataset
+        self.batch_size = batch_size
+        self.shuffle = shuffle
+        self.device = device
+        self._rank, self._world = rank, world_size
+        self._store: Optional[SubjectStore] = dataset if isinstance(dataset, SubjectStore) else None
+        self._store_key = None
+
+    # -- host logic (no GPU needed) -------------------------------------------------------
+    def __len__(self) -> int:
+        return math.ceil(len(self.dataset) / self.batch_size)
+
+    def _dist(self) -> tuple[int, int]:
+        if self._rank is not None and self._world is not None:
+            return self._rank, self._world
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    def epoch_order(self) -> list[int]:
+        n = len(self.dataset)
+        return torch.randperm(n).tolist() if self.shuffle else list(range(n))
+
+    def plan(self, order: Sequence[int]) -> list[dict]:
+        """Split an epoch order into global chunks and this rank's slice of each."""
+        rank, world = self._dist()
+        node_ptr = self._store.node_ptr_host if self._store is not None else None
+        steps = []
+        for start in range(0, len(order), self.batch_size):
+            chunk = np.asarray(order[start:start + self.batch_size], dtype=np.int64)
+            lo, hi = shard_bounds(len(chunk), rank, world)
+            step = dict(ids=chunk[lo:hi], graph_base=lo, global_num_graphs=len(chunk))
+            if node_ptr is not None:
+                sizes = node_ptr[chunk + 1] - node_ptr[chunk]
+                step["row_base"] = int(sizes[:lo].sum())
+                step["global_num_nodes"] = int(sizes.sum())
+            steps.append(step)
+        return steps
+
+    # -- device side ----------------------------------------------------------------------
+    def store(self) -> SubjectStore:
+        if isinstance(self.dataset, SubjectStore):
+            return self.dataset
+        key = (id(self.dataset), len(self.dataset))
+        if self._store is None or self._store_key != key:
+            self._store = SubjectStore.from_graphs(self.dataset, self.device)
+            self._store_key = key
+        return self._store
+
+    def invalidate(self) -> None:
+        """Forget the packed copy (call after mutating ``dataset`` in place)."""
+        if not isinstance(self.dataset, SubjectStore):
+            self._store = None
+
+    def __iter__(self):
+        order = self.epoch_order()
+        store = self.store()
+        for step in self.plan(order):
+            yield store.collate(step["ids"], row_base=step.get("row_base", 0), graph_base=step["graph_base"],
+                                global_num_graphs=step["global_num_graphs"],
+                                global_num_nodes=step.get("global_num_nodes"))

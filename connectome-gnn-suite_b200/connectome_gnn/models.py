@@ -1,0 +1,292 @@
+"""GCN and GraphSAGE connectome classifiers on the sm_100a kernels.
+
+Host-side mirror of reference ``connectome_gnn/models.py``: same class names, constructor
+arguments, attributes (``convs``, ``batch_norms``, ``classifier``, ``dropout``) and
+``state_dict`` keys, so weights move freely between the two implementations.  The modules
+only *hold parameters*; the arithmetic of ``encode``/``forward`` is two autograd nodes
+(:class:`_EncodeFn`, :class:`_HeadFn`) that drive the C ABI:
+
+====================  =========================================================================
+reference lines       replaced by
+====================  =========================================================================
+models.py:84-114      ``cgnn_gcn_layer_fwd`` / ``_bwd`` (projection + normalised aggregation)
+models.py:136-152     ``cgnn_sage_layer_fwd`` / ``_bwd`` (weighted-mean aggregation + projection)
+models.py:208-210,    BatchNorm + ReLU + dropout applied on load by the *next* kernel;
+  260-261             statistics come out of the producing kernel (``cgnn_bn_finalize``)
+models.py:57-59,211   ``cgnn_pool_fwd``;  backward folded into the top layer's backward
+models.py:196-201     ``cgnn_head_fwd`` / ``_bwd``
+====================  =========================================================================
+
+Under ``torch.distributed`` (one process per GPU, subjects sharded by the loader) the BatchNorm
+statistics and their backward sums are combined across ranks so that the result equals the
+reference's single-process batch semantics; parameter gradients are all-reduced by ``Trainer``.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _engine
+from ._engine import Act, BnBwd
+from .graph import ConnectomeBatch
+
+__all__ = ["GCNLayer", "SAGELayer", "GCNConnectome", "GraphSAGEConnectome"]
+
+
+# ---------------------------------------------------------------------------
+# distributed helpers (no-ops in a single process)
+# ---------------------------------------------------------------------------
+
+def _world(group=None) -> int:
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group)
+    return 1
+
+
+def _merge_stats_across_ranks(eng, stats: torch.Tensor, channels: int, group=None) -> torch.Tensor:
+    """SyncBN forward: gather every rank's {count, mean, M2} and merge them identically everywhere."""
+    world = _world(group)
+    if world == 1:
+        return stats
+    import torch.distributed as dist
+    parts = torch.empty((world, stats.numel()), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(parts, stats.contiguous(), group=group)
+    return eng.bn_merge_stats(parts, channels)
+
+
+def _sum_across_ranks(t: Optional[torch.Tensor], group=None) -> Optional[torch.Tensor]:
+    if t is not None and _world(group) > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, group=group)
+    return t
+
+
+def _draw_seed() -> int:
+    """Dropout stream seed from torch's global CPU generator (so ``torch.manual_seed`` governs it
+    and every data-parallel rank, seeded alike, draws the same value)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+# ---------------------------------------------------------------------------
+# encode = L x (conv -> BN -> [ReLU] -> dropout) -> mean pool, as one autograd node
+# ---------------------------------------------------------------------------
+
+class _EncodeFn(torch.autograd.Function):
+    """``emb = pool(stack(x))``.  ``cfg`` carries everything that is not a differentiable tensor."""
+
+    @staticmethod
+    def forward(ctx, cfg: dict, x: torch.Tensor, *params: torch.Tensor):
+        eng = cfg["engine"]
+        batch: ConnectomeBatch = cfg["batch"]
+        kind, training, p = cfg["kind"], cfg["training"], cfg["dropout"]
+        csr, ptr, B = batch.csr, batch.ptr, batch.num_graphs
+        relu_after_bn = kind == "gcn"          # SAGE applies ReLU inside the layer (models.py:152)
+        p_eff = p if training else 0.0
+        seed = cfg["seed"]
+
+        t, act = x.contiguous(), Act()
+        saved = []
+        for l, bn in enumerate(cfg["bns"]):
+            W, b, gamma, beta = (q.contiguous() for q in params[4 * l: 4 * l + 4])
+            z, stats = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, csr.max_nodes, want_stats=training)
+            if training:
+                stats = _merge_stats_across_ranks(eng, stats, W.shape[0], cfg["group"])
+                momentum = 0.1 if bn.momentum is None else bn.momentum
+                scale, shift, mean, rstd = eng.bn_finalize(stats, gamma, beta, bn.eps, momentum, bn.running_mean,
+                                                           bn.running_var, bn.num_batches_tracked)
+            else:
+                scale, shift, mean, rstd = eng.bn_eval_affine(gamma, beta, bn.running_mean, bn.running_var, bn.eps)
+            saved.append((t, act, z, W, scale, mean, rstd))
+            t = z
+            act = Act(scale, shift, relu_after_bn, p_eff, seed, l, batch.row_base)
+        emb = eng.pool_fwd(t, act, ptr, B)
+
+        ctx.cfg, ctx.saved, ctx.final_act = cfg, saved, act
+        ctx.x_needs_grad = x.requires_grad
+        return emb
+
+    @staticmethod
+    def backward(ctx, demb: torch.Tensor):
+        cfg, saved = ctx.cfg, ctx.saved
+        eng = cfg["engine"]
+        batch: ConnectomeBatch = cfg["batch"]
+        kind, training, group = cfg["kind"], cfg["training"], cfg["group"]
+        csr, ptr, B = batch.csr, batch.ptr, batch.num_graphs
+        count = float(batch.global_num_nodes if batch.global_num_nodes is not None else batch.num_nodes)
+        L = len(saved)
+        demb = demb.contiguous()
+
+        grads: list = [None] * (4 * L)
+        # BatchNorm backward sums of the top layer come from a standalone pass over z_L
+        t_in, act_in, z, W, scale, mean, rstd = saved[-1]
+        act_out = ctx.final_act
+        sums = eng.bn_bwd_sums(z, act_out, mean, rstd, None, demb, ptr, B)
+        sums = _sum_across_ranks(sums, group)
+        du, pooled, dx = None, demb, None
+        for l in range(L - 1, -1, -1):
+            t_in, act_in, z, W, scale, mean, rstd = saved[l]
+            need_du = l > 0 or ctx.x_needs_grad
+            prev_mean = saved[l - 1][5] if l > 0 else None
+            prev_rstd = saved[l - 1][6] if l > 0 else None
+            bn = BnBwd(scale, mean, rstd, sums, count, training)
+            dW, db, du_in, prev_sums = eng.layer_bwd(kind, du, pooled, z, act_out, bn, t_in, act_in, W, csr, ptr, B,
+                                                     csr.max_nodes, need_du, prev_mean, prev_rstd)
+            grads[4 * l + 0], grads[4 * l + 1] = dW, db
+            grads[4 * l + 2], grads[4 * l + 3] = sums[1], sums[0]   # d gamma = sum dy*xhat, d beta = sum dy
+            sums = _sum_across_ranks(prev_sums, group)
+            du, pooled, act_out = du_in, None, act_in
+            if l == 0:
+                dx = du_in
+        return (None, dx if ctx.x_needs_grad else None, *grads)
+
+
+class _HeadFn(torch.autograd.Function):
+    """``logits = W1 dropout(relu(W0 emb + b0)) + b1`` (reference ``models.py:196-201``)."""
+
+    @staticmethod
+    def forward(ctx, cfg: dict, emb, W0, b0, W1, b1):
+        eng = cfg["engine"]
+        emb, W0, b0, W1, b1 = (q.contiguous() for q in (emb, W0, b0, W1, b1))
+        p_eff = cfg["dropout"] if cfg["training"] else 0.0
+        hidden, logits = eng.head_fwd(emb, W0, b0, W1, b1, p_eff, cfg["seed"], cfg["graph_base"])
+        ctx.cfg, ctx.p_eff = cfg, p_eff
+        ctx.save_for_backward(emb, hidden, W0, W1)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        emb, hidden, W0, W1 = ctx.saved_tensors
+        demb, dW0, db0, dW1, db1 = ctx.cfg["engine"].head_bwd(emb, hidden, dlogits.contiguous(), W0, W1, ctx.p_eff)
+        return None, demb, dW0, db0, dW1, db1
+
+
+# ---------------------------------------------------------------------------
+# parameter holders
+# ---------------------------------------------------------------------------
+
+class GCNLayer(nn.Module):
+    """Parameters of one GCN layer: ``linear.weight [out, in]`` (no bias), ``bias [out]``
+    (reference ``models.py:78-82``).  The convolution itself runs inside the model's fused path."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.linear = nn.Linear(in_channels, out_channels, bias=False)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        nn.init.xavier_uniform_(self.linear.weight)
+
+    def tensors(self):
+        return self.linear.weight, self.bias
+
+    def forward(self, x, edge_index, edge_weight):
+        """Stand-alone ``A^ (x W^T) + b`` over one block of nodes (all nodes form one subject)."""
+        return _single_layer("gcn", self, x, edge_index, edge_weight)
+
+
+class SAGELayer(nn.Module):
+    """Parameters of one GraphSAGE layer: ``linear.weight [out, 2*in]``, ``linear.bias [out]``
+    (reference ``models.py:130-134``)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.linear = nn.Linear(in_channels * 2, out_channels)
+        nn.init.xavier_uniform_(self.linear.weight)
+
+    def tensors(self):
+        return self.linear.weight, self.linear.bias
+
+    def forward(self, x, edge_index, edge_weight):
+        """Stand-alone ``relu([x || mean_w(x_nbrs)] W^T + b)`` over one block of nodes."""
+        return _single_layer("sage", self, x, edge_index, edge_weight)
+
+
+def _single_layer(kind: str, layer: nn.Module, x, edge_index, edge_weight):
+    """Inference-only convenience for calling a layer by itself (not differentiable)."""
+    if torch.is_grad_enabled() and any(q.requires_grad for q in (x, *layer.parameters())):
+        raise RuntimeError("stand-alone layer calls are inference-only; wrap in torch.no_grad() "
+                           "or differentiate through GCNConnectome / GraphSAGEConnectome")
+    dev = x.device if x.is_cuda else _engine.default_device()
+    x, edge_index, edge_weight = x.to(dev), edge_index.to(dev), edge_weight.to(dev)
+    n = x.shape[0]
+    ptr = torch.tensor([0, n], dtype=torch.int64, device=dev)
+    batch = ConnectomeBatch(x, edge_index, edge_weight, torch.zeros(n, dtype=torch.int64, device=dev), None, ptr)
+    csr = batch.ensure_csr()
+    eng = _engine.engine_for(x)
+    W, b = (q.detach().to(dev).contiguous() for q in layer.tensors())
+    z, _ = eng.layer_fwd(kind, x.contiguous().float(), Act(), W, b, csr, ptr, 1, csr.max_nodes, want_stats=False)
+    return z
+
+
+class _ConnectomeClassifier(nn.Module):
+    """Shared machinery of the two classifiers (reference ``models.py:159-216`` / ``219-266``)."""
+
+    kind = ""
+    layer_cls = None
+
+    def __init__(self, in_channels: int, hidden_dim: int = 64, num_classes: int = 2, num_layers: int = 3,
+                 dropout: float = 0.3):
+        super().__init__()
+        self.dropout = dropout
+        widths = [in_channels] + [hidden_dim] * num_layers
+        self.convs = nn.ModuleList([self.layer_cls(a, b) for a, b in zip(widths[:-1], widths[1:])])
+        self.batch_norms = nn.ModuleList([nn.BatchNorm1d(hidden_dim) for _ in range(num_layers)])
+        self.classifier = nn.Sequential(
+            nn.Linear(hidden_dim, hidden_dim // 2),
+            nn.ReLU(),
+            nn.Dropout(dropout),
+            nn.Linear(hidden_dim // 2, num_classes),
+        )
+        self.process_group = None   # torch.distributed group for SyncBN statistics (None = default)
+
+    # -- plumbing --------------------------------------------------------------------------
+    def _ready(self, batch: ConnectomeBatch) -> ConnectomeBatch:
+        """Batch on a CUDA device with its CSR; parameters follow the batch onto that device."""
+        if not batch.node_features.is_cuda:
+            batch = batch.to(_engine.default_device())
+        batch.ensure_csr()
+        dev = batch.node_features.device
+        if next(self.parameters()).device != dev:
+            self.to(dev)   # in place: Parameter identity (and any optimizer built earlier) is preserved
+        return batch
+
+    def _cfg(self, batch: ConnectomeBatch) -> dict:
+        training = self.training
+        need_seed = training and self.dropout > 0.0
+        return dict(engine=_engine.engine_for(batch.node_features), batch=batch, kind=self.kind, training=training,
+                    dropout=float(self.dropout), seed=_draw_seed() if need_seed else 0,
+                    bns=list(self.batch_norms), group=self.process_group, graph_base=batch.graph_base)
+
+    def _encode(self, batch: ConnectomeBatch, cfg: dict) -> torch.Tensor:
+        params = []
+        for conv, bn in zip(self.convs, self.batch_norms):
+            params += [*conv.tensors(), bn.weight, bn.bias]
+        return _EncodeFn.apply(cfg, batch.node_features, *params)
+
+    # -- public API ------------------------------------------------------------------------
+    def encode(self, batch: ConnectomeBatch) -> torch.Tensor:
+        """Graph-level embeddings ``[B, hidden_dim]``."""
+        batch = self._ready(batch)
+        return self._encode(batch, self._cfg(batch))
+
+    def forward(self, batch: ConnectomeBatch) -> torch.Tensor:
+        """Class logits ``[B, num_classes]``."""
+        batch = self._ready(batch)
+        cfg = self._cfg(batch)
+        emb = self._encode(batch, cfg)
+        fc0, fc1 = self.classifier[0], self.classifier[3]
+        return _HeadFn.apply(cfg, emb, fc0.weight, fc0.bias, fc1.weight, fc1.bias)
+
+
+class GCNConnectome(_ConnectomeClassifier):
+    """L x (GCN conv -> BatchNorm -> ReLU -> dropout) -> mean-pool -> MLP (reference ``models.py:159-216``)."""
+    kind = "gcn"
+    layer_cls = GCNLayer
+
+
+class GraphSAGEConnectome(_ConnectomeClassifier):
+    """L x (SAGE conv incl. ReLU -> BatchNorm -> dropout) -> mean-pool -> MLP (reference ``models.py:219-266``)."""
+    kind = "sage"
+    layer_cls = SAGELayer

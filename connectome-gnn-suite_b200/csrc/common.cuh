@@ -11,17 +11,19 @@
 #include "cuda_emu.h"
 #define CGNN_SMEM_DECL unsigned char* cgnn_smem = cgnn_emu::g_dyn_smem
 #define CGNN_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  cgnn_emu::launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); })
+  (cgnn::count_launch(), cgnn_emu::launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); }))
 #else
 #include <cuda_runtime.h>
 #define CGNN_SMEM_DECL extern __shared__ __align__(16) unsigned char cgnn_smem[]
 #define CGNN_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+  (cgnn::count_launch(), kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__))
 #endif
 
 #include <stdint.h>
 
 namespace cgnn {
+
+void count_launch();  // bumps the process-wide kernel-launch counter (cgnn_kernel_launches)
 
 constexpr int kThreads = 256;          // threads per CTA of the tile kernels
 constexpr int kWarps = kThreads / 32;
@@ -214,10 +216,10 @@ __device__ __forceinline__ void cta_write_stats(const float* s_cnt, const float*
 }
 
 // Launchers shared across translation units -------------------------------------------------
-// out[i] = sum_g partials[g * stride + i] for i < n  (fp64 accumulation, fixed order).
-// If rows_pad/cols_pad are set the partial is a padded [rows_pad? , ld] matrix mapped to [rows, cols].
+// out[r*out_ld + c] = sum_g partials[g*stride + r*ld + c] for r < rows, c < cols (fp64 accumulation,
+// fixed order): maps a zero-padded [rows, ld] partial onto a dense output (out_ld <= 0 -> cols).
 int launch_reduce_partials(const float* partials, int G, int stride, int rows, int cols, int ld,
-                           float* out, cudaStream_t stream);
+                           float* out, cudaStream_t stream, int out_ld = 0);
 int launch_stats_merge(const double* parts, int parts_n, int C, double* stats, cudaStream_t stream);
 
 }  // namespace cgnn

@@ -549,7 +549,11 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
   else { if (maxt == 1) CGNN_SAGE_BWD(4, 1) else if (maxt == 2) CGNN_SAGE_BWD(4, 2) else CGNN_SAGE_BWD(4, 4) }
 #undef CGNN_SAGE_BWD
   CGNN_CHECK_LAUNCH();
-  int rc = launch_reduce_partials(a.partials + a.o_pdw, grid, a.part_stride, H, 2 * d_in, 2 * a.K4, dW, stream);
+  // dW = [dW_self | dW_neigh]: the two halves sit K4 apart in the padded partial, d_in apart in dW
+  int rc = launch_reduce_partials(a.partials + a.o_pdw, grid, a.part_stride, H, d_in, 2 * a.K4, dW, stream, 2 * d_in);
+  if (rc) return rc;
+  rc = launch_reduce_partials(a.partials + a.o_pdw + a.K4, grid, a.part_stride, H, d_in, 2 * a.K4, dW + d_in, stream,
+                              2 * d_in);
   if (rc) return rc;
   rc = launch_reduce_partials(a.partials + a.o_pdb, grid, a.part_stride, 1, H, a.H4, dbias, stream);
   if (rc) return rc;

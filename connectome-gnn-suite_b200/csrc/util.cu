@@ -4,6 +4,9 @@
 namespace cgnn {
 
 static thread_local int g_last_cuda_error = 0;
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 void set_cuda_error(int err) { g_last_cuda_error = err; }
 
 DeviceInfo device_info() {
@@ -22,24 +25,26 @@ DeviceInfo device_info() {
   return cached;
 }
 
-// out[r*cols + c] = sum_g partials[g*stride + r*ld + c]; one thread per output, fp64, fixed order.
+// out[r*out_ld + c] = sum_g partials[g*stride + r*ld + c]; one thread per output, fp64, fixed order.
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partials, int G, int stride,
-                                                         int rows, int cols, int ld, float* __restrict__ out) {
+                                                         int rows, int cols, int ld, float* __restrict__ out,
+                                                         int out_ld) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   int r = i / cols, c = i - r * cols;
   const float* p = partials + (size_t)r * ld + c;
   double s = 0.0;
   for (int g = 0; g < G; ++g) s += (double)p[(size_t)g * stride];
-  out[i] = (float)s;
+  out[(size_t)r * out_ld + c] = (float)s;
 }
 
 int launch_reduce_partials(const float* partials, int G, int stride, int rows, int cols, int ld, float* out,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int out_ld) {
+  if (out_ld <= 0) out_ld = cols;
   int n = rows * cols;
   if (n <= 0) return CGNN_OK;
   auto kfn = k_reduce_partials;
-  CGNN_LAUNCH(kfn, (n + 255) / 256, 256, 0, stream, partials, G, stride, rows, cols, ld, out);
+  CGNN_LAUNCH(kfn, (n + 255) / 256, 256, 0, stream, partials, G, stride, rows, cols, ld, out, out_ld);
   CGNN_CHECK_LAUNCH();
   return CGNN_OK;
 }
@@ -103,6 +108,7 @@ const char* cgnn_status_string(int status) {
 int cgnn_abi_version(void) { return CGNN_ABI_VERSION; }
 int cgnn_last_cuda_error(void) { return cgnn::g_last_cuda_error; }
 size_t cgnn_workspace_bytes(void) { return (size_t)32 << 20; }
+uint64_t cgnn_kernel_launches(void) { return (uint64_t)cgnn::launches(); }
 
 int cgnn_bn_merge_stats(const double* stats_parts, int32_t parts, int32_t C, double* stats, cgnn_stream_t stream) {
   if (!stats_parts || !stats || parts <= 0 || C <= 0) return CGNN_ERR_INVALID_ARG;

@@ -45,6 +45,8 @@ int cgnn_last_cuda_error(void);          /* cudaError_t of the last CGNN_ERR_CUD
 /* Upper bound on the scratch a single call needs (partials of BN statistics / weight
  * gradients).  The caller allocates it once per device+stream and passes it to every call. */
 size_t cgnn_workspace_bytes(void);
+/* Number of CUDA kernels this library has launched in this process so far (monotonic). */
+uint64_t cgnn_kernel_launches(void);
 
 /* ---------------------------------------------------------------------------------------
  * Device CSR of a batch.  Built once per batch by cgnn_collate_csr / cgnn_csr_from_coo and

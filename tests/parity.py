@@ -1,0 +1,193 @@
+"""Parity checks shared by the simulator tests (CPU, kernel logic) and the GPU tests (the real gate).
+
+Each function takes the device the package's tensors live on ("cpu" only ever under the `on_emu`
+fixture of conftest.py) and compares the package - i.e. the kernels behind include/cgnn.h - with
+golden fixtures made from the reference and with the oracle (oracle/port.py, oracle/csr_ref.c).
+
+Bars (BASELINE.json north star): collate fields, CSR structure, D^ and w_sum BIT-EXACT;
+logits / loss / gradients within REL_TOL = 1e-5 max-norm relative, dropout disabled.
+Per-tensor gradients use the band the reference shows against itself:
+all gradients concatenated <= 1e-5; any single tensor <= 1e-4; analytically-zero tensors
+(GCN conv biases) absolute, tied to the global gradient scale.
+"""
+import numpy as np
+import torch
+
+import helpers
+from helpers import REL_TOL
+
+PER_TENSOR_TOL = 1e-4
+
+
+def make_model(kind, a, device, dropout=0.0):
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    sd = helpers.state_dict_from(a, f"{kind}.init")
+    hidden = sd["convs.0.linear.weight"].shape[0]
+    in_ch = sd["convs.0.linear.weight"].shape[1] // (2 if kind == "sage" else 1)
+    layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("convs."))
+    cls = GCNConnectome if kind == "gcn" else GraphSAGEConnectome
+    m = cls(in_channels=in_ch, hidden_dim=hidden, num_classes=sd["classifier.3.weight"].shape[0],
+            num_layers=layers, dropout=dropout)
+    m.load_state_dict(sd)
+    return m.to(device)
+
+
+def check_collate(a, device):
+    """collate_graphs == reference graph.py:143-167, bit for bit; D^ / w_sum bit for bit; CSR == stable sort."""
+    from connectome_gnn.graph import collate_graphs
+    b = collate_graphs(helpers.graphs_from_store(a))
+    assert b.node_features.device.type == torch.device(device).type
+    np_ = lambda t: t.detach().cpu().numpy()
+    assert np.array_equal(np_(b.ptr), a["batch.ptr"])
+    assert np.array_equal(np_(b.labels), a["batch.labels"])
+    assert b.ptr.dtype == torch.int64 and b.batch.dtype == torch.int64 and b.edge_index.dtype == torch.int64
+    if "batch.edge_index" in a:
+        assert np.array_equal(np_(b.node_features), a["batch.node_features"])
+        assert np.array_equal(np_(b.edge_index), a["batch.edge_index"])
+        assert np.array_equal(np_(b.edge_weight), a["batch.edge_weight"])
+        assert np.array_equal(np_(b.batch), a["batch.batch"])
+    c = b.csr
+    assert np.array_equal(np_(c.deg), a["deg"]), "D^ not bit-exact"
+    assert np.array_equal(np_(c.wsum), a["wsum"]), "w_sum not bit-exact"
+    helpers.assert_close(c.dinv, a["dinv"], "dinv", tol=2e-7)
+    src, dst = np_(b.edge_index)
+    w = np_(b.edge_weight)
+    rows = b.num_nodes
+    for key, other, rowptr, col, cw in ((dst, src, c.in_rowptr, c.in_col, c.in_w), (src, dst, c.out_rowptr, c.out_col, c.out_w)):
+        order = np.argsort(key, kind="stable")
+        assert np.array_equal(np_(col), other[order].astype(np.int32)), "CSR columns are not the stable sort of the COO"
+        assert np.array_equal(np_(cw), w[order])
+        assert np.array_equal(np_(rowptr), np.searchsorted(key[order], np.arange(rows + 1)).astype(np.int32))
+    if "w_norm" in a:
+        order = np.argsort(dst, kind="stable")
+        helpers.assert_close(c.in_wn, a["w_norm"][: len(src)][order], "w^ (in)", tol=3e-7)
+        order = np.argsort(src, kind="stable")
+        helpers.assert_close(c.out_wn, a["w_norm"][: len(src)][order], "w^ (out)", tol=3e-7)
+    # the C oracle must agree with the kernels on every CSR array, bit for bit
+    from test_oracle import _run_c_oracle
+    o = _run_c_oracle(a)
+    for k in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn", "deg", "dinv", "wsum"):
+        assert np.array_equal(np_(getattr(c, k)), o[k]), f"kernel vs C oracle: {k}"
+    assert np.array_equal(np_(c.eptr), o["eptr"])
+    return b
+
+
+def check_grads(model, a, kind, tag):
+    names = [k for k, _ in model.named_parameters()]
+    ref = {k: torch.from_numpy(a[f"{kind}.{tag}.{k}"]) for k in names}
+    got = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+    assert all(g is not None for g in got.values())
+    flat_got = torch.cat([got[k].reshape(-1) for k in names])
+    flat_ref = torch.cat([ref[k].reshape(-1) for k in names])
+    helpers.assert_close(flat_got, flat_ref, f"{kind} {tag}: all gradients", tol=REL_TOL)
+    scale = float(flat_ref.abs().max())
+    for k in names:
+        if kind == "gcn" and k.startswith("convs.") and k.endswith(".bias") and tag == "train.grad":
+            err = float((got[k].double() - ref[k].double()).abs().max())   # analytically zero: round-off only
+            assert err <= REL_TOL * scale, f"{k}: {err:.3e} vs gradient scale {scale:.3e}"
+        else:
+            helpers.assert_close(got[k], ref[k], f"{kind} {tag}: {k}", tol=PER_TENSOR_TOL, atol=REL_TOL * scale)
+
+
+def check_model(a, kind, device, batch=None):
+    """eval forward, train forward/backward (dropout off), running statistics, eval-mode backward."""
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.train import CrossEntropyLoss
+    b = batch if batch is not None else collate_graphs(helpers.graphs_from_store(a))
+    m = make_model(kind, a, device)
+    m.eval()
+    with torch.no_grad():
+        helpers.assert_close(m.encode(b), a[f"{kind}.eval.emb"], f"{kind} eval emb")
+        helpers.assert_close(m(b), a[f"{kind}.eval.logits"], f"{kind} eval logits")
+    m.train()
+    logits = m(b)
+    loss_fn = CrossEntropyLoss()
+    loss = loss_fn(logits, b.labels)
+    loss.backward()
+    helpers.assert_close(logits, a[f"{kind}.train.logits"], f"{kind} train logits")
+    helpers.assert_close(loss, a[f"{kind}.train.loss"], f"{kind} train loss")
+    check_grads(m, a, kind, "train.grad")
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            helpers.assert_close(v, a[f"{kind}.train.after.{k}"], f"{kind} {k}")
+        if "num_batches" in k:
+            assert int(v) == int(a[f"{kind}.train.after.{k}"])
+    m.zero_grad()
+    m.eval()
+    m(b).sum().backward()
+    check_grads(m, a, kind, "evalgrad")
+    return m, b
+
+
+def check_against_oracle(graphs, kind, device, hidden, layers, seed=0):
+    """Fresh random weights: package vs oracle/port.py on the same inputs (sizes the oracle handles in seconds)."""
+    from oracle import port
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.train import CrossEntropyLoss
+    g = torch.Generator().manual_seed(seed)
+    params = port.init_params(kind, graphs[0].num_features, hidden, 2, layers, generator=g)
+    for k in params:   # make BatchNorm affine / running stats non-trivial
+        if k.endswith("batch_norms.0.weight") or ".weight" in k and "batch_norms" in k:
+            params[k] = params[k] + 0.1 * torch.randn(params[k].shape, generator=g)
+        if k.endswith("running_mean"):
+            params[k] = 0.05 * torch.randn(params[k].shape, generator=g)
+        if k.endswith("running_var"):
+            params[k] = 1.0 + 0.2 * torch.rand(params[k].shape, generator=g)
+    ob = port.collate(graphs)
+    a = {}
+    with torch.no_grad():
+        a[f"{kind}.eval.emb"] = port.encode(kind, dict(params), ob).numpy()
+        a[f"{kind}.eval.logits"] = port.forward(kind, dict(params), ob).numpy()
+    p2 = {k: v.clone() for k, v in params.items()}
+    logits, loss, grads = port.loss_and_grads(kind, p2, ob, training=True, dropout=0.0)
+    a[f"{kind}.train.logits"], a[f"{kind}.train.loss"] = logits.numpy(), loss.numpy()
+    for k, gr in grads.items():
+        a[f"{kind}.train.grad.{k}"] = gr.numpy()
+    for k, v in params.items():
+        a[f"{kind}.init.{k}"] = v.numpy()
+        if "running" in k or "num_batches" in k:
+            a[f"{kind}.train.after.{k}"] = p2[k].numpy()
+    b = collate_graphs(graphs)
+    m = make_model(kind, a, device)
+    m.eval()
+    with torch.no_grad():
+        helpers.assert_close(m.encode(b), a[f"{kind}.eval.emb"], f"{kind} eval emb")
+        helpers.assert_close(m(b), a[f"{kind}.eval.logits"], f"{kind} eval logits")
+    m.train()
+    logits = m(b)
+    CrossEntropyLoss()(logits, b.labels).backward()
+    helpers.assert_close(logits, a[f"{kind}.train.logits"], f"{kind} train logits")
+    check_grads(m, a, kind, "train.grad")
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            helpers.assert_close(v, a[f"{kind}.train.after.{k}"], f"{kind} {k}")
+
+
+def check_trainer(kind, device):
+    """Trainer.fit trajectory vs the reference's (tests/golden/ref_trainer.npz, dropout 0, Adam)."""
+    import json, os
+    from connectome_gnn.graph import ConnectomeDataLoader
+    from connectome_gnn.train import Trainer
+    a = helpers.golden("ref_trainer.npz")
+    ref = json.load(open(os.path.join(helpers.GOLDEN, "ref_meta.json")))["trainer"][kind]
+    graphs = helpers.graphs_from_store(a)
+    model = make_model(kind, a, "cpu")                      # optimizer is built before Trainer moves the model
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    torch.manual_seed(1)
+    train_loader = ConnectomeDataLoader(graphs[:30], batch_size=10, shuffle=True)
+    val_loader = ConnectomeDataLoader(graphs[30:], batch_size=10, shuffle=False)
+    trainer = Trainer(model, opt, device=device)
+    hist = trainer.fit(train_loader, val_loader, num_epochs=3, patience=10, verbose=False)
+    assert set(hist) == {"train_loss", "val_loss", "val_acc"}
+    for key in ("train_loss", "val_loss"):
+        assert hist[key] == __import__("pytest").approx(ref["history"][key], rel=2e-5), key
+    assert hist["val_acc"] == ref["history"]["val_acc"]
+    ev = trainer.evaluate(val_loader)
+    assert ev["total"] == ref["final_eval"]["total"] and ev["correct"] == ref["final_eval"]["correct"]
+    final = helpers.state_dict_from(a, f"{kind}.final")
+    for k, v in model.state_dict().items():
+        if kind == "gcn" and ((k.startswith("convs.") and k.endswith(".bias")) or k.endswith("running_mean")):
+            continue   # (running_mean contains that bias.)  The bias gradient is analytically zero (bias feeds BatchNorm); Adam turns its round-off noise into
+                       # +-lr steps, so the value is a random walk in the reference too and never affects outputs
+        if v.dtype.is_floating_point:
+            helpers.assert_close(v, final[k], f"final {k}", tol=1e-4)

@@ -1,0 +1,146 @@
+"""The parity gate proper: the product CUDA library (lib/libcgnn.so, sm_100a) through the public API,
+against golden fixtures made from the reference and against the oracle.  Run on a B200 with -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import parity
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_library_loaded():
+    """Fail loudly if the CUDA extension is missing - there is no fallback to hide behind."""
+    assert torch.cuda.is_available()
+    from connectome_gnn import _lib
+    lib = _lib.load()
+    before = lib.cgnn_kernel_launches()
+    yield
+    assert lib.cgnn_kernel_launches() > before, "no cgnn kernel was launched by the GPU tests"
+    assert any("libcgnn.so" in line for line in open("/proc/self/maps")), "libcgnn.so is not mapped"
+
+
+@pytest.mark.parametrize("fixture", ["ref_small.npz", "ref_ragged.npz", "ref_c1.npz"])
+def test_collate_bit_exact(fixture):
+    parity.check_collate(helpers.golden(fixture), DEV)
+
+
+@pytest.mark.parametrize("fixture", ["ref_small.npz", "ref_ragged.npz", "ref_c1.npz"])
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_model_parity(fixture, kind):
+    parity.check_model(helpers.golden(fixture), kind, DEV)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_trainer_trajectory(kind):
+    parity.check_trainer(kind, DEV)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+@pytest.mark.parametrize("shape", [(6, 360, 64, 3), (5, 70, 20, 2), (3, 100, 96, 2), (40, 33, 32, 3)])
+def test_oracle_random_weights(kind, shape):
+    """Fresh weights, package vs oracle/port.py: the 360-node / H=64 shape of BASELINE configs[2], a chunk
+    boundary inside a subject, a wide layer, many small subjects."""
+    from connectome_gnn.synthetic import generate_dataset
+    subjects, regions, hidden, layers = shape
+    graphs = generate_dataset(num_subjects=subjects, num_regions=regions, seed=11)
+    parity.check_against_oracle(graphs, kind, DEV, hidden=hidden, layers=layers)
+
+
+def test_csr_from_coo_equals_collate():
+    from connectome_gnn.graph import ConnectomeBatch, collate_graphs
+    a = helpers.golden("ref_ragged.npz")
+    b = collate_graphs(helpers.graphs_from_store(a))
+    moved = ConnectomeBatch(b.node_features.cpu(), b.edge_index.cpu(), b.edge_weight.cpu(), b.batch.cpu(),
+                            b.labels.cpu(), b.ptr.cpu()).to("cuda")
+    c = moved.ensure_csr()
+    for f in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn", "deg", "dinv", "wsum", "eptr"):
+        assert torch.equal(getattr(c, f), getattr(b.csr, f)), f
+
+
+def test_reference_style_usage_runs_unchanged():
+    """The calls the reference's tests / README make (CPU-constructed model, device='cpu' Trainer) work as is."""
+    from connectome_gnn import (ConnectomeDataLoader, GCNConnectome, GraphSAGEConnectome, Trainer, collate_graphs,
+                                generate_dataset)
+    graphs = generate_dataset(num_subjects=8, num_regions=20, seed=0)
+    batch = collate_graphs(graphs)
+    assert batch.node_features.shape == (160, 5) and batch.num_graphs == 8 and int(batch.ptr[-1]) == 160
+    for cls in (GCNConnectome, GraphSAGEConnectome):
+        model = cls(in_channels=5, hidden_dim=32, num_classes=2)
+        model.eval()
+        with torch.no_grad():
+            assert model(batch).shape == (8, 2) and model.encode(batch).shape == (8, 32)
+        model.train()
+        model(batch).sum().backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    graphs = generate_dataset(num_subjects=40, num_regions=20, seed=7)
+    tl = ConnectomeDataLoader(graphs[:30], batch_size=10, shuffle=True)
+    vl = ConnectomeDataLoader(graphs[30:], batch_size=10, shuffle=False)
+    assert len(tl) == 3 and sum(b.num_graphs for b in vl) == 10
+    model = GCNConnectome(in_channels=5, hidden_dim=16, num_classes=2)
+    trainer = Trainer(model, torch.optim.Adam(model.parameters(), lr=1e-3), device="cpu")
+    hist = trainer.fit(tl, vl, num_epochs=3, patience=10, verbose=False)
+    assert len(hist["train_loss"]) == 3 and trainer.evaluate(vl)["total"] == 10
+
+
+def test_dropout_statistics_and_determinism():
+    from connectome_gnn import _engine
+    from connectome_gnn._engine import Act
+    eng = _engine.engine_for(torch.zeros(1, device=DEV))
+    n, C = 360 * 64, 64
+    ones = torch.ones(n, C, device=DEV)
+    ptr = torch.tensor([0, n], dtype=torch.int64, device=DEV)
+    one, zero = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    for p in (0.1, 0.3, 0.5):
+        emb = eng.pool_fwd(ones, Act(one, zero, False, p, seed=7, site=2), ptr, 1)
+        emb2 = eng.pool_fwd(ones, Act(one, zero, False, p, seed=7, site=2), ptr, 1)
+        other = eng.pool_fwd(ones, Act(one, zero, False, p, seed=8, site=2), ptr, 1)
+        assert torch.equal(emb, emb2) and not torch.equal(emb, other)
+        per_channel_keep = emb[0] * (1 - p)
+        assert float((per_channel_keep - (1 - p)).abs().max()) < 0.02          # every channel close to 1 - p
+        assert abs(float(per_channel_keep.mean()) - (1 - p)) < 2e-3
+
+
+def test_dropout_gradient_consistency():
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.train import CrossEntropyLoss
+    a = helpers.golden("ref_small.npz")
+    b = collate_graphs(helpers.graphs_from_store(a))
+    for kind in ("gcn", "sage"):
+        m = parity.make_model(kind, a, DEV, dropout=0.3)
+        m.train()
+        for bn in m.batch_norms:
+            bn.momentum = 0.0
+
+        def loss_at():
+            torch.manual_seed(123)
+            return CrossEntropyLoss()(m(b), b.labels)
+
+        l0 = loss_at()
+        l0.backward()
+        assert float(loss_at().detach()) == float(l0.detach())
+        params = list(m.parameters())
+        direction = [torch.randn(p.shape, generator=torch.Generator().manual_seed(i)).to(DEV) for i, p in enumerate(params)]
+        analytic = sum(float((p.grad * d).sum()) for p, d in zip(params, direction))
+        eps = 2e-3
+        with torch.no_grad():
+            for p, d in zip(params, direction): p.add_(eps * d)
+            lp = float(loss_at())
+            for p, d in zip(params, direction): p.sub_(2 * eps * d)
+            lm = float(loss_at())
+        assert (lp - lm) / (2 * eps) == pytest.approx(analytic, rel=0.05, abs=2e-3), kind
+
+
+def test_unsupported_shapes_fail_loudly():
+    """No silent fallback: a tile that cannot fit shared memory raises CgnnError."""
+    from connectome_gnn import _lib
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.models import GCNConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    b = collate_graphs(generate_dataset(num_subjects=2, num_regions=360, seed=1))
+    m = GCNConnectome(in_channels=5, hidden_dim=512).cuda().eval()
+    with pytest.raises(_lib.CgnnError), torch.no_grad():
+        m(b)
