@@ -1,0 +1,399 @@
+#!/usr/bin/env python3
+"""bench.py - graphs/sec of the batched message-passing hot path (GCN + GraphSAGE, train & infer).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (N>1: under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[2], the largest single-GPU configuration): 360-node synthetic
+Watts-Strogatz connectomes, batch 4096 subjects per GPU, hidden 64, 3 layers, dropout 0.3.
+One STEP = the four legs of BASELINE.json's metric on one batch each:
+    GCN train (collate + fwd + loss + bwd + Adam) | SAGE train | GCN infer (collate + fwd + loss/acc) | SAGE infer
+`value` = subjects processed by the four legs of all ranks / device time (inputs resident in HBM);
+`e2e`   = the same through the public API from HOST buffers (pinned host -> device copy of the batch's
+          subjects, collate, step, loss read back to the host - all inside the timed region).
+Weak scaling: every rank runs the same per-GPU batch; training is data parallel (SyncBN statistics +
+one flat gradient all-reduce over NCCL), inference is collective-free.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "connectome-gnn-suite_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+METRIC = "graphs/sec GCN+SAGE train & infer at 1/2/4/8 B200; % of HBM roofline"
+LEGS = ("gcn_train", "sage_train", "gcn_infer", "sage_infer")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="subjects per GPU per leg")
+    ap.add_argument("--regions", type=int, default=360)
+    ap.add_argument("--hidden", type=int, default=64)
+    ap.add_argument("--layers", type=int, default=3)
+    ap.add_argument("--dropout", type=float, default=0.3)
+    ap.add_argument("--pool", type=int, default=256, help="unique generated subjects, tiled to --batch")
+    ap.add_argument("--cpu-sample", type=int, default=96, help="subjects per leg for the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {
+        "workload": f"BASELINE configs[2]: GCN+SAGE train & infer, {a.regions}-node synthetic Watts-Strogatz connectomes, "
+                    f"batch {a.batch}/GPU, hidden {a.hidden}, {a.layers} layers, dropout {a.dropout}, Adam",
+        "per_gpu_batch": a.batch, "global_batch": a.batch * world, "regions": a.regions, "edges_per_subject": 8 * a.regions,
+        "hidden": a.hidden, "layers": a.layers, "unique_subjects": a.pool,
+        "parallelism": f"dp{world}" if world > 1 else "single",
+        "cache": "inputs larger than L2 (one activation tensor = %.0f MB vs 126 MB L2)" % (a.batch * a.regions * a.hidden * 4 / 1e6),
+        "step": "4 legs x 1 batch: gcn_train, sage_train, gcn_infer, sage_infer",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic bytes: S = 8E + 8N + 4 per subject and layer
+# ---------------------------------------------------------------------------------------------
+
+def bytes_per_graph(n, hidden, layers, feats=5, classes=2):
+    e = 8 * n
+    s = 8 * e + 8 * n + 4
+    infer = 4 * n * feats + 2 * layers * 4 * n * hidden + layers * s + 4 * classes
+    train = (24 * layers - 8) * n * hidden + 8 * n * feats + 2 * layers * s + 4 * classes
+    return {"infer": infer, "train": train}
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi fields via NVML)
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port (the reference's own op sequence) on the host cores
+# ---------------------------------------------------------------------------------------------
+
+def cpu_legs(a, graphs, steps, warmup):
+    """Times the reference algorithm (oracle/port.py: collate + forward (+ backward + Adam)) per leg on a
+    bounded sample of the same workload.  Returns (graphs/s combined, per-leg graphs/s, seconds/step)."""
+    from oracle import port   # bench.py is allowed to execute the oracle ONLY here (cpu_baseline / --impl reference)
+    sample = graphs[: a.cpu_sample]
+    torch.manual_seed(0)
+    mods, opts = {}, {}
+    for kind in ("gcn", "sage"):
+        mods[kind] = port.Module(kind, port.init_params(kind, 5, a.hidden, 2, a.layers), dropout=a.dropout)
+        opts[kind] = torch.optim.Adam(mods[kind].parameters(), lr=1e-3, weight_decay=1e-4)
+
+    def run(leg):
+        kind, mode = leg.split("_")
+        if mode == "train":
+            port.train_epoch(mods[kind], opts[kind], sample, len(sample), shuffle=True)
+        else:
+            port.evaluate(mods[kind], sample, len(sample))
+
+    per_leg = {leg: [] for leg in LEGS}
+    for it in range(warmup + steps):
+        for leg in LEGS:
+            t0 = time.perf_counter()
+            run(leg)
+            if it >= warmup:
+                per_leg[leg].append(time.perf_counter() - t0)
+    leg_s = {leg: float(np.mean(v)) for leg, v in per_leg.items()}
+    step_s = sum(leg_s.values())
+    return len(LEGS) * len(sample) / step_s, {leg: len(sample) / s for leg, s in leg_s.items()}, step_s
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return   # the CPU arm runs once per box
+    from connectome_gnn.synthetic import generate_dataset
+    graphs = generate_dataset(num_subjects=a.cpu_sample, num_regions=a.regions, seed=42)
+    steps, warmup = max(1, a.steps), max(0, a.warmup)
+    value, legs, step_s = cpu_legs(a, graphs, steps, warmup)
+    cores = torch.get_num_threads()
+    sample = f"{a.cpu_sample} subjects per leg per step ({steps} steps after {warmup} warm-up), same shapes as the GPU arm"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": a.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1), "legs": legs,
+        "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# the sm_100a arm
+# ---------------------------------------------------------------------------------------------
+
+def run_b200(a):
+    import torch.distributed as dist
+    from connectome_gnn import _engine, _lib
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    # ---- synthetic inputs: a pool of unique reference-identical subjects, tiled to the batch -------------
+    t0 = time.time()
+    pool = generate_dataset(num_subjects=a.pool, num_regions=a.regions, k=8, beta=0.15, trait_idx=0, seed=42)
+    reps = -(-a.batch // a.pool)
+    graphs = (pool * reps)[: a.batch]
+    packed = pack_graphs(graphs)
+    gen_s = time.time() - t0
+    store = SubjectStore(packed, dev)
+    pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in packed.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in packed.values() if isinstance(v, torch.Tensor))
+    n_per = a.regions
+    meta = dict(row_base=rank * a.batch * n_per, graph_base=rank * a.batch, global_num_graphs=a.batch * world,
+                global_num_nodes=a.batch * world * n_per)
+
+    torch.manual_seed(1234)   # same seed on every rank: identical initial weights and dropout seeds
+    trainers = {}
+    for kind, cls in (("gcn", GCNConnectome), ("sage", GraphSAGEConnectome)):
+        model = cls(in_channels=5, hidden_dim=a.hidden, num_classes=2, num_layers=a.layers, dropout=a.dropout).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+        trainers[kind] = Trainer(model, opt, device=dev)
+    order_gen = torch.Generator().manual_seed(99 + rank)
+
+    def leg(name, st):
+        kind, mode = name.split("_")
+        tr = trainers[kind]
+        ids = torch.randperm(a.batch, generator=order_gen).numpy()
+        batch = st.collate(ids, **meta)
+        if mode == "train":
+            tr.model.train()
+            return tr.train_step(batch)
+        tr.model.eval()
+        return tr.eval_step(batch)[0]
+
+    def step_resident():
+        for name in LEGS:
+            leg(name, store)
+
+    def step_e2e():
+        out = None
+        for name in LEGS:
+            st = SubjectStore(pinned, dev)           # pinned host -> device copy of this batch's subjects
+            out = float(leg(name, st))               # loss read back to the host
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    warm = max(a.warmup, 3)
+    for _ in range(warm):
+        step_resident()
+    launches0 = lib.cgnn_kernel_launches()
+    with ClockSampler(local) as clocks:
+        ms = timed(step_resident, a.steps)
+    launches = lib.cgnn_kernel_launches() - launches0
+    graphs_per_step = len(LEGS) * a.batch * world
+    value = graphs_per_step * a.steps / (ms / 1e3)
+
+    # ---- per-leg device time (CUDA events on the launching stream) -------------------------------------
+    leg_ms = {}
+    for name in LEGS:
+        leg_ms[name] = timed(lambda: leg(name, store), a.steps) / a.steps
+    bpg = bytes_per_graph(a.regions, a.hidden, a.layers)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    legs = {}
+    for name in LEGS:
+        gps = a.batch / (leg_ms[name] / 1e3)
+        b = bpg["train" if name.endswith("train") else "infer"]
+        legs[name] = {"graphs_per_s_per_gpu": gps, "ms": leg_ms[name], "algorithmic_bytes_per_graph": b,
+                      "hbm_gbs": gps * b / 1e9, "roofline_frac": gps * b / 1e9 / peak}
+
+    # ---- dominant kernel: per-call device time via CUDA events around every C-ABI call ---------------------
+    roofline = profile_calls(a, _engine.engine_for(store.x), lambda: step_resident(), peak, peak_src)
+
+    # ---- end to end from host buffers -----------------------------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        e2e_steps = max(2, min(a.steps, 5))
+        ms_e = timed(step_e2e, e2e_steps)
+        e2e = {"value": graphs_per_step * e2e_steps / (ms_e / 1e3), "unit": "graphs/s",
+               "h2d_bytes_per_step": int(h2d_bytes * len(LEGS)), "d2h_bytes_per_step": 4 * len(LEGS),
+               "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
+               "path": "pinned host arena -> SubjectStore (H2D) -> collate -> Trainer.train_step/eval_step -> float(loss)"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, cl, s = cpu_legs(a, pool, steps=2, warmup=1)
+        cpu = {"value": v, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port", "legs": cl,
+               "sample": f"{a.cpu_sample} subjects per leg per step (2 steps after 1 warm-up) of the same shapes",
+               "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": a.steps, "warmup": warm,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": f"synthetic ({a.pool} unique generated subjects tiled to {a.batch}, generated in {gen_s:.1f}s)",
+            "config": workload_config(a, world), "legs": legs, "clocks": clocks.summary(), "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_calls(a, eng, step_fn, peak, peak_src):
+    """Time every C-ABI call of one step with CUDA events on the launching stream; return the roofline
+    record of the dominant entry point (algorithmic bytes per launch / average launch duration)."""
+    records = []
+    orig = eng._call
+    rows = a.batch * a.regions
+    edges = 8 * rows
+    H, F = a.hidden, 5
+    csr = 4 * (rows + 1) + 8 * edges + 4 * rows      # rowptr + col + weight + dinv/wsum
+
+    def algorithmic(name, args):
+        if name.endswith("layer_fwd"):
+            d_in = args[8]
+            return 4 * rows * d_in + 4 * rows * H + csr
+        if name.endswith("layer_bwd"):
+            d_in = args[12]
+            pooled = args[0] is None
+            need_du = args[17] is not None
+            return (4 * rows * H) * (1 if pooled else 2) + 4 * rows * d_in + (4 * rows * d_in if need_du else 0) + csr
+        if name == "cgnn_bn_bwd_sums" or name == "cgnn_pool_fwd":
+            return 4 * rows * H
+        if name == "cgnn_collate_csr":
+            read = rows * F * 4 + edges * 12
+            write = rows * F * 4 + edges * 20 + rows * 8 + 2 * (4 * (rows + 1) + edges * 12) + 12 * rows
+            return read + write
+        return 0
+
+    def timed_call(name, *args):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(name, *args)
+        e1.record()
+        records.append((name, algorithmic(name, args), e0, e1))
+
+    eng._call = timed_call
+    try:
+        for _ in range(3):
+            step_fn()
+        torch.cuda.synchronize()
+    finally:
+        eng._call = orig
+    agg = {}
+    for name, nbytes, e0, e1 in records:
+        t = e0.elapsed_time(e1)
+        r = agg.setdefault(name, {"ms": 0.0, "bytes": 0, "calls": 0})
+        r["ms"] += t
+        r["bytes"] += nbytes
+        r["calls"] += 1
+    total = sum(r["ms"] for r in agg.values())
+    top = max(agg, key=lambda k: agg[k]["ms"])
+    r = agg[top]
+    achieved = r["bytes"] / (r["ms"] / 1e3) / 1e9 if r["ms"] > 0 else 0.0
+    return {
+        "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_src, "avg_launch_ms": r["ms"] / r["calls"], "launches_timed": r["calls"],
+        "algorithmic_bytes_per_launch": r["bytes"] / r["calls"], "share_of_step": r["ms"] / total if total else None,
+        "per_entry_point": {k: {"ms_per_step": v["ms"] / 3, "calls_per_step": v["calls"] / 3,
+                                "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
+                            for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -105,22 +105,37 @@ class Trainer:
             return []
         return torch.stack([v.detach().reshape(()).double() for v in values]).cpu().tolist()
 
+    # -- one batch (the loop bodies of reference train.py:45-53 and 61-68) ----------------------
+    def train_step(self, batch) -> torch.Tensor:
+        """zero_grad -> forward -> loss -> backward -> (gradient all-reduce) -> optimizer step.
+        Returns this rank's share of the global mean loss as a device scalar (no host sync)."""
+        batch = batch.to(self.device)
+        global_b = batch.global_num_graphs if batch.global_num_graphs is not None else batch.num_graphs
+        self.optimizer.zero_grad()
+        logits = self.model(batch)
+        loss = self.loss_fn(logits, batch.labels, global_b)
+        loss.backward()
+        self._sync_gradients()
+        self.optimizer.step()
+        return loss.detach()
+
+    @torch.no_grad()
+    def eval_step(self, batch):
+        """forward -> loss and argmax-accuracy count, both device scalars (no host sync)."""
+        batch = batch.to(self.device)
+        global_b = batch.global_num_graphs if batch.global_num_graphs is not None else batch.num_graphs
+        logits = self.model(batch)
+        loss = self.loss_fn(logits, batch.labels, global_b)
+        return loss, self.loss_fn.last_correct
+
     # -- reference API -----------------------------------------------------------------------
     def train_epoch(self, loader) -> float:
         """One pass over ``loader`` with parameter updates; returns the mean loss (``train.py:41-54``)."""
         self.model.train()
         losses, sizes = [], []
         for batch in loader:
-            batch = batch.to(self.device)
-            global_b = batch.global_num_graphs if batch.global_num_graphs is not None else batch.num_graphs
-            self.optimizer.zero_grad()
-            logits = self.model(batch)
-            loss = self.loss_fn(logits, batch.labels, global_b)
-            loss.backward()
-            self._sync_gradients()
-            self.optimizer.step()
-            losses.append(loss.detach())
-            sizes.append(global_b)
+            losses.append(self.train_step(batch))
+            sizes.append(batch.global_num_graphs if batch.global_num_graphs is not None else batch.num_graphs)
         if _dist_world() > 1 and losses:
             import torch.distributed as dist
             stacked = torch.stack(losses)
@@ -138,12 +153,10 @@ class Trainer:
         self.model.eval()
         losses, corrects, sizes = [], [], []
         for batch in loader:
-            batch = batch.to(self.device)
-            global_b = batch.global_num_graphs if batch.global_num_graphs is not None else batch.num_graphs
-            logits = self.model(batch)
-            losses.append(self.loss_fn(logits, batch.labels, global_b))
-            corrects.append(self.loss_fn.last_correct)
-            sizes.append(global_b)
+            loss, correct_count = self.eval_step(batch)
+            losses.append(loss)
+            corrects.append(correct_count)
+            sizes.append(batch.global_num_graphs if batch.global_num_graphs is not None else batch.num_graphs)
         if _dist_world() > 1 and losses:
             import torch.distributed as dist
             stacked = torch.stack([torch.stack(losses).double(), torch.stack(corrects).double()])

@@ -119,6 +119,59 @@ def check_model(a, kind, device, batch=None):
     return m, b
 
 
+class _float64:
+    """Run the oracle in double precision: the reference's own op sequence, evaluated without fp32
+    round-off.  SURVEY A.3: the fp32 reference disagrees with ITSELF by up to 3e-3 per gradient tensor
+    between thread counts at N=360 (BatchNorm over near-dead ReLU channels amplifies reduction-order
+    noise), so for fresh weights the stable yardstick is the fp64 evaluation; the fp32 oracle's own
+    distance to it is measured in the same run and must not be (much) smaller than ours."""
+
+    def __enter__(self):
+        self.old = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64)
+
+    def __exit__(self, *exc):
+        torch.set_default_dtype(self.old)
+
+
+def oracle_reference(kind, params, graphs):
+    """(fp64 truth, fp32 oracle at 8 threads) as fixture-style dicts for the package to be compared with."""
+    from oracle import port
+    ob = port.collate(graphs)
+    out = {}
+    for tag, cast in (("f64", torch.float64), ("f32", torch.float32)):
+        conv = lambda v: v.to(cast) if (v is not None and v.is_floating_point()) else v
+        p = {k: conv(v.clone()) for k, v in params.items()}
+        b = {k: conv(v) for k, v in ob.items()}
+        old_threads = torch.get_num_threads()
+        torch.set_num_threads(8)
+        try:
+            ctx = _float64() if cast == torch.float64 else _nullctx()
+            with ctx:
+                a = {}
+                with torch.no_grad():
+                    a[f"{kind}.eval.emb"] = port.encode(kind, dict(p), b).numpy()
+                    a[f"{kind}.eval.logits"] = port.forward(kind, dict(p), b).numpy()
+                p2 = {k: v.clone() for k, v in p.items()}
+                logits, loss, grads = port.loss_and_grads(kind, p2, b, training=True, dropout=0.0)
+        finally:
+            torch.set_num_threads(old_threads)
+        a[f"{kind}.train.logits"], a[f"{kind}.train.loss"] = logits.numpy(), loss.numpy()
+        for k, gr in grads.items():
+            a[f"{kind}.train.grad.{k}"] = gr.numpy()
+        for k, v in params.items():
+            a[f"{kind}.init.{k}"] = v.numpy()
+            if "running" in k or "num_batches" in k:
+                a[f"{kind}.train.after.{k}"] = p2[k].numpy()
+        out[tag] = a
+    return out
+
+
+class _nullctx:
+    def __enter__(self): return self
+    def __exit__(self, *exc): return False
+
+
 def check_against_oracle(graphs, kind, device, hidden, layers, seed=0):
     """Fresh random weights: package vs oracle/port.py on the same inputs (sizes the oracle handles in seconds)."""
     from oracle import port
@@ -127,28 +180,16 @@ def check_against_oracle(graphs, kind, device, hidden, layers, seed=0):
     g = torch.Generator().manual_seed(seed)
     params = port.init_params(kind, graphs[0].num_features, hidden, 2, layers, generator=g)
     for k in params:   # make BatchNorm affine / running stats non-trivial
-        if k.endswith("batch_norms.0.weight") or ".weight" in k and "batch_norms" in k:
+        if ".weight" in k and "batch_norms" in k:
             params[k] = params[k] + 0.1 * torch.randn(params[k].shape, generator=g)
         if k.endswith("running_mean"):
             params[k] = 0.05 * torch.randn(params[k].shape, generator=g)
         if k.endswith("running_var"):
             params[k] = 1.0 + 0.2 * torch.rand(params[k].shape, generator=g)
-    ob = port.collate(graphs)
-    a = {}
-    with torch.no_grad():
-        a[f"{kind}.eval.emb"] = port.encode(kind, dict(params), ob).numpy()
-        a[f"{kind}.eval.logits"] = port.forward(kind, dict(params), ob).numpy()
-    p2 = {k: v.clone() for k, v in params.items()}
-    logits, loss, grads = port.loss_and_grads(kind, p2, ob, training=True, dropout=0.0)
-    a[f"{kind}.train.logits"], a[f"{kind}.train.loss"] = logits.numpy(), loss.numpy()
-    for k, gr in grads.items():
-        a[f"{kind}.train.grad.{k}"] = gr.numpy()
-    for k, v in params.items():
-        a[f"{kind}.init.{k}"] = v.numpy()
-        if "running" in k or "num_batches" in k:
-            a[f"{kind}.train.after.{k}"] = p2[k].numpy()
+    refs = oracle_reference(kind, params, graphs)
+    a, a32 = refs["f64"], refs["f32"]
     b = collate_graphs(graphs)
-    m = make_model(kind, a, device)
+    m = make_model(kind, a32, device)
     m.eval()
     with torch.no_grad():
         helpers.assert_close(m.encode(b), a[f"{kind}.eval.emb"], f"{kind} eval emb")
@@ -157,7 +198,14 @@ def check_against_oracle(graphs, kind, device, hidden, layers, seed=0):
     logits = m(b)
     CrossEntropyLoss()(logits, b.labels).backward()
     helpers.assert_close(logits, a[f"{kind}.train.logits"], f"{kind} train logits")
+    helpers.assert_close(logits, a32[f"{kind}.train.logits"], f"{kind} train logits (fp32 oracle)")
     check_grads(m, a, kind, "train.grad")
+    # the fp32 oracle must sit in the same band around the fp64 truth (it is usually further away than we are)
+    names = [k for k, _ in m.named_parameters()]
+    cat = lambda src: torch.cat([torch.as_tensor(src[f"{kind}.train.grad.{k}"]).reshape(-1).double() for k in names])
+    ours = helpers.max_rel(torch.cat([p.grad.reshape(-1) for _, p in m.named_parameters()]), cat(a))
+    theirs = helpers.max_rel(cat(a32), cat(a))
+    assert ours <= max(REL_TOL, 10 * theirs), (ours, theirs)
     for k, v in m.state_dict().items():
         if "running" in k:
             helpers.assert_close(v, a[f"{kind}.train.after.{k}"], f"{kind} {k}")
