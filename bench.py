@@ -346,7 +346,7 @@ def profile_calls(a, eng, step_fn, peak, peak_src):
         if name.endswith("layer_bwd"):
             d_in = args[12]
             pooled = args[0] is None
-            need_du = args[17] is not None
+            need_du = args[18] is not None
             return (4 * rows * H) * (1 if pooled else 2) + 4 * rows * d_in + (4 * rows * d_in if need_du else 0) + csr
         if name == "cgnn_bn_bwd_sums" or name == "cgnn_pool_fwd":
             return 4 * rows * H

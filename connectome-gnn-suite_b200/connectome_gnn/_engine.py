@@ -83,9 +83,10 @@ class Engine:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
     # -- K0 ---------------------------------------------------------------------------------
-    def new_csr(self, rows: int, edges: int) -> dict:
+    def new_csr(self, rows: int, edges: int, graphs: int) -> dict:
         e = self.empty
         return dict(
+            graph_meta=e((graphs, 4), torch.int32),
             in_rowptr=e(rows + 1, torch.int32), in_col=e(edges, torch.int32), in_w=e(edges), in_wn=e(edges),
             out_rowptr=e(rows + 1, torch.int32), out_col=e(edges, torch.int32), out_w=e(edges), out_wn=e(edges),
             deg=e(rows), dinv=e(rows), wsum=e(rows))
@@ -94,7 +95,7 @@ class Engine:
     def csr_struct(c) -> CsrT:
         g = (lambda k: c[k]) if isinstance(c, dict) else (lambda k: getattr(c, k))
         return CsrT(*[_p(g(k)) for k in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col",
-                                         "out_w", "out_wn", "deg", "dinv", "wsum")])
+                                         "out_w", "out_wn", "deg", "dinv", "wsum", "graph_meta")])
 
     def collate_csr(self, store: StoreT, ids: torch.Tensor, num_graphs: int, rows: int, edges: int, max_nodes: int,
                     num_features: int, with_labels: bool):
@@ -103,7 +104,7 @@ class Engine:
             node_features=e((rows, num_features)), edge_index=e((2, edges), torch.int64), edge_weight=e(edges),
             batch=e(rows, torch.int64), labels=e(num_graphs, torch.int64) if with_labels else None,
             ptr=e(num_graphs + 1, torch.int64), eptr=e(num_graphs + 1, torch.int64))
-        csr = self.new_csr(rows, edges)
+        csr = self.new_csr(rows, edges, num_graphs)
         cs = self.csr_struct(csr)
         self._call("cgnn_collate_csr", C.byref(store), _p(ids), num_graphs, rows, edges, max_nodes,
                    _p(out["node_features"]), _p(out["edge_index"]), _p(out["edge_weight"]), _p(out["batch"]),
@@ -111,7 +112,7 @@ class Engine:
         return out, csr
 
     def csr_from_coo(self, edge_index, edge_weight, ptr, num_graphs: int, rows: int, edges: int, max_nodes: int):
-        csr = self.new_csr(rows, edges)
+        csr = self.new_csr(rows, edges, num_graphs)
         eptr = self.empty(num_graphs + 1, torch.int64)
         cs = self.csr_struct(csr)
         self._call("cgnn_csr_from_coo", _p(edge_index), _p(edge_weight), _p(ptr), num_graphs, rows, edges,
@@ -119,15 +120,14 @@ class Engine:
         return csr, eptr
 
     # -- K1 / K2 ------------------------------------------------------------------------------
-    def layer_fwd(self, kind: str, t_in, act: Act, W, bias, csr, ptr, num_graphs: int, max_nodes: int,
-                  want_stats: bool):
+    def layer_fwd(self, kind: str, t_in, act: Act, W, bias, csr, ptr, num_graphs: int, want_stats: bool):
         rows, d_in = t_in.shape
         H = W.shape[0]
         z = self.empty((rows, H))
         stats = self.empty(1 + 2 * H, torch.float64) if want_stats else None
         a, cs = act.struct(), self.csr_struct(csr)
         self._call(f"cgnn_{kind}_layer_fwd", _p(t_in), C.byref(a), _p(W), _p(bias), C.byref(cs), _p(ptr),
-                   num_graphs, rows, d_in, H, max_nodes, _p(z), _p(stats), _p(self.workspace),
+                   num_graphs, rows, d_in, H, csr.max_nodes, csr.max_edges, _p(z), _p(stats), _p(self.workspace),
                    self.workspace_bytes, self.stream())
         return z, stats
 
@@ -200,7 +200,7 @@ class Engine:
         return sums
 
     def layer_bwd(self, kind: str, du, demb, z, act_out: Act, bn: Optional[BnBwd], t_in, act_in: Act, W, csr, ptr,
-                  num_graphs: int, max_nodes: int, need_du: bool, prev_mean, prev_rstd):
+                  num_graphs: int, need_du: bool, prev_mean, prev_rstd):
         rows, d_in = t_in.shape
         H = z.shape[1]
         dW, db = self.empty(W.shape), self.empty(H)
@@ -210,7 +210,8 @@ class Engine:
         ao, ai, cs = act_out.struct(), act_in.struct(), self.csr_struct(csr)
         bs = bn.struct() if bn is not None else None
         args = [_p(du), _p(demb), _p(z), C.byref(ao), C.byref(bs) if bs is not None else None, _p(t_in),
-                C.byref(ai), _p(W), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, max_nodes, _p(dW), _p(db),
+                C.byref(ai), _p(W), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, csr.max_nodes, csr.max_edges,
+                _p(dW), _p(db),
                 _p(du_in), _p(prev_mean) if want_prev else None, _p(prev_rstd) if want_prev else None,
                 _p(prev_sums)]
         if kind == "sage":

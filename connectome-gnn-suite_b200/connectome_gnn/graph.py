@@ -91,14 +91,17 @@ class BatchCSR:
     deg: torch.Tensor
     dinv: torch.Tensor
     wsum: torch.Tensor
+    graph_meta: torch.Tensor  # [B, 4] int32 {first row, rows, first edge, edges} per subject
     eptr: torch.Tensor        # [B+1] int64 edge prefix sums
     max_nodes: int            # largest subject of the batch (sizes shared-memory tiles)
+    max_edges: int            # most edges in one subject
 
     _FIELDS = ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn",
-               "deg", "dinv", "wsum", "eptr")
+               "deg", "dinv", "wsum", "graph_meta", "eptr")
 
     def to(self, device) -> "BatchCSR":
-        return BatchCSR(*[getattr(self, f).to(device) for f in self._FIELDS], max_nodes=self.max_nodes)
+        return BatchCSR(*[getattr(self, f).to(device) for f in self._FIELDS], max_nodes=self.max_nodes,
+                        max_edges=self.max_edges)
 
 
 @dataclass
@@ -153,7 +156,8 @@ class ConnectomeBatch:
             ei = self.edge_index.contiguous()
             csr, eptr = eng.csr_from_coo(ei, self.edge_weight.contiguous(), self.ptr.contiguous(), self.num_graphs,
                                          self.num_nodes, int(ei.shape[1]), max_nodes)
-            self.csr = BatchCSR(**csr, eptr=eptr, max_nodes=max_nodes)
+            max_edges = int((eptr[1:] - eptr[:-1]).max().item()) if self.num_graphs else 0
+            self.csr = BatchCSR(**csr, eptr=eptr, max_nodes=max_nodes, max_edges=max_edges)
         return self.csr
 
 
@@ -241,6 +245,7 @@ class SubjectStore:
         e_sel = self.edge_ptr_host[ids_np + 1] - self.edge_ptr_host[ids_np]
         rows, edges = int(n_sel.sum()), int(e_sel.sum())
         max_nodes = int(n_sel.max()) if ids_np.size else 0
+        max_edges = int(e_sel.max()) if ids_np.size else 0
         labelled = self.has_label[ids_np]
         all_labelled = bool(labelled.all()) and ids_np.size > 0
         if ids_device is None:
@@ -255,7 +260,7 @@ class SubjectStore:
             labels = self.label[torch.from_numpy(ids_np[labelled]).to(self.device)]
         return ConnectomeBatch(
             out["node_features"], out["edge_index"], out["edge_weight"], out["batch"], labels, out["ptr"],
-            BatchCSR(**csr, eptr=out["eptr"], max_nodes=max_nodes), row_base, graph_base,
+            BatchCSR(**csr, eptr=out["eptr"], max_nodes=max_nodes, max_edges=max_edges), row_base, graph_base,
             global_num_graphs, global_num_nodes)
 
 

@@ -92,7 +92,7 @@ class _EncodeFn(torch.autograd.Function):
         saved = []
         for l, bn in enumerate(cfg["bns"]):
             W, b, gamma, beta = (q.contiguous() for q in params[4 * l: 4 * l + 4])
-            z, stats = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, csr.max_nodes, want_stats=training)
+            z, stats = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, want_stats=training)
             if training:
                 stats = _merge_stats_across_ranks(eng, stats, W.shape[0], cfg["group"])
                 momentum = 0.1 if bn.momentum is None else bn.momentum
@@ -134,7 +134,7 @@ class _EncodeFn(torch.autograd.Function):
             prev_rstd = saved[l - 1][6] if l > 0 else None
             bn = BnBwd(scale, mean, rstd, sums, count, training)
             dW, db, du_in, prev_sums = eng.layer_bwd(kind, du, pooled, z, act_out, bn, t_in, act_in, W, csr, ptr, B,
-                                                     csr.max_nodes, need_du, prev_mean, prev_rstd)
+                                                     need_du, prev_mean, prev_rstd)
             grads[4 * l + 0], grads[4 * l + 1] = dW, db
             grads[4 * l + 2], grads[4 * l + 3] = sums[1], sums[0]   # d gamma = sum dy*xhat, d beta = sum dy
             sums = _sum_across_ranks(prev_sums, group)
@@ -216,7 +216,7 @@ def _single_layer(kind: str, layer: nn.Module, x, edge_index, edge_weight):
     csr = batch.ensure_csr()
     eng = _engine.engine_for(x)
     W, b = (q.detach().to(dev).contiguous() for q in layer.tensors())
-    z, _ = eng.layer_fwd(kind, x.contiguous().float(), Act(), W, b, csr, ptr, 1, csr.max_nodes, want_stats=False)
+    z, _ = eng.layer_fwd(kind, x.contiguous().float(), Act(), W, b, csr, ptr, 1, want_stats=False)
     return z
 
 

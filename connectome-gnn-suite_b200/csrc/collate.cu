@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   const long long nb = p.ptr[g], eb = p.eptr[g];
   const int n = (int)(p.ptr[g + 1] - nb);
   const int m = (int)(p.eptr[g + 1] - eb);
+  if (tid == 0) reinterpret_cast<int4*>(p.csr.graph_meta)[g] = make_int4((int)nb, n, (int)eb, m);
   if (n > p.max_nodes) return;  // host contract violated: never index past the shared arrays
 
   int* cur_in = reinterpret_cast<int*>(cgnn_smem);   // [n] counts -> row starts -> cursors
@@ -246,7 +247,7 @@ using namespace cgnn;
 
 static bool csr_out_ok(const cgnn_csr_out_t* c) {
   return c && c->in_rowptr && c->in_col && c->in_w && c->in_wn && c->out_rowptr && c->out_col && c->out_w &&
-         c->out_wn && c->deg && c->dinv && c->wsum;
+         c->out_wn && c->deg && c->dinv && c->wsum && c->graph_meta;
 }
 
 // Dynamic shared memory (two cursor arrays + dinv) is sized for the largest subject of the batch.

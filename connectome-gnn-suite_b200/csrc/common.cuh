@@ -47,7 +47,7 @@ void set_cuda_error(int err);
     }                                               \
   } while (0)
 
-static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline __host__ __device__ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // Persistent grid: one CTA per work item up to `resident` CTAs per SM.
 static inline int persistent_grid(long long items, size_t smem_bytes, const DeviceInfo& d, int threads) {
@@ -125,6 +125,51 @@ __device__ __forceinline__ float act_bwd(const Act& a, bool affine, float t, flo
   bool pass = !(a.relu && !(y > 0.0f));
   if (a.drop) { pass = pass && drop_keep(a, row_hash, c); du *= a.keep_scale; }
   return pass ? du : 0.0f;
+}
+
+// ---- asynchronous global->shared copies (LDGSTS) ---------------------------------------------
+// Under the simulator these degrade to immediate copies, which is a legal (stronger) ordering.
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+#ifdef CGNN_EMU
+  memcpy(smem, gmem, 16);
+#else
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+#ifdef CGNN_EMU
+  memcpy(smem, gmem, 4);
+#else
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef CGNN_EMU
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+// Wait until at most N of the most recently committed groups are still in flight.
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef CGNN_EMU
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+#endif
+}
+// Copy `count` 4-byte words global->shared with the whole CTA; 16-byte transfers when both sides allow.
+__device__ __forceinline__ void cp_async_words(void* smem, const void* gmem, int count) {
+  const bool wide = ((((uintptr_t)smem) | ((uintptr_t)gmem)) & 15u) == 0;
+  if (wide) {
+    const int n16 = count >> 2;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x)
+      cp_async_16(reinterpret_cast<char*>(smem) + 16 * i, reinterpret_cast<const char*>(gmem) + 16 * i);
+    for (int i = (n16 << 2) + threadIdx.x; i < count; i += blockDim.x)
+      cp_async_4(reinterpret_cast<char*>(smem) + 4 * i, reinterpret_cast<const char*>(gmem) + 4 * i);
+  } else {
+    for (int i = threadIdx.x; i < count; i += blockDim.x)
+      cp_async_4(reinterpret_cast<char*>(smem) + 4 * i, reinterpret_cast<const char*>(gmem) + 4 * i);
+  }
 }
 
 // ---- warp helpers ----------------------------------------------------------------------

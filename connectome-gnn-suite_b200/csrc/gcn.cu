@@ -15,12 +15,18 @@ namespace cgnn {
 struct GcnFwdArgs {
   const float* t_in; Act act; const float* W; const float* bias;
   const int32_t* in_rowptr; const int32_t* in_col; const float* in_wn; const float* dinv;
-  const long long* ptr; long long B;
-  int K, H, K4, H4, ldx, max_nodes, vec_in;
+  const int32_t* meta; long long B;   // meta[g] = {first row, rows, first edge, edges}
+  int K, H, K4, H4, ldx, max_nodes, max_edges, csr_smem;
   float* z; double* partials;
-  int o_wt, o_scale, o_shift, o_bias, o_x, o_p, o_st;  // shared-memory offsets in floats
+  // shared-memory offsets in floats
+  int o_wt, o_scale, o_shift, o_bias, o_raw, o_x, o_p, o_st, o_csr;
 };
 
+// Pipeline per CTA (persistent over subjects g = blockIdx.x, +gridDim.x, ...):
+//   cp.async double buffer of raw 64-row chunks  ->  BN/ReLU/dropout into the padded GEMM operand
+//   ->  4x4 register-tile projection into the subject's P tile  ->  (all chunks done)
+//   aggregation over the subject's CSR, staged in shared memory by cp.async while the projection runs.
+// The first chunk of the NEXT subject is already in flight during the aggregation.
 template <int HC>
 __global__ void __launch_bounds__(kThreads) k_gcn_fwd(GcnFwdArgs p) {
   CGNN_SMEM_DECL;
@@ -29,14 +35,18 @@ __global__ void __launch_bounds__(kThreads) k_gcn_fwd(GcnFwdArgs p) {
   float* s_scale = sm + p.o_scale;  // [K4]
   float* s_shift = sm + p.o_shift;  // [K4]
   float* s_bias = sm + p.o_bias;    // [H4]
-  float* s_x = sm + p.o_x;          // [kChunkRows][ldx]
+  float* s_raw = sm + p.o_raw;      // [2][kChunkRows * K]  raw rows as they sit in HBM
+  float* s_x = sm + p.o_x;          // [kChunkRows][ldx]    transformed, padded GEMM operand
   float* s_p = sm + p.o_p;          // [max_nodes][H4]
   float* s_cnt = sm + p.o_st;       // [kWarps]
   float* s_mean = s_cnt + kWarps;   // [kWarps][H4]
   float* s_m2 = s_mean + kWarps * p.H4;
+  float* s_csr = sm + p.o_csr;      // staged CSR of the current subject (rp | col | wn | dinv)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = p.K, H = p.H, K4 = p.K4, H4 = p.H4, ldx = p.ldx;
+  const int raw_stride = kChunkRows * K;
+  const bool affine = p.act.scale != nullptr;
 
   for (int idx = tid; idx < K4 * H4; idx += kThreads) {
     const int k = idx / H4, h = idx - k * H4;
@@ -44,23 +54,69 @@ __global__ void __launch_bounds__(kThreads) k_gcn_fwd(GcnFwdArgs p) {
   }
   stage_affine(p.act, K, K4, s_scale, s_shift);
   for (int h = tid; h < H4; h += kThreads) s_bias[h] = (h < H && p.bias) ? p.bias[h] : 0.0f;
-  __syncthreads();
 
   WarpStats<HC> st;
   st.init();
   const int tiles_x = H4 >> 2;
   const int ntiles = (kChunkRows >> 2) * tiles_x;
 
-  for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
-    const long long nb = p.ptr[g];
-    int n = (int)(p.ptr[g + 1] - nb);
-    if (n > p.max_nodes) n = p.max_nodes;  // host contract; never index past the tile
+  // Subject metadata comes as one 16-byte record, loaded one subject ahead so its latency never shows.
+  const int4* meta = reinterpret_cast<const int4*>(p.meta);
+  auto load_meta = [&](long long g) -> int4 {
+    int4 m = make_int4(0, 0, 0, 0);
+    if (g < p.B) { m = meta[g]; if (m.y > p.max_nodes) m.y = p.max_nodes; }   // host contract; never index past the tiles
+    return m;
+  };
+  auto issue_chunk = [&](const int4& m, int r0, int buf) {
+    const int rows = min(kChunkRows, m.y - r0);
+    if (rows > 0) cp_async_words(s_raw + buf * raw_stride, p.t_in + ((long long)m.x + r0) * K, rows * K);
+  };
 
-    // ---- projection, kChunkRows rows at a time -----------------------------------------
+  long long g = blockIdx.x;
+  int4 cur = load_meta(g);
+  int buf = 0;
+  issue_chunk(cur, 0, 0);
+  cp_async_commit();
+  __syncthreads();   // constants staged
+
+  while (g < p.B) {
+    const long long g_next = g + gridDim.x;
+    const int4 nxt = load_meta(g_next);
+    const long long nb = cur.x;
+    const int n = cur.y, eb = cur.z, m = cur.w;
+    const bool csr_here = p.csr_smem && m <= p.max_edges;
+    if (n == 0) {   // empty subject: keep the "next chunk is in flight" invariant
+      issue_chunk(nxt, 0, buf ^ 1);
+      cp_async_commit();
+      buf ^= 1;
+    }
+
+    // ---- projection, kChunkRows rows at a time, next chunk always in flight ------------------
     for (int r0 = 0; r0 < n; r0 += kChunkRows) {
       const int rows = min(kChunkRows, n - r0);
-      if (p.vec_in) stage_rows<true>(p.t_in, nb + r0, rows, kChunkRows, K, K4, ldx, p.act, s_scale, s_shift, s_x, nullptr);
-      else stage_rows<false>(p.t_in, nb + r0, rows, kChunkRows, K, K4, ldx, p.act, s_scale, s_shift, s_x, nullptr);
+      if (r0 + kChunkRows < n) issue_chunk(cur, r0 + kChunkRows, buf ^ 1);
+      else issue_chunk(nxt, 0, buf ^ 1);
+      cp_async_commit();
+      if (r0 == 0) {
+        // the subject's CSR rides behind the next chunk; needed only by the aggregation
+        if (csr_here) stage_csr_async(s_csr, p.max_nodes, p.max_edges, p.in_rowptr, p.in_col, p.in_wn, p.dinv, nb, n, eb, m);
+        cp_async_commit();
+        cp_async_wait<2>();
+      } else {
+        cp_async_wait<1>();
+      }
+      __syncthreads();
+      // BN affine + ReLU + dropout of the previous layer, raw chunk -> padded operand
+      const float* raw = s_raw + buf * raw_stride;
+      for (int idx = tid; idx < kChunkRows * K4; idx += kThreads) {
+        const int r = idx / K4, c = idx - r * K4;
+        float v = 0.0f;
+        if (r < rows && c < K) {
+          const uint32_t rh = p.act.drop ? drop_row_hash(p.act, p.act.row_base + nb + r0 + r) : 0u;
+          v = act_fwd(p.act, affine, raw[r * K + c], s_scale[c], s_shift[c], rh, c);
+        }
+        s_x[r * ldx + c] = v;
+      }
       __syncthreads();
       for (int t = tid; t < ntiles; t += kThreads) {
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
@@ -74,33 +130,21 @@ __global__ void __launch_bounds__(kThreads) k_gcn_fwd(GcnFwdArgs p) {
             *reinterpret_cast<float4*>(s_p + row * H4 + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
       }
-      __syncthreads();
+      buf ^= 1;
     }
+    if (n <= kChunkRows) cp_async_wait<0>();   // single-chunk subject: its CSR group was the most recent one
+    __syncthreads();
 
     // ---- aggregation: one warp per destination row, lanes over channels -------------------
+    const float* dinv_g = p.dinv + nb;
+    RowCsr rc{p.in_rowptr + nb, p.in_col, p.in_wn};
+    if (csr_here) rc = staged_csr(s_csr, p.max_nodes, p.max_edges, eb, &dinv_g);
     for (int i = warp; i < n; i += kWarps) {
-      const int e0 = p.in_rowptr[nb + i], e1 = p.in_rowptr[nb + i + 1];
       float acc[HC];
 #pragma unroll
       for (int j = 0; j < HC; ++j) acc[j] = 0.0f;
-      for (int eb = e0; eb < e1; eb += 32) {
-        const int e = eb + lane;
-        int colv = 0; float wv = 0.0f;
-        if (e < e1) { colv = (int)(p.in_col[e] - nb); wv = p.in_wn[e]; }
-        const int cnt = min(32, e1 - eb);
-        for (int k = 0; k < cnt; ++k) {
-          const int c = __shfl_sync(kFull, colv, k);
-          const float w = __shfl_sync(kFull, wv, k);
-          if ((unsigned)c < (unsigned)n) {
-#pragma unroll
-            for (int j = 0; j < HC; ++j) {
-              const int ch = lane + 32 * j;
-              if (ch < H4) acc[j] = __fadd_rn(acc[j], __fmul_rn(s_p[c * H4 + ch], w));
-            }
-          }
-        }
-      }
-      const float d = p.dinv[nb + i];
+      gather_row<HC, true>(rc, i, nb, n, s_p, H4, H4, acc);
+      const float d = dinv_g[i];
       const float wself = __fmul_rn(d, d);
       float inv;
       st.begin_row(inv);
@@ -115,8 +159,11 @@ __global__ void __launch_bounds__(kThreads) k_gcn_fwd(GcnFwdArgs p) {
         }
       }
     }
-    __syncthreads();  // s_p is rewritten by the next subject
+    __syncthreads();  // s_p and the staged CSR are rewritten by the next subject
+    g = g_next;
+    cur = nxt;
   }
+  cp_async_wait<0>();
 
   if (p.partials) {
     st.deposit(s_cnt, s_mean, s_m2, H4, H4);
@@ -132,17 +179,27 @@ struct GcnBwdArgs {
   float inv_count; int bn_train; int has_bn;
   const float* t_in; Act act_in; const float* W;
   const int32_t* out_rowptr; const int32_t* out_col; const float* out_wn; const float* dinv;
-  const long long* ptr; long long B;
-  int K, H, K4, H4, ldp, ldu, max_nodes, vec_in;
+  const int32_t* meta; long long B;
+  int K, H, K4, H4, ldp, ldu, max_nodes, max_edges, csr_smem, vec_h;
   float* du_in; const float* prev_mean; const float* prev_rstd; int want_prev;
   float* partials; int part_stride, o_pdw, o_pdb, o_pprev;
   // shared-memory offsets (floats)
-  int o_w, o_co, o_ci, o_dz, o_dp, o_u, o_raw, o_red;
+  int o_w, o_co, o_ci, o_dz, o_dp, o_u, o_raw, o_red, o_csr;
 };
 
 // Per-channel constant rows staged in shared memory.
 enum { CO_SCALE = 0, CO_SHIFT, CO_BSC, CO_MEAN, CO_RSTD, CO_S1N, CO_S2N, CO_ROWS };  // x H4
 enum { CI_SCALE = 0, CI_SHIFT, CI_MEAN, CI_RSTD, CI_ROWS };                          // x K4
+
+// dz of one element: dropout/ReLU backward of the upstream gradient, then BatchNorm backward.
+__device__ __forceinline__ float gcn_dz(const GcnBwdArgs& p, const float* s_co, int H4, bool aff_out, float t, float up,
+                                        uint32_t rh, int c) {
+  const float dy = act_bwd(p.act_out, aff_out, t, s_co[CO_SCALE * H4 + c], s_co[CO_SHIFT * H4 + c], rh, c, up);
+  if (!p.has_bn) return dy;
+  if (!p.bn_train) return s_co[CO_BSC * H4 + c] * dy;
+  const float xh = (t - s_co[CO_MEAN * H4 + c]) * s_co[CO_RSTD * H4 + c];
+  return s_co[CO_BSC * H4 + c] * (dy - s_co[CO_S1N * H4 + c] - xh * s_co[CO_S2N * H4 + c]);
+}
 
 template <int HC, int MAXT>
 __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
@@ -153,12 +210,14 @@ __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
   float* s_ci = sm + p.o_ci;    // [CI_ROWS][K4]
   float* s_dz = sm + p.o_dz;    // [max_nodes][H4]
   float* s_dp = sm + p.o_dp;    // [kChunkRows][ldp]
-  float* s_u = sm + p.o_u;      // [kChunkRows][ldu]
-  float* s_raw = sm + p.o_raw;  // [kChunkRows][ldu]
+  float* s_u = sm + p.o_u;      // [kChunkRows][ldu]   transformed layer input (GEMM operand)
+  float* s_raw = sm + p.o_raw;  // [2][kChunkRows*K]   raw layer input as it sits in HBM (cp.async double buffer)
   float* s_red = sm + p.o_red;  // reduction scratch
+  float* s_csr = sm + p.o_csr;  // staged by-source CSR of the current subject
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = p.K, H = p.H, K4 = p.K4, H4 = p.H4, ldp = p.ldp, ldu = p.ldu;
+  const int raw_stride = kChunkRows * K;
   const bool aff_out = p.act_out.scale != nullptr, aff_in = p.act_in.scale != nullptr;
 
   for (int idx = tid; idx < H4 * K4; idx += kThreads) {
@@ -180,7 +239,6 @@ __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
     s_ci[CI_MEAN * K4 + c] = ok ? p.prev_mean[c] : 0.0f;
     s_ci[CI_RSTD * K4 + c] = ok ? p.prev_rstd[c] : 0.0f;
   }
-  __syncthreads();
 
   const int tk = K4 >> 2;                         // channel quads of the input width
   const int ntiles_w = (H4 >> 2) * tk;            // dW register tiles
@@ -199,47 +257,108 @@ __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
   for (int j = 0; j < HC; ++j) acc_db[j] = 0.0f;
   float ps1[4] = {0.f, 0.f, 0.f, 0.f}, ps2[4] = {0.f, 0.f, 0.f, 0.f};
 
-  for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
-    const long long nb = p.ptr[g];
-    int n = (int)(p.ptr[g + 1] - nb);
-    if (n > p.max_nodes) n = p.max_nodes;
-    const float inv_n = 1.0f / ((float)n + 1e-8f);
+  const int4* meta = reinterpret_cast<const int4*>(p.meta);
+  auto load_meta = [&](long long g) -> int4 {
+    int4 m = make_int4(0, 0, 0, 0);
+    if (g < p.B) { m = meta[g]; if (m.y > p.max_nodes) m.y = p.max_nodes; }
+    return m;
+  };
+  auto issue_chunk = [&](const int4& m, int r0, int buf) {
+    const int rows = min(kChunkRows, m.y - r0);
+    if (rows > 0) cp_async_words(s_raw + buf * raw_stride, p.t_in + ((long long)m.x + r0) * K, rows * K);
+  };
 
-    // ---- phase 1: dz tile ---------------------------------------------------------------
-    for (int idx = tid; idx < n * H4; idx += kThreads) {
-      const int i = idx / H4, c = idx - i * H4;
-      float dz = 0.0f;
-      if (c < H) {
-        const float t = p.z[(nb + i) * H + c];
-        const float up = p.du ? p.du[(nb + i) * H + c] : p.demb[g * H + c] * inv_n;
-        const uint32_t rh = p.act_out.drop ? drop_row_hash(p.act_out, p.act_out.row_base + nb + i) : 0u;
-        const float dy = act_bwd(p.act_out, aff_out, t, s_co[CO_SCALE * H4 + c], s_co[CO_SHIFT * H4 + c], rh, c, up);
-        if (p.has_bn) {
-          if (p.bn_train) {
-            const float xh = (t - s_co[CO_MEAN * H4 + c]) * s_co[CO_RSTD * H4 + c];
-            dz = s_co[CO_BSC * H4 + c] * (dy - s_co[CO_S1N * H4 + c] - xh * s_co[CO_S2N * H4 + c]);
-          } else {
-            dz = s_co[CO_BSC * H4 + c] * dy;
+  long long g = blockIdx.x;
+  int4 cur = load_meta(g);
+  int buf = 0;
+  issue_chunk(cur, 0, 0);
+  cp_async_commit();
+  __syncthreads();   // constants staged
+
+  while (g < p.B) {
+    const long long g_next = g + gridDim.x;
+    const int4 nxt = load_meta(g_next);
+    const long long nb = cur.x;
+    const int n = cur.y, eb = cur.z, m = cur.w;
+    const bool csr_here = p.csr_smem && m <= p.max_edges;
+    const float inv_n = 1.0f / ((float)n + 1e-8f);
+    if (csr_here) stage_csr_async(s_csr, p.max_nodes, p.max_edges, p.out_rowptr, p.out_col, p.out_wn, p.dinv, nb, n, eb, m);
+    cp_async_commit();
+
+    // ---- phase 1: dz tile (streams z and the upstream gradient once) -------------------------
+    if (p.vec_h) {
+      const int q4 = H4 >> 2;
+      const int total = n * q4;
+      for (int base = tid; base < total; base += 4 * kThreads) {
+        float4 zv[4], uv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * kThreads;
+          if (idx < total) {
+            const int i = idx / q4, c = (idx - i * q4) << 2;
+            zv[u] = *reinterpret_cast<const float4*>(p.z + (nb + i) * H + c);
+            if (p.du) uv[u] = *reinterpret_cast<const float4*>(p.du + (nb + i) * H + c);
           }
-        } else {
-          dz = dy;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * kThreads;
+          if (idx < total) {
+            const int i = idx / q4, c = (idx - i * q4) << 2;
+            if (!p.du) {
+              const float4 e = *reinterpret_cast<const float4*>(p.demb + g * H + c);
+              uv[u] = make_float4(e.x * inv_n, e.y * inv_n, e.z * inv_n, e.w * inv_n);
+            }
+            const uint32_t rh = p.act_out.drop ? drop_row_hash(p.act_out, p.act_out.row_base + nb + i) : 0u;
+            float4 o;
+            o.x = gcn_dz(p, s_co, H4, aff_out, zv[u].x, uv[u].x, rh, c);
+            o.y = gcn_dz(p, s_co, H4, aff_out, zv[u].y, uv[u].y, rh, c + 1);
+            o.z = gcn_dz(p, s_co, H4, aff_out, zv[u].z, uv[u].z, rh, c + 2);
+            o.w = gcn_dz(p, s_co, H4, aff_out, zv[u].w, uv[u].w, rh, c + 3);
+            *reinterpret_cast<float4*>(s_dz + i * H4 + c) = o;
+          }
         }
       }
-      s_dz[idx] = dz;
-    }
-    __syncthreads();
-    // bias gradient: column sums of dz
-    for (int i = warp; i < n; i += kWarps) {
-#pragma unroll
-      for (int j = 0; j < HC; ++j) {
-        const int ch = lane + 32 * j;
-        if (ch < H4) acc_db[j] += s_dz[i * H4 + ch];
+    } else {
+      for (int idx = tid; idx < n * H4; idx += kThreads) {
+        const int i = idx / H4, c = idx - i * H4;
+        float dz = 0.0f;
+        if (c < H) {
+          const float t = p.z[(nb + i) * H + c];
+          const float up = p.du ? p.du[(nb + i) * H + c] : p.demb[g * H + c] * inv_n;
+          const uint32_t rh = p.act_out.drop ? drop_row_hash(p.act_out, p.act_out.row_base + nb + i) : 0u;
+          dz = gcn_dz(p, s_co, H4, aff_out, t, up, rh, c);
+        }
+        s_dz[idx] = dz;
       }
     }
+    if (n == 0) {   // empty subject: keep the "next chunk is in flight" invariant
+      issue_chunk(nxt, 0, buf ^ 1);
+      cp_async_commit();
+      buf ^= 1;
+    }
+
+    const float* dinv_g = p.dinv + nb;
+    RowCsr rc{p.out_rowptr + nb, p.out_col, p.out_wn};
+    if (csr_here) rc = staged_csr(s_csr, p.max_nodes, p.max_edges, eb, &dinv_g);
 
     // ---- phase 2: row chunks --------------------------------------------------------------
     for (int j0 = 0; j0 < n; j0 += kChunkRows) {
       const int rows = min(kChunkRows, n - j0);
+      cp_async_wait<0>();   // this chunk's raw rows and the subject's CSR have landed (this thread's copies)
+      __syncthreads();      // ... everyone's; s_dz complete; previous chunk's readers are done
+      if (j0 + kChunkRows < n) issue_chunk(cur, j0 + kChunkRows, buf ^ 1);
+      else issue_chunk(nxt, 0, buf ^ 1);
+      cp_async_commit();
+      if (j0 == 0) {   // bias gradient: column sums of dz
+        for (int i = warp; i < n; i += kWarps) {
+#pragma unroll
+          for (int j = 0; j < HC; ++j) {
+            const int ch = lane + 32 * j;
+            if (ch < H4) acc_db[j] += s_dz[i * H4 + ch];
+          }
+        }
+      }
       // (a) dP = A^T dz for the chunk's source rows (by-source CSR), self-loop included
       for (int r = warp; r < kChunkRows; r += kWarps) {
         float acc[HC];
@@ -247,25 +366,8 @@ __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
         for (int j = 0; j < HC; ++j) acc[j] = 0.0f;
         if (r < rows) {
           const int jr = j0 + r;
-          const int e0 = p.out_rowptr[nb + jr], e1 = p.out_rowptr[nb + jr + 1];
-          for (int eb = e0; eb < e1; eb += 32) {
-            const int e = eb + lane;
-            int colv = 0; float wv = 0.0f;
-            if (e < e1) { colv = (int)(p.out_col[e] - nb); wv = p.out_wn[e]; }
-            const int cnt = min(32, e1 - eb);
-            for (int k = 0; k < cnt; ++k) {
-              const int c = __shfl_sync(kFull, colv, k);
-              const float w = __shfl_sync(kFull, wv, k);
-              if ((unsigned)c < (unsigned)n) {
-#pragma unroll
-                for (int j = 0; j < HC; ++j) {
-                  const int ch = lane + 32 * j;
-                  if (ch < H4) acc[j] = fmaf(s_dz[c * H4 + ch], w, acc[j]);
-                }
-              }
-            }
-          }
-          const float d = p.dinv[nb + jr];
+          gather_row<HC, false>(rc, jr, nb, n, s_dz, H4, H4, acc);
+          const float d = dinv_g[jr];
           const float wself = d * d;
 #pragma unroll
           for (int j = 0; j < HC; ++j) {
@@ -279,10 +381,17 @@ __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
           if (ch < H4) s_dp[r * ldp + ch] = acc[j];
         }
       }
-      // (b) this layer's input rows, transformed (u) and raw
-      float* raw = p.want_prev ? s_raw : nullptr;
-      if (p.vec_in) stage_rows<true>(p.t_in, nb + j0, rows, kChunkRows, K, K4, ldu, p.act_in, s_ci + CI_SCALE * K4, s_ci + CI_SHIFT * K4, s_u, raw);
-      else stage_rows<false>(p.t_in, nb + j0, rows, kChunkRows, K, K4, ldu, p.act_in, s_ci + CI_SCALE * K4, s_ci + CI_SHIFT * K4, s_u, raw);
+      // (b) this layer's input rows: raw chunk -> transformed operand
+      const float* raw = s_raw + buf * raw_stride;
+      for (int idx = tid; idx < kChunkRows * K4; idx += kThreads) {
+        const int r = idx / K4, c = idx - r * K4;
+        float v = 0.0f;
+        if (r < rows && c < K) {
+          const uint32_t rh = p.act_in.drop ? drop_row_hash(p.act_in, p.act_in.row_base + nb + j0 + r) : 0u;
+          v = act_fwd(p.act_in, aff_in, raw[r * K + c], s_ci[CI_SCALE * K4 + c], s_ci[CI_SHIFT * K4 + c], rh, c);
+        }
+        s_u[r * ldu + c] = v;
+      }
       __syncthreads();
       // (c) dW += dP^T u
 #pragma unroll
@@ -313,7 +422,7 @@ __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
               if (ch < K) {
                 p.du_in[grow * K + ch] = acc[i][q];
                 if (p.want_prev) {
-                  const float t0 = s_raw[r * ldu + ch];
+                  const float t0 = raw[r * K + ch];
                   const float dyp = act_bwd(p.act_in, aff_in, t0, s_ci[CI_SCALE * K4 + ch], s_ci[CI_SHIFT * K4 + ch], rh, ch, acc[i][q]);
                   const float xh = (t0 - s_ci[CI_MEAN * K4 + ch]) * s_ci[CI_RSTD * K4 + ch];
                   ps1[q] += dyp;
@@ -324,9 +433,13 @@ __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
           }
         }
       }
-      __syncthreads();
+      buf ^= 1;
     }
+    __syncthreads();   // s_dz, the staged CSR and the chunk buffers are rewritten by the next subject
+    g = g_next;
+    cur = nxt;
   }
+  cp_async_wait<0>();
 
   // ---- per-CTA partial record: [dW H4*K4][db H4][prev 2*K4] ----------------------------------
   float* part = p.partials + (size_t)blockIdx.x * p.part_stride;
@@ -361,7 +474,7 @@ __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
       const int which = c / K4, ch = c - which * K4;
       const int tx = ch >> 2, q = ch & 3;
       float s = 0.0f;
-      for (int m = tx; m < ntu; m += tk) s += s_red[m * 8 + which * 4 + q];
+      for (int mth = tx; mth < ntu; mth += tk) s += s_red[mth * 8 + which * 4 + q];
       part[p.o_pprev + c] = s;
     }
   }
@@ -371,18 +484,18 @@ __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
 
 using namespace cgnn;
 
-static bool csr_in_ok(const cgnn_csr_t* c) { return c && c->in_rowptr && c->in_col && c->in_wn && c->dinv; }
-static bool csr_out_ok_(const cgnn_csr_t* c) { return c && c->out_rowptr && c->out_col && c->out_wn && c->dinv; }
+static bool csr_in_ok(const cgnn_csr_t* c) { return c && c->in_rowptr && c->in_col && c->in_wn && c->dinv && c->graph_meta; }
+static bool csr_out_ok_(const cgnn_csr_t* c) { return c && c->out_rowptr && c->out_col && c->out_wn && c->dinv && c->graph_meta; }
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 extern "C" {
 
 int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
                        const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
-                       int32_t d_in, int32_t H, int32_t max_nodes, float* z, double* bn_stats,
+                       int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, double* bn_stats,
                        void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0) return CGNN_ERR_INVALID_ARG;
+  if (num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0 || max_edges < 0) return CGNN_ERR_INVALID_ARG;
   if (num_graphs == 0 || rows == 0) {  // a rank may hold no subjects: empty statistics record
     if (bn_stats) cudaMemsetAsync(bn_stats, 0, (size_t)(1 + 2 * H) * sizeof(double), stream);
     return CGNN_OK;
@@ -392,10 +505,10 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
   GcnFwdArgs a;
   a.t_in = t_in; a.act = make_act(act); a.W = W; a.bias = bias;
   a.in_rowptr = csr->in_rowptr; a.in_col = csr->in_col; a.in_wn = csr->in_wn; a.dinv = csr->dinv;
-  a.ptr = (const long long*)ptr; a.B = num_graphs;
+  a.meta = csr->graph_meta; a.B = num_graphs;
   a.K = d_in; a.H = H; a.K4 = round_up(d_in, 4); a.H4 = round_up(H, 4); a.ldx = a.K4 + 4;
   a.max_nodes = max_nodes < 1 ? 1 : max_nodes;
-  a.vec_in = (d_in % 4 == 0) && aligned16(t_in);
+  a.max_edges = max_edges;
   a.z = z;
   if (a.H4 > 256) return CGNN_ERR_TILE_TOO_LARGE;
   int off = 0;
@@ -403,9 +516,15 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
   a.o_scale = off; off += a.K4;
   a.o_shift = off; off += a.K4;
   a.o_bias = off; off += a.H4;
+  a.o_raw = off; off += 2 * round_up(kChunkRows * d_in, 4);
   a.o_x = off; off += kChunkRows * a.ldx;
   a.o_p = off; off += a.max_nodes * a.H4;
-  a.o_st = off; off += kWarps + 2 * kWarps * a.H4;
+  a.o_st = off; off += round_up(kWarps + 2 * kWarps * a.H4, 4);
+  // the subject's CSR goes to shared memory when it fits next to the tiles, else rows read it from L2
+  const int csr_words = cgnn::csr_words(a.max_nodes, a.max_edges);
+  a.csr_smem = ((size_t)(off + csr_words) * sizeof(float) <= (size_t)dev.smem_optin) ? 1 : 0;
+  a.o_csr = off;
+  if (a.csr_smem) off += csr_words;
   const size_t smem = (size_t)off * sizeof(float);
   if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   int grid = persistent_grid(num_graphs, smem, dev, kThreads);
@@ -433,10 +552,11 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
 int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
                        const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in, const float* W,
                        const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
-                       int32_t d_in, int32_t H, int32_t max_nodes, float* dW, float* dbias, float* du_in,
-                       const float* prev_mean, const float* prev_rstd, float* prev_sums, void* workspace,
+                       int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* dW, float* dbias,
+                       float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, void* workspace,
                        size_t workspace_bytes, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (max_edges < 0) return CGNN_ERR_INVALID_ARG;
   if (!dW || !dbias || num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0) return CGNN_ERR_INVALID_ARG;
   if (num_graphs == 0 || rows == 0) {  // a rank may hold no subjects: zero contributions
     cudaMemsetAsync(dW, 0, (size_t)H * d_in * sizeof(float), stream);
@@ -458,11 +578,12 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
   a.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
   a.t_in = t_in; a.act_in = make_act(act_in); a.W = W;
   a.out_rowptr = csr->out_rowptr; a.out_col = csr->out_col; a.out_wn = csr->out_wn; a.dinv = csr->dinv;
-  a.ptr = (const long long*)ptr; a.B = num_graphs;
+  a.meta = csr->graph_meta; a.B = num_graphs;
   a.K = d_in; a.H = H; a.K4 = round_up(d_in, 4); a.H4 = round_up(H, 4);
   a.ldp = a.H4 + 4; a.ldu = a.K4 + 4;
   a.max_nodes = max_nodes < 1 ? 1 : max_nodes;
-  a.vec_in = (d_in % 4 == 0) && aligned16(t_in);
+  a.max_edges = max_edges;
+  a.vec_h = (H % 4 == 0) && aligned16(z) && (!du || aligned16(du)) && (!demb || aligned16(demb));
   a.du_in = du_in; a.prev_mean = prev_mean; a.prev_rstd = prev_rstd; a.want_prev = prev_sums ? 1 : 0;
   const int ntiles_w = (a.H4 / 4) * (a.K4 / 4);
   if (a.H4 > 128 || ntiles_w > 4 * kThreads) return CGNN_ERR_TILE_TOO_LARGE;
@@ -473,8 +594,12 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
   a.o_dz = off; off += a.max_nodes * a.H4;
   a.o_dp = off; off += kChunkRows * a.ldp;
   a.o_u = off; off += kChunkRows * a.ldu;
-  a.o_raw = off; off += kChunkRows * a.ldu;
+  a.o_raw = off; off += 2 * kChunkRows * d_in;
   a.o_red = off; off += (kThreads * 8 > kWarps * a.H4 ? kThreads * 8 : kWarps * a.H4);
+  const int csr_w = cgnn::csr_words(a.max_nodes, a.max_edges);
+  a.csr_smem = ((size_t)(off + csr_w) * sizeof(float) <= (size_t)dev.smem_optin) ? 1 : 0;
+  a.o_csr = off;
+  if (a.csr_smem) off += csr_w;
   const size_t smem = (size_t)off * sizeof(float);
   if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   a.o_pdw = 0; a.o_pdb = a.H4 * a.K4; a.o_pprev = a.o_pdb + a.H4;

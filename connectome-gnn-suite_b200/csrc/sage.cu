@@ -13,9 +13,7 @@ namespace cgnn {
 // Weighted-mean neighbourhood rows for a chunk: s_cat[r] = [u_i || agg_i], i = r0 + r.
 template <int CC>
 __device__ __forceinline__ void sage_cat_rows(const float* s_u, int K4, float* s_cat, int ldc, int r0, int rows,
-                                              int n, long long nb, const int32_t* __restrict__ in_rowptr,
-                                              const int32_t* __restrict__ in_col, const float* __restrict__ in_w,
-                                              const float* __restrict__ wsum) {
+                                              int n, long long nb, const RowCsr& rc, const float* wsum_g) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = warp; r < kChunkRows; r += kWarps) {
     float acc[CC];
@@ -23,26 +21,8 @@ __device__ __forceinline__ void sage_cat_rows(const float* s_u, int K4, float* s
     for (int j = 0; j < CC; ++j) acc[j] = 0.0f;
     float denom = 1.0f;
     if (r < rows) {
-      const int i = r0 + r;
-      const int e0 = in_rowptr[nb + i], e1 = in_rowptr[nb + i + 1];
-      for (int eb = e0; eb < e1; eb += 32) {
-        const int e = eb + lane;
-        int colv = 0; float wv = 0.0f;
-        if (e < e1) { colv = (int)(in_col[e] - nb); wv = in_w[e]; }
-        const int cnt = min(32, e1 - eb);
-        for (int k = 0; k < cnt; ++k) {
-          const int c = __shfl_sync(kFull, colv, k);
-          const float w = __shfl_sync(kFull, wv, k);
-          if ((unsigned)c < (unsigned)n) {
-#pragma unroll
-            for (int j = 0; j < CC; ++j) {
-              const int ch = lane + 32 * j;
-              if (ch < K4) acc[j] = __fadd_rn(acc[j], __fmul_rn(s_u[c * K4 + ch], w));
-            }
-          }
-        }
-      }
-      denom = __fadd_rn(wsum[nb + i], 1e-8f);
+      gather_row<CC, true>(rc, r0 + r, nb, n, s_u, K4, K4, acc);
+      denom = __fadd_rn(wsum_g[r0 + r], 1e-8f);
     }
 #pragma unroll
     for (int j = 0; j < CC; ++j) {
@@ -55,13 +35,27 @@ __device__ __forceinline__ void sage_cat_rows(const float* s_u, int K4, float* s
   }
 }
 
+// Whole-subject input tile: async raw copy into s_u (row stride K), CSR alongside; then the previous layer's
+// BatchNorm/dropout in place (row stride becomes K4 only when K == K4, otherwise a strided rewrite back to front).
+__device__ __forceinline__ void sage_transform_tile(float* s_u, int n, int K, int K4, const Act& act, const float* s_scale,
+                                                    const float* s_shift, long long nb) {
+  const bool affine = act.scale != nullptr;
+  if (K == K4) {
+    for (int idx = threadIdx.x; idx < n * K4; idx += blockDim.x) {
+      const int r = idx / K4, c = idx - r * K4;
+      const uint32_t rh = act.drop ? drop_row_hash(act, act.row_base + nb + r) : 0u;
+      s_u[idx] = act_fwd(act, affine, s_u[idx], s_scale[c], s_shift[c], rh, c);
+    }
+  }
+}
+
 struct SageFwdArgs {
   const float* t_in; Act act; const float* W; const float* bias;
   const int32_t* in_rowptr; const int32_t* in_col; const float* in_w; const float* wsum;
-  const long long* ptr; long long B;
-  int K, H, K4, H4, ldc, max_nodes, vec_in;
+  const int32_t* meta; long long B;
+  int K, H, K4, H4, ldc, max_nodes, max_edges, csr_smem;
   float* z; double* partials;
-  int o_wt, o_scale, o_shift, o_bias, o_u, o_cat, o_out, o_st;
+  int o_wt, o_scale, o_shift, o_bias, o_u, o_cat, o_out, o_st, o_csr;
 };
 
 template <int CC>
@@ -78,9 +72,11 @@ __global__ void __launch_bounds__(kThreads) k_sage_fwd(SageFwdArgs p) {
   float* s_cnt = sm + p.o_st;
   float* s_mean = s_cnt + kWarps;
   float* s_m2 = s_mean + kWarps * p.H4;
+  float* s_csr = sm + p.o_csr;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = p.K, H = p.H, K4 = p.K4, H4 = p.H4, ldc = p.ldc;
+  const bool affine = p.act.scale != nullptr;
 
   for (int idx = tid; idx < 2 * K4 * H4; idx += kThreads) {
     const int kk = idx / H4, h = idx - kk * H4;
@@ -95,17 +91,42 @@ __global__ void __launch_bounds__(kThreads) k_sage_fwd(SageFwdArgs p) {
   st.init();
   const int tiles_x = H4 >> 2;
   const int ntiles = (kChunkRows >> 2) * tiles_x;
+  const int4* meta = reinterpret_cast<const int4*>(p.meta);
 
   for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
-    const long long nb = p.ptr[g];
-    int n = (int)(p.ptr[g + 1] - nb);
-    if (n > p.max_nodes) n = p.max_nodes;
-    if (p.vec_in) stage_rows<true>(p.t_in, nb, n, n, K, K4, K4, p.act, s_scale, s_shift, s_u, nullptr);
-    else stage_rows<false>(p.t_in, nb, n, n, K, K4, K4, p.act, s_scale, s_shift, s_u, nullptr);
+    int4 cur = meta[g];
+    if (cur.y > p.max_nodes) cur.y = p.max_nodes;
+    const long long nb = cur.x;
+    const int n = cur.y, eb = cur.z, m = cur.w;
+    const bool csr_here = p.csr_smem && m <= p.max_edges;
+    // whole input tile + CSR in one async burst
+    if (K == K4) cp_async_words(s_u, p.t_in + nb * K, n * K);
+    if (csr_here) stage_csr_async(s_csr, p.max_nodes, p.max_edges, p.in_rowptr, p.in_col, p.in_w, p.wsum, nb, n, eb, m);
+    cp_async_commit();
+    if (K != K4) {   // narrow first layer: rows are not 16-byte multiples, stage with plain loads
+      for (int idx = tid; idx < n * K4; idx += kThreads) {
+        const int r = idx / K4, c = idx - r * K4;
+        float v = 0.0f;
+        if (c < K) {
+          const uint32_t rh = p.act.drop ? drop_row_hash(p.act, p.act.row_base + nb + r) : 0u;
+          v = act_fwd(p.act, affine, p.t_in[(nb + r) * K + c], s_scale[c], s_shift[c], rh, c);
+        }
+        s_u[idx] = v;
+      }
+    }
+    cp_async_wait<0>();
     __syncthreads();
+    if (K == K4) {
+      sage_transform_tile(s_u, n, K, K4, p.act, s_scale, s_shift, nb);
+      __syncthreads();
+    }
+    const float* wsum_g = p.wsum + nb;
+    RowCsr rc{p.in_rowptr + nb, p.in_col, p.in_w};
+    if (csr_here) rc = staged_csr(s_csr, p.max_nodes, p.max_edges, eb, &wsum_g);
+
     for (int r0 = 0; r0 < n; r0 += kChunkRows) {
       const int rows = min(kChunkRows, n - r0);
-      sage_cat_rows<CC>(s_u, K4, s_cat, ldc, r0, rows, n, nb, p.in_rowptr, p.in_col, p.in_w, p.wsum);
+      sage_cat_rows<CC>(s_u, K4, s_cat, ldc, r0, rows, n, nb, rc, wsum_g);
       __syncthreads();
       for (int t = tid; t < ntiles; t += kThreads) {
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
@@ -134,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) k_sage_fwd(SageFwdArgs p) {
         }
       }
     }
-    __syncthreads();  // s_u / s_out are rewritten by the next subject
+    __syncthreads();  // s_u / s_out / staged CSR are rewritten by the next subject
   }
 
   if (p.partials) {
@@ -151,14 +172,30 @@ struct SageBwdArgs {
   float inv_count; int bn_train; int has_bn;
   const float* t_in; Act act_in; const float* W;
   const int32_t* in_rowptr; const int32_t* in_col; const float* in_w; const float* wsum;
-  const long long* ptr; long long B;
-  int K, H, K4, H4, ldc, ldq, max_nodes, vec_in, need_du;
+  const int32_t* meta; long long B;
+  int K, H, K4, H4, ldc, ldq, max_nodes, max_edges, csr_smem, vec_h, need_du;
   float* direct; float* nbr;  // scratch [rows, K] each
   float* partials; int part_stride, o_pdw, o_pdb;
-  int o_w, o_co, o_ci, o_u, o_cat, o_dq, o_red;
+  int o_w, o_co, o_ci, o_u, o_cat, o_dq, o_red, o_csr;
 };
 
 enum { SO_SCALE = 0, SO_SHIFT, SO_BSC, SO_MEAN, SO_RSTD, SO_S1N, SO_S2N, SO_ROWS };
+
+// dq of one element: dropout backward, BatchNorm backward, ReLU mask of the layer's own output.
+__device__ __forceinline__ float sage_dq(const SageBwdArgs& p, const float* s_co, int H4, bool aff_out, float t, float up,
+                                         uint32_t rh, int c) {
+  const float dy = act_bwd(p.act_out, aff_out, t, s_co[SO_SCALE * H4 + c], s_co[SO_SHIFT * H4 + c], rh, c, up);
+  float dz = dy;
+  if (p.has_bn) {
+    if (p.bn_train) {
+      const float xh = (t - s_co[SO_MEAN * H4 + c]) * s_co[SO_RSTD * H4 + c];
+      dz = s_co[SO_BSC * H4 + c] * (dy - s_co[SO_S1N * H4 + c] - xh * s_co[SO_S2N * H4 + c]);
+    } else {
+      dz = s_co[SO_BSC * H4 + c] * dy;
+    }
+  }
+  return t > 0.0f ? dz : 0.0f;
+}
 
 template <int CC, int MAXT>
 __global__ void __launch_bounds__(kThreads) k_sage_bwd_a(SageBwdArgs p) {
@@ -171,10 +208,11 @@ __global__ void __launch_bounds__(kThreads) k_sage_bwd_a(SageBwdArgs p) {
   float* s_cat = sm + p.o_cat;  // [kChunkRows][ldc]
   float* s_dq = sm + p.o_dq;    // [kChunkRows][ldq]
   float* s_red = sm + p.o_red;
+  float* s_csr = sm + p.o_csr;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = p.K, H = p.H, K4 = p.K4, H4 = p.H4, ldc = p.ldc, ldq = p.ldq, K8 = 2 * p.K4;
-  const bool aff_out = p.act_out.scale != nullptr;
+  const bool aff_out = p.act_out.scale != nullptr, aff_in = p.act_in.scale != nullptr;
 
   for (int idx = tid; idx < H4 * K8; idx += kThreads) {
     const int h = idx / K8, kk = idx - h * K8;
@@ -207,43 +245,93 @@ __global__ void __launch_bounds__(kThreads) k_sage_bwd_a(SageBwdArgs p) {
   float acc_db[CC];
 #pragma unroll
   for (int j = 0; j < CC; ++j) acc_db[j] = 0.0f;
+  const int4* meta = reinterpret_cast<const int4*>(p.meta);
 
   for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
-    const long long nb = p.ptr[g];
-    int n = (int)(p.ptr[g + 1] - nb);
-    if (n > p.max_nodes) n = p.max_nodes;
+    int4 cur = meta[g];
+    if (cur.y > p.max_nodes) cur.y = p.max_nodes;
+    const long long nb = cur.x;
+    const int n = cur.y, eb = cur.z, m = cur.w;
+    const bool csr_here = p.csr_smem && m <= p.max_edges;
     const float inv_n = 1.0f / ((float)n + 1e-8f);
-    if (p.vec_in) stage_rows<true>(p.t_in, nb, n, n, K, K4, K4, p.act_in, s_ci, s_ci + K4, s_u, nullptr);
-    else stage_rows<false>(p.t_in, nb, n, n, K, K4, K4, p.act_in, s_ci, s_ci + K4, s_u, nullptr);
+    if (K == K4) cp_async_words(s_u, p.t_in + nb * K, n * K);
+    if (csr_here) stage_csr_async(s_csr, p.max_nodes, p.max_edges, p.in_rowptr, p.in_col, p.in_w, p.wsum, nb, n, eb, m);
+    cp_async_commit();
+    if (K != K4) {
+      for (int idx = tid; idx < n * K4; idx += kThreads) {
+        const int r = idx / K4, c = idx - r * K4;
+        float v = 0.0f;
+        if (c < K) {
+          const uint32_t rh = p.act_in.drop ? drop_row_hash(p.act_in, p.act_in.row_base + nb + r) : 0u;
+          v = act_fwd(p.act_in, aff_in, p.t_in[(nb + r) * K + c], s_ci[c], s_ci[K4 + c], rh, c);
+        }
+        s_u[idx] = v;
+      }
+    }
+    cp_async_wait<0>();
     __syncthreads();
+    if (K == K4) {
+      sage_transform_tile(s_u, n, K, K4, p.act_in, s_ci, s_ci + K4, nb);
+      __syncthreads();
+    }
+    const float* wsum_g = p.wsum + nb;
+    RowCsr rc{p.in_rowptr + nb, p.in_col, p.in_w};
+    if (csr_here) rc = staged_csr(s_csr, p.max_nodes, p.max_edges, eb, &wsum_g);
 
     for (int r0 = 0; r0 < n; r0 += kChunkRows) {
       const int rows = min(kChunkRows, n - r0);
-      // (a) [u || agg] rows
-      sage_cat_rows<CC>(s_u, K4, s_cat, ldc, r0, rows, n, nb, p.in_rowptr, p.in_col, p.in_w, p.wsum);
-      // (b) dq = relu'(z) * bn_bwd(dropout_bwd(du))
-      for (int idx = tid; idx < kChunkRows * H4; idx += kThreads) {
-        const int r = idx / H4, c = idx - r * H4;
-        float dq = 0.0f;
-        if (r < rows && c < H) {
-          const long long grow = nb + r0 + r;
-          const float t = p.z[grow * H + c];
-          const float up = p.du ? p.du[grow * H + c] : p.demb[g * H + c] * inv_n;
-          const uint32_t rh = p.act_out.drop ? drop_row_hash(p.act_out, p.act_out.row_base + grow) : 0u;
-          const float dy = act_bwd(p.act_out, aff_out, t, s_co[SO_SCALE * H4 + c], s_co[SO_SHIFT * H4 + c], rh, c, up);
-          float dz = dy;
-          if (p.has_bn) {
-            if (p.bn_train) {
-              const float xh = (t - s_co[SO_MEAN * H4 + c]) * s_co[SO_RSTD * H4 + c];
-              dz = s_co[SO_BSC * H4 + c] * (dy - s_co[SO_S1N * H4 + c] - xh * s_co[SO_S2N * H4 + c]);
-            } else {
-              dz = s_co[SO_BSC * H4 + c] * dy;
+      // (b) dq = relu'(z) * bn_bwd(dropout_bwd(du)): issue the global loads first, they fly during (a)
+      if (p.vec_h) {
+        const int q4 = H4 >> 2;
+        const int total = rows * q4;
+        for (int base = tid; base < kChunkRows * q4; base += 4 * kThreads) {
+          float4 zv[4], uv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * kThreads;
+            if (idx < total) {
+              const int r = idx / q4, c = (idx - r * q4) << 2;
+              zv[u] = *reinterpret_cast<const float4*>(p.z + (nb + r0 + r) * H + c);
+              if (p.du) uv[u] = *reinterpret_cast<const float4*>(p.du + (nb + r0 + r) * H + c);
             }
           }
-          dq = t > 0.0f ? dz : 0.0f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * kThreads;
+            if (idx < kChunkRows * q4) {
+              const int r = idx / q4, c = (idx - r * q4) << 2;
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (idx < total) {
+                if (!p.du) {
+                  const float4 e = *reinterpret_cast<const float4*>(p.demb + g * H + c);
+                  uv[u] = make_float4(e.x * inv_n, e.y * inv_n, e.z * inv_n, e.w * inv_n);
+                }
+                const uint32_t rh = p.act_out.drop ? drop_row_hash(p.act_out, p.act_out.row_base + nb + r0 + r) : 0u;
+                o.x = sage_dq(p, s_co, H4, aff_out, zv[u].x, uv[u].x, rh, c);
+                o.y = sage_dq(p, s_co, H4, aff_out, zv[u].y, uv[u].y, rh, c + 1);
+                o.z = sage_dq(p, s_co, H4, aff_out, zv[u].z, uv[u].z, rh, c + 2);
+                o.w = sage_dq(p, s_co, H4, aff_out, zv[u].w, uv[u].w, rh, c + 3);
+              }
+              *reinterpret_cast<float4*>(s_dq + r * ldq + c) = o;
+            }
+          }
         }
-        s_dq[r * ldq + c] = dq;
+      } else {
+        for (int idx = tid; idx < kChunkRows * H4; idx += kThreads) {
+          const int r = idx / H4, c = idx - r * H4;
+          float dq = 0.0f;
+          if (r < rows && c < H) {
+            const long long grow = nb + r0 + r;
+            const float t = p.z[grow * H + c];
+            const float up = p.du ? p.du[grow * H + c] : p.demb[g * H + c] * inv_n;
+            const uint32_t rh = p.act_out.drop ? drop_row_hash(p.act_out, p.act_out.row_base + grow) : 0u;
+            dq = sage_dq(p, s_co, H4, aff_out, t, up, rh, c);
+          }
+          s_dq[r * ldq + c] = dq;
+        }
       }
+      // (a) [u || agg] rows
+      sage_cat_rows<CC>(s_u, K4, s_cat, ldc, r0, rows, n, nb, rc, wsum_g);
       __syncthreads();
       for (int r = warp; r < rows; r += kWarps) {
 #pragma unroll
@@ -274,7 +362,7 @@ __global__ void __launch_bounds__(kThreads) k_sage_bwd_a(SageBwdArgs p) {
             if (r >= rows) continue;
             const long long grow = nb + r0 + r;
             const bool is_nbr = 4 * tx >= K4;
-            const float sc = is_nbr ? 1.0f / __fadd_rn(p.wsum[grow], 1e-8f) : 1.0f;
+            const float sc = is_nbr ? 1.0f / __fadd_rn(wsum_g[r0 + r], 1e-8f) : 1.0f;
             float* dst = is_nbr ? p.nbr : p.direct;
             const int kb = 4 * tx - (is_nbr ? K4 : 0);
 #pragma unroll
@@ -316,10 +404,10 @@ struct SageBwdBArgs {
   const float* direct; const float* nbr; const float* t_in; Act act_in;
   const int32_t* out_rowptr; const int32_t* out_col; const float* out_w;
   const float* prev_mean; const float* prev_rstd; int want_prev;
-  const long long* ptr; long long B;
-  int K, K4, max_nodes;
+  const int32_t* meta; long long B;
+  int K, K4, max_nodes, max_edges, csr_smem;
   float* du_in; float* partials;  // [grid][2*K4]
-  int o_g, o_ci, o_red;
+  int o_g, o_ci, o_red, o_csr;
 };
 
 // du_in[j] = direct[j] + sum_{e: src=j} w_e * nbr[dst(e)]   (nbr already divided by wsum+1e-8)
@@ -330,6 +418,7 @@ __global__ void __launch_bounds__(kThreads) k_sage_bwd_b(SageBwdBArgs p) {
   float* s_g = sm + p.o_g;      // [max_nodes][K4]
   float* s_ci = sm + p.o_ci;    // [4][K4] scale, shift, mean, rstd
   float* s_red = sm + p.o_red;  // [kWarps][2*K4]
+  float* s_csr = sm + p.o_csr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = p.K, K4 = p.K4;
   const bool aff_in = p.act_in.scale != nullptr;
@@ -345,42 +434,38 @@ __global__ void __launch_bounds__(kThreads) k_sage_bwd_b(SageBwdBArgs p) {
   float ps1[CC], ps2[CC];
 #pragma unroll
   for (int j = 0; j < CC; ++j) { ps1[j] = 0.0f; ps2[j] = 0.0f; }
+  const int4* meta = reinterpret_cast<const int4*>(p.meta);
 
   for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
-    const long long nb = p.ptr[g];
-    int n = (int)(p.ptr[g + 1] - nb);
-    if (n > p.max_nodes) n = p.max_nodes;
-    for (int idx = tid; idx < n * K4; idx += kThreads) {
-      const int i = idx / K4, c = idx - i * K4;
-      s_g[idx] = c < K ? p.nbr[(nb + i) * K + c] : 0.0f;
+    int4 cur = meta[g];
+    if (cur.y > p.max_nodes) cur.y = p.max_nodes;
+    const long long nb = cur.x;
+    const int n = cur.y, eb = cur.z, m = cur.w;
+    const bool csr_here = p.csr_smem && m <= p.max_edges;
+    if (K == K4) cp_async_words(s_g, p.nbr + nb * K, n * K);
+    if (csr_here) stage_csr_async(s_csr, p.max_nodes, p.max_edges, p.out_rowptr, p.out_col, p.out_w, nullptr, nb, n, eb, m);
+    cp_async_commit();
+    if (K != K4) {
+      for (int idx = tid; idx < n * K4; idx += kThreads) {
+        const int i = idx / K4, c = idx - i * K4;
+        s_g[idx] = c < K ? p.nbr[(nb + i) * K + c] : 0.0f;
+      }
     }
+    cp_async_wait<0>();
     __syncthreads();
+    const float* unused = nullptr;
+    RowCsr rc{p.out_rowptr + nb, p.out_col, p.out_w};
+    if (csr_here) rc = staged_csr(s_csr, p.max_nodes, p.max_edges, eb, &unused);
     for (int jr = warp; jr < n; jr += kWarps) {
       const long long grow = nb + jr;
-      float acc[CC];
+      float acc[CC], t0[CC];
 #pragma unroll
       for (int j = 0; j < CC; ++j) {
         const int ch = lane + 32 * j;
         acc[j] = ch < K ? p.direct[grow * K + ch] : 0.0f;
+        t0[j] = (p.want_prev && ch < K) ? p.t_in[grow * K + ch] : 0.0f;
       }
-      const int e0 = p.out_rowptr[grow], e1 = p.out_rowptr[grow + 1];
-      for (int eb = e0; eb < e1; eb += 32) {
-        const int e = eb + lane;
-        int colv = 0; float wv = 0.0f;
-        if (e < e1) { colv = (int)(p.out_col[e] - nb); wv = p.out_w[e]; }
-        const int cnt = min(32, e1 - eb);
-        for (int k = 0; k < cnt; ++k) {
-          const int c = __shfl_sync(kFull, colv, k);
-          const float w = __shfl_sync(kFull, wv, k);
-          if ((unsigned)c < (unsigned)n) {
-#pragma unroll
-            for (int j = 0; j < CC; ++j) {
-              const int ch = lane + 32 * j;
-              if (ch < K4) acc[j] = fmaf(s_g[c * K4 + ch], w, acc[j]);
-            }
-          }
-        }
-      }
+      gather_row<CC, false>(rc, jr, nb, n, s_g, K4, K4, acc);
       const uint32_t rh = (p.want_prev && p.act_in.drop) ? drop_row_hash(p.act_in, p.act_in.row_base + grow) : 0u;
 #pragma unroll
       for (int j = 0; j < CC; ++j) {
@@ -388,9 +473,8 @@ __global__ void __launch_bounds__(kThreads) k_sage_bwd_b(SageBwdBArgs p) {
         if (ch < K) {
           p.du_in[grow * K + ch] = acc[j];
           if (p.want_prev) {
-            const float t0 = p.t_in[grow * K + ch];
-            const float dyp = act_bwd(p.act_in, aff_in, t0, s_ci[ch], s_ci[K4 + ch], rh, ch, acc[j]);
-            const float xh = (t0 - s_ci[2 * K4 + ch]) * s_ci[3 * K4 + ch];
+            const float dyp = act_bwd(p.act_in, aff_in, t0[j], s_ci[ch], s_ci[K4 + ch], rh, ch, acc[j]);
+            const float xh = (t0[j] - s_ci[2 * K4 + ch]) * s_ci[3 * K4 + ch];
             ps1[j] += dyp;
             ps2[j] = fmaf(dyp, xh, ps2[j]);
           }
@@ -427,24 +511,25 @@ extern "C" {
 
 int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
                         const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
-                        int32_t d_in, int32_t H, int32_t max_nodes, float* z, double* bn_stats, void* workspace,
-                        size_t workspace_bytes, cgnn_stream_t stream_) {
+                        int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, double* bn_stats,
+                        void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0) return CGNN_ERR_INVALID_ARG;
+  if (num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0 || max_edges < 0) return CGNN_ERR_INVALID_ARG;
   if (num_graphs == 0 || rows == 0) {
     if (bn_stats) cudaMemsetAsync(bn_stats, 0, (size_t)(1 + 2 * H) * sizeof(double), stream);
     return CGNN_OK;
   }
-  if (!t_in || !W || !csr || !csr->in_rowptr || !csr->in_col || !csr->in_w || !csr->wsum || !ptr || !z)
+  if (!t_in || !W || !csr || !csr->in_rowptr || !csr->in_col || !csr->in_w || !csr->wsum || !csr->graph_meta || !ptr || !z)
     return CGNN_ERR_INVALID_ARG;
+  if (d_in % 4 == 0 && !aligned16(t_in)) return CGNN_ERR_INVALID_ARG;
   const DeviceInfo dev = device_info();
   SageFwdArgs a;
   a.t_in = t_in; a.act = make_act(act); a.W = W; a.bias = bias;
   a.in_rowptr = csr->in_rowptr; a.in_col = csr->in_col; a.in_w = csr->in_w; a.wsum = csr->wsum;
-  a.ptr = (const long long*)ptr; a.B = num_graphs;
+  a.meta = csr->graph_meta; a.B = num_graphs;
   a.K = d_in; a.H = H; a.K4 = round_up(d_in, 4); a.H4 = round_up(H, 4); a.ldc = 2 * a.K4 + 4;
   a.max_nodes = max_nodes < 1 ? 1 : max_nodes;
-  a.vec_in = (d_in % 4 == 0) && aligned16(t_in);
+  a.max_edges = max_edges;
   a.z = z;
   if (a.H4 > 256 || a.K4 > 256) return CGNN_ERR_TILE_TOO_LARGE;
   int off = 0;
@@ -455,7 +540,13 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
   a.o_u = off; off += a.max_nodes * a.K4;
   a.o_cat = off; off += kChunkRows * a.ldc;
   a.o_out = off; off += kChunkRows * a.H4;
-  a.o_st = off; off += kWarps + 2 * kWarps * a.H4;
+  a.o_st = off; off += round_up(kWarps + 2 * kWarps * a.H4, 4);
+  {
+    const int csr_w = cgnn::csr_words(a.max_nodes, a.max_edges);
+    a.csr_smem = ((size_t)(off + csr_w) * sizeof(float) <= (size_t)dev.smem_optin) ? 1 : 0;
+    a.o_csr = off;
+    if (a.csr_smem) off += csr_w;
+  }
   const size_t smem = (size_t)off * sizeof(float);
   if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   int grid = persistent_grid(num_graphs, smem, dev, kThreads);
@@ -483,10 +574,11 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
 int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
                         const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in, const float* W,
                         const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
-                        int32_t d_in, int32_t H, int32_t max_nodes, float* dW, float* dbias, float* du_in,
-                        const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
+                        int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* dW, float* dbias,
+                        float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
                         void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (max_edges < 0) return CGNN_ERR_INVALID_ARG;
   if (!dW || !dbias || num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0) return CGNN_ERR_INVALID_ARG;
   if (num_graphs == 0 || rows == 0) {
     cudaMemsetAsync(dW, 0, (size_t)H * 2 * d_in * sizeof(float), stream);
@@ -495,8 +587,10 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
     return CGNN_OK;
   }
   if ((du == nullptr) == (demb == nullptr)) return CGNN_ERR_INVALID_ARG;
-  if (!z || !t_in || !W || !csr || !csr->in_rowptr || !csr->in_col || !csr->in_w || !csr->wsum || !ptr || !workspace)
+  if (!z || !t_in || !W || !csr || !csr->in_rowptr || !csr->in_col || !csr->in_w || !csr->wsum || !csr->graph_meta ||
+      !ptr || !workspace)
     return CGNN_ERR_INVALID_ARG;
+  if (d_in % 4 == 0 && (!aligned16(t_in) || (scratch && !aligned16(scratch)))) return CGNN_ERR_INVALID_ARG;
   if (du_in && (!scratch || !csr->out_rowptr || !csr->out_col || !csr->out_w)) return CGNN_ERR_INVALID_ARG;
   if (prev_sums && (!du_in || !prev_mean || !prev_rstd)) return CGNN_ERR_INVALID_ARG;
   if (bn && (!bn->scale || !bn->mean || !bn->rstd || (bn->train && (!bn->s1 || !bn->s2)))) return CGNN_ERR_INVALID_ARG;
@@ -510,11 +604,12 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
   a.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
   a.t_in = t_in; a.act_in = make_act(act_in); a.W = W;
   a.in_rowptr = csr->in_rowptr; a.in_col = csr->in_col; a.in_w = csr->in_w; a.wsum = csr->wsum;
-  a.ptr = (const long long*)ptr; a.B = num_graphs;
+  a.meta = csr->graph_meta; a.B = num_graphs;
   a.K = d_in; a.H = H; a.K4 = round_up(d_in, 4); a.H4 = round_up(H, 4);
   a.ldc = 2 * a.K4 + 4; a.ldq = a.H4 + 4;
   a.max_nodes = max_nodes < 1 ? 1 : max_nodes;
-  a.vec_in = (d_in % 4 == 0) && aligned16(t_in);
+  a.max_edges = max_edges;
+  a.vec_h = (H % 4 == 0) && aligned16(z) && (!du || aligned16(du)) && (!demb || aligned16(demb));
   a.need_du = du_in ? 1 : 0;
   a.direct = scratch; a.nbr = scratch ? scratch + (size_t)rows * d_in : nullptr;
   const int ntiles_w = (a.H4 / 4) * (2 * a.K4 / 4);
@@ -527,6 +622,10 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
   a.o_cat = off; off += kChunkRows * a.ldc;
   a.o_dq = off; off += kChunkRows * a.ldq;
   a.o_red = off; off += kWarps * a.H4;
+  const int csr_w = cgnn::csr_words(a.max_nodes, a.max_edges);
+  a.csr_smem = ((size_t)(off + csr_w) * sizeof(float) <= (size_t)dev.smem_optin) ? 1 : 0;
+  a.o_csr = off;
+  if (a.csr_smem) off += csr_w;
   const size_t smem = (size_t)off * sizeof(float);
   if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   a.o_pdw = 0; a.o_pdb = a.H4 * 2 * a.K4;
@@ -564,12 +663,16 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
   b.direct = a.direct; b.nbr = a.nbr; b.t_in = t_in; b.act_in = a.act_in;
   b.out_rowptr = csr->out_rowptr; b.out_col = csr->out_col; b.out_w = csr->out_w;
   b.prev_mean = prev_mean; b.prev_rstd = prev_rstd; b.want_prev = prev_sums ? 1 : 0;
-  b.ptr = (const long long*)ptr; b.B = num_graphs; b.K = d_in; b.K4 = a.K4; b.max_nodes = a.max_nodes;
+  b.meta = csr->graph_meta; b.B = num_graphs; b.K = d_in; b.K4 = a.K4; b.max_nodes = a.max_nodes;
+  b.max_edges = a.max_edges;
   b.du_in = du_in;
   int offb = 0;
   b.o_g = offb; offb += a.max_nodes * a.K4;
   b.o_ci = offb; offb += 4 * a.K4;
   b.o_red = offb; offb += kWarps * 2 * a.K4;
+  b.csr_smem = ((size_t)(offb + csr_w) * sizeof(float) <= (size_t)dev.smem_optin) ? 1 : 0;
+  b.o_csr = offb;
+  if (b.csr_smem) offb += csr_w;
   const size_t smem_b = (size_t)offb * sizeof(float);
   if (smem_b > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   int grid_b = persistent_grid(num_graphs, smem_b, dev, kThreads);

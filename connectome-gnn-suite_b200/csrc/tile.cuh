@@ -80,6 +80,64 @@ struct WarpStats {
   }
 };
 
+// ---- one subject's CSR rows, either staged in shared memory or read in place ---------------
+// All three arrays are indexed with ABSOLUTE positions (rp[i] are global edge positions, col/w are
+// pre-offset by -first_edge when they live in shared memory), so the same loop serves both homes.
+struct RowCsr {
+  const int* rp;     // [n+1] row i owns edges [rp[i], rp[i+1])
+  const int* col;    // global row id of the neighbour
+  const float* w;
+};
+
+static inline __host__ __device__ int csr_words(int max_nodes, int max_edges) {
+  return round_up(max_nodes + 1, 4) + 2 * round_up(max_edges, 4) + round_up(max_nodes, 4);
+}
+
+// Start the async copy of a subject's CSR slice (+ one per-row float array) into shared memory.
+// s_base layout: [rp: max_nodes+1][col: max_edges][w: max_edges][extra: max_nodes] (each rounded up to 4 words).
+__device__ __forceinline__ void stage_csr_async(float* s_base, int max_nodes, int max_edges, const int32_t* rowptr,
+                                                const int32_t* col, const float* w, const float* extra, long long nb,
+                                                int n, int eb, int m) {
+  int* s_rp = reinterpret_cast<int*>(s_base);
+  int* s_col = s_rp + round_up(max_nodes + 1, 4);
+  float* s_w = reinterpret_cast<float*>(s_col + round_up(max_edges, 4));
+  float* s_extra = s_w + round_up(max_edges, 4);
+  cp_async_words(s_rp, rowptr + nb, n + 1);
+  cp_async_words(s_col, col + eb, m);
+  cp_async_words(s_w, w + eb, m);
+  if (extra) cp_async_words(s_extra, extra + nb, n);
+}
+__device__ __forceinline__ RowCsr staged_csr(float* s_base, int max_nodes, int max_edges, int eb, const float** extra) {
+  int* s_rp = reinterpret_cast<int*>(s_base);
+  int* s_col = s_rp + round_up(max_nodes + 1, 4);
+  float* s_w = reinterpret_cast<float*>(s_col + round_up(max_edges, 4));
+  *extra = s_w + round_up(max_edges, 4);
+  return RowCsr{s_rp, s_col - eb, s_w - eb};
+}
+
+// acc[j] (+)= sum over the edges of row i of w_e * tile[(col_e - nb) * ld + lane + 32 j].
+// EXACT keeps the reference's rounding (product rounded, then added, in COO order); otherwise FMA.
+template <int HC, bool EXACT>
+__device__ __forceinline__ void gather_row(const RowCsr& c, int i, long long nb, int n, const float* __restrict__ tile,
+                                           int ld, int C4, float (&acc)[HC]) {
+  const int lane = threadIdx.x & 31;
+  const int e0 = c.rp[i], e1 = c.rp[i + 1];
+  for (int e = e0; e < e1; ++e) {
+    const int src = (int)(c.col[e] - nb);
+    const float w = c.w[e];
+    if ((unsigned)src < (unsigned)n) {
+#pragma unroll
+      for (int j = 0; j < HC; ++j) {
+        const int ch = lane + 32 * j;
+        if (ch < C4) {
+          const float v = tile[src * ld + ch];
+          acc[j] = EXACT ? __fadd_rn(acc[j], __fmul_rn(v, w)) : fmaf(v, w, acc[j]);
+        }
+      }
+    }
+  }
+}
+
 static inline int pick_hc(int C4) { return C4 <= 32 ? 1 : (C4 <= 64 ? 2 : (C4 <= 128 ? 4 : 8)); }
 
 }  // namespace cgnn

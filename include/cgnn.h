@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGNN_ABI_VERSION 1
+#define CGNN_ABI_VERSION 2
 
 typedef void* cgnn_stream_t; /* cudaStream_t */
 
@@ -50,7 +50,8 @@ uint64_t cgnn_kernel_launches(void);
 
 /* ---------------------------------------------------------------------------------------
  * Device CSR of a batch.  Built once per batch by cgnn_collate_csr / cgnn_csr_from_coo and
- * read by every layer; replaces the per-layer recomputation in reference models.py:94-108
+ * read by every layer (max_nodes / max_edges = largest subject of the batch, they size the
+ * shared-memory tiles); replaces the per-layer recomputation in reference models.py:94-108
  * (self-loops, D^, d^-1/2, w^) and models.py:147-148 (w_sum).
  *
  *   in_*   rows = destination node, entries in COO order (stable), col = source node id
@@ -75,6 +76,7 @@ typedef struct {
   const float*   deg;        /* [rows] */
   const float*   dinv;       /* [rows] */
   const float*   wsum;       /* [rows] */
+  const int32_t* graph_meta; /* [B][4] per subject {first row, rows, first edge, edges}: one 16-byte load per subject */
 } cgnn_csr_t;
 
 /* How a stored activation tensor t [rows, C] is turned into the layer input u on load:
@@ -128,6 +130,7 @@ typedef struct {
   int32_t* in_rowptr;  int32_t* in_col;  float* in_w;  float* in_wn;
   int32_t* out_rowptr; int32_t* out_col; float* out_w; float* out_wn;
   float* deg; float* dinv; float* wsum;
+  int32_t* graph_meta;
 } cgnn_csr_out_t;
 
 /* Gather `num_graphs` subjects (ids into the store, device int64) into one batch.
@@ -159,7 +162,7 @@ int cgnn_csr_from_coo(const int64_t* edge_index, const float* edge_weight, const
  * [1 + 2H] = {count, mean[H], M2[H]} (Welford/Chan merged, deterministic). */
 int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
                        const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
-                       int32_t d_in, int32_t H, int32_t max_nodes, float* z, double* bn_stats,
+                       int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, double* bn_stats,
                        void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
 
 /* GraphSAGE layer (reference models.py:136-152):
@@ -167,7 +170,7 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
  * W [H, 2*d_in], b [H]. */
 int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
                         const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
-                        int32_t d_in, int32_t H, int32_t max_nodes, float* z, double* bn_stats,
+                        int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, double* bn_stats,
                         void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
 
 /* ---- K3: BatchNorm1d bookkeeping (reference models.py:191-193, 208, 260) -------------- */
@@ -237,7 +240,7 @@ int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, c
 int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
                        const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in,
                        const float* W, const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs,
-                       int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes,
+                       int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
                        float* dW, float* dbias, float* du_in,
                        const float* prev_mean, const float* prev_rstd, float* prev_sums,
                        void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
@@ -248,7 +251,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
 int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
                         const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in,
                         const float* W, const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs,
-                        int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes,
+                        int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
                         float* dW, float* dbias, float* du_in,
                         const float* prev_mean, const float* prev_rstd, float* prev_sums,
                         float* scratch, void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
