@@ -131,6 +131,14 @@ class Engine:
                    self.workspace_bytes, self.stream())
         return z, stats
 
+    def project_tf32x3(self, X, W):
+        """P = X W^T on the tensor cores (3xTF32, fp32-grade)."""
+        rows, K = X.shape
+        N = W.shape[0]
+        P = self.empty((rows, N))
+        self._call("cgnn_project_tf32x3", _p(X), _p(W), rows, K, N, _p(P), self.stream())
+        return P
+
     # -- K3 -------------------------------------------------------------------------------------
     def bn_merge_stats(self, parts: torch.Tensor, C_: int) -> torch.Tensor:
         out = self.empty(1 + 2 * C_, torch.float64)

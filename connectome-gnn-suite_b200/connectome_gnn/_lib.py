@@ -70,6 +70,7 @@ PROTOTYPES = {
                                      _p, _sz, _p]),
     "cgnn_sage_layer_fwd": (C.c_int, [_p, _P(ActT), _p, _p, _P(CsrT), _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p,
                                       _p, _sz, _p]),
+    "cgnn_project_tf32x3": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p]),
     "cgnn_bn_merge_stats": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "cgnn_bn_finalize": (C.c_int, [_p, _p, _p, _i32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "cgnn_bn_eval_affine": (C.c_int, [_p, _p, _p, _p, _i32, _f32, _p, _p, _p, _p, _p]),

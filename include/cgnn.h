@@ -173,6 +173,14 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
                         int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, double* bn_stats,
                         void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
 
+/* ---- K10: the dense contraction on tensor cores ---------------------------------------------
+ * P[rows, N] = X[rows, K] W[N, K]^T (reference models.py:111 `self.linear(x)`), fp32-grade: three TF32
+ * tcgen05 MMAs per K step on hi/lo splits of both operands, fp32 accumulators in tensor memory.
+ * K and N multiples of 32, <= 256; pointers 16-byte aligned.  The layer kernels embed the same sequence;
+ * this entry exposes it on its own (and is how the descriptor plumbing is tested). */
+int cgnn_project_tf32x3(const float* X, const float* W, int64_t rows, int32_t K, int32_t N, float* P,
+                        cgnn_stream_t stream);
+
 /* ---- K3: BatchNorm1d bookkeeping (reference models.py:191-193, 208, 260) -------------- */
 
 /* Merge `parts` statistic records [parts, 1+2C] (one per rank) into one (Chan, fp64). */
