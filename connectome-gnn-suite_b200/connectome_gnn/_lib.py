@@ -63,6 +63,7 @@ PROTOTYPES = {
     "cgnn_last_cuda_error": (C.c_int, []),
     "cgnn_workspace_bytes": (_sz, []),
     "cgnn_kernel_launches": (C.c_uint64, []),
+    "cgnn_set_option": (C.c_int, [_i32, _i32]),
     "cgnn_collate_csr": (C.c_int, [_P(StoreT), _p, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p,
                                    _P(CsrT), _p]),
     "cgnn_csr_from_coo": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i32, _p, _P(CsrT), _p]),

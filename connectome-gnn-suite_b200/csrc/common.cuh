@@ -267,4 +267,14 @@ int launch_reduce_partials(const float* partials, int G, int stride, int rows, i
                            float* out, cudaStream_t stream, int out_ld = 0);
 int launch_stats_merge(const double* parts, int parts_n, int C, double* stats, cudaStream_t stream);
 
+// Process-wide switch (cgnn_set_option): 1 = eligible shapes run on the tcgen05 kernels (default),
+// 0 = everything on the generic SIMT kernels (used to cross-check the two on the device).
+bool tensor_cores_enabled();
+#ifndef CGNN_EMU
+// gcn_tc.cu: returns CGNN_OK when launched, -1 when the shape is not eligible, else an error status.
+int launch_gcn_fwd_tc(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+                      int64_t num_graphs, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
+                      double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream);
+#endif
+
 }  // namespace cgnn

@@ -501,6 +501,16 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
     return CGNN_OK;
   }
   if (!t_in || !W || !csr_in_ok(csr) || !ptr || !z) return CGNN_ERR_INVALID_ARG;
+  if (bn_stats && (!workspace || workspace_bytes < (size_t)(1 + 2 * H) * sizeof(double))) return CGNN_ERR_WORKSPACE;
+#ifndef CGNN_EMU
+  if (tensor_cores_enabled()) {   // tcgen05 / TMEM edition for the shapes it covers
+    int tc_grid = 0;
+    const int rc = launch_gcn_fwd_tc(t_in, act, W, bias, csr, num_graphs, d_in, H, max_nodes, max_edges, z,
+                                     bn_stats ? (double*)workspace : nullptr, &tc_grid, workspace_bytes, stream);
+    if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;
+    if (rc > 0) return rc;
+  }
+#endif
   const DeviceInfo dev = device_info();
   GcnFwdArgs a;
   a.t_in = t_in; a.act = make_act(act); a.W = W; a.bias = bias;

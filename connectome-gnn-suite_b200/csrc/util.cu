@@ -7,7 +7,11 @@ static thread_local int g_last_cuda_error = 0;
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+static int g_use_tensor_cores = 1;
+bool tensor_cores_enabled() { return g_use_tensor_cores != 0; }
+void set_tensor_cores(int on) { g_use_tensor_cores = on; }
 void set_cuda_error(int err) { g_last_cuda_error = err; }
+void set_tensor_cores(int on);
 
 DeviceInfo device_info() {
   static thread_local int cached_dev = -1;
@@ -109,6 +113,10 @@ int cgnn_abi_version(void) { return CGNN_ABI_VERSION; }
 int cgnn_last_cuda_error(void) { return cgnn::g_last_cuda_error; }
 size_t cgnn_workspace_bytes(void) { return (size_t)32 << 20; }
 uint64_t cgnn_kernel_launches(void) { return (uint64_t)cgnn::launches(); }
+int cgnn_set_option(int32_t key, int32_t value) {
+  if (key == CGNN_OPT_TENSOR_CORES) { cgnn::set_tensor_cores(value); return CGNN_OK; }
+  return CGNN_ERR_INVALID_ARG;
+}
 
 int cgnn_bn_merge_stats(const double* stats_parts, int32_t parts, int32_t C, double* stats, cgnn_stream_t stream) {
   if (!stats_parts || !stats || parts <= 0 || C <= 0) return CGNN_ERR_INVALID_ARG;

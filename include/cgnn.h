@@ -47,6 +47,11 @@ int cgnn_last_cuda_error(void);          /* cudaError_t of the last CGNN_ERR_CUD
 size_t cgnn_workspace_bytes(void);
 /* Number of CUDA kernels this library has launched in this process so far (monotonic). */
 uint64_t cgnn_kernel_launches(void);
+/* Process-wide options.  CGNN_OPT_TENSOR_CORES: 1 (default) = eligible layer shapes run the tcgen05/TMEM
+ * kernels, 0 = every shape runs the generic SIMT kernels (same results to fp32 round-off; used to
+ * cross-check the two paths on the device). */
+#define CGNN_OPT_TENSOR_CORES 1
+int cgnn_set_option(int32_t key, int32_t value);
 
 /* ---------------------------------------------------------------------------------------
  * Device CSR of a batch.  Built once per batch by cgnn_collate_csr / cgnn_csr_from_coo and

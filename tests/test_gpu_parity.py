@@ -160,3 +160,35 @@ def test_tensor_core_projection_is_fp32_grade(rows, K, N):
     err = helpers.max_rel(P, ref)
     fp32 = helpers.max_rel(X @ W.T, ref)
     assert err <= 2e-6, (err, fp32)
+
+
+@pytest.mark.parametrize("shape", [(6, 360, 5, 64), (6, 360, 64, 64), (9, 84, 64, 64), (5, 100, 32, 32), (4, 77, 64, 128), (3, 50, 128, 64)])
+@pytest.mark.parametrize("drop", [0.0, 0.3])
+def test_tensor_core_layer_kernels_match_the_generic_kernels(shape, drop):
+    """Every tcgen05/TMEM layer kernel against the generic SIMT kernel of the same entry point on the same device
+    inputs (CGNN_OPT_TENSOR_CORES toggled): identical up to fp32 summation order, with and without dropout."""
+    from connectome_gnn import _engine, _lib
+    from connectome_gnn._engine import Act
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    subjects, regions, d_in, H = shape
+    eng = _engine.engine_for(torch.zeros(1, device=DEV))
+    b = collate_graphs(generate_dataset(num_subjects=subjects, num_regions=regions, seed=5))
+    g = torch.Generator().manual_seed(1)
+    rows = b.num_nodes
+    t_in = torch.randn(rows, d_in, generator=g).to(DEV)
+    W = (torch.randn(H, d_in, generator=g) * 0.2).to(DEV)
+    bias = (torch.randn(H, generator=g) * 0.1).to(DEV)
+    act = Act((1 + 0.1 * torch.randn(d_in, generator=g)).to(DEV), (0.1 * torch.randn(d_in, generator=g)).to(DEV),
+              True, drop, seed=77, site=1, row_base=1000)
+    out = {}
+    for use_tc in (1, 0):
+        assert eng.lib.cgnn_set_option(1, use_tc) == 0
+        try:
+            out[use_tc] = eng.layer_fwd("gcn", t_in, act, W, bias, b.csr, b.ptr, b.num_graphs, True)
+        finally:
+            eng.lib.cgnn_set_option(1, 1)
+    helpers.assert_close(out[1][0], out[0][0], "gcn fwd z: tensor-core vs generic", tol=2e-6)
+    assert float(out[1][1][0]) == float(out[0][1][0]) == rows
+    helpers.assert_close(out[1][1][1:1 + H], out[0][1][1:1 + H], "BN mean", tol=2e-6)
+    helpers.assert_close(out[1][1][1 + H:], out[0][1][1 + H:], "BN M2", tol=2e-5)
