@@ -25,7 +25,7 @@ namespace cgnn {
 
 void count_launch();  // bumps the process-wide kernel-launch counter (cgnn_kernel_launches)
 
-constexpr int kThreads = 256;          // threads per CTA of the tile kernels
+constexpr int kThreads = 512;          // threads per CTA of the tile kernels
 constexpr int kWarps = kThreads / 32;
 constexpr int kChunkRows = 64;         // rows per projection chunk
 constexpr unsigned kFull = 0xffffffffu;

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_tc(GcnTcArgs p) {
         const int half = warp >> 2;                       // which half of the columns (H >= 64), else warps 4-7 idle
         const int ncol_w = H >= 64 ? H / 2 : H;
         const int c_begin = H >= 64 ? half * ncol_w : 0;
-        const int c_end = (H >= 64 || half == 0) ? c_begin + ncol_w : 0;
+        const int c_end = ((H >= 64 && half < 2) || half == 0) ? c_begin + ncol_w : 0;
         for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           float v[32];
           tc::tmem_ld32(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
