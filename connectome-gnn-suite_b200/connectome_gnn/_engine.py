@@ -91,11 +91,32 @@ class Engine:
             out_rowptr=e(rows + 1, torch.int32), out_col=e(edges, torch.int32), out_w=e(edges), out_wn=e(edges),
             deg=e(rows), dinv=e(rows), wsum=e(rows))
 
+    KINDS = {"gcn": 0, "sage": 1}
+
     @staticmethod
-    def csr_struct(c) -> CsrT:
+    def csr_struct(c, kind: Optional[str] = None) -> CsrT:
+        """``cgnn_csr_t`` of a CSR (dict or BatchCSR); ``kind`` attaches that model family's aggregation blobs."""
         g = (lambda k: c[k]) if isinstance(c, dict) else (lambda k: getattr(c, k))
-        return CsrT(*[_p(g(k)) for k in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col",
-                                         "out_w", "out_wn", "deg", "dinv", "wsum", "graph_meta")])
+        base = [_p(g(k)) for k in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col",
+                                   "out_w", "out_wn", "deg", "dinv", "wsum", "graph_meta")]
+        blobs = None if (kind is None or isinstance(c, dict)) else (getattr(c, "agg", None) or {}).get(kind)
+        if blobs is None:
+            return CsrT(*base, None, None, None, -1)
+        return CsrT(*base, _p(blobs[0]), _p(blobs[1]), _p(blobs[2]), Engine.KINDS[kind])
+
+    def ensure_agg(self, csr, kind: str, num_graphs: int, rows: int, edges: int):
+        """Packed aggregation blobs of one model family for this batch (built once, cached on the CSR)."""
+        if getattr(csr, "agg", None) is None:
+            csr.agg = {}
+        if kind not in csr.agg:
+            words = int(self.lib.cgnn_agg_words(rows, edges, num_graphs))
+            agg_in, agg_out = self.empty(words, torch.int32), self.empty(words, torch.int32)
+            row_graph = self.empty(max(rows, 1), torch.int32)
+            cs = self.csr_struct(csr)
+            self._call("cgnn_build_agg", C.byref(cs), Engine.KINDS[kind], num_graphs, rows, edges, csr.max_nodes,
+                       _p(agg_in), _p(agg_out), _p(row_graph), self.stream())
+            csr.agg[kind] = (agg_in, agg_out, row_graph)
+        return csr.agg[kind]
 
     def collate_csr(self, store: StoreT, ids: torch.Tensor, num_graphs: int, rows: int, edges: int, max_nodes: int,
                     num_features: int, with_labels: bool):
@@ -121,15 +142,21 @@ class Engine:
 
     # -- K1 / K2 ------------------------------------------------------------------------------
     def layer_fwd(self, kind: str, t_in, act: Act, W, bias, csr, ptr, num_graphs: int, want_stats: bool):
+        """Returns (z, stats, agg): ``agg`` is GraphSAGE's aggregated neighbourhood [rows, d_in] (kept for backward)."""
         rows, d_in = t_in.shape
         H = W.shape[0]
         z = self.empty((rows, H))
         stats = self.empty(1 + 2 * H, torch.float64) if want_stats else None
-        a, cs = act.struct(), self.csr_struct(csr)
-        self._call(f"cgnn_{kind}_layer_fwd", _p(t_in), C.byref(a), _p(W), _p(bias), C.byref(cs), _p(ptr),
-                   num_graphs, rows, d_in, H, csr.max_nodes, csr.max_edges, _p(z), _p(stats), _p(self.workspace),
-                   self.workspace_bytes, self.stream())
-        return z, stats
+        self.ensure_agg(csr, kind, num_graphs, rows, int(csr.in_col.shape[0]))
+        a, cs = act.struct(), self.csr_struct(csr, kind)
+        args = [_p(t_in), C.byref(a), _p(W), _p(bias), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, csr.max_nodes,
+                csr.max_edges, _p(z), _p(stats)]
+        agg = None
+        if kind == "sage":
+            agg = self.empty((rows, d_in))
+            args.append(_p(agg))
+        self._call(f"cgnn_{kind}_layer_fwd", *args, _p(self.workspace), self.workspace_bytes, self.stream())
+        return z, stats, agg
 
     def project_tf32x3(self, X, W):
         """P = X W^T on the tensor cores (3xTF32, fp32-grade)."""
@@ -208,24 +235,26 @@ class Engine:
         return sums
 
     def layer_bwd(self, kind: str, du, demb, z, act_out: Act, bn: Optional[BnBwd], t_in, act_in: Act, W, csr, ptr,
-                  num_graphs: int, need_du: bool, prev_mean, prev_rstd):
+                  num_graphs: int, need_du: bool, prev_mean, prev_rstd, agg=None):
         rows, d_in = t_in.shape
         H = z.shape[1]
         dW, db = self.empty(W.shape), self.empty(H)
         du_in = self.empty((rows, d_in)) if need_du else None
         want_prev = need_du and prev_mean is not None
         prev_sums = self.empty((2, d_in)) if want_prev else None
-        ao, ai, cs = act_out.struct(), act_in.struct(), self.csr_struct(csr)
+        self.ensure_agg(csr, kind, num_graphs, rows, int(csr.in_col.shape[0]))
+        ao, ai, cs = act_out.struct(), act_in.struct(), self.csr_struct(csr, kind)
         bs = bn.struct() if bn is not None else None
-        args = [_p(du), _p(demb), _p(z), C.byref(ao), C.byref(bs) if bs is not None else None, _p(t_in),
-                C.byref(ai), _p(W), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, csr.max_nodes, csr.max_edges,
-                _p(dW), _p(db),
-                _p(du_in), _p(prev_mean) if want_prev else None, _p(prev_rstd) if want_prev else None,
-                _p(prev_sums)]
+        args = [_p(du), _p(demb), _p(z), C.byref(ao), C.byref(bs) if bs is not None else None, _p(t_in)]
         if kind == "sage":
-            scratch = self.empty((2, rows, d_in)) if need_du else None
-            args.append(_p(scratch))
-        args += [_p(self.workspace), self.workspace_bytes, self.stream()]
+            args.append(_p(agg))
+        args += [C.byref(ai), _p(W), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, csr.max_nodes, csr.max_edges,
+                 _p(dW), _p(db),
+                 _p(du_in), _p(prev_mean) if want_prev else None, _p(prev_rstd) if want_prev else None,
+                 _p(prev_sums)]
+        # scratch between the two kernels of one call: GCN dP [rows, H]; GraphSAGE [2, rows, d_in]
+        scratch = self.empty((rows, H)) if kind == "gcn" else self.empty((2, rows, d_in))
+        args += [_p(scratch), _p(self.workspace), self.workspace_bytes, self.stream()]
         self._call(f"cgnn_{kind}_layer_bwd", *args)
         return dW, db, du_in, prev_sums
 

@@ -14,7 +14,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcgnn.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_f32p = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 c_ptr = C.c_void_p
@@ -25,7 +25,8 @@ class CsrT(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "in_rowptr", "in_col", "in_w", "in_wn",
         "out_rowptr", "out_col", "out_w", "out_wn",
-        "deg", "dinv", "wsum", "graph_meta")]
+        "deg", "dinv", "wsum", "graph_meta",
+        "agg_in", "agg_out", "row_graph")] + [("agg_kind", C.c_int32)]
 
 
 class ActT(C.Structure):
@@ -67,10 +68,12 @@ PROTOTYPES = {
     "cgnn_collate_csr": (C.c_int, [_P(StoreT), _p, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p,
                                    _P(CsrT), _p]),
     "cgnn_csr_from_coo": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i32, _p, _P(CsrT), _p]),
+    "cgnn_agg_words": (_sz, [_i64, _i64, _i64]),
+    "cgnn_build_agg": (C.c_int, [_P(CsrT), _i32, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),
     "cgnn_gcn_layer_fwd": (C.c_int, [_p, _P(ActT), _p, _p, _P(CsrT), _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p,
                                      _p, _sz, _p]),
     "cgnn_sage_layer_fwd": (C.c_int, [_p, _P(ActT), _p, _p, _P(CsrT), _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p,
-                                      _p, _sz, _p]),
+                                      _p, _p, _sz, _p]),
     "cgnn_project_tf32x3": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p]),
     "cgnn_bn_merge_stats": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "cgnn_bn_finalize": (C.c_int, [_p, _p, _p, _i32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -83,8 +86,8 @@ PROTOTYPES = {
                                 _p]),
     "cgnn_bn_bwd_sums": (C.c_int, [_p, _P(ActT), _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _sz, _p]),
     "cgnn_gcn_layer_bwd": (C.c_int, [_p, _p, _p, _P(ActT), _P(BnBwdT), _p, _P(ActT), _p, _P(CsrT), _p, _i64, _i64,
-                                     _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "cgnn_sage_layer_bwd": (C.c_int, [_p, _p, _p, _P(ActT), _P(BnBwdT), _p, _P(ActT), _p, _P(CsrT), _p, _i64,
+                                     _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "cgnn_sage_layer_bwd": (C.c_int, [_p, _p, _p, _P(ActT), _P(BnBwdT), _p, _p, _P(ActT), _p, _P(CsrT), _p, _i64,
                                       _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 

@@ -95,6 +95,7 @@ class BatchCSR:
     eptr: torch.Tensor        # [B+1] int64 edge prefix sums
     max_nodes: int            # largest subject of the batch (sizes shared-memory tiles)
     max_edges: int            # most edges in one subject
+    agg: Optional[dict] = None  # model family -> (agg_in, agg_out, row_graph) packed blobs, built lazily by the engine
 
     _FIELDS = ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn",
                "deg", "dinv", "wsum", "graph_meta", "eptr")

@@ -92,7 +92,7 @@ class _EncodeFn(torch.autograd.Function):
         saved = []
         for l, bn in enumerate(cfg["bns"]):
             W, b, gamma, beta = (q.contiguous() for q in params[4 * l: 4 * l + 4])
-            z, stats = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, want_stats=training)
+            z, stats, agg = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, want_stats=training)
             if training:
                 stats = _merge_stats_across_ranks(eng, stats, W.shape[0], cfg["group"])
                 momentum = 0.1 if bn.momentum is None else bn.momentum
@@ -100,7 +100,7 @@ class _EncodeFn(torch.autograd.Function):
                                                            bn.running_var, bn.num_batches_tracked)
             else:
                 scale, shift, mean, rstd = eng.bn_eval_affine(gamma, beta, bn.running_mean, bn.running_var, bn.eps)
-            saved.append((t, act, z, W, scale, mean, rstd))
+            saved.append((t, act, z, W, scale, mean, rstd, agg))
             t = z
             act = Act(scale, shift, relu_after_bn, p_eff, seed, l, batch.row_base)
         emb = eng.pool_fwd(t, act, ptr, B)
@@ -122,19 +122,19 @@ class _EncodeFn(torch.autograd.Function):
 
         grads: list = [None] * (4 * L)
         # BatchNorm backward sums of the top layer come from a standalone pass over z_L
-        t_in, act_in, z, W, scale, mean, rstd = saved[-1]
+        t_in, act_in, z, W, scale, mean, rstd, agg = saved[-1]
         act_out = ctx.final_act
         sums = eng.bn_bwd_sums(z, act_out, mean, rstd, None, demb, ptr, B)
         sums = _sum_across_ranks(sums, group)
         du, pooled, dx = None, demb, None
         for l in range(L - 1, -1, -1):
-            t_in, act_in, z, W, scale, mean, rstd = saved[l]
+            t_in, act_in, z, W, scale, mean, rstd, agg = saved[l]
             need_du = l > 0 or ctx.x_needs_grad
             prev_mean = saved[l - 1][5] if l > 0 else None
             prev_rstd = saved[l - 1][6] if l > 0 else None
             bn = BnBwd(scale, mean, rstd, sums, count, training)
             dW, db, du_in, prev_sums = eng.layer_bwd(kind, du, pooled, z, act_out, bn, t_in, act_in, W, csr, ptr, B,
-                                                     need_du, prev_mean, prev_rstd)
+                                                     need_du, prev_mean, prev_rstd, agg)
             grads[4 * l + 0], grads[4 * l + 1] = dW, db
             grads[4 * l + 2], grads[4 * l + 3] = sums[1], sums[0]   # d gamma = sum dy*xhat, d beta = sum dy
             sums = _sum_across_ranks(prev_sums, group)
@@ -216,7 +216,7 @@ def _single_layer(kind: str, layer: nn.Module, x, edge_index, edge_weight):
     csr = batch.ensure_csr()
     eng = _engine.engine_for(x)
     W, b = (q.detach().to(dev).contiguous() for q in layer.tensors())
-    z, _ = eng.layer_fwd(kind, x.contiguous().float(), Act(), W, b, csr, ptr, 1, want_stats=False)
+    z, _, _ = eng.layer_fwd(kind, x.contiguous().float(), Act(), W, b, csr, ptr, 1, want_stats=False)
     return z
 
 

@@ -9,6 +9,7 @@
 //   by-source CSR, dW = dP^T u, du_in = dP W, and the BatchNorm backward sums of the previous
 //   layer accumulated on the fly.
 #include "tile.cuh"
+#include "agg.cuh"
 
 namespace cgnn {
 
@@ -563,8 +564,8 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
                        const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in, const float* W,
                        const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
                        int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* dW, float* dbias,
-                       float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, void* workspace,
-                       size_t workspace_bytes, cgnn_stream_t stream_) {
+                       float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
+                       void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (max_edges < 0) return CGNN_ERR_INVALID_ARG;
   if (!dW || !dbias || num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0) return CGNN_ERR_INVALID_ARG;
@@ -578,6 +579,44 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
   if (!z || !t_in || !W || !csr_out_ok_(csr) || !ptr || !workspace) return CGNN_ERR_INVALID_ARG;
   if (prev_sums && (!du_in || !prev_mean || !prev_rstd)) return CGNN_ERR_INVALID_ARG;
   if (bn && (!bn->scale || !bn->mean || !bn->rstd || (bn->train && (!bn->s1 || !bn->s2)))) return CGNN_ERR_INVALID_ARG;
+#ifndef CGNN_EMU
+  // Tensor-core generation: gather kernel (dz on load, dP = A^^T dz, dbias) + tcgen05 contractions (du_in, dW).
+  if (tensor_cores_enabled() && scratch && csr->agg_out && csr->agg_kind == AGG_GCN && (H == 32 || H == 64 || H == 128) &&
+      d_in <= 128 && (d_in + 31) / 32 != 3 && aligned16(scratch) && aligned16(z) && (!du || aligned16(du)) &&
+      (!demb || aligned16(demb))) {
+    const size_t region_a = (size_t)2 * 160 * 128 * sizeof(float);   // dbias partials of <= 2 CTAs per SM
+    const int part_stride = H * d_in + 2 * d_in;
+    if (workspace_bytes > region_a + (size_t)part_stride * sizeof(float)) {
+      GatherArgs ga{};
+      ga.meta = csr->graph_meta; ga.B = num_graphs; ga.blob = csr->agg_out;
+      ga.C = H; ga.max_nodes = max_nodes;
+      ga.src = z; ga.act = make_act(act_out); ga.du = du; ga.demb = demb;
+      ga.has_bn = bn ? 1 : 0;
+      ga.bn_scale = bn ? bn->scale : nullptr; ga.bn_mean = bn ? bn->mean : nullptr; ga.bn_rstd = bn ? bn->rstd : nullptr;
+      ga.bn_s1 = bn ? bn->s1 : nullptr; ga.bn_s2 = bn ? bn->s2 : nullptr;
+      ga.bn_train = bn ? bn->train : 0;
+      ga.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
+      ga.out = scratch; ga.partials = (float*)workspace; ga.part_stride = H;
+      int g1 = 0, g2 = 0;
+      int rc = launch_gather(GATHER_GCN_BWD, ga, &g1, stream);
+      if (rc > 0) return rc;
+      if (rc == CGNN_OK) {
+        float* parts_b = (float*)((char*)workspace + region_a);
+        rc = launch_gcn_bwd_gemm(scratch, t_in, act_in, W, rows, d_in, H, du_in, prev_mean, prev_rstd, prev_sums ? 1 : 0,
+                                 parts_b, part_stride, H * d_in, &g2, workspace_bytes - region_a, stream);
+        if (rc > 0) return rc;
+        if (rc == CGNN_OK) {
+          rc = launch_reduce_partials((const float*)workspace, g1, H, 1, H, H, dbias, stream);
+          if (rc) return rc;
+          rc = launch_reduce_partials(parts_b, g2, part_stride, H, d_in, d_in, dW, stream);
+          if (rc) return rc;
+          if (prev_sums) rc = launch_reduce_partials(parts_b + H * d_in, g2, part_stride, 2, d_in, d_in, prev_sums, stream);
+          return rc;
+        }
+      }
+    }
+  }
+#endif
   const DeviceInfo dev = device_info();
   GcnBwdArgs a;
   a.du = du; a.demb = demb; a.z = z; a.act_out = make_act(act_out);

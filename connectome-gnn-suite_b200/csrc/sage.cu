@@ -7,6 +7,7 @@
 // Backward: kernel A (row-local: dq, dW, db, d[u||agg] = dq W) and kernel B (transposed
 //   neighbour aggregation of the agg-gradient + previous layer's BatchNorm backward sums).
 #include "tile.cuh"
+#include "agg.cuh"
 
 namespace cgnn {
 
@@ -512,7 +513,7 @@ extern "C" {
 int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
                         const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
                         int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, double* bn_stats,
-                        void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
+                        float* agg, void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0 || max_edges < 0) return CGNN_ERR_INVALID_ARG;
   if (num_graphs == 0 || rows == 0) {
@@ -522,6 +523,26 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
   if (!t_in || !W || !csr || !csr->in_rowptr || !csr->in_col || !csr->in_w || !csr->wsum || !csr->graph_meta || !ptr || !z)
     return CGNN_ERR_INVALID_ARG;
   if (d_in % 4 == 0 && !aligned16(t_in)) return CGNN_ERR_INVALID_ARG;
+  if (bn_stats && (!workspace || workspace_bytes < (size_t)(1 + 2 * H) * sizeof(double))) return CGNN_ERR_WORKSPACE;
+#ifndef CGNN_EMU
+  // Tensor-core generation: gather kernel (weighted mean of the neighbours) + tcgen05 contraction.
+  if (tensor_cores_enabled() && agg && csr->agg_in && csr->agg_kind == AGG_SAGE && (H == 32 || H == 64 || H == 128) &&
+      2 * d_in <= 128 && (2 * d_in + 31) / 32 != 3 && (d_in <= 32 || d_in % 32 == 0) && aligned16(agg) && aligned16(z)) {
+    GatherArgs ga{};
+    ga.meta = csr->graph_meta; ga.B = num_graphs; ga.blob = csr->agg_in;
+    ga.C = d_in; ga.max_nodes = max_nodes;
+    ga.src = t_in; ga.act = make_act(act); ga.out = agg;
+    int g1 = 0, g2 = 0;
+    int rc = launch_gather(GATHER_SAGE_FWD, ga, &g1, stream);
+    if (rc > 0) return rc;
+    if (rc == CGNN_OK) {
+      rc = launch_sage_fwd_gemm(t_in, act, agg, W, bias, rows, d_in, H, z, bn_stats ? (double*)workspace : nullptr, &g2,
+                                workspace_bytes, stream);
+      if (rc > 0) return rc;
+      if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, g2, H, bn_stats, stream) : CGNN_OK;
+    }
+  }
+#endif
   const DeviceInfo dev = device_info();
   SageFwdArgs a;
   a.t_in = t_in; a.act = make_act(act); a.W = W; a.bias = bias;
@@ -572,12 +593,13 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
 }
 
 int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
-                        const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in, const float* W,
+                        const cgnn_bn_bwd_t* bn, const float* t_in, const float* agg, const cgnn_act_t* act_in, const float* W,
                         const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
                         int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* dW, float* dbias,
                         float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
                         void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  (void)agg;
   if (max_edges < 0) return CGNN_ERR_INVALID_ARG;
   if (!dW || !dbias || num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0) return CGNN_ERR_INVALID_ARG;
   if (num_graphs == 0 || rows == 0) {

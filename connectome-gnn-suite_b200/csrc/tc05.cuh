@@ -42,9 +42,31 @@ __device__ __forceinline__ void store_split4(unsigned char* hi_base, unsigned ch
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
-__device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operands (the contraction runs over the ROWS of a staged tile X[r][c], i.e. X^T Y products).  For 32-bit
+// (tf32) elements the only MN-major layout the tensor core accepts is SWIZZLE_128B_BASE32B (cute
+// Layout_MN_SW128_32B_Atom, layout type 1): 128-byte rows hold 32 consecutive M (or N) indices as four 32-byte
+// chunks, chunk index XORed with (k mod 4); 4 consecutive K indices form one 512-byte atom.  lbo = bytes between
+// 32-wide MN groups, sbo = bytes between 4-deep K groups.  This is NOT the byte image of the K-major 128B swizzle,
+// so a tile that feeds both X W and X^T Y is staged twice.
+__device__ __forceinline__ uint32_t mn32_offset(int row, int c, int rows) {   // element (k = row, mn = c)
+  return (uint32_t)((c >> 5) * rows * 128 + (row >> 2) * 512 + (row & 3) * 128 + (((((c & 31) >> 3) ^ (row & 3))) << 5) + ((c & 7) << 2));
+}
+__device__ __forceinline__ void store_split4_mn32(unsigned char* hi_base, unsigned char* lo_base, int row, int c, int rows, float4 v) {
+  const uint32_t off = mn32_offset(row, c, rows);
+  float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  *reinterpret_cast<float4*>(hi_base + off) = h;
+  *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (1ull << 61);
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32; bit 15 / 16 = A / B is
+// MN-major (0 = K-major)
+__device__ __forceinline__ uint32_t idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---- tensor memory ------------------------------------------------------------------------------------
@@ -122,6 +144,50 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 lanes x N columns (N = 8, 16, 32) WITHOUT the wait: issue several, then tmem_ld_wait() once.
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// N columns (8 / 16 / 32) of this warp's 32 lanes as floats
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[N]) {
+  static_assert(N == 8 || N == 16 || N == 32, "tmem_ld_cols: 8, 16 or 32 columns");
+  if constexpr (N == 32) {
+    tmem_ld32(taddr, v);
+  } else if constexpr (N == 16) {
+    uint32_t r[16];
+    tmem_ld16_nowait(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  } else {
+    uint32_t r[8];
+    tmem_ld8_nowait(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+  }
+}
+
+// One K = 8 step of the three-term product with explicit descriptors (hi/lo operand pairs).
+__device__ __forceinline__ void mma_tf32x3_step(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                uint32_t idesc, uint32_t accumulate) {
+  mma_tf32(d_tmem, a_lo, b_hi, idesc, accumulate);   // small terms first
+  mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+  mma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
 }
 
 }  // namespace tc

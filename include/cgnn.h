@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGNN_ABI_VERSION 2
+#define CGNN_ABI_VERSION 3
 
 typedef void* cgnn_stream_t; /* cudaStream_t */
 
@@ -82,6 +82,18 @@ typedef struct {
   const float*   dinv;       /* [rows] */
   const float*   wsum;       /* [rows] */
   const int32_t* graph_meta; /* [B][4] per subject {first row, rows, first edge, edges}: one 16-byte load per subject */
+  /* Optional packed aggregation blobs built by cgnn_build_agg (NULL = not built: the layer entry points then run
+   * their generic kernels).  One 16-byte aligned blob per subject and direction, at word offset
+   * 8*first_row + 2*(first_edge rounded up to even) + 4*subject inside the buffer:
+   *   [rows x int4 {rec_begin, rec_end, aux bits, 0}] [records int2 {neighbour's local row, weight bits}]
+   * Every row's record list is padded to an even length with zero-weight records; agg_kind 0 (GCN) carries the
+   * normalised weights w^ and ends every row with the self-loop record {row, dinv^2} (reference models.py:98-100
+   * puts self-loops last); agg_kind 1 (GraphSAGE) carries w with aux = w_sum by destination, and
+   * w / (w_sum[dst] + 1e-8) by source (the adjoint of models.py:146-149). */
+  const int32_t* agg_in;     /* rows = destination nodes, neighbours = sources       */
+  const int32_t* agg_out;    /* rows = source nodes,      neighbours = destinations  */
+  const int32_t* row_graph;  /* [rows] subject index of every row (ConnectomeBatch.batch as int32) */
+  int32_t agg_kind;          /* 0 = GCN, 1 = GraphSAGE, -1 = none */
 } cgnn_csr_t;
 
 /* How a stored activation tensor t [rows, C] is turned into the layer input u on load:
@@ -159,6 +171,13 @@ int cgnn_csr_from_coo(const int64_t* edge_index, const float* edge_weight, const
                       int64_t num_graphs, int64_t total_rows, int64_t total_edges, int32_t max_nodes,
                       int64_t* eptr, const cgnn_csr_out_t* csr, cgnn_stream_t stream);
 
+/* Packed aggregation blobs for one model family (kind 0 = GCN, 1 = GraphSAGE) from a built CSR: fills
+ * agg_in / agg_out (each cgnn_agg_words(...) int32 words) and row_graph [rows].  Pure re-layout of the CSR
+ * arrays above plus the self-loop / mean weights; nothing the reference computes is changed. */
+size_t cgnn_agg_words(int64_t rows, int64_t edges, int64_t num_graphs);
+int cgnn_build_agg(const cgnn_csr_t* csr, int32_t kind, int64_t num_graphs, int64_t rows, int64_t edges,
+                   int32_t max_nodes, int32_t* agg_in, int32_t* agg_out, int32_t* row_graph, cgnn_stream_t stream);
+
 /* ---- K1/K2: layer forward ------------------------------------------------------------ */
 
 /* GCN layer (reference models.py:84-114):  z = A^ (u W^T) + bias,  u = act(t_in).
@@ -172,11 +191,13 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
 
 /* GraphSAGE layer (reference models.py:136-152):
  *   agg_i = sum_{e: dst=i} w_e u_src / (wsum_i + 1e-8);  z = relu([u || agg] W^T + b)
- * W [H, 2*d_in], b [H]. */
+ * W [H, 2*d_in], b [H].  agg [rows, d_in] (may be NULL) receives the aggregated neighbourhood: with it (and the
+ * blobs of cgnn_build_agg) the layer runs as a gather kernel plus a tensor-core contraction, and backward reuses
+ * it instead of gathering again. */
 int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
                         const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
                         int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, double* bn_stats,
-                        void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
+                        float* agg, void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
 
 /* ---- K10: the dense contraction on tensor cores ---------------------------------------------
  * P[rows, N] = X[rows, K] W[N, K]^T (reference models.py:111 `self.linear(x)`), fp32-grade: three TF32
@@ -249,20 +270,23 @@ int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, c
  *   t_in [rows,d_in] this layer's stored input, act_in how it was transformed on load
  * Outputs: dW [H,d_in], dbias [H]; du_in [rows,d_in] = gradient w.r.t. act_in(t_in) (NULL for
  * the first layer); prev_sums [2*d_in] = BN backward sums of the previous layer computed
- * from du_in on the fly (NULL to skip; needs prev_mean/prev_rstd). */
+ * from du_in on the fly (NULL to skip; needs prev_mean/prev_rstd).
+ * scratch [rows, H] fp32 (may be NULL) holds dP = A^^T dz between the gather kernel and the tensor-core
+ * contraction; without it (or without the blobs of cgnn_build_agg) the generic kernel runs. */
 int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
                        const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in,
                        const float* W, const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs,
                        int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
                        float* dW, float* dbias, float* du_in,
                        const float* prev_mean, const float* prev_rstd, float* prev_sums,
-                       void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
+                       float* scratch, void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
 
 /* GraphSAGE layer backward (autograd of models.py:136-152 plus the BN/dropout that follows).
  * Same contract as cgnn_gcn_layer_bwd; W [H, 2*d_in].  scratch [2, rows, d_in] fp32 holds the
- * direct and neighbour parts of the input gradient between the two kernels of this call. */
+ * direct and neighbour parts of the input gradient between the two kernels of this call.  agg [rows, d_in] is the
+ * aggregate cgnn_sage_layer_fwd stored (NULL: it is gathered again by the generic kernel). */
 int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
-                        const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in,
+                        const cgnn_bn_bwd_t* bn, const float* t_in, const float* agg, const cgnn_act_t* act_in,
                         const float* W, const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs,
                         int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
                         float* dW, float* dbias, float* du_in,

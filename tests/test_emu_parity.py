@@ -97,7 +97,7 @@ def test_syncbn_statistics_merge(on_emu, emu_engine):
     W = torch.from_numpy(a["gcn.init.convs.0.linear.weight"]); bias = torch.zeros(W.shape[0])
     def stats_of(ids):
         b = store.collate(ids)
-        _, st = emu_engine.layer_fwd("gcn", b.node_features, Act(), W, bias, b.csr, b.ptr, b.num_graphs, True)
+        _, st, _ = emu_engine.layer_fwd("gcn", b.node_features, Act(), W, bias, b.csr, b.ptr, b.num_graphs, True)
         return st
     whole = stats_of(np.arange(8))
     merged = emu_engine.bn_merge_stats(torch.stack([stats_of(np.arange(0, 5)), stats_of(np.arange(5, 8))]), W.shape[0])

@@ -192,3 +192,78 @@ def test_tensor_core_layer_kernels_match_the_generic_kernels(shape, drop):
     assert float(out[1][1][0]) == float(out[0][1][0]) == rows
     helpers.assert_close(out[1][1][1:1 + H], out[0][1][1:1 + H], "BN mean", tol=2e-6)
     helpers.assert_close(out[1][1][1 + H:], out[0][1][1 + H:], "BN M2", tol=2e-5)
+
+
+@pytest.mark.parametrize("shape", [(6, 360, 5, 64), (6, 360, 64, 64), (9, 84, 64, 64), (5, 100, 32, 32), (4, 77, 64, 128), (3, 50, 32, 64)])
+@pytest.mark.parametrize("drop", [0.0, 0.3])
+def test_tensor_core_sage_forward_matches_the_generic_kernel(shape, drop):
+    """GraphSAGE forward as gather kernel + tcgen05 contraction against the generic SIMT kernel (same entry point)."""
+    from connectome_gnn import _engine
+    from connectome_gnn._engine import Act
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    subjects, regions, d_in, H = shape
+    eng = _engine.engine_for(torch.zeros(1, device=DEV))
+    b = collate_graphs(generate_dataset(num_subjects=subjects, num_regions=regions, seed=6))
+    g = torch.Generator().manual_seed(2)
+    rows = b.num_nodes
+    t_in = torch.randn(rows, d_in, generator=g).to(DEV)
+    W = (torch.randn(H, 2 * d_in, generator=g) * 0.2).to(DEV)
+    bias = (torch.randn(H, generator=g) * 0.1).to(DEV)
+    act = Act((1 + 0.1 * torch.randn(d_in, generator=g)).to(DEV), (0.1 * torch.randn(d_in, generator=g)).to(DEV),
+              False, drop, seed=78, site=2, row_base=500)
+    out = {}
+    for use_tc in (1, 0):
+        assert eng.lib.cgnn_set_option(1, use_tc) == 0
+        try:
+            out[use_tc] = eng.layer_fwd("sage", t_in, act, W, bias, b.csr, b.ptr, b.num_graphs, True)
+        finally:
+            eng.lib.cgnn_set_option(1, 1)
+    helpers.assert_close(out[1][0], out[0][0], "sage fwd z: tensor-core vs generic", tol=2e-6)
+    assert float(out[1][1][0]) == float(out[0][1][0]) == rows
+    helpers.assert_close(out[1][1][1:1 + H], out[0][1][1:1 + H], "BN mean", tol=2e-6)
+    helpers.assert_close(out[1][1][1 + H:], out[0][1][1 + H:], "BN M2", tol=2e-5)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+@pytest.mark.parametrize("shape", [(6, 360, 5, 64), (6, 360, 64, 64), (9, 84, 64, 64), (5, 100, 32, 32), (4, 77, 64, 128), (3, 50, 32, 64)])
+@pytest.mark.parametrize("top", [False, True])
+def test_tensor_core_backward_matches_the_generic_kernels(kind, shape, top):
+    """Layer backward (gather kernel + tcgen05 contractions) against the generic SIMT kernels: dW, dbias, du_in and
+    the BatchNorm-backward sums of the layer below, for a middle layer (per-row upstream) and the top layer
+    (pooled upstream), with dropout on both sides."""
+    from connectome_gnn import _engine
+    from connectome_gnn._engine import Act, BnBwd
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    subjects, regions, d_in, H = shape
+    eng = _engine.engine_for(torch.zeros(1, device=DEV))
+    b = collate_graphs(generate_dataset(num_subjects=subjects, num_regions=regions, seed=7))
+    g = torch.Generator().manual_seed(3)
+    rows, B = b.num_nodes, b.num_graphs
+    rn = lambda *s: torch.randn(*s, generator=g)
+    t_in = rn(rows, d_in).to(DEV)
+    W = (rn(H, d_in if kind == "gcn" else 2 * d_in) * 0.2).to(DEV)
+    bias = (rn(H) * 0.1).to(DEV)
+    act_in = Act((1 + 0.1 * rn(d_in)).to(DEV), (0.1 * rn(d_in)).to(DEV), kind == "gcn", 0.3, seed=79, site=0, row_base=64)
+    assert eng.lib.cgnn_set_option(1, 0) == 0
+    try:
+        z, _, agg = eng.layer_fwd(kind, t_in, act_in, W, bias, b.csr, b.ptr, B, False)
+    finally:
+        eng.lib.cgnn_set_option(1, 1)
+    act_out = Act((1 + 0.1 * rn(H)).to(DEV), (0.1 * rn(H)).to(DEV), kind == "gcn", 0.3, seed=79, site=1, row_base=64)
+    mean, rstd = (0.1 * rn(H)).to(DEV), (1 + 0.1 * rn(H)).abs().to(DEV)
+    sums = (rn(2, H) * 0.5).to(DEV)
+    bn = BnBwd(act_out.scale, mean, rstd, sums, float(rows), True)
+    du = None if top else rn(rows, H).to(DEV)
+    demb = rn(B, H).to(DEV) if top else None
+    pmean, prstd = (0.1 * rn(d_in)).to(DEV), (1 + 0.1 * rn(d_in)).abs().to(DEV)
+    out = {}
+    for use_tc in (1, 0):
+        assert eng.lib.cgnn_set_option(1, use_tc) == 0
+        try:
+            out[use_tc] = eng.layer_bwd(kind, du, demb, z, act_out, bn, t_in, act_in, W, b.csr, b.ptr, B, True, pmean, prstd, agg)
+        finally:
+            eng.lib.cgnn_set_option(1, 1)
+    for name, got, ref in zip(("dW", "dbias", "du_in", "prev_sums"), out[1], out[0]):
+        helpers.assert_close(got, ref, f"{kind} bwd {name}: tensor-core vs generic", tol=5e-6)
