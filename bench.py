@@ -344,9 +344,10 @@ def profile_calls(a, eng, step_fn, peak, peak_src):
             d_in = args[8]
             return 4 * rows * d_in + 4 * rows * H + csr
         if name.endswith("layer_bwd"):
-            d_in = args[12]
+            o = 1 if name == "cgnn_sage_layer_bwd" else 0     # GraphSAGE takes one more pointer (agg) before act_in
+            d_in = args[12 + o]
             pooled = args[0] is None
-            need_du = args[18] is not None
+            need_du = args[18 + o] is not None
             return (4 * rows * H) * (1 if pooled else 2) + 4 * rows * d_in + (4 * rows * d_in if need_du else 0) + csr
         if name == "cgnn_bn_bwd_sums" or name == "cgnn_pool_fwd":
             return 4 * rows * H

@@ -21,10 +21,23 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int k, int rows) {
   const int kb = k >> 5, kk = k & 31;
   return (uint32_t)(kb * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7)) << 4)) + ((kk & 3) << 2));
 }
-__device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// hi part of the split: the top 19 bits of x (truncation).  x - hi is exact, and the tensor core drops the low 13
+// bits of a tf32 operand anyway, so this is one LOP3 where cvt.rna.tf32 costs four instructions; the three-term
+// product keeps ~2^-21 relative accuracy (measured in tests/test_gpu_parity.py).
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// 1024-byte aligned start of the dynamic shared memory, as a pointer the compiler still knows to be shared
+// (an integer round trip would turn every access into a generic LD/ST with descriptor moves).
+__device__ __forceinline__ unsigned char* smem_align1024(unsigned char* smem_raw) {
+  return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// hi / lo parts of 4 values to two operand tiles at a precomputed byte offset
+__device__ __forceinline__ void store_split4_at(uint32_t hi_addr, uint32_t lo_addr, float4 v) {
+  const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  st_shared_f4(hi_addr, h);
+  st_shared_f4(lo_addr, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
 }
 // write 4 consecutive k (k % 4 == 0) of one row as hi / lo parts
 __device__ __forceinline__ void store_split4(unsigned char* hi_base, unsigned char* lo_base, int row, int k, int rows, float4 v) {
