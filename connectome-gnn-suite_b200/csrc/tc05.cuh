@@ -21,10 +21,11 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int k, int rows) {
   const int kb = k >> 5, kk = k & 31;
   return (uint32_t)(kb * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7)) << 4)) + ((kk & 3) << 2));
 }
-// hi part of the split: the top 19 bits of x (truncation).  x - hi is exact, and the tensor core drops the low 13
-// bits of a tf32 operand anyway, so this is one LOP3 where cvt.rna.tf32 costs four instructions; the three-term
-// product keeps ~2^-21 relative accuracy (measured in tests/test_gpu_parity.py).
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// hi part of the split: x rounded to the nearest tf32 (10 explicit mantissa bits) with an integer add + mask, two
+// instructions where cvt.rna.tf32 compiles to four.  x - hi is exact and |x - hi| <= 2^-11 |x|; the tensor core
+// ignores the low 13 bits of a tf32 operand, so the three-term product keeps ~2^-21 relative accuracy (measured
+// in tests/test_gpu_parity.py).
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 // 1024-byte aligned start of the dynamic shared memory, as a pointer the compiler still knows to be shared
 // (an integer round trip would turn every access into a generic LD/ST with descriptor moves).
 __device__ __forceinline__ unsigned char* smem_align1024(unsigned char* smem_raw) {

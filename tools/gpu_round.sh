@@ -11,6 +11,7 @@ mkdir -p $OUT
 if [ "$TESTS" = "tests" ]; then
   timeout 900 python -m pytest tests -m gpu -x -q > $OUT/gpu_tests_$TAG.log 2>&1
   echo "pytest rc=$?" | tee -a $OUT/gpu_tests_$TAG.log
+  grep -E "^(FAILED|ERROR|E  )" $OUT/gpu_tests_$TAG.log | head -20
   tail -3 $OUT/gpu_tests_$TAG.log
 fi
 timeout 600 python bench.py --steps 10 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
@@ -21,8 +22,15 @@ timeout 300 $CMD > $OUT/plain_$TAG.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 700 --csv \
     --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
-timeout 300 $CMD > $OUT/plain2_$TAG.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KREGEX" -s 87 -c 29 \
-    -f -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
-echo "full capture rc=$?"
-ls -la $OUT | tail -12
+# full captures: matched launches of one step are, in order,
+#   gcn train: fwd_tc x3, (gather, gemm) x3 | sage train: (gather, gemm) x3, bwd kernels | gcn infer | sage infer
+# 29 per step, 3 warm-up steps + 3 ... = skip 87; keep each report small (<= 64 MiB comes back in total)
+i=0
+for SPEC in ${SPECS:-"89:5" "98:2"}; do
+  S=${SPEC%%:*}; C=${SPEC##*:}; i=$((i+1))
+  timeout 300 $CMD > $OUT/plain2_$TAG.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KREGEX" -s $S -c $C \
+      -f -o $OUT/prof_${TAG}_$i $CMD > $OUT/ncu_full_${TAG}_$i.log 2>&1
+  echo "full capture $i ($SPEC) rc=$?"
+done
+du -sh $OUT; ls -la $OUT | tail -14
