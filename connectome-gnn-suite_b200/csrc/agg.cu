@@ -10,6 +10,7 @@
 // The dense contractions around them live in gemm_tc.cu.
 #include "agg.cuh"
 #include "tile.cuh"
+#include "rowtile.cuh"
 
 namespace cgnn {
 
@@ -89,243 +90,205 @@ __global__ void __launch_bounds__(256) k_build_agg(BuildAggArgs p) {
 // ------------------------------------------------------------------------------------------------------------
 // gather kernels
 // ------------------------------------------------------------------------------------------------------------
-template <int MODE, int VW>
-__global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
+#ifndef CGNN_EMU
+// One CTA works on one 4*LPR-channel slab of one subject at a time (two CTAs per SM for the 32-channel slabs of a
+// 360-node subject): the subject's blob arrives by cp.async while the threads transform their channel quad of the
+// tile on the way into shared memory; then 32 / LPR rows per warp are gathered with float4 lanes from shared memory.
+template <int MODE, int LPR>
+__global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p, int vec) {
   CGNN_SMEM_DECL;
-  float* sm = reinterpret_cast<float*>(cgnn_smem);
-  const int C = p.C, ld = p.ld;
-  float* s_co = sm;                              // [GC_ROWS][ld] per-channel constants
-  float* s_red = s_co + GC_ROWS * ld;            // [kWarps][2*32*VW] end-of-kernel reduction
-  float* s_tile = s_red + kWarps * 64 * VW;      // [max_nodes][ld] (+32 floats of slack)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool affine = p.act.scale != nullptr;
+  constexpr int RP = kThreads / LPR;    // tile rows per load pass
+  constexpr int RPW = 32 / LPR;         // rows per warp in the gather
+  float4* s_tile = reinterpret_cast<float4*>(cgnn_smem);                       // [max_nodes][LPR]
+  int32_t* s_blob = reinterpret_cast<int32_t*>(s_tile + (size_t)p.max_nodes * LPR);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int cl = tid % LPR, rl = tid / LPR;
+  const int C = p.C, nslab = p.nslab;
+  const int slab = blockIdx.x % nslab;
+  const int c0 = slab * 4 * LPR + 4 * cl;
+  const bool live_quad = c0 < C;
 
-  stage_affine(p.act, C, ld, s_co + GC_SCALE * ld, s_co + GC_SHIFT * ld);
-  for (int c = tid; c < ld; c += kThreads) {
-    float bsc = c < C ? 1.0f : 0.0f, mean = 0.0f, rstd = 0.0f, s1n = 0.0f, s2n = 0.0f;
-    if (MODE == GATHER_GCN_BWD && c < C && p.has_bn) {
-      bsc = p.bn_scale[c]; mean = p.bn_mean[c]; rstd = p.bn_rstd[c];
-      if (p.bn_train) { s1n = p.bn_s1[c] * p.inv_count; s2n = p.bn_s2[c] * p.inv_count; }
-    }
-    if (MODE == GATHER_SAGE_BWD && c < C && p.want_prev) { mean = p.prev_mean[c]; rstd = p.prev_rstd[c]; }
-    s_co[GC_BSC * ld + c] = bsc; s_co[GC_MEAN * ld + c] = mean; s_co[GC_RSTD * ld + c] = rstd;
-    s_co[GC_S1N * ld + c] = s1n; s_co[GC_S2N * ld + c] = s2n;
-  }
-  __syncthreads();
-
-  // dz of one element (GCN_BWD): dropout / ReLU backward of the upstream gradient, then BatchNorm backward
-  auto dz_of = [&](float t, float up, uint32_t rh, int c) -> float {
-    const float dy = act_bwd(p.act, affine, t, s_co[GC_SCALE * ld + c], s_co[GC_SHIFT * ld + c], rh, c, up);
-    if (!p.has_bn) return dy;
-    if (!p.bn_train) return s_co[GC_BSC * ld + c] * dy;
-    const float xh = (t - s_co[GC_MEAN * ld + c]) * s_co[GC_RSTD * ld + c];
-    return s_co[GC_BSC * ld + c] * (dy - s_co[GC_S1N * ld + c] - xh * s_co[GC_S2N * ld + c]);
-  };
-
-  float colsum[4] = {0.f, 0.f, 0.f, 0.f};          // GCN_BWD: dbias, this thread's channel quad (vec) or channel
-  float ps1[VW], ps2[VW];                          // SAGE_BWD: sums of the layer below, channels VW*lane + j
+  rt::ChanQuad cq;
+  rt::chan_quad_init(cq, p.act, c0, C);
+  rt::BnBwdDev bn;
+  bn.scale = p.bn_scale; bn.mean = p.bn_mean; bn.rstd = p.bn_rstd; bn.s1 = p.bn_s1; bn.s2 = p.bn_s2;
+  bn.inv_count = p.inv_count; bn.train = p.bn_train; bn.has = p.has_bn;
+  rt::BnQuad bq;
+  if (MODE == GATHER_GCN_BWD) rt::bn_quad_init(bq, bn, c0, C);
+  float pmean[4] = {0.f, 0.f, 0.f, 0.f}, prstd[4] = {0.f, 0.f, 0.f, 0.f};
+  if (MODE == GATHER_SAGE_BWD && p.want_prev) {
 #pragma unroll
-  for (int j = 0; j < VW; ++j) { ps1[j] = 0.f; ps2[j] = 0.f; }
+    for (int j = 0; j < 4; ++j)
+      if (c0 + j < C) { pmean[j] = p.prev_mean[c0 + j]; prstd[j] = p.prev_rstd[c0 + j]; }
+  }
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};   // GCN_BWD: s1 = dbias; SAGE_BWD: sums of the layer below
 
   const int4* meta = reinterpret_cast<const int4*>(p.meta);
-  for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
+  const long long gstep = gridDim.x / nslab;
+  for (long long g = blockIdx.x / nslab; g < p.B; g += gstep) {
     const int4 m = meta[g];
     const long long nb = m.x, eb = m.z;
-    const int n = min(m.y, p.max_nodes);
-    // ---- load phase: the subject's tile, transformed on the way in ---------------------------------------
-    if (p.vec) {
-      const int Q = C >> 2;
-      const int total = n * Q;
-      const float inv_n = 1.0f / ((float)n + 1e-8f);
-      for (int base = tid; base < total; base += 4 * kThreads) {
-        float4 a[4], b[4];
+    const int n = min(m.y, p.max_nodes), me = min(m.w, p.max_edges);
+    // ---- the subject's blob: one asynchronous burst ------------------------------------------------------------
+    {
+      const int32_t* gb = p.blob + agg_base_words(nb, eb, g);
+      const int n16 = (agg_copy_words(n, me) + 3) >> 2;
+      for (int i = tid; i < n16; i += kThreads) cp_async_16(s_blob + 4 * i, gb + 4 * i);
+      cp_async_commit();
+    }
+    // ---- load phase: this thread's channel quad of rows rl, rl + RP, ... transformed on the way in --------------
+    const float inv_n = 1.0f / ((float)n + 1e-8f);
+    float4 pooled = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == GATHER_GCN_BWD && !p.du && live_quad) {
+      pooled = vec ? rt::ld_quad<true>(p.demb, g, C, c0) : rt::ld_quad<false>(p.demb, g, C, c0);
+      pooled = make_float4(pooled.x * inv_n, pooled.y * inv_n, pooled.z * inv_n, pooled.w * inv_n);
+    }
+    for (int r = rl; r < n; r += 2 * RP) {
+      float4 a[2], b[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * kThreads;
-          if (idx < total) {
-            const int i = idx / Q, c = (idx - i * Q) << 2;
-            a[u] = *reinterpret_cast<const float4*>(p.src + (nb + i) * C + c);
-            if (MODE == GATHER_GCN_BWD && p.du) b[u] = *reinterpret_cast<const float4*>(p.du + (nb + i) * C + c);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * kThreads;
-          if (idx < total) {
-            const int i = idx / Q, c = (idx - i * Q) << 2;
-            float4 o = a[u];
-            if (MODE == GATHER_SAGE_FWD) {
-              const uint32_t rh = p.act.drop ? drop_row_hash(p.act, p.act.row_base + nb + i) : 0u;
-              o.x = act_fwd(p.act, affine, a[u].x, s_co[GC_SCALE * ld + c + 0], s_co[GC_SHIFT * ld + c + 0], rh, c + 0);
-              o.y = act_fwd(p.act, affine, a[u].y, s_co[GC_SCALE * ld + c + 1], s_co[GC_SHIFT * ld + c + 1], rh, c + 1);
-              o.z = act_fwd(p.act, affine, a[u].z, s_co[GC_SCALE * ld + c + 2], s_co[GC_SHIFT * ld + c + 2], rh, c + 2);
-              o.w = act_fwd(p.act, affine, a[u].w, s_co[GC_SCALE * ld + c + 3], s_co[GC_SHIFT * ld + c + 3], rh, c + 3);
-            } else if (MODE == GATHER_GCN_BWD) {
-              if (!p.du) {
-                const float4 e = *reinterpret_cast<const float4*>(p.demb + g * C + c);
-                b[u] = make_float4(e.x * inv_n, e.y * inv_n, e.z * inv_n, e.w * inv_n);
-              }
-              const uint32_t rh = p.act.drop ? drop_row_hash(p.act, p.act.row_base + nb + i) : 0u;
-              o.x = dz_of(a[u].x, b[u].x, rh, c + 0);
-              o.y = dz_of(a[u].y, b[u].y, rh, c + 1);
-              o.z = dz_of(a[u].z, b[u].z, rh, c + 2);
-              o.w = dz_of(a[u].w, b[u].w, rh, c + 3);
-              colsum[0] += o.x; colsum[1] += o.y; colsum[2] += o.z; colsum[3] += o.w;   // quad fixed: kThreads % Q == 0
-            }
-            *reinterpret_cast<float4*>(s_tile + i * ld + c) = o;
-          }
+      for (int u = 0; u < 2; ++u) {
+        const int rr = r + u * RP;
+        a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        b[u] = pooled;
+        if (rr < n && live_quad) {
+          a[u] = vec ? rt::ld_quad<true>(p.src, nb + rr, C, c0) : rt::ld_quad<false>(p.src, nb + rr, C, c0);
+          if (MODE == GATHER_GCN_BWD && p.du) b[u] = vec ? rt::ld_quad<true>(p.du, nb + rr, C, c0) : rt::ld_quad<false>(p.du, nb + rr, C, c0);
         }
       }
-    } else {
-      const float inv_n = 1.0f / ((float)n + 1e-8f);
-      for (int idx = tid; idx < n * ld; idx += kThreads) {
-        const int i = idx / ld, c = idx - i * ld;
-        float o = 0.0f;
-        if (c < C) {
-          const float t = p.src[(nb + i) * C + c];
-          const uint32_t rh = p.act.drop ? drop_row_hash(p.act, p.act.row_base + nb + i) : 0u;
-          if (MODE == GATHER_SAGE_FWD) o = act_fwd(p.act, affine, t, s_co[GC_SCALE * ld + c], s_co[GC_SHIFT * ld + c], rh, c);
-          else if (MODE == GATHER_GCN_BWD) {
-            const float up = p.du ? p.du[(nb + i) * C + c] : p.demb[g * C + c] * inv_n;
-            o = dz_of(t, up, rh, c);
-          } else o = t;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int rr = r + u * RP;
+        if (rr < n) {
+          float4 o = a[u];
+          if (MODE == GATHER_SAGE_FWD) o = rt::act_fwd4(p.act, cq, a[u], nb + rr);
+          if (MODE == GATHER_GCN_BWD) {
+            o = rt::bn_bwd4(bn, bq, a[u], rt::act_bwd4(p.act, cq, a[u], b[u], nb + rr));
+            o = rt::mask_quad(o, c0, C);
+            s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
+          }
+          o = rt::mask_quad(o, c0, C);
+          s_tile[rr * LPR + cl] = o;
         }
-        s_tile[idx] = o;
       }
     }
+    cp_async_wait<0>();
     __syncthreads();
-    // ---- gather phase: one warp per output row --------------------------------------------------------------
-    const AggView av = agg_view(p.blob, nb, n, eb, g);
-    const float* tile_lane = s_tile + VW * lane;
-    const int c0 = VW * lane;
-    for (int i = warp; i < n; i += kWarps) {
-      float acc[VW];
-#pragma unroll
-      for (int j = 0; j < VW; ++j) acc[j] = 0.0f;
-      const float aux = agg_gather_row<VW>(av, i, tile_lane, ld, acc);
-      const long long grow = nb + i;
+    // ---- gather phase --------------------------------------------------------------------------------------------
+    const int4* s_desc = reinterpret_cast<const int4*>(s_blob);
+    const int4* s_rec2 = reinterpret_cast<const int4*>(s_blob + 4 * n);
+    for (int i0 = warp * RPW; i0 < n; i0 += kWarps * RPW) {
+      float4 acc;
+      float aux;
+      int row;
+      const bool valid = agg_gather_group<LPR>(s_desc, s_rec2, s_tile, i0, n, acc, aux, row);
+      if (!valid || !live_quad) continue;
+      const long long grow = nb + row;
       if (MODE == GATHER_SAGE_FWD) {
         const float inv = 1.0f / (aux + 1e-8f);
-#pragma unroll
-        for (int j = 0; j < VW; ++j) acc[j] *= inv;
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
       }
       if (MODE == GATHER_SAGE_BWD) {
-        float dir[VW], raw[VW];
-        if (VW == 2) {
-          const float2 d2 = *reinterpret_cast<const float2*>(p.direct + grow * C + c0); dir[0] = d2.x; dir[1] = d2.y;
-        } else if (VW == 4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(p.direct + grow * C + c0);
-          dir[0] = d4.x; dir[1] = d4.y; dir[2] = d4.z; dir[3] = d4.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < VW; ++j) dir[j] = c0 + j < C ? p.direct[grow * C + c0 + j] : 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < VW; ++j) acc[j] += dir[j];
+        const float4 d = vec ? rt::ld_quad<true>(p.direct, grow, C, c0) : rt::ld_quad<false>(p.direct, grow, C, c0);
+        acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
         if (p.want_prev) {
-          if (VW == 2) {
-            const float2 r2 = *reinterpret_cast<const float2*>(p.t_raw + grow * C + c0); raw[0] = r2.x; raw[1] = r2.y;
-          } else if (VW == 4) {
-            const float4 r4 = *reinterpret_cast<const float4*>(p.t_raw + grow * C + c0);
-            raw[0] = r4.x; raw[1] = r4.y; raw[2] = r4.z; raw[3] = r4.w;
-          } else {
+          const float4 raw = vec ? rt::ld_quad<true>(p.t_raw, grow, C, c0) : rt::ld_quad<false>(p.t_raw, grow, C, c0);
+          const float4 dyp = rt::act_bwd4(p.act, cq, raw, acc, grow);
+          const float rv[4] = {raw.x, raw.y, raw.z, raw.w}, dv[4] = {dyp.x, dyp.y, dyp.z, dyp.w};
 #pragma unroll
-            for (int j = 0; j < VW; ++j) raw[j] = c0 + j < C ? p.t_raw[grow * C + c0 + j] : 0.0f;
-          }
-          const uint32_t rh = p.act.drop ? drop_row_hash(p.act, p.act.row_base + grow) : 0u;
-#pragma unroll
-          for (int j = 0; j < VW; ++j) {
-            const int c = c0 + j;
-            if (c < C) {
-              const float dyp = act_bwd(p.act, affine, raw[j], s_co[GC_SCALE * ld + c], s_co[GC_SHIFT * ld + c], rh, c, acc[j]);
-              const float xh = (raw[j] - s_co[GC_MEAN * ld + c]) * s_co[GC_RSTD * ld + c];
-              ps1[j] += dyp;
-              ps2[j] = fmaf(dyp, xh, ps2[j]);
+          for (int j = 0; j < 4; ++j) {
+            if (c0 + j < C) {
+              const float xh = (rv[j] - pmean[j]) * prstd[j];
+              s1[j] += dv[j];
+              s2[j] = fmaf(dv[j], xh, s2[j]);
             }
           }
         }
       }
-      float* dst = p.out + grow * C + c0;
-      if (VW == 2) *reinterpret_cast<float2*>(dst) = make_float2(acc[0], acc[1]);
-      else if (VW == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      else {
-#pragma unroll
-        for (int j = 0; j < VW; ++j) if (c0 + j < C) dst[j] = acc[j];
-      }
+      if (vec) rt::st_quad<true>(p.out, grow, C, c0, acc);
+      else rt::st_quad<false>(p.out, grow, C, c0, acc);
     }
-    __syncthreads();   // the tile is rewritten by the next subject
+    __syncthreads();   // tile and blob are rewritten by the next subject
   }
 
-  // ---- per-CTA partial records ------------------------------------------------------------------------------
-  if (MODE == GATHER_GCN_BWD && p.partials) {
-    // vec path: thread's quad = tid % Q; sum the kThreads / Q threads that share it
-    const int Q = C >> 2;
-    float* red = s_tile;   // free now: [kThreads][4]
-    *reinterpret_cast<float4*>(red + 4 * tid) = make_float4(colsum[0], colsum[1], colsum[2], colsum[3]);
+  // ---- per-CTA partial records (zero outside this CTA's slab) ---------------------------------------------------------
+  const bool want = (MODE == GATHER_GCN_BWD && p.partials) || (MODE == GATHER_SAGE_BWD && p.partials && p.want_prev);
+  if (want) {
+    float* red = reinterpret_cast<float*>(s_tile);   // [kThreads][8]
+    *reinterpret_cast<float4*>(red + 8 * tid) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    *reinterpret_cast<float4*>(red + 8 * tid + 4) = make_float4(s2[0], s2[1], s2[2], s2[3]);
     __syncthreads();
-    for (int c = tid; c < C; c += kThreads) {
-      const int q = c >> 2, j = c & 3;
+    const int nrec = MODE == GATHER_GCN_BWD ? 1 : 2;
+    for (int idx = tid; idx < nrec * C; idx += kThreads) {
+      const int which = idx / C, c = idx - which * C;
       float s = 0.0f;
-      for (int t = q; t < kThreads; t += Q) s += red[4 * t + j];
-      p.partials[(size_t)blockIdx.x * p.part_stride + c] = s;
+      if (c / (4 * LPR) == slab) {
+        const int q = (c % (4 * LPR)) >> 2, j = c & 3;
+        for (int t = q; t < kThreads; t += LPR) s += red[8 * t + 4 * which + j];
+      }
+      p.partials[(size_t)blockIdx.x * p.part_stride + idx] = s;
     }
   }
-  if (MODE == GATHER_SAGE_BWD && p.partials && p.want_prev) {
-#pragma unroll
-    for (int j = 0; j < VW; ++j) {
-      s_red[warp * 64 * VW + VW * lane + j] = ps1[j];
-      s_red[warp * 64 * VW + 32 * VW + VW * lane + j] = ps2[j];
-    }
-    __syncthreads();
-    for (int c = tid; c < 2 * C; c += kThreads) {
-      const int which = c / C, ch = c - which * C;
-      float s = 0.0f;
-      for (int w = 0; w < kWarps; ++w) s += s_red[w * 64 * VW + which * 32 * VW + ch];
-      p.partials[(size_t)blockIdx.x * p.part_stride + c] = s;
-    }
-  }
+  (void)RP;
 }
+#endif  // CGNN_EMU
 
 // ---- host side -------------------------------------------------------------------------------------------------
+static bool gather_shape(int C, int max_nodes, int max_edges, int* lpr, int* nslab, size_t* smem) {
+  if (C <= 0 || C > 128) return false;
+  int L, S;
+  if (C <= 8) { L = 2; S = 1; }
+  else if (C <= 32) { L = 8; S = 1; }
+  else if (C % 32 == 0) { L = 8; S = C / 32; }
+  else return false;
+  if (max_nodes < 1) max_nodes = 1;
+  size_t bytes = (size_t)max_nodes * L * 16 + (size_t)agg_smem_words(max_nodes, max_edges) * 4;
+  if (bytes < (size_t)kThreads * 8 * 4) bytes = (size_t)kThreads * 8 * 4;
+  *lpr = L; *nslab = S; *smem = bytes;
+  return bytes <= (size_t)device_info().smem_optin;
+}
+bool gather_supported(int C, int max_nodes, int max_edges) {
+  int l, s; size_t b;
+  return gather_shape(C, max_nodes, max_edges, &l, &s, &b);
+}
+
 // Launches one gather kernel; returns the grid through *grid_out (the caller reduces `partials` over it).
-// Shapes: C a multiple of 32 up to 128, or C <= 32 (one channel per lane).
 int launch_gather(int mode, GatherArgs& a, int* grid_out, cudaStream_t stream) {
+#ifdef CGNN_EMU
+  (void)mode; (void)a; (void)grid_out; (void)stream;
+  return -1;
+#else
   const DeviceInfo dev = device_info();
-  const int C = a.C;
-  if (C <= 0 || C > 128 || (C > 32 && C % 32 != 0)) return -1;
-  const int VW = C <= 32 ? 1 : C / 32;
-  if (VW == 3) return -1;
-  a.ld = round_up(C, 4);
-  a.vec = (C % 4 == 0) && ((((uintptr_t)a.src) & 15u) == 0) && (!a.du || (((uintptr_t)a.du) & 15u) == 0) &&
-          (!a.demb || (((uintptr_t)a.demb) & 15u) == 0) && (kThreads % (C / 4) == 0);
-  if (mode == GATHER_GCN_BWD && !a.vec) return -1;    // dbias column sums need the fixed-quad mapping
+  int LPR = 0, nslab = 0;
+  size_t smem = 0;
   if (a.max_nodes < 1) a.max_nodes = 1;
-  const size_t words = (size_t)GC_ROWS * a.ld + (size_t)kWarps * 64 * VW + (size_t)a.max_nodes * a.ld + 32 +
-                       (mode == GATHER_GCN_BWD ? 4 * kThreads : 0);
-  const size_t smem = words * sizeof(float);
-  if (smem > (size_t)dev.smem_optin) return -1;
+  if (!gather_shape(a.C, a.max_nodes, a.max_edges, &LPR, &nslab, &smem)) return -1;
+  a.nslab = nslab;
+  const int C = a.C;
+  auto al16 = [](const void* p) { return p == nullptr || (((uintptr_t)p) & 15u) == 0; };
+  const int vec = (C % 4 == 0) && al16(a.src) && al16(a.du) && al16(a.demb) && al16(a.direct) && al16(a.t_raw) && al16(a.out);
   int per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)per_sm * dev.sm_count;
-  if (grid > a.B) grid = a.B;
-  if (grid < 1) grid = 1;
+  grid -= grid % nslab;
+  if (grid > a.B * nslab) grid = a.B * nslab;
+  if (grid < nslab) grid = nslab;
   *grid_out = (int)grid;
-#define CGNN_GATHER(MODE_, VW_)                                                                          \
+#define CGNN_GATHER(MODE_, LPR_)                                                                         \
   {                                                                                                      \
-    auto kfn = k_gather<MODE_, VW_>;                                                                     \
+    auto kfn = k_gather<MODE_, LPR_>;                                                                    \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    CGNN_LAUNCH(kfn, (unsigned)grid, kThreads, smem, stream, a);                                         \
+    CGNN_LAUNCH(kfn, (unsigned)grid, kThreads, smem, stream, a, vec);                                    \
   }
-#define CGNN_GATHER_VW(MODE_)                                                                            \
-  { if (VW == 1) CGNN_GATHER(MODE_, 1) else if (VW == 2) CGNN_GATHER(MODE_, 2) else CGNN_GATHER(MODE_, 4) }
-  if (mode == GATHER_SAGE_FWD) CGNN_GATHER_VW(GATHER_SAGE_FWD)
-  else if (mode == GATHER_GCN_BWD) CGNN_GATHER_VW(GATHER_GCN_BWD)
-  else CGNN_GATHER_VW(GATHER_SAGE_BWD)
-#undef CGNN_GATHER_VW
+#define CGNN_GATHER_L(MODE_) { if (LPR == 2) CGNN_GATHER(MODE_, 2) else CGNN_GATHER(MODE_, 8) }
+  if (mode == GATHER_SAGE_FWD) CGNN_GATHER_L(GATHER_SAGE_FWD)
+  else if (mode == GATHER_GCN_BWD) CGNN_GATHER_L(GATHER_GCN_BWD)
+  else CGNN_GATHER_L(GATHER_SAGE_BWD)
+#undef CGNN_GATHER_L
 #undef CGNN_GATHER
   CGNN_CHECK_LAUNCH();
   return CGNN_OK;
+#endif
 }
 
 }  // namespace cgnn

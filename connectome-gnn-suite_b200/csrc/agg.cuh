@@ -22,49 +22,56 @@ static inline size_t agg_total_words(long long rows, long long edges, long long 
   return (size_t)(8 * rows + 2 * (edges + 1) + 4 * graphs + 8);
 }
 
-struct AggView {
-  const int4* desc;   // [n]
-  const int4* rec2;   // record pairs; desc.x / desc.y index single records (even)
-};
-static __device__ __forceinline__ AggView agg_view(const int32_t* blob, long long nb, int n, long long eb, long long g) {
-  const int32_t* b = blob + agg_base_words(nb, eb, g);
-  AggView v;
-  v.desc = reinterpret_cast<const int4*>(b);
-  v.rec2 = reinterpret_cast<const int4*>(b + 4 * (long long)n);
-  return v;
-}
+// ---- gather over a blob staged in shared memory -------------------------------------------------------------------
+// words a CTA copies for one subject: descriptors + records + padding, always inside the blob buffer (the next blob
+// starts 8n + 2m (+2) + 4 words further, agg_total_words adds 8 words of slack at the end)
+static inline __host__ __device__ int agg_copy_words(int n, int m) { return 8 * n + 2 * m + 4; }
+static inline __host__ __device__ int agg_smem_words(int max_nodes, int max_edges) { return 8 * max_nodes + 2 * max_edges + 8; }
 
-// acc[j] += sum over the records of row i of w * tile[nbr * ld + VW * lane + j]; returns the row's aux word.
-// `tile` lives in shared memory, the records are read through the read-only path (all lanes the same address).
-template <int VW>
-static __device__ __forceinline__ float agg_gather_row(const AggView& a, int i, const float* __restrict__ tile_lane, int ld,
-                                                       float (&acc)[VW]) {
-  const int4 d = __ldg(a.desc + i);
-  for (int e = d.x; e < d.y; e += 2) {
-    const int4 r = __ldg(a.rec2 + (e >> 1));
-    const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
-    const float* p0 = tile_lane + r.x * ld;
-    const float* p1 = tile_lane + r.z * ld;
-    if (VW == 1) {
-      const float v0 = p0[0], v1 = p1[0];
-      acc[0] = fmaf(v0, w0, acc[0]);
-      acc[0] = fmaf(v1, w1, acc[0]);
-    } else if (VW == 2) {
-      const float2 v0 = *reinterpret_cast<const float2*>(p0), v1 = *reinterpret_cast<const float2*>(p1);
-      acc[0] = fmaf(v0.x, w0, acc[0]); acc[1] = fmaf(v0.y, w0, acc[1]);
-      acc[0] = fmaf(v1.x, w1, acc[0]); acc[1] = fmaf(v1.y, w1, acc[1]);
-    } else {
+// One warp, 32 / LPR consecutive rows at a time: lane owns the channel quad (lane % LPR) of row i0 + lane / LPR and
+// returns acc = sum over that row's records of w * tile[nbr][quad] (tile rows are LPR float4 wide), the row's aux
+// word and whether the row exists.  Records are read two at a time (rows are padded to an even count); the rows of a
+// group run in lock step up to the shortest one, the remainder is predicated.
+template <int LPR>
+static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__ s_desc, const int4* __restrict__ s_rec2,
+                                                        const float4* __restrict__ tile4, int i0, int n, float4& acc, float& aux,
+                                                        int& row) {
+  const int lane = threadIdx.x & 31, cl = lane % LPR;
+  row = i0 + lane / LPR;
+  const bool valid = row < n;
+  int4 d = make_int4(0, 0, 0, 0);
+  if (valid) d = s_desc[row];
+  int e = d.x;
+  const int len = d.y - d.x;
+  int lmin = len, lmax = len;
 #pragma unroll
-      for (int q = 0; q < VW; q += 4) {
-        const float4 v0 = *reinterpret_cast<const float4*>(p0 + q), v1 = *reinterpret_cast<const float4*>(p1 + q);
-        acc[q + 0] = fmaf(v0.x, w0, acc[q + 0]); acc[q + 1] = fmaf(v0.y, w0, acc[q + 1]);
-        acc[q + 2] = fmaf(v0.z, w0, acc[q + 2]); acc[q + 3] = fmaf(v0.w, w0, acc[q + 3]);
-        acc[q + 0] = fmaf(v1.x, w1, acc[q + 0]); acc[q + 1] = fmaf(v1.y, w1, acc[q + 1]);
-        acc[q + 2] = fmaf(v1.z, w1, acc[q + 2]); acc[q + 3] = fmaf(v1.w, w1, acc[q + 3]);
-      }
+  for (int o = LPR; o < 32; o <<= 1) {
+    lmin = min(lmin, __shfl_xor_sync(kFull, lmin, o));
+    lmax = max(lmax, __shfl_xor_sync(kFull, lmax, o));
+  }
+  const float4* t4 = tile4 + cl;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int k = 0;
+#pragma unroll 2
+  for (; k < lmin; k += 2, e += 2) {
+    const int4 r = s_rec2[e >> 1];
+    const float4 v0 = t4[r.x * LPR], v1 = t4[r.z * LPR];
+    const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
+    a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
+    a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
+  }
+  for (; k < lmax; k += 2, e += 2) {
+    if (k < len) {
+      const int4 r = s_rec2[e >> 1];
+      const float4 v0 = t4[r.x * LPR], v1 = t4[r.z * LPR];
+      const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
+      a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
+      a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
     }
   }
-  return __int_as_float(d.z);
+  acc = a;
+  aux = __int_as_float(d.z);
+  return valid;
 }
 
 enum { GATHER_SAGE_FWD = 0, GATHER_GCN_BWD = 1, GATHER_SAGE_BWD = 2 };
@@ -72,7 +79,7 @@ enum { GC_SCALE = 0, GC_SHIFT, GC_BSC, GC_MEAN, GC_RSTD, GC_S1N, GC_S2N, GC_ROWS
 
 struct GatherArgs {
   const int32_t* meta; long long B; const int32_t* blob;
-  int C, ld, vec, max_nodes;
+  int C, max_nodes, max_edges, nslab;
   // tile source
   const float* src;        // SAGE_FWD: t_in   GCN_BWD: z   SAGE_BWD: d_agg
   Act act;                 // SAGE_FWD: act on load   GCN_BWD: act_out (its backward)   SAGE_BWD: act_in (for the sums)
@@ -100,6 +107,13 @@ int launch_gcn_bwd_gemm(const float* dP, const float* t_in, const cgnn_act_t* ac
                         int32_t d_in, int32_t H, float* du_in, const float* prev_mean, const float* prev_rstd, int want_prev,
                         float* partials, int part_stride, int o_pprev, int* grid_out, size_t partial_bytes,
                         cudaStream_t stream);
+int launch_sage_bwd_gemm(const float* du, const float* demb, const int32_t* row_graph, const int32_t* meta, const float* z,
+                         const cgnn_act_t* act_out, const cgnn_bn_bwd_t* bn, const float* t_in, const float* agg,
+                         const cgnn_act_t* act_in, const float* W, int64_t rows, int32_t C, int32_t H, float* direct,
+                         float* nbr, float* partials, int part_stride, int o_pdb, int* grid_out, size_t partial_bytes,
+                         cudaStream_t stream);
 #endif
+// true when launch_gather covers C channels (checked before a tensor-core contraction commits to the gather that follows)
+bool gather_supported(int C, int max_nodes, int max_edges);
 
 }  // namespace cgnn

@@ -226,6 +226,18 @@ __device__ __forceinline__ void outer_4x4(const float* __restrict__ P, int ldp, 
   }
 }
 
+// 1 / x to ~1 ulp (MUFU.RCP): the Welford updates below only need 1 / count approximately, the exact division
+// compiles to a dozen instructions with a slow path.
+__device__ __forceinline__ float fast_rcp(float x) {
+#ifdef CGNN_EMU
+  return 1.0f / x;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+
 // ---- Welford accumulators for BatchNorm statistics --------------------------------------
 struct Welford {
   float mean, m2;

@@ -589,7 +589,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
     if (workspace_bytes > region_a + (size_t)part_stride * sizeof(float)) {
       GatherArgs ga{};
       ga.meta = csr->graph_meta; ga.B = num_graphs; ga.blob = csr->agg_out;
-      ga.C = H; ga.max_nodes = max_nodes;
+      ga.C = H; ga.max_nodes = max_nodes; ga.max_edges = max_edges;
       ga.src = z; ga.act = make_act(act_out); ga.du = du; ga.demb = demb;
       ga.has_bn = bn ? 1 : 0;
       ga.bn_scale = bn ? bn->scale : nullptr; ga.bn_mean = bn ? bn->mean : nullptr; ga.bn_rstd = bn ? bn->rstd : nullptr;

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_tc(GcnTcArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* base = tc::smem_align1024(smem_raw);
   unsigned char* a_hi = base + p.o_ahi;
   unsigned char* a_lo = base + p.o_alo;
   unsigned char* b_hi = base + p.o_bhi;

@@ -1,0 +1,214 @@
+// rowtile.cuh - building blocks of the row-tile streaming kernels in gemm_tc.cu (sm_100a only).
+//
+// A row tile is TR consecutive rows of the batch (TR = 128 or 64).  Every thread owns ONE channel quad (4 consecutive
+// channels) of a tile and the rows r, r + RS, r + 2 RS, ... of it, so everything per channel - BatchNorm scale/shift,
+// dropout stream constants, bias, column sums, swizzled operand offsets - is computed once and lives in registers;
+// per tile a thread only adds a constant byte stride to its operand addresses.
+#pragma once
+#include "tc05.cuh"
+
+#ifndef CGNN_EMU
+namespace cgnn {
+namespace rt {
+
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// thread <-> (quad column q, first row r) for a tile of TR rows x 4*Q channels; Q in {8, 16, 32}
+template <int Q, int TR>
+struct QuadMap {
+  static constexpr int RS = kThreads / Q;    // rows between two quads of one thread
+  static constexpr int NQ = TR / RS;         // quads per thread per tile
+  static_assert(kThreads % Q == 0 && RS % 8 == 0 && TR % RS == 0 && NQ >= 1, "unsupported tile shape");
+};
+
+// byte offset of the quad (row, 4q) in a K-major 128B-swizzled operand of `rows` rows per 32-channel block
+__device__ __forceinline__ uint32_t kmajor_quad_offset(int row, int q, int rows) {
+  return (uint32_t)((q >> 3) * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + ((((q & 7) ^ (row & 7))) << 4));
+}
+// the same quad in an MN-major SWIZZLE_128B_BASE32B operand (row = contraction index, `rows` of them)
+__device__ __forceinline__ uint32_t mnmajor_quad_offset(int row, int q, int rows) {
+  return (uint32_t)((q >> 3) * rows * 128 + (row >> 2) * 512 + (row & 3) * 128 + (((((q & 7) >> 1) ^ (row & 3))) << 5) + ((q & 1) << 4));
+}
+// advancing a thread's row by RS (a multiple of 8) moves either offset by RS * 128 bytes
+constexpr uint32_t kRowBytes = 128;
+
+__device__ __forceinline__ void split4(float4 v, float4& h, float4& l) {
+  h = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
+  l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+__device__ __forceinline__ void sts4(unsigned char* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---- per-thread constants of one channel quad of an Act ---------------------------------------------------------
+struct ChanQuad {
+  float sc[4], sh[4];
+  uint32_t ck0, ck1;   // dropout: (c >> 1) * 0x632BE5AB + k1 for the two channel pairs of the quad
+};
+__device__ __forceinline__ void chan_quad_init(ChanQuad& cq, const Act& a, int c0, int C) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool ok = a.scale != nullptr && c0 + j < C;
+    cq.sc[j] = ok ? a.scale[c0 + j] : 1.0f;
+    cq.sh[j] = ok ? a.shift[c0 + j] : 0.0f;
+  }
+  cq.ck0 = (uint32_t)(c0 >> 1) * 0x632BE5ABu + a.k1;
+  cq.ck1 = (uint32_t)((c0 >> 1) + 1) * 0x632BE5ABu + a.k1;
+}
+// keep masks of the quad's 4 channels at global row `grow` (bit j = channel c0 + j kept); same stream as drop_keep()
+__device__ __forceinline__ uint32_t drop_keep4(const Act& a, const ChanQuad& cq, long long grow) {
+  const uint32_t rh = drop_row_hash(a, a.row_base + grow);
+  const uint32_t w0 = fmix32(rh + cq.ck0), w1 = fmix32(rh + cq.ck1);
+  return ((w0 & 0xffffu) >= a.thresh ? 1u : 0u) | ((w0 >> 16) >= a.thresh ? 2u : 0u) |
+         ((w1 & 0xffffu) >= a.thresh ? 4u : 0u) | ((w1 >> 16) >= a.thresh ? 8u : 0u);
+}
+// u = dropout(relu?(sc t + sh)) on the quad
+__device__ __forceinline__ float4 act_fwd4(const Act& a, const ChanQuad& cq, float4 t, long long grow) {
+  float y[4] = {t.x, t.y, t.z, t.w};
+  if (a.scale != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = fmaf(y[j], cq.sc[j], cq.sh[j]);
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.0f);
+  }
+  if (a.drop) {
+    const uint32_t keep = drop_keep4(a, cq, grow);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = ((keep >> j) & 1u) ? y[j] * a.keep_scale : 0.0f;
+  }
+  return make_float4(y[0], y[1], y[2], y[3]);
+}
+// dy = d act / d y * du on the quad (t = the stored pre-activation value)
+__device__ __forceinline__ float4 act_bwd4(const Act& a, const ChanQuad& cq, float4 t, float4 du, long long grow) {
+  const float tv[4] = {t.x, t.y, t.z, t.w};
+  float d[4] = {du.x, du.y, du.z, du.w};
+  uint32_t pass = 0xfu;
+  if (a.relu) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float y = a.scale != nullptr ? fmaf(tv[j], cq.sc[j], cq.sh[j]) : tv[j];
+      if (!(y > 0.0f)) pass &= ~(1u << j);
+    }
+  }
+  if (a.drop) {
+    pass &= drop_keep4(a, cq, grow);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] *= a.keep_scale;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) d[j] = ((pass >> j) & 1u) ? d[j] : 0.0f;
+  return make_float4(d[0], d[1], d[2], d[3]);
+}
+
+// BatchNorm-backward coefficients of one channel quad:  dz = bsc * (dy - s1n - xhat * s2n), xhat = (t - mean) * rstd
+struct BnQuad {
+  float bsc[4], mean[4], rstd[4], s1n[4], s2n[4];
+};
+struct BnBwdDev {
+  const float* scale; const float* mean; const float* rstd; const float* s1; const float* s2;
+  float inv_count; int train, has;
+};
+__device__ __forceinline__ void bn_quad_init(BnQuad& b, const BnBwdDev& bn, int c0, int C) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool ok = bn.has && c0 + j < C;
+    b.bsc[j] = ok ? bn.scale[c0 + j] : 1.0f;
+    b.mean[j] = ok ? bn.mean[c0 + j] : 0.0f;
+    b.rstd[j] = ok ? bn.rstd[c0 + j] : 0.0f;
+    b.s1n[j] = (ok && bn.train) ? bn.s1[c0 + j] * bn.inv_count : 0.0f;
+    b.s2n[j] = (ok && bn.train) ? bn.s2[c0 + j] * bn.inv_count : 0.0f;
+  }
+}
+__device__ __forceinline__ float4 bn_bwd4(const BnBwdDev& bn, const BnQuad& b, float4 t, float4 dy) {
+  if (!bn.has) return dy;
+  const float tv[4] = {t.x, t.y, t.z, t.w};
+  float d[4] = {dy.x, dy.y, dy.z, dy.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (bn.train) {
+      const float xh = (tv[j] - b.mean[j]) * b.rstd[j];
+      d[j] = b.bsc[j] * (d[j] - b.s1n[j] - xh * b.s2n[j]);
+    } else {
+      d[j] = b.bsc[j] * d[j];
+    }
+  }
+  return make_float4(d[0], d[1], d[2], d[3]);
+}
+
+// 4 channels c0.. of row `row` of a dense [rows, C] tensor; VEC: one 16-byte load, else bounded scalar loads
+template <bool VEC>
+__device__ __forceinline__ float4 ld_quad(const float* __restrict__ base, long long row, int C, int c0) {
+  if (VEC) return *reinterpret_cast<const float4*>(base + row * C + c0);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* s = base + row * C + c0;
+  if (c0 + 0 < C) v.x = s[0];
+  if (c0 + 1 < C) v.y = s[1];
+  if (c0 + 2 < C) v.z = s[2];
+  if (c0 + 3 < C) v.w = s[3];
+  return v;
+}
+template <bool VEC>
+__device__ __forceinline__ void st_quad(float* __restrict__ base, long long row, int C, int c0, float4 v) {
+  float* d = base + row * C + c0;
+  if (VEC) { *reinterpret_cast<float4*>(d) = v; return; }
+  if (c0 + 0 < C) d[0] = v.x;
+  if (c0 + 1 < C) d[1] = v.y;
+  if (c0 + 2 < C) d[2] = v.z;
+  if (c0 + 3 < C) d[3] = v.w;
+}
+__device__ __forceinline__ float4 mask_quad(float4 v, int c0, int C) {   // zero the channels >= C
+  if (c0 + 0 >= C) v.x = 0.0f;
+  if (c0 + 1 >= C) v.y = 0.0f;
+  if (c0 + 2 >= C) v.z = 0.0f;
+  if (c0 + 3 >= C) v.w = 0.0f;
+  return v;
+}
+
+// ---- accumulator tile -> XOR-swizzled staging [TR][NC] in shared memory (lane = row) ----------------------------
+// float4 index of quad q of row r: r * (NC/4) + (q ^ (r & 7)): conflict-free for the row-per-lane writes below and for
+// the quad-per-thread reads of the epilogues.
+__device__ __forceinline__ int stage_index(int row, int q, int QN) { return row * QN + (q ^ (row & 7)); }
+
+template <int NC>
+__device__ __forceinline__ void drain_rows_to_staging(uint32_t taddr, float4* stage, int warp, int lane) {
+  constexpr int CW = NC / 4;   // columns per warp: 4 lane quarters x 4 column groups = 16 warps
+  const int lq = warp & 3, cg = warp >> 2, row = 32 * lq + lane;
+  float v[CW];
+  tc::tmem_ld_cols<CW>(taddr + ((uint32_t)(32 * lq) << 16) + (uint32_t)(cg * CW), v);
+#pragma unroll
+  for (int j = 0; j < CW / 4; ++j)
+    stage[stage_index(row, cg * (CW / 4) + j, NC / 4)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
+// ---- MMA issue loops (one thread) -----------------------------------------------------------------------------------
+// D (+)= A B^T with K-major 128B-swizzled operands of a_rows / b_rows rows per 32-channel block, `ksteps` steps of 8
+__device__ __forceinline__ void issue_kmajor_x3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_rows, uint32_t b_hi,
+                                                uint32_t b_lo, int b_rows, int ksteps, uint32_t idesc, bool accumulate) {
+#pragma unroll 1
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t kb = (uint32_t)(ks >> 2), ko = (uint32_t)((ks & 3) * 32);
+    const uint32_t ao = kb * (uint32_t)a_rows * 128u + ko, bo = kb * (uint32_t)b_rows * 128u + ko;
+    tc::mma_tf32x3_step(d_tmem, tc::smem_desc_sw128(a_hi + ao), tc::smem_desc_sw128(a_lo + ao), tc::smem_desc_sw128(b_hi + bo),
+                        tc::smem_desc_sw128(b_lo + bo), idesc, (accumulate || ks > 0) ? 1u : 0u);
+  }
+}
+// D (+)= A^T B with MN-major operands whose contraction index is the tile row (`krows` rows, 8 per step)
+__device__ __forceinline__ void issue_mnmajor_x3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                 int krows, uint32_t idesc, bool accumulate) {
+  const uint32_t lbo = (uint32_t)krows * 128u;
+#pragma unroll 1
+  for (int ks = 0; ks < krows / 8; ++ks) {
+    const uint32_t off = (uint32_t)ks * 1024u;
+    tc::mma_tf32x3_step(d_tmem, tc::smem_desc_mn32(a_hi + off, lbo, 512u), tc::smem_desc_mn32(a_lo + off, lbo, 512u),
+                        tc::smem_desc_mn32(b_hi + off, lbo, 512u), tc::smem_desc_mn32(b_lo + off, lbo, 512u), idesc,
+                        (accumulate || ks > 0) ? 1u : 0u);
+  }
+}
+
+}  // namespace rt
+}  // namespace cgnn
+#endif

@@ -55,7 +55,7 @@ struct SageFwdArgs {
   const int32_t* in_rowptr; const int32_t* in_col; const float* in_w; const float* wsum;
   const int32_t* meta; long long B;
   int K, H, K4, H4, ldc, max_nodes, max_edges, csr_smem;
-  float* z; double* partials;
+  float* z; double* partials; float* agg_out;
   int o_wt, o_scale, o_shift, o_bias, o_u, o_cat, o_out, o_st, o_csr;
 };
 
@@ -129,6 +129,15 @@ __global__ void __launch_bounds__(kThreads) k_sage_fwd(SageFwdArgs p) {
       const int rows = min(kChunkRows, n - r0);
       sage_cat_rows<CC>(s_u, K4, s_cat, ldc, r0, rows, n, nb, rc, wsum_g);
       __syncthreads();
+      if (p.agg_out) {   // the aggregated neighbourhood, kept for backward
+        for (int r = warp; r < rows; r += kWarps) {
+#pragma unroll
+          for (int j = 0; j < CC; ++j) {
+            const int ch = lane + 32 * j;
+            if (ch < K) p.agg_out[(nb + r0 + r) * K + ch] = s_cat[r * ldc + K4 + ch];
+          }
+        }
+      }
       for (int t = tid; t < ntiles; t += kThreads) {
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
         if (4 * ty >= rows) continue;
@@ -530,7 +539,7 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
       2 * d_in <= 128 && (2 * d_in + 31) / 32 != 3 && (d_in <= 32 || d_in % 32 == 0) && aligned16(agg) && aligned16(z)) {
     GatherArgs ga{};
     ga.meta = csr->graph_meta; ga.B = num_graphs; ga.blob = csr->agg_in;
-    ga.C = d_in; ga.max_nodes = max_nodes;
+    ga.C = d_in; ga.max_nodes = max_nodes; ga.max_edges = max_edges;
     ga.src = t_in; ga.act = make_act(act); ga.out = agg;
     int g1 = 0, g2 = 0;
     int rc = launch_gather(GATHER_SAGE_FWD, ga, &g1, stream);
@@ -551,7 +560,7 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
   a.K = d_in; a.H = H; a.K4 = round_up(d_in, 4); a.H4 = round_up(H, 4); a.ldc = 2 * a.K4 + 4;
   a.max_nodes = max_nodes < 1 ? 1 : max_nodes;
   a.max_edges = max_edges;
-  a.z = z;
+  a.z = z; a.agg_out = agg;
   if (a.H4 > 256 || a.K4 > 256) return CGNN_ERR_TILE_TOO_LARGE;
   int off = 0;
   a.o_wt = off; off += 2 * a.K4 * a.H4;
@@ -616,6 +625,42 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
   if (du_in && (!scratch || !csr->out_rowptr || !csr->out_col || !csr->out_w)) return CGNN_ERR_INVALID_ARG;
   if (prev_sums && (!du_in || !prev_mean || !prev_rstd)) return CGNN_ERR_INVALID_ARG;
   if (bn && (!bn->scale || !bn->mean || !bn->rstd || (bn->train && (!bn->s1 || !bn->s2)))) return CGNN_ERR_INVALID_ARG;
+#ifndef CGNN_EMU
+  // Tensor-core generation: tcgen05 contractions (dz on load, [d_u || d_agg], dW, dbias) + transposed gather kernel.
+  if (tensor_cores_enabled() && agg && csr->agg_out && csr->row_graph && csr->agg_kind == AGG_SAGE &&
+      (H == 32 || H == 64 || H == 128) && 2 * d_in <= 128 && (2 * d_in + 31) / 32 != 3 && (d_in <= 32 || d_in % 32 == 0) &&
+      aligned16(z) && (!du || aligned16(du)) && (!demb || aligned16(demb)) && (!du_in || (scratch && aligned16(scratch))) &&
+      (!du_in || gather_supported(d_in, max_nodes, max_edges))) {
+    const int part_stride = H * 2 * d_in + H;
+    const size_t region_a = (size_t)160 * part_stride * sizeof(float);   // partial records of <= 160 CTAs
+    if (workspace_bytes > region_a + (size_t)2 * 160 * 2 * d_in * sizeof(float)) {
+      int g1 = 0, g2 = 0;
+      float* direct = du_in ? scratch : nullptr;
+      float* nbr = du_in ? scratch + (size_t)rows * d_in : nullptr;
+      int rc = launch_sage_bwd_gemm(du, demb, csr->row_graph, csr->graph_meta, z, act_out, bn, t_in, agg, act_in, W, rows, d_in, H,
+                                    direct, nbr, (float*)workspace, part_stride, H * 2 * d_in, &g1, region_a, stream);
+      if (rc > 0) return rc;
+      if (rc == CGNN_OK) {
+        rc = launch_reduce_partials((const float*)workspace, g1, part_stride, H, 2 * d_in, 2 * d_in, dW, stream);
+        if (rc) return rc;
+        rc = launch_reduce_partials((const float*)workspace + H * 2 * d_in, g1, part_stride, 1, H, H, dbias, stream);
+        if (rc) return rc;
+        if (!du_in) return CGNN_OK;
+        GatherArgs ga{};
+        ga.meta = csr->graph_meta; ga.B = num_graphs; ga.blob = csr->agg_out;
+        ga.C = d_in; ga.max_nodes = max_nodes; ga.max_edges = max_edges;
+        ga.src = nbr; ga.act = make_act(act_in); ga.direct = direct; ga.t_raw = t_in;
+        ga.prev_mean = prev_mean; ga.prev_rstd = prev_rstd; ga.want_prev = prev_sums ? 1 : 0;
+        ga.out = du_in;
+        ga.partials = (float*)((char*)workspace + region_a); ga.part_stride = 2 * d_in;
+        rc = launch_gather(GATHER_SAGE_BWD, ga, &g2, stream);
+        if (rc != CGNN_OK) return rc > 0 ? rc : CGNN_ERR_TILE_TOO_LARGE;
+        if (prev_sums) return launch_reduce_partials(ga.partials, g2, 2 * d_in, 2, d_in, d_in, prev_sums, stream);
+        return CGNN_OK;
+      }
+    }
+  }
+#endif
   const DeviceInfo dev = device_info();
   SageBwdArgs a;
   a.du = du; a.demb = demb; a.z = z; a.act_out = make_act(act_out);

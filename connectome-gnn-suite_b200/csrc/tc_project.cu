@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(128) k_project_tf32x3(const float* __restrict_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* base = tc::smem_align1024(smem_raw);
   const int kblocks = K >> 5;
   unsigned char* a_hi = base;
   unsigned char* a_lo = a_hi + kblocks * kTcRows * 128;

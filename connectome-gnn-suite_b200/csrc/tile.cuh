@@ -67,7 +67,7 @@ struct WarpStats {
 #pragma unroll
     for (int j = 0; j < HC; ++j) w[j].init();
   }
-  __device__ __forceinline__ void begin_row(float& inv) { rows += 1; inv = 1.0f / (float)rows; }
+  __device__ __forceinline__ void begin_row(float& inv) { rows += 1; inv = fast_rcp((float)rows); }
   // Deposit into shared scratch: s_cnt[warp], s_mean[warp*ldc + c], s_m2[...]
   __device__ __forceinline__ void deposit(float* s_cnt, float* s_mean, float* s_m2, int ldc, int C4) const {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
