@@ -32,7 +32,7 @@ static inline __host__ __device__ int agg_smem_words(int max_nodes, int max_edge
 // returns acc = sum over that row's records of w * tile[nbr][quad] (tile rows are LPR float4 wide), the row's aux
 // word and whether the row exists.  Records are read two at a time (rows are padded to an even count); the rows of a
 // group run in lock step up to the shortest one, the remainder is predicated.
-template <int LPR>
+template <int LPR, int PITCH = LPR>
 static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__ s_desc, const int4* __restrict__ s_rec2,
                                                         const float4* __restrict__ tile4, int i0, int n, float4& acc, float& aux,
                                                         int& row) {
@@ -55,7 +55,7 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
 #pragma unroll 2
   for (; k < lmin; k += 2, e += 2) {
     const int4 r = s_rec2[e >> 1];
-    const float4 v0 = t4[r.x * LPR], v1 = t4[r.z * LPR];
+    const float4 v0 = t4[r.x * PITCH], v1 = t4[r.z * PITCH];
     const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
     a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
     a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
@@ -63,7 +63,7 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
   for (; k < lmax; k += 2, e += 2) {
     if (k < len) {
       const int4 r = s_rec2[e >> 1];
-      const float4 v0 = t4[r.x * LPR], v1 = t4[r.z * LPR];
+      const float4 v0 = t4[r.x * PITCH], v1 = t4[r.z * PITCH];
       const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
       a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
       a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
@@ -112,6 +112,10 @@ int launch_sage_bwd_gemm(const float* du, const float* demb, const int32_t* row_
                          const cgnn_act_t* act_in, const float* W, int64_t rows, int32_t C, int32_t H, float* direct,
                          float* nbr, float* partials, int part_stride, int o_pdb, int* grid_out, size_t partial_bytes,
                          cudaStream_t stream);
+// gcn_fused.cu: the whole GCN forward layer (gather -> tensor-core projection) in one kernel
+int launch_gcn_fwd_fused(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+                         int64_t num_graphs, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
+                         double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream);
 #endif
 // true when launch_gather covers C channels (checked before a tensor-core contraction commits to the gather that follows)
 bool gather_supported(int C, int max_nodes, int max_edges);
