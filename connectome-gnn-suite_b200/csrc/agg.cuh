@@ -41,7 +41,6 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
   const bool valid = row < n;
   int4 d = make_int4(0, 0, 0, 0);
   if (valid) d = s_desc[row];
-  int e = d.x;
   const int len = d.y - d.x;
   int lmin = len, lmax = len;
 #pragma unroll
@@ -50,24 +49,25 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
     lmax = max(lmax, __shfl_xor_sync(kFull, lmax, o));
   }
   const float4* t4 = tile4 + cl;
+  const int4* rp = s_rec2 + (d.x >> 1);
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   int k = 0;
-#pragma unroll 2
-  for (; k < lmin; k += 2, e += 2) {
-    const int4 r = s_rec2[e >> 1];
+#pragma unroll 1
+  for (; k < lmin; k += 2, ++rp) {        // every row of the group has these records
+    const int4 r = *rp;
     const float4 v0 = t4[r.x * PITCH], v1 = t4[r.z * PITCH];
     const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
     a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
     a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
   }
-  for (; k < lmax; k += 2, e += 2) {
-    if (k < len) {
-      const int4 r = s_rec2[e >> 1];
-      const float4 v0 = t4[r.x * PITCH], v1 = t4[r.z * PITCH];
-      const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
-      a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
-      a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
-    }
+#pragma unroll 1
+  for (; k < lmax; k += 2, ++rp) {        // rows that have ended contribute zero weights (and read row 0)
+    int4 r = make_int4(0, 0, 0, 0);
+    if (k < len) r = *rp;
+    const float4 v0 = t4[r.x * PITCH], v1 = t4[r.z * PITCH];
+    const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
+    a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
+    a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
   }
   acc = a;
   aux = __int_as_float(d.z);

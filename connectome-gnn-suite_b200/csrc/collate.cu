@@ -161,52 +161,78 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
     if ((unsigned)s >= (unsigned)n || (unsigned)d >= (unsigned)n) { s = 0; d = 0; w = 0.0f; }
   };
 
-  for (int i = tid; i < n; i += kThreads) { cur_in[i] = 0; cur_out[i] = 0; }
+  // Stable counting sort by destination (in-CSR) and by source (out-CSR), all 16 warps: the COO list is cut into
+  // kChunks contiguous chunks; warp (dir, chunk) counts its chunk's keys, a scan over (key, chunk) turns the counts
+  // into the first slot of every (chunk, key) pair, then every warp places its chunk 32 edges at a time - lanes that
+  // share a key take consecutive slots in lane order, so the order inside a row is the COO order.
+  constexpr int kChunks = kWarps / 2;
+  int* cnt = reinterpret_cast<int*>(s_dinv + n);        // [2][kChunks][n]
+  const int dir = warp / kChunks, chunk = warp % kChunks;
+  const int clen = (((m + kChunks - 1) / kChunks) + 31) & ~31;
+  const int e_lo = min(chunk * clen, m), e_hi = min(e_lo + clen, m);
+  int* my_cnt = cnt + (size_t)(dir * kChunks + chunk) * n;
+  for (int i = tid; i < 2 * kChunks * n; i += kThreads) cnt[i] = 0;
   __syncthreads();
   if (n > 0)
-    for (int e = tid; e < m; e += kThreads) {
+    for (int e = e_lo + lane; e < e_hi; e += 32) {
       int s, d; float w; edge(e, s, d, w);
-      atomicAdd(&cur_in[d], 1);
-      atomicAdd(&cur_out[s], 1);
+      atomicAdd(&my_cnt[dir == 0 ? d : s], 1);
     }
+  __syncthreads();
+  for (int idx = tid; idx < 2 * n; idx += kThreads) {
+    const int dd = idx / n, i = idx - dd * n;
+    int t = 0;
+    for (int c = 0; c < kChunks; ++c) t += cnt[(size_t)(dd * kChunks + c) * n + i];
+    (dd == 0 ? cur_in : cur_out)[i] = t;
+  }
   __syncthreads();
   block_excl_scan(cur_in, n, s_warp);
   block_excl_scan(cur_out, n, s_warp);
-  for (int i = tid; i < n; i += kThreads) {
-    p.csr.in_rowptr[nb + i] = (int32_t)(eb + cur_in[i]);
-    p.csr.out_rowptr[nb + i] = (int32_t)(eb + cur_out[i]);
+  for (int idx = tid; idx < 2 * n; idx += kThreads) {
+    const int dd = idx / n, i = idx - dd * n;
+    int run = (dd == 0 ? cur_in : cur_out)[i];
+    (dd == 0 ? p.csr.in_rowptr : p.csr.out_rowptr)[nb + i] = (int32_t)(eb + run);
+    for (int c = 0; c < kChunks; ++c) {
+      int* q = &cnt[(size_t)(dd * kChunks + c) * n + i];
+      const int t = *q;
+      *q = run;
+      run += t;
+    }
   }
   if (g == p.B - 1 && tid == 0) {
     p.csr.in_rowptr[p.total_rows] = (int32_t)p.total_edges;
     p.csr.out_rowptr[p.total_rows] = (int32_t)p.total_edges;
   }
   __syncthreads();
-
-  // Stable placement: warp 0 builds the by-destination CSR, warp 1 the by-source CSR.  Edges are
-  // visited 32 at a time in COO order; lanes that share a row take consecutive slots in lane order.
-  if (warp < 2 && n > 0) {
-    int* cur = warp == 0 ? cur_in : cur_out;
-    int32_t* col = warp == 0 ? p.csr.in_col : p.csr.out_col;
-    float* wv = warp == 0 ? p.csr.in_w : p.csr.out_w;
-    for (int e0 = 0; e0 < m; e0 += 32) {
+  if (n > 0) {
+    int32_t* col = dir == 0 ? p.csr.in_col : p.csr.out_col;
+    float* wv = dir == 0 ? p.csr.in_w : p.csr.out_w;
+    for (int e0 = e_lo; e0 < e_hi; e0 += 32) {
       const int e = e0 + lane;
       int s = 0, d = 0; float w = 0.0f;
-      const bool live = e < m;
+      const bool live = e < e_hi;
       if (live) edge(e, s, d, w);
-      const int key = live ? (warp == 0 ? d : s) : -1 - lane;
+      const int key = live ? (dir == 0 ? d : s) : -1 - lane;
       const unsigned peers = __match_any_sync(kFull, key);
       const int rank = __popc(peers & ((1u << lane) - 1u));
       int start = 0;
-      if (live) start = cur[key];
+      if (live) start = my_cnt[key];
       __syncwarp();
       if (live) {
         const long long pos = eb + start + rank;
-        col[pos] = (int32_t)(nb + (warp == 0 ? s : d));
+        col[pos] = (int32_t)(nb + (dir == 0 ? s : d));
         wv[pos] = w;
-        if (rank == 0) cur[key] = start + __popc(peers);
+        if (rank == 0) my_cnt[key] = start + __popc(peers);
       }
       __syncwarp();
     }
+  }
+  __syncthreads();
+  // cur_in / cur_out hold the exclusive row starts; the passes below want the inclusive ends (start of row i + 1)
+  for (int idx = tid; idx < 2 * n; idx += kThreads) {
+    const int dd = idx / n, i = idx - dd * n;
+    const int* c = cnt + (size_t)(dd * kChunks + kChunks - 1) * n;
+    (dd == 0 ? cur_in : cur_out)[i] = c[i];     // the last chunk's cursor of row i ended at the row's end
   }
   __syncthreads();
 
@@ -254,7 +280,7 @@ static bool csr_out_ok(const cgnn_csr_out_t* c) {
 static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaStream_t stream) {
   const DeviceInfo dev = device_info();
   if (max_nodes < 1) max_nodes = 1;
-  size_t smem = (size_t)max_nodes * 12 + 16;
+  size_t smem = (size_t)max_nodes * (12 + 4 * kWarps) + 16;   // cursors, dinv, per-chunk counters
   if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   a.max_nodes = max_nodes;
   if (a.B <= 0) return CGNN_OK;
