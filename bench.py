@@ -188,7 +188,7 @@ def run_reference(a):
 def run_b200(a):
     import torch.distributed as dist
     from connectome_gnn import _engine, _lib
-    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.graph import StreamingStore, SubjectStore, pack_graphs
     from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
     from connectome_gnn.synthetic import generate_dataset
     from connectome_gnn.train import Trainer
@@ -241,10 +241,17 @@ def run_b200(a):
         for name in LEGS:
             leg(name, store)
 
+    streaming = StreamingStore(pinned, dev)
+
     def step_e2e():
+        """Every leg's subjects travel pinned host -> device inside the timed region; the upload of leg k+1 runs on
+        the loader's copy stream while leg k computes, and every leg ends with its loss read back to the host."""
         out = None
-        for name in LEGS:
-            st = SubjectStore(pinned, dev)           # pinned host -> device copy of this batch's subjects
+        streaming.prefetch(pinned)
+        for i, name in enumerate(LEGS):
+            st = streaming.next()
+            if i + 1 < len(LEGS):
+                streaming.prefetch(pinned)
             out = float(leg(name, st))               # loss read back to the host
         return out
 
@@ -306,7 +313,7 @@ def run_b200(a):
         e2e = {"value": graphs_per_step * e2e_steps / (ms_e / 1e3), "unit": "graphs/s",
                "h2d_bytes_per_step": int(h2d_bytes * len(LEGS)), "d2h_bytes_per_step": 4 * len(LEGS),
                "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
-               "path": "pinned host arena -> SubjectStore (H2D) -> collate -> Trainer.train_step/eval_step -> float(loss)"}
+               "path": "pinned host arena -> StreamingStore (H2D on a copy stream, double-buffered) -> collate -> Trainer.train_step/eval_step -> float(loss)"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------------
     cpu = None

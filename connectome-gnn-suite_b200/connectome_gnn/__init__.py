@@ -16,6 +16,7 @@ from .graph import (  # noqa: E402
     ConnectomeBatch,
     ConnectomeDataLoader,
     ConnectomeGraph,
+    StreamingStore,
     SubjectStore,
     collate_graphs,
 )
@@ -27,5 +28,6 @@ __all__ = [
     "ConnectomeGraph", "ConnectomeBatch", "ConnectomeDataLoader", "collate_graphs",
     "generate_connectome", "generate_dataset", "REGION_NAMES",
     "GCNConnectome", "GraphSAGEConnectome", "Trainer",
+    "StreamingStore",
     "SubjectStore",
 ]

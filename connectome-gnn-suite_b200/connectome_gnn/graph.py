@@ -16,6 +16,8 @@ import math
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
+import contextlib
+
 import numpy as np
 import torch
 
@@ -231,6 +233,26 @@ class SubjectStore:
     def from_graphs(cls, graphs: Sequence[ConnectomeGraph], device=None) -> "SubjectStore":
         return cls(pack_graphs(graphs), device)
 
+    def reload(self, packed: dict, stream: Optional["torch.cuda.Stream"] = None) -> "SubjectStore":
+        """Overwrite this store's device arenas with another packed set of the same shapes (host tensors, ideally
+        pinned), enqueued on ``stream`` (default: the current stream).  ``collate`` makes the consuming stream wait
+        for the upload, so a side stream overlaps the copy with whatever the compute stream is still doing - the
+        building block of :class:`StreamingStore`."""
+        names = ("x", "src", "dst", "w", "node_ptr", "edge_ptr", "label")
+        for k in names:
+            if tuple(packed[k].shape) != tuple(getattr(self, k).shape) or packed[k].dtype != getattr(self, k).dtype:
+                raise ValueError(f"reload: '{k}' differs in shape or dtype from the resident arena")
+        self.node_ptr_host = packed["node_ptr"].numpy()
+        self.edge_ptr_host = packed["edge_ptr"].numpy()
+        self.has_label = np.asarray(packed["has_label"], dtype=bool)
+        ctx = torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+        with ctx:
+            for k in names:
+                getattr(self, k).copy_(packed[k], non_blocking=True)
+            self._ready = torch.cuda.Event()
+            self._ready.record()
+        return self
+
     def __len__(self) -> int:
         return int(self.node_ptr_host.shape[0]) - 1
 
@@ -251,6 +273,9 @@ class SubjectStore:
         all_labelled = bool(labelled.all()) and ids_np.size > 0
         if ids_device is None:
             ids_device = torch.from_numpy(ids_np).to(self.device, non_blocking=True)
+        ready = getattr(self, "_ready", None)
+        if ready is not None:      # an upload enqueued on another stream (reload): order this stream after it
+            torch.cuda.current_stream(self.device).wait_event(ready)
         eng = _engine.engine_for(self.x)
         out, csr = eng.collate_csr(self._struct, ids_device, int(ids_np.size), rows, edges, max_nodes,
                                    self.num_features, all_labelled)
@@ -263,6 +288,42 @@ class SubjectStore:
             out["node_features"], out["edge_index"], out["edge_weight"], out["batch"], labels, out["ptr"],
             BatchCSR(**csr, eptr=out["eptr"], max_nodes=max_nodes, max_edges=max_edges), row_base, graph_base,
             global_num_graphs, global_num_nodes)
+
+
+class StreamingStore:
+    """Subjects that live in (pinned) host memory and visit the GPU one packed set at a time: two device arenas, the
+    upload of set k+1 runs on a side stream while set k is being collated and processed (pinned-host
+    staging for datasets that do not stay resident).  Usage::
+
+        ss = StreamingStore(packed_sets[0], device)
+        ss.prefetch(packed_sets[0])
+        for k in range(len(packed_sets)):
+            store = ss.next()                       # set k, upload ordered before this stream's next kernels
+            if k + 1 < len(packed_sets):
+                ss.prefetch(packed_sets[k + 1])     # starts now, overlaps the work below
+            batch = store.collate(ids)
+            ...
+
+    All sets must have the shapes of the first one (same subjects-per-set layout); the caller must have finished
+    using arena k-2 (e.g. by reading a result back to the host) before ``prefetch`` reuses it."""
+
+    def __init__(self, packed: dict, device=None):
+        self.device = torch.device(device) if device is not None else _engine.default_device()
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._arenas = [SubjectStore(packed, self.device), SubjectStore(packed, self.device)]
+        torch.cuda.current_stream(self.device).synchronize()
+        self._filled, self._taken = 0, 0
+
+    def prefetch(self, packed: dict) -> None:
+        self._arenas[self._filled % 2].reload(packed, self.stream)
+        self._filled += 1
+
+    def next(self) -> SubjectStore:
+        if self._taken >= self._filled:
+            raise RuntimeError("StreamingStore.next() without a matching prefetch()")
+        store = self._arenas[self._taken % 2]
+        self._taken += 1
+        return store
 
 
 def collate_graphs(graphs: list) -> ConnectomeBatch:

@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(256) k_build_agg(BuildAggArgs p) {
 // One CTA works on one 4*LPR-channel slab of one subject at a time (two CTAs per SM for the 32-channel slabs of a
 // 360-node subject): the subject's blob arrives by cp.async while the threads transform their channel quad of the
 // tile on the way into shared memory; then 32 / LPR rows per warp are gathered with float4 lanes from shared memory.
-template <int MODE, int LPR>
-__global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p, int vec) {
+template <int MODE, int LPR, bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
   CGNN_SMEM_DECL;
   constexpr int RP = kThreads / LPR;    // tile rows per load pass
   constexpr int RPW = 32 / LPR;         // rows per warp in the gather
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p, int vec) {
 
   rt::ChanQuad cq;
   rt::chan_quad_init(cq, p.act, c0, C);
+  const rt::RowKey rk = rt::row_key(p.act);
   rt::BnBwdDev bn;
   bn.scale = p.bn_scale; bn.mean = p.bn_mean; bn.rstd = p.bn_rstd; bn.s1 = p.bn_s1; bn.s2 = p.bn_s2;
   bn.inv_count = p.inv_count; bn.train = p.bn_train; bn.has = p.has_bn;
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p, int vec) {
     const float inv_n = 1.0f / ((float)n + 1e-8f);
     float4 pooled = make_float4(0.f, 0.f, 0.f, 0.f);
     if (MODE == GATHER_GCN_BWD && !p.du && live_quad) {
-      pooled = vec ? rt::ld_quad<true>(p.demb, g, C, c0) : rt::ld_quad<false>(p.demb, g, C, c0);
+      pooled = rt::ld_quad<VEC>(p.demb, g, C, c0);
       pooled = make_float4(pooled.x * inv_n, pooled.y * inv_n, pooled.z * inv_n, pooled.w * inv_n);
     }
     for (int r = rl; r < n; r += 2 * RP) {
@@ -151,8 +152,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p, int vec) {
         a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         b[u] = pooled;
         if (rr < n && live_quad) {
-          a[u] = vec ? rt::ld_quad<true>(p.src, nb + rr, C, c0) : rt::ld_quad<false>(p.src, nb + rr, C, c0);
-          if (MODE == GATHER_GCN_BWD && p.du) b[u] = vec ? rt::ld_quad<true>(p.du, nb + rr, C, c0) : rt::ld_quad<false>(p.du, nb + rr, C, c0);
+          a[u] = rt::ld_quad<VEC>(p.src, nb + rr, C, c0);
+          if (MODE == GATHER_GCN_BWD && p.du) b[u] = rt::ld_quad<VEC>(p.du, nb + rr, C, c0);
         }
       }
 #pragma unroll
@@ -160,13 +161,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p, int vec) {
         const int rr = r + u * RP;
         if (rr < n) {
           float4 o = a[u];
-          if (MODE == GATHER_SAGE_FWD) o = rt::act_fwd4(p.act, cq, a[u], nb + rr);
+          if (MODE == GATHER_SAGE_FWD) o = rt::act_fwd4(p.act, cq, a[u], rk, (uint32_t)(nb + rr));
           if (MODE == GATHER_GCN_BWD) {
-            o = rt::bn_bwd4(bn, bq, a[u], rt::act_bwd4(p.act, cq, a[u], b[u], nb + rr));
-            o = rt::mask_quad(o, c0, C);
+            o = rt::bn_bwd4(bn, bq, a[u], rt::act_bwd4(p.act, cq, a[u], b[u], rk, (uint32_t)(nb + rr)));
+            if (!VEC) o = rt::mask_quad(o, c0, C);
             s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
           }
-          o = rt::mask_quad(o, c0, C);
+          if (!VEC) o = rt::mask_quad(o, c0, C);
           s_tile[rr * LPR + cl] = o;
         }
       }
@@ -188,11 +189,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p, int vec) {
         acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
       }
       if (MODE == GATHER_SAGE_BWD) {
-        const float4 d = vec ? rt::ld_quad<true>(p.direct, grow, C, c0) : rt::ld_quad<false>(p.direct, grow, C, c0);
+        const float4 d = rt::ld_quad<VEC>(p.direct, grow, C, c0);
         acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
         if (p.want_prev) {
-          const float4 raw = vec ? rt::ld_quad<true>(p.t_raw, grow, C, c0) : rt::ld_quad<false>(p.t_raw, grow, C, c0);
-          const float4 dyp = rt::act_bwd4(p.act, cq, raw, acc, grow);
+          const float4 raw = rt::ld_quad<VEC>(p.t_raw, grow, C, c0);
+          const float4 dyp = rt::act_bwd4(p.act, cq, raw, acc, rk, (uint32_t)grow);
           const float rv[4] = {raw.x, raw.y, raw.z, raw.w}, dv[4] = {dyp.x, dyp.y, dyp.z, dyp.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -204,8 +205,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p, int vec) {
           }
         }
       }
-      if (vec) rt::st_quad<true>(p.out, grow, C, c0, acc);
-      else rt::st_quad<false>(p.out, grow, C, c0, acc);
+      rt::st_quad<VEC>(p.out, grow, C, c0, acc);
     }
     __syncthreads();   // tile and blob are rewritten by the next subject
   }
@@ -274,13 +274,17 @@ int launch_gather(int mode, GatherArgs& a, int* grid_out, cudaStream_t stream) {
   if (grid > a.B * nslab) grid = a.B * nslab;
   if (grid < nslab) grid = nslab;
   *grid_out = (int)grid;
-#define CGNN_GATHER(MODE_, LPR_)                                                                         \
+#define CGNN_GATHER(MODE_, LPR_, VEC_)                                                                   \
   {                                                                                                      \
-    auto kfn = k_gather<MODE_, LPR_>;                                                                    \
+    auto kfn = k_gather<MODE_, LPR_, VEC_>;                                                              \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    CGNN_LAUNCH(kfn, (unsigned)grid, kThreads, smem, stream, a, vec);                                    \
+    CGNN_LAUNCH(kfn, (unsigned)grid, kThreads, smem, stream, a);                                         \
   }
-#define CGNN_GATHER_L(MODE_) { if (LPR == 2) CGNN_GATHER(MODE_, 2) else CGNN_GATHER(MODE_, 8) }
+#define CGNN_GATHER_L(MODE_)                                                                             \
+  {                                                                                                      \
+    if (LPR == 2) { if (vec) CGNN_GATHER(MODE_, 2, true) else CGNN_GATHER(MODE_, 2, false) }             \
+    else { if (vec) CGNN_GATHER(MODE_, 8, true) else CGNN_GATHER(MODE_, 8, false) }                      \
+  }
   if (mode == GATHER_SAGE_FWD) CGNN_GATHER_L(GATHER_SAGE_FWD)
   else if (mode == GATHER_GCN_BWD) CGNN_GATHER_L(GATHER_GCN_BWD)
   else CGNN_GATHER_L(GATHER_SAGE_BWD)

@@ -32,8 +32,8 @@ struct GcnFusedArgs {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // KB = padded K / 32, HB = H / 32, LPR = float4 lanes per tile row (K / 4 when K is a multiple of 32, else 2: K <= 8)
-template <int KB, int HB, int LPR>
-__global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_fused(GcnFusedArgs p, int vec) {
+template <int KB, int HB, int LPR, bool VEC>
+__global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_fused(GcnFusedArgs p) {
   constexpr int KP = 32 * KB, H = 32 * HB, TR = 128;
   constexpr int A_HALF = KB * TR * 128, B_HALF = KB * H * 128;
   constexpr int RP = kThreads / LPR;                    // tile rows per load pass
@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_fused(GcnFusedArgs p, i
   }
   rt::ChanQuad cq;
   rt::chan_quad_init(cq, p.act, c0, K);
+  const rt::RowKey rk = rt::row_key(p.act);
   const int qh = tid % QH, rh = tid / QH;
   float bias4[4];
 #pragma unroll
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_fused(GcnFusedArgs p, i
     for (int i = 0; i < NPF; ++i) {
       const int r = rl + i * RP;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < m.y && live_quad) v = vec ? rt::ld_quad<true>(p.t_in, (long long)m.x + r, K, c0) : rt::ld_quad<false>(p.t_in, (long long)m.x + r, K, c0);
+      if (r < m.y && live_quad) v = rt::ld_quad<VEC>(p.t_in, (long long)m.x + r, K, c0);
       pre[i] = v;
     }
   };
@@ -115,12 +116,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_fused(GcnFusedArgs p, i
 #pragma unroll
     for (int i = 0; i < NPF; ++i) {
       const int r = rl + i * RP;
-      if (r < m.y) s_tile[r * LPR + cl] = rt::mask_quad(rt::act_fwd4(p.act, cq, pre[i], (long long)m.x + r), c0, K);
+      if (r < m.y) s_tile[r * LPR + cl] = rt::mask_quad(rt::act_fwd4(p.act, cq, pre[i], rk, (uint32_t)(m.x + r)), c0, K);
     }
     for (int r = rl + NPF * RP; r < m.y; r += RP) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live_quad) v = vec ? rt::ld_quad<true>(p.t_in, (long long)m.x + r, K, c0) : rt::ld_quad<false>(p.t_in, (long long)m.x + r, K, c0);
-      s_tile[r * LPR + cl] = rt::mask_quad(rt::act_fwd4(p.act, cq, v, (long long)m.x + r), c0, K);
+      if (live_quad) v = rt::ld_quad<VEC>(p.t_in, (long long)m.x + r, K, c0);
+      s_tile[r * LPR + cl] = rt::mask_quad(rt::act_fwd4(p.act, cq, v, rk, (uint32_t)(m.x + r)), c0, K);
     }
   };
 
@@ -294,14 +295,16 @@ int launch_gcn_fwd_fused(const float* t_in, const cgnn_act_t* act, const float* 
   }
   if (grid < 1) return -1;
   *grid_out = (int)grid;
-#define CGNN_GF(KB_, HB_, LPR_)                                                                        \
+#define CGNN_GF(KB_, HB_, LPR_, VEC_)                                                                 \
   {                                                                                                   \
-    auto kfn = k_gcn_fwd_fused<KB_, HB_, LPR_>;                                                       \
+    auto kfn = k_gcn_fwd_fused<KB_, HB_, LPR_, VEC_>;                                                 \
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
-    CGNN_LAUNCH(kfn, (unsigned)grid, kThreads, smem, stream, a, vec);                                 \
+    CGNN_LAUNCH(kfn, (unsigned)grid, kThreads, smem, stream, a);                                      \
   }
-#define CGNN_GF_H(KB_, LPR_) { if (HB == 1) CGNN_GF(KB_, 1, LPR_) else if (HB == 2) CGNN_GF(KB_, 2, LPR_) else CGNN_GF(KB_, 4, LPR_) }
-  if (LPR == 2) CGNN_GF_H(1, 2) else if (LPR == 8) CGNN_GF_H(1, 8) else CGNN_GF_H(2, 16)
+#define CGNN_GF_H(KB_, LPR_, VEC_) { if (HB == 1) CGNN_GF(KB_, 1, LPR_, VEC_) else if (HB == 2) CGNN_GF(KB_, 2, LPR_, VEC_) else CGNN_GF(KB_, 4, LPR_, VEC_) }
+  if (LPR == 2) { if (vec) CGNN_GF_H(1, 2, true) else CGNN_GF_H(1, 2, false) }
+  else if (!vec) return -1;
+  else if (LPR == 8) CGNN_GF_H(1, 8, true) else CGNN_GF_H(2, 16, true)
 #undef CGNN_GF_H
 #undef CGNN_GF
   CGNN_CHECK_LAUNCH();

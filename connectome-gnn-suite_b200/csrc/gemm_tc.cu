@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_fwd_gemm(SageFwdGemmArgs p
   const int qc = tid % QC, rc = tid / QC;
   rt::ChanQuad cq;
   rt::chan_quad_init(cq, p.act, 4 * qc, C);
+  const rt::RowKey rk = rt::row_key(p.act);
   const uint32_t koff_u = rt::kmajor_quad_offset(rc, qc, TR);
   const uint32_t koff_a = WIDE ? rt::kmajor_quad_offset(rc, qc + QC, TR) : 0u;
   const int qh = tid % QH, rh = tid / QH;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_fwd_gemm(SageFwdGemmArgs p
       const bool live = row < p.rows;
       float4 h, l;
       if constexpr (WIDE) {
-        const float4 u = live ? rt::act_fwd4(p.act, cq, pu[i], row) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 u = live ? rt::act_fwd4(p.act, cq, pu[i], rk, (uint32_t)row) : make_float4(0.f, 0.f, 0.f, 0.f);
         rt::split4(u, h, l);
         rt::sts4(a_hi + koff_u + i * MC::RS * rt::kRowBytes, h);
         rt::sts4(a_lo + koff_u + i * MC::RS * rt::kRowBytes, l);
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_bwd_gemm(GcnBwdGemmArgs p) 
   const uint32_t moff2 = rt::mnmajor_quad_offset(r2, q2, TR);
   rt::ChanQuad cq;
   rt::chan_quad_init(cq, p.act_in, c2, Kin);
+  const rt::RowKey rk = rt::row_key(p.act_in);
   float pmean[4], prstd[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_bwd_gemm(GcnBwdGemmArgs p) 
         const long long row = r0 + r2 + i * M2::RS;
         tcur[i] = tin[i];
         float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < p.rows) u = rt::mask_quad(rt::act_fwd4(p.act_in, cq, tin[i], row), c2, Kin);
+        if (row < p.rows) u = rt::mask_quad(rt::act_fwd4(p.act_in, cq, tin[i], rk, (uint32_t)row), c2, Kin);
         float4 h, l;
         rt::split4(u, h, l);
         rt::sts4(a2_hi + moff2 + i * M2::RS * rt::kRowBytes, h);
@@ -448,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_bwd_gemm(GcnBwdGemmArgs p) 
             const float4 d = stage[rt::stage_index(r, q2, Q2)];
             rt::st_quad<WIDE>(p.du_in, row, Kin, c2, d);
             if (p.want_prev) {
-              const float4 dyp = rt::act_bwd4(p.act_in, cq, tcur[i], d, row);
+              const float4 dyp = rt::act_bwd4(p.act_in, cq, tcur[i], d, rk, (uint32_t)row);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 if (WIDE || c2 + j < Kin) {
@@ -608,6 +610,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p
   rt::ChanQuad cq_out, cq_in;
   rt::chan_quad_init(cq_out, p.act_out, 4 * qh, H);
   rt::chan_quad_init(cq_in, p.act_in, 4 * qc, C);
+  const rt::RowKey rk_out = rt::row_key(p.act_out), rk_in = rt::row_key(p.act_in);
   rt::BnQuad bq;
   rt::bn_quad_init(bq, p.bn, 4 * qh, H);
   const uint32_t koff_z = rt::kmajor_quad_offset(rh, qh, TR), moff_z = rt::mnmajor_quad_offset(rh, qh, TR);
@@ -680,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p
       const long long row = r0 + rh + i * MHq::RS;
       float4 dz = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < p.rows) {
-        const float4 dy = rt::act_bwd4(p.act_out, cq_out, zq[i], uq[i], row);
+        const float4 dy = rt::act_bwd4(p.act_out, cq_out, zq[i], uq[i], rk_out, (uint32_t)row);
         dz = rt::bn_bwd4(p.bn, bq, zq[i], dy);
         if (!(zq[i].x > 0.0f)) dz.x = 0.0f;
         if (!(zq[i].y > 0.0f)) dz.y = 0.0f;
@@ -704,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p
       const bool live = row < p.rows;
       float4 h, l;
       if constexpr (WIDE) {
-        const float4 u = live ? rt::act_fwd4(p.act_in, cq_in, tq[i], row) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 u = live ? rt::act_fwd4(p.act_in, cq_in, tq[i], rk_in, (uint32_t)row) : make_float4(0.f, 0.f, 0.f, 0.f);
         rt::split4(u, h, l);
         rt::sts4(ua_hi + moff_u + i * MCq::RS * rt::kRowBytes, h);
         rt::sts4(ua_lo + moff_u + i * MCq::RS * rt::kRowBytes, l);

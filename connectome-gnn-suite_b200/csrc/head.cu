@@ -5,6 +5,7 @@
 // These are O(B*H) - negligible next to the layer kernels - so they are written for
 // clarity and determinism rather than peak throughput.
 #include "tile.cuh"
+#include "rowtile.cuh"
 
 namespace cgnn {
 
@@ -59,6 +60,47 @@ __global__ void __launch_bounds__(kThreads) k_pool_fwd(PoolArgs p) {
     __syncthreads();
   }
 }
+
+#ifndef CGNN_EMU
+// Channel-quad edition (C a multiple of 4 up to 128, 16-byte aligned rows): thread = one channel quad, four
+// independent 16-byte loads in flight per thread, two CTAs of 512 threads per SM.
+template <int Q>
+__global__ void __launch_bounds__(kThreads, 2) k_pool_fwd_quad(PoolArgs p) {
+  __shared__ float4 s_red[kThreads];
+  constexpr int RS = kThreads / Q;
+  const int tid = threadIdx.x, q = tid % Q, r = tid / Q;
+  const int C = p.C;
+  rt::ChanQuad cq;
+  rt::chan_quad_init(cq, p.act, 4 * q, C);
+  const rt::RowKey rk = rt::row_key(p.act);
+  for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
+    const long long nb = p.ptr[g];
+    const int n = (int)(p.ptr[g + 1] - nb);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = r; i < n; i += 4 * RS) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * RS < n) v[u] = rt::ld_quad<true>(p.t, nb + i + u * RS, C, 4 * q);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * RS < n) {
+          const float4 y = rt::act_fwd4(p.act, cq, v[u], rk, (uint32_t)(nb + i + u * RS));
+          acc.x += y.x; acc.y += y.y; acc.z += y.z; acc.w += y.w;
+        }
+    }
+    s_red[tid] = acc;
+    __syncthreads();
+    if (tid < C) {
+      const int qq = tid >> 2, j = tid & 3;
+      float s = 0.0f;
+      for (int t = qq; t < kThreads; t += Q) s += reinterpret_cast<const float*>(&s_red[t])[j];
+      p.emb[g * C + tid] = s / ((float)n + 1e-8f);
+    }
+    __syncthreads();
+  }
+}
+#endif
 
 // ---- MLP head forward: one warp per graph -------------------------------------------------
 struct HeadArgs {
@@ -235,6 +277,17 @@ int cgnn_pool_fwd(const float* t_in, const cgnn_act_t* act, const int64_t* ptr, 
   a.t = t_in; a.act = make_act(act); a.ptr = (const long long*)ptr; a.B = num_graphs; a.C = C; a.C4 = round_up(C, 4);
   a.emb = emb;
   if (a.C4 > 256) return CGNN_ERR_TILE_TOO_LARGE;
+#ifndef CGNN_EMU
+  if ((C == 32 || C == 64 || C == 128) && (((uintptr_t)t_in) & 15u) == 0) {
+    long long g2 = 2LL * dev.sm_count;
+    if (g2 > num_graphs) g2 = num_graphs;
+    if (C == 32) { auto kfn = k_pool_fwd_quad<8>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
+    else if (C == 64) { auto kfn = k_pool_fwd_quad<16>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
+    else { auto kfn = k_pool_fwd_quad<32>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
+    CGNN_CHECK_LAUNCH();
+    return CGNN_OK;
+  }
+#endif
   const size_t smem = (size_t)(2 * a.C4 + kWarps * a.C4) * sizeof(float);
   const int grid = persistent_grid(num_graphs, smem, dev, kThreads);
   const int cc = pick_hc(a.C4);

@@ -2,6 +2,7 @@
 // 208, 260 -> nn.BatchNorm1d defaults: eps 1e-5, momentum 0.1, affine, running stats) and the
 // standalone BatchNorm-backward reduction used for the top layer.
 #include "tile.cuh"
+#include "rowtile.cuh"
 
 namespace cgnn {
 
@@ -106,6 +107,68 @@ __global__ void __launch_bounds__(kThreads) k_bn_bwd_sums(BnSumsArgs p) {
   }
 }
 
+#ifndef CGNN_EMU
+// Channel-quad edition of k_bn_bwd_sums (C = 32 / 64 / 128, 16-byte aligned rows).
+template <int Q>
+__global__ void __launch_bounds__(kThreads, 2) k_bn_bwd_sums_quad(BnSumsArgs p) {
+  __shared__ float4 s_red[2 * kThreads];
+  constexpr int RS = kThreads / Q;
+  const int tid = threadIdx.x, q = tid % Q, r = tid / Q;
+  const int C = p.C;
+  rt::ChanQuad cq;
+  rt::chan_quad_init(cq, p.act, 4 * q, C);
+  const rt::RowKey rk = rt::row_key(p.act);
+  float mean[4], rstd[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { mean[j] = p.mean[4 * q + j]; rstd[j] = p.rstd[4 * q + j]; }
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
+    const long long nb = p.ptr[g];
+    const int n = (int)(p.ptr[g + 1] - nb);
+    float4 pooled = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!p.du) {
+      const float inv_n = 1.0f / ((float)n + 1e-8f);
+      pooled = rt::ld_quad<true>(p.demb, g, C, 4 * q);
+      pooled = make_float4(pooled.x * inv_n, pooled.y * inv_n, pooled.z * inv_n, pooled.w * inv_n);
+    }
+    for (int i = r; i < n; i += 4 * RS) {
+      float4 zv[4], uv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uv[u] = pooled;
+        if (i + u * RS < n) {
+          zv[u] = rt::ld_quad<true>(p.z, nb + i + u * RS, C, 4 * q);
+          if (p.du) uv[u] = rt::ld_quad<true>(p.du, nb + i + u * RS, C, 4 * q);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * RS < n) {
+          const float4 dy = rt::act_bwd4(p.act, cq, zv[u], uv[u], rk, (uint32_t)(nb + i + u * RS));
+          const float tv[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w}, dv[4] = {dy.x, dy.y, dy.z, dy.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xh = (tv[j] - mean[j]) * rstd[j];
+            s1[j] += dv[j];
+            s2[j] = fmaf(dv[j], xh, s2[j]);
+          }
+        }
+    }
+  }
+  s_red[tid] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+  s_red[kThreads + tid] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+  __syncthreads();
+  float* part = p.partials + (size_t)blockIdx.x * 2 * p.C4;
+  for (int idx = tid; idx < 2 * C; idx += kThreads) {
+    const int which = idx / C, c = idx - which * C;
+    const int qq = c >> 2, j = c & 3;
+    float s = 0.0f;
+    for (int t = qq; t < kThreads; t += Q) s += reinterpret_cast<const float*>(&s_red[which * kThreads + t])[j];
+    part[which * p.C4 + c] = s;
+  }
+}
+#endif
+
 }  // namespace cgnn
 
 using namespace cgnn;
@@ -158,6 +221,19 @@ int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, c
   if (workspace_bytes < rec) return CGNN_ERR_WORKSPACE;
   if ((size_t)grid * rec > workspace_bytes) grid = (int)(workspace_bytes / rec);
   a.partials = (float*)workspace;
+#ifndef CGNN_EMU
+  if ((C == 32 || C == 64 || C == 128) && (((uintptr_t)z) & 15u) == 0 && (!du || (((uintptr_t)du) & 15u) == 0) &&
+      (!demb || (((uintptr_t)demb) & 15u) == 0)) {
+    long long g2 = 2LL * dev.sm_count;
+    if (g2 > num_graphs) g2 = num_graphs;
+    if ((size_t)g2 * rec > workspace_bytes) g2 = (long long)(workspace_bytes / rec);
+    if (C == 32) { auto kfn = k_bn_bwd_sums_quad<8>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
+    else if (C == 64) { auto kfn = k_bn_bwd_sums_quad<16>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
+    else { auto kfn = k_bn_bwd_sums_quad<32>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
+    CGNN_CHECK_LAUNCH();
+    return launch_reduce_partials(a.partials, (int)g2, 2 * a.C4, 2, C, a.C4, sums, stream);
+  }
+#endif
   const int cc = pick_hc(a.C4);
 #define CGNN_BN_SUMS(CC_)                                                  \
   {                                                                        \

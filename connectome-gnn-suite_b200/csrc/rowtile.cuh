@@ -57,15 +57,34 @@ __device__ __forceinline__ void chan_quad_init(ChanQuad& cq, const Act& a, int c
   cq.ck0 = (uint32_t)(c0 >> 1) * 0x632BE5ABu + a.k1;
   cq.ck1 = (uint32_t)((c0 >> 1) + 1) * 0x632BE5ABu + a.k1;
 }
-// keep masks of the quad's 4 channels at global row `grow` (bit j = channel c0 + j kept); same stream as drop_keep()
-__device__ __forceinline__ uint32_t drop_keep4(const Act& a, const ChanQuad& cq, long long grow) {
-  const uint32_t rh = drop_row_hash(a, a.row_base + grow);
+// Dropout row key: the per-row hash of common.cuh::drop_row_hash for global row ids (row_base + row) computed from
+// 32-bit pieces - the high word's hash is formed once per kernel (and once more for rows behind a 2^32 boundary).
+struct RowKey {
+  uint32_t lo0, hh0, hh1;
+};
+__device__ __forceinline__ RowKey row_key(const Act& a) {
+  RowKey k;
+  const unsigned long long base = (unsigned long long)a.row_base;
+  k.lo0 = (uint32_t)base;
+  const uint32_t hi = (uint32_t)(base >> 32);
+  k.hh0 = fmix32(hi + a.k1);
+  k.hh1 = fmix32(hi + 1u + a.k1);
+  return k;
+}
+__device__ __forceinline__ uint32_t row_hash_at(const Act& a, const RowKey& k, uint32_t row) {
+  const uint32_t lo = k.lo0 + row;
+  const uint32_t hh = lo >= k.lo0 ? k.hh0 : k.hh1;
+  return fmix32((lo * 0x9E3779B1u) ^ a.k0 ^ hh);
+}
+// keep masks of the quad's 4 channels at row `row` of the batch (bit j = channel c0 + j kept); same stream as drop_keep()
+__device__ __forceinline__ uint32_t drop_keep4(const Act& a, const ChanQuad& cq, const RowKey& rk, uint32_t row) {
+  const uint32_t rh = row_hash_at(a, rk, row);
   const uint32_t w0 = fmix32(rh + cq.ck0), w1 = fmix32(rh + cq.ck1);
   return ((w0 & 0xffffu) >= a.thresh ? 1u : 0u) | ((w0 >> 16) >= a.thresh ? 2u : 0u) |
          ((w1 & 0xffffu) >= a.thresh ? 4u : 0u) | ((w1 >> 16) >= a.thresh ? 8u : 0u);
 }
 // u = dropout(relu?(sc t + sh)) on the quad
-__device__ __forceinline__ float4 act_fwd4(const Act& a, const ChanQuad& cq, float4 t, long long grow) {
+__device__ __forceinline__ float4 act_fwd4(const Act& a, const ChanQuad& cq, float4 t, const RowKey& rk, uint32_t row) {
   float y[4] = {t.x, t.y, t.z, t.w};
   if (a.scale != nullptr) {
 #pragma unroll
@@ -76,14 +95,14 @@ __device__ __forceinline__ float4 act_fwd4(const Act& a, const ChanQuad& cq, flo
     for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.0f);
   }
   if (a.drop) {
-    const uint32_t keep = drop_keep4(a, cq, grow);
+    const uint32_t keep = drop_keep4(a, cq, rk, row);
 #pragma unroll
     for (int j = 0; j < 4; ++j) y[j] = ((keep >> j) & 1u) ? y[j] * a.keep_scale : 0.0f;
   }
   return make_float4(y[0], y[1], y[2], y[3]);
 }
 // dy = d act / d y * du on the quad (t = the stored pre-activation value)
-__device__ __forceinline__ float4 act_bwd4(const Act& a, const ChanQuad& cq, float4 t, float4 du, long long grow) {
+__device__ __forceinline__ float4 act_bwd4(const Act& a, const ChanQuad& cq, float4 t, float4 du, const RowKey& rk, uint32_t row) {
   const float tv[4] = {t.x, t.y, t.z, t.w};
   float d[4] = {du.x, du.y, du.z, du.w};
   uint32_t pass = 0xfu;
@@ -95,7 +114,7 @@ __device__ __forceinline__ float4 act_bwd4(const Act& a, const ChanQuad& cq, flo
     }
   }
   if (a.drop) {
-    pass &= drop_keep4(a, cq, grow);
+    pass &= drop_keep4(a, cq, rk, row);
 #pragma unroll
     for (int j = 0; j < 4; ++j) d[j] *= a.keep_scale;
   }

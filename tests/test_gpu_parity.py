@@ -267,3 +267,26 @@ def test_tensor_core_backward_matches_the_generic_kernels(kind, shape, top):
             eng.lib.cgnn_set_option(1, 1)
     for name, got, ref in zip(("dW", "dbias", "du_in", "prev_sums"), out[1], out[0]):
         helpers.assert_close(got, ref, f"{kind} bwd {name}: tensor-core vs generic", tol=5e-6)
+
+
+def test_streaming_store_matches_resident_store():
+    """Double-buffered host->device staging (uploads on a side stream) collates exactly what a resident store does."""
+    from connectome_gnn.graph import StreamingStore, SubjectStore, pack_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    sets = [pack_graphs(generate_dataset(num_subjects=12, num_regions=40, seed=s)) for s in (11, 12, 13)]
+    pinned = [{k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in p.items()} for p in sets]
+    ss = StreamingStore(pinned[0], DEV)
+    ids = np.arange(12)[::-1].copy()
+    ss.prefetch(pinned[0])
+    for k in range(3):
+        st = ss.next()
+        if k + 1 < 3:
+            ss.prefetch(pinned[k + 1])
+        got = st.collate(ids)
+        ref = SubjectStore(sets[k], DEV).collate(ids)
+        for f in ("node_features", "edge_index", "edge_weight", "batch", "labels", "ptr"):
+            assert torch.equal(getattr(got, f), getattr(ref, f)), f
+        assert torch.equal(got.csr.deg, ref.csr.deg) and torch.equal(got.csr.in_col, ref.csr.in_col)
+        torch.cuda.synchronize()
+    with pytest.raises(RuntimeError):
+        ss.next()
