@@ -212,8 +212,9 @@ def run_b200(a):
     packed = pack_graphs(graphs)
     gen_s = time.time() - t0
     store = SubjectStore(packed, dev)
-    pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in packed.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in packed.values() if isinstance(v, torch.Tensor))
+    packed_c = pack_graphs(graphs, compact=True)     # host format of the e2e path: both endpoints of an edge in one int32
+    pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in packed_c.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in packed_c.values() if isinstance(v, torch.Tensor))
     n_per = a.regions
     meta = dict(row_base=rank * a.batch * n_per, graph_base=rank * a.batch, global_num_graphs=a.batch * world,
                 global_num_nodes=a.batch * world * n_per)
@@ -242,16 +243,16 @@ def run_b200(a):
             leg(name, store)
 
     streaming = StreamingStore(pinned, dev)
+    streaming.prefetch(pinned)   # primes the pipeline once, before any timed region
 
     def step_e2e():
-        """Every leg's subjects travel pinned host -> device inside the timed region; the upload of leg k+1 runs on
-        the loader's copy stream while leg k computes, and every leg ends with its loss read back to the host."""
+        """Every leg's subjects travel pinned host -> device on the loader's copy stream while the previous leg
+        computes; a step consumes four uploads and issues four (the last one is the next step's first leg), and every
+        leg ends with its loss read back to the host."""
         out = None
-        streaming.prefetch(pinned)
-        for i, name in enumerate(LEGS):
+        for name in LEGS:
             st = streaming.next()
-            if i + 1 < len(LEGS):
-                streaming.prefetch(pinned)
+            streaming.prefetch(pinned)
             out = float(leg(name, st))               # loss read back to the host
         return out
 

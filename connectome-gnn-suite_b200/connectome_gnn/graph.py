@@ -168,7 +168,7 @@ class ConnectomeBatch:
 # Subject store: the dataset packed once
 # ---------------------------------------------------------------------------
 
-def pack_graphs(graphs: Sequence[ConnectomeGraph]) -> dict:
+def pack_graphs(graphs: Sequence[ConnectomeGraph], compact: bool = False) -> dict:
     """Host packing of a list of subjects into arena arrays (pure indexing, no arithmetic).
 
     Returns CPU tensors: ``x [sum N, F]`` f32, ``src/dst [sum E]`` int32 subject-local ids,
@@ -200,8 +200,17 @@ def pack_graphs(graphs: Sequence[ConnectomeGraph]) -> dict:
     if has_label.any():
         vals = torch.stack([cpu(g.label).reshape(()).to(torch.int64) for g in graphs if g.label is not None])
         label[torch.from_numpy(np.nonzero(has_label)[0])] = vals
+    if compact:
+        # both endpoints of an edge in one int32 (src | dst << 16): 4 bytes less per edge over PCIe
+        if n_nodes.size and int(n_nodes.max()) > 65535:
+            raise ValueError("compact packing needs every subject to have < 65536 nodes")
+        src = (ei[0] | (ei[1] << 16)).to(torch.int64)
+        src = torch.where(src >= 2 ** 31, src - 2 ** 32, src).to(torch.int32).contiguous()
+        dst = torch.zeros(0, dtype=torch.int32)
+    else:
+        src, dst = ei[0].to(torch.int32).contiguous(), ei[1].to(torch.int32).contiguous()
     return dict(
-        x=x, src=ei[0].to(torch.int32).contiguous(), dst=ei[1].to(torch.int32).contiguous(), w=w,
+        x=x, src=src, dst=dst, w=w,
         node_ptr=torch.from_numpy(node_ptr), edge_ptr=torch.from_numpy(edge_ptr), label=label,
         has_label=has_label, num_features=feat)
 
@@ -225,7 +234,8 @@ class SubjectStore:
         self.x, self.src, self.dst, self.w = nb(packed["x"]), nb(packed["src"]), nb(packed["dst"]), nb(packed["w"])
         self.node_ptr, self.edge_ptr = nb(packed["node_ptr"]), nb(packed["edge_ptr"])
         self.label = nb(packed["label"])
-        self._struct = StoreT(self.x.data_ptr(), self.src.data_ptr(), self.dst.data_ptr(), self.w.data_ptr(),
+        compact = self.dst.numel() == 0 and self.src.numel() > 0     # pack_graphs(compact=True): src | dst << 16
+        self._struct = StoreT(self.x.data_ptr(), self.src.data_ptr(), None if compact else self.dst.data_ptr(), self.w.data_ptr(),
                               self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), self.label.data_ptr(),
                               self.num_features)
 

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   if (FROM_STORE) {
     const long long sid = p.ids[g];
     const long long sn = p.store.node_ptr[sid], se = p.store.edge_ptr[sid];
-    lsrc = p.store.src + se; ldst = p.store.dst + se; lw = p.store.w + se;
+    lsrc = p.store.src + se; ldst = p.store.dst ? p.store.dst + se : nullptr; lw = p.store.w + se;
     const int F = p.store.num_features;
     const float* sx = p.store.x + sn * F;
     float* dx = p.x + nb * F;
@@ -145,8 +145,10 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
     for (int i = tid; i < n; i += kThreads) p.batch[nb + i] = g;
     if (tid == 0 && p.labels && p.store.label) p.labels[g] = p.store.label[sid];
     for (int e = tid; e < m; e += kThreads) {
-      p.edge_index[eb + e] = (long long)lsrc[e] + nb;
-      p.edge_index[p.total_edges + eb + e] = (long long)ldst[e] + nb;
+      const uint32_t v = (uint32_t)lsrc[e];
+      const int s = ldst ? (int)v : (int)(v & 0xffffu), d = ldst ? ldst[e] : (int)(v >> 16);
+      p.edge_index[eb + e] = (long long)s + nb;
+      p.edge_index[p.total_edges + eb + e] = (long long)d + nb;
       p.edge_weight[eb + e] = lw[e];
     }
   } else {
@@ -155,7 +157,10 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   // Local endpoints of edge e.  Endpoints outside the subject (malformed hand-built batches)
   // are redirected to a zero-weight self edge on node 0 so the CSR stays consistent.
   auto edge = [&](int e, int& s, int& d, float& w) {
-    if (FROM_STORE) { s = lsrc[e]; d = ldst[e]; }
+    if (FROM_STORE) {
+      const uint32_t v = (uint32_t)lsrc[e];
+      if (ldst) { s = (int)v; d = ldst[e]; } else { s = (int)(v & 0xffffu); d = (int)(v >> 16); }   // packed pairs
+    }
     else { s = (int)(gsrc[e] - nb); d = (int)(gdst[e] - nb); }
     w = lw[e];
     if ((unsigned)s >= (unsigned)n || (unsigned)d >= (unsigned)n) { s = 0; d = 0; w = 0.0f; }
@@ -308,7 +313,7 @@ int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int6
       !csr_out_ok(csr) || !store->node_ptr || !store->edge_ptr || store->num_features <= 0)
     return CGNN_ERR_INVALID_ARG;
   if (total_rows > 0 && (!node_features || !batch || !store->x)) return CGNN_ERR_INVALID_ARG;
-  if (total_edges > 0 && (!edge_index || !edge_weight || !store->src || !store->dst || !store->w))
+  if (total_edges > 0 && (!edge_index || !edge_weight || !store->src || !store->w))
     return CGNN_ERR_INVALID_ARG;
   if (total_edges >= ((int64_t)1 << 31) || total_rows >= ((int64_t)1 << 31)) return CGNN_ERR_INVALID_ARG;
   {

@@ -134,7 +134,8 @@ typedef struct {
 typedef struct {
   const float*   x;         /* [sum N_s, F] */
   const int32_t* src;       /* [sum E_s] local source id      (edge_index[0]) */
-  const int32_t* dst;       /* [sum E_s] local destination id (edge_index[1]) */
+  const int32_t* dst;       /* [sum E_s] local destination id (edge_index[1]); NULL = compact store: src[e] holds
+                             * both endpoints as src | dst << 16 (every subject has < 65536 nodes)            */
   const float*   w;         /* [sum E_s] */
   const int64_t* node_ptr;  /* [S+1] */
   const int64_t* edge_ptr;  /* [S+1] */

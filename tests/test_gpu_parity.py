@@ -290,3 +290,17 @@ def test_streaming_store_matches_resident_store():
         torch.cuda.synchronize()
     with pytest.raises(RuntimeError):
         ss.next()
+
+
+def test_compact_store_collates_identically():
+    """pack_graphs(compact=True) (src | dst << 16 in one int32, dst pointer NULL) gives the same batch bit for bit."""
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    graphs = generate_dataset(num_subjects=9, num_regions=84, seed=21)
+    ids = np.array([3, 0, 8, 5, 5, 1])
+    a = SubjectStore(pack_graphs(graphs), DEV).collate(ids)
+    b = SubjectStore(pack_graphs(graphs, compact=True), DEV).collate(ids)
+    for f in ("node_features", "edge_index", "edge_weight", "batch", "labels", "ptr"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+    for f in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn", "deg", "dinv", "wsum"):
+        assert torch.equal(getattr(a.csr, f), getattr(b.csr, f)), f
