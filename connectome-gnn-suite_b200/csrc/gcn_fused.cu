@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_fused(GcnFusedArgs p) {
   const uint32_t a_hi_u = tc::smem_u32(a_hi), a_lo_u = tc::smem_u32(a_lo), b_hi_u = tc::smem_u32(b_hi), b_lo_u = tc::smem_u32(b_lo);
   const uint32_t idesc = tc::idesc_tf32(TR, H);
   const int ksteps = (K + 7) / 8;
+  const rt::OperandDescs od = rt::kmajor_descs(a_hi_u, a_lo_u, b_hi_u, b_lo_u);
 
   const int4* meta = reinterpret_cast<const int4*>(p.meta);
   auto load_meta = [&](long long g) -> int4 {
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_fused(GcnFusedArgs p) {
       __syncthreads();
       tc::fence_after_sync();
       if (tid == 0) {
-        rt::issue_kmajor_x3(taddr, a_hi_u, a_lo_u, TR, b_hi_u, b_lo_u, H, ksteps, idesc, false);
+        rt::issue_kmajor_x3<KP / 8, TR, H>(taddr, od, ksteps, idesc, false);
         tc::mma_commit(&mbar);
       }
       pending = true;

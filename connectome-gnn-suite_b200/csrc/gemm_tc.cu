@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_fwd_gemm(SageFwdGemmArgs p
   const uint32_t a_hi_u = tc::smem_u32(a_hi), a_lo_u = tc::smem_u32(a_lo), b_hi_u = tc::smem_u32(b_hi), b_lo_u = tc::smem_u32(b_lo);
   const uint32_t idesc = tc::idesc_tf32(TR, H);
   const int ksteps = WIDE ? KP / 8 : (K + 7) / 8;
+  const rt::OperandDescs od = rt::kmajor_descs(a_hi_u, a_lo_u, b_hi_u, b_lo_u);
 
   const long long ntiles = (p.rows + TR - 1) / TR;
   float4 pu[MC::NQ], pa[WIDE ? MC::NQ : 1];
@@ -156,9 +157,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_fwd_gemm(SageFwdGemmArgs p
 #pragma unroll
   for (int j = 0; j < 4; ++j) wf[j].init();
 
+  // accumulators of the tile starting at row r0 (TMEM buffer b) -> bias + ReLU -> z, BatchNorm statistics
+  auto epilogue = [&](long long r0, uint32_t b) {
+    rt::drain_rows_to_staging<H>(taddr + b * (uint32_t)H, stage, warp, lane);
+    tc::fence_before_sync();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MH::NQ; ++i) {
+      const int r = rh + i * MH::RS;
+      if (r0 + r < p.rows) {
+        float4 v = stage[rt::stage_index(r, qh, QH)];
+        v.x = fmaxf(v.x + bias4[0], 0.0f);
+        v.y = fmaxf(v.y + bias4[1], 0.0f);
+        v.z = fmaxf(v.z + bias4[2], 0.0f);
+        v.w = fmaxf(v.w + bias4[3], 0.0f);
+        *reinterpret_cast<float4*>(p.z + (r0 + r) * H + 4 * qh) = v;
+        cnt += 1;
+        const float inv = rt::rcp_fast((float)cnt);
+        wf[0].push(v.x, inv); wf[1].push(v.y, inv); wf[2].push(v.z, inv); wf[3].push(v.w, inv);
+      }
+    }
+  };
+
   long long t = blockIdx.x;
   load_tile(t);
-  uint32_t phase = 0;
+  uint32_t phase = 0, buf = 0;
+  bool have_prev = false;
+  long long prev_r0 = 0;
   for (; t < ntiles; t += gridDim.x) {
     const long long r0 = t * TR;
     // (1) previous layer's BatchNorm / dropout on the u half, hi/lo split, swizzled operand stores
@@ -193,34 +218,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_fwd_gemm(SageFwdGemmArgs p
     __syncthreads();
     tc::fence_after_sync();
     if (tid == 0) {
-      rt::issue_kmajor_x3(taddr, a_hi_u, a_lo_u, TR, b_hi_u, b_lo_u, H, ksteps, idesc, false);
+      rt::issue_kmajor_x3<KP / 8, TR, H>(taddr + buf * (uint32_t)H, od, ksteps, idesc, false);
       tc::mma_commit(&mbar);
     }
     load_tile(t + gridDim.x);          // next tile's loads fly during the MMA and the epilogue
-    tc::mbar_wait(&mbar, phase);
+    if (have_prev) epilogue(prev_r0, buf ^ 1u);   // the previous tile's accumulators leave while this tile multiplies
+    tc::mbar_wait(&mbar, phase);       // the operand tile may be rewritten once this tile's MMAs have read it
     phase ^= 1;
-    tc::fence_after_sync();
-    rt::drain_rows_to_staging<H>(taddr, stage, warp, lane);
-    tc::fence_before_sync();
-    __syncthreads();
-    // (2) bias + ReLU, coalesced store, BatchNorm statistics (fixed channel quad per thread)
-#pragma unroll
-    for (int i = 0; i < MH::NQ; ++i) {
-      const int r = rh + i * MH::RS;
-      if (r0 + r < p.rows) {
-        float4 v = stage[rt::stage_index(r, qh, QH)];
-        v.x = fmaxf(v.x + bias4[0], 0.0f);
-        v.y = fmaxf(v.y + bias4[1], 0.0f);
-        v.z = fmaxf(v.z + bias4[2], 0.0f);
-        v.w = fmaxf(v.w + bias4[3], 0.0f);
-        *reinterpret_cast<float4*>(p.z + (r0 + r) * H + 4 * qh) = v;
-        cnt += 1;
-        const float inv = rt::rcp_fast((float)cnt);
-        wf[0].push(v.x, inv); wf[1].push(v.y, inv); wf[2].push(v.z, inv); wf[3].push(v.w, inv);
-      }
-    }
-    __syncthreads();   // staging (= operand tile when wide) is rewritten by the next tile
+    have_prev = true;
+    prev_r0 = r0;
+    buf ^= 1u;
   }
+  if (have_prev) {
+    tc::fence_after_sync();
+    epilogue(prev_r0, buf ^ 1u);
+  }
+  __syncthreads();
 
   if (p.partials) {
     float* rec = reinterpret_cast<float*>(stage);   // [kThreads][9]
@@ -266,15 +279,15 @@ int launch_sage_fwd_gemm(const float* t_in, const cgnn_act_t* act, const float* 
   a.rows = rows; a.C = C; a.H = H;
   a.z = z; a.partials = partials;
   a.tmem_cols = 32;
-  while (a.tmem_cols < (uint32_t)H) a.tmem_cols <<= 1;
+  while (a.tmem_cols < (uint32_t)(2 * H)) a.tmem_cols <<= 1;   // two accumulator buffers
   const int KP = 32 * KB;
   const size_t a_bytes = (size_t)2 * KB * kRows * 128, b_bytes = (size_t)2 * KB * H * 128;
   const size_t c_bytes = (size_t)2 * KP * 4;
   size_t stage_bytes = (size_t)kRows * H * 4;
   if (stage_bytes < (size_t)kThreads * 9 * 4) stage_bytes = (size_t)kThreads * 9 * 4;
   size_t total = a_bytes + b_bytes + c_bytes;
-  if (wide && stage_bytes <= a_bytes) a.o_stage = 0;
-  else { a.o_stage = (int)((total + 15) & ~(size_t)15); total = a.o_stage + stage_bytes; }
+  a.o_stage = (int)((total + 15) & ~(size_t)15);      // never aliases the operand: the epilogue of tile t-1 runs
+  total = a.o_stage + stage_bytes;                      // while the MMAs of tile t read it
   const size_t smem = total + 1024;
   if (smem > (size_t)dev.smem_optin) return -1;
   const long long ntiles = (rows + kRows - 1) / kRows;
@@ -372,6 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_bwd_gemm(GcnBwdGemmArgs p) 
   const uint32_t a1kh = tc::smem_u32(a1k_hi), a1kl = tc::smem_u32(a1k_lo);
   const uint32_t b1h = tc::smem_u32(b1_hi), b1l = tc::smem_u32(b1_lo);
   const uint32_t id1 = tc::idesc_tf32(TR, KP), id2 = tc::idesc_tf32(MM, KP, 1, 1);
+  const rt::OperandDescs od1 = rt::kmajor_descs(a1kh, a1kl, b1h, b1l), od2 = rt::mnmajor_descs(a1h, a1l, a2h, a2l, TR);
 
   const long long ntiles = (p.rows + TR - 1) / TR;
   float4 dpn[M1::NQ], tin[M2::NQ], tcur[M2::NQ];
@@ -426,9 +440,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_bwd_gemm(GcnBwdGemmArgs p) 
     __syncthreads();
     tc::fence_after_sync();
     if (tid == 0) {
-      if (p.du_in) rt::issue_kmajor_x3(taddr, a1kh, a1kl, TR, b1h, b1l, KP, H / 8, id1, false);   // du_in tile = dP W
+      if (p.du_in) rt::issue_kmajor_x3<H / 8, TR, KP>(taddr, od1, H / 8, id1, false);   // du_in tile = dP W
       // dW += dP^T u : M = H (MN-major view of the dP tile), N = KP (MN-major view of the u tile), K = 128 rows
-      rt::issue_mnmajor_x3(taddr + (uint32_t)KP, a1h, a1l, a2h, a2l, TR, id2, !first);
+      rt::issue_mnmajor_x3<TR>(taddr + (uint32_t)KP, od2, id2, !first);
       tc::mma_commit(&mbar);
     }
     first = false;
@@ -624,7 +638,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p
   const uint32_t dzkh = tc::smem_u32(dzk_hi), dzkl = tc::smem_u32(dzk_lo), dzmh = tc::smem_u32(dzm_hi), dzml = tc::smem_u32(dzm_lo);
   const uint32_t uah = tc::smem_u32(ua_hi), ual = tc::smem_u32(ua_lo), wkh = tc::smem_u32(wk_hi), wkl = tc::smem_u32(wk_lo);
   const uint32_t id1 = tc::idesc_tf32(MP, TR), id2 = tc::idesc_tf32(MP, H, 1, 1);
-  const uint32_t t_du = taddr, t_dw = taddr + (uint32_t)TR;
+  const uint32_t t_du = taddr, t_dw = taddr + (uint32_t)(2 * TR);   // two [d_u || d_agg] buffers, one dW accumulator
+  const rt::OperandDescs od1 = rt::kmajor_descs(wkh, wkl, dzkh, dzkl), od2 = rt::mnmajor_descs(uah, ual, dzmh, dzml, TR);
 
   const long long ntiles = (p.rows + TR - 1) / TR;
   float4 zq[MHq::NQ], uq[MHq::NQ], tq[MCq::NQ], aq[WIDE ? MCq::NQ : 1];
@@ -670,11 +685,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p
     }
   };
 
+  // [d_u || d_agg] rows of the tile at r0 (accumulator buffer b): lane = output channel j, 16 tile rows per warp -
+  // every store instruction writes 32 consecutive channels of one row
+  auto store_du = [&](long long r0, uint32_t b) {
+    const int lq = warp & 3, cg = warp >> 2;
+    float v[16];
+    tc::tmem_ld_cols<16>(t_du + b * (uint32_t)TR + ((uint32_t)(32 * lq) << 16) + (uint32_t)(16 * cg), v);
+    const int j = 32 * lq + lane;
+    if (j < K2) {
+      float* dst = (j < C ? p.direct + j : p.nbr + (j - C)) + (r0 + 16 * cg) * C;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr)
+        if (r0 + 16 * cg + rr < p.rows) dst[(long long)rr * C] = v[rr];
+    }
+  };
+
   float colsum[4] = {0.f, 0.f, 0.f, 0.f};
   long long t = blockIdx.x;
   load_tile(t);
-  uint32_t phase = 0;
-  bool first = true;
+  uint32_t phase = 0, buf = 0;
+  bool first = true, have_prev = false;
+  long long prev_r0 = 0;
   for (; t < ntiles; t += gridDim.x) {
     const long long r0 = t * TR;
     // (1) dz = relu'(z) * BatchNorm backward of the dropout backward of the upstream gradient; both operand layouts
@@ -733,32 +764,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p
     tc::fence_after_sync();
     if (tid == 0) {
       // [d_u || d_agg]^T tile = W^T dz^T : M = 128 (j), N = 64 tile rows, K = H
-      if (need_du) rt::issue_kmajor_x3(t_du, wkh, wkl, MP, dzkh, dzkl, TR, H / 8, id1, false);
+      if (need_du) rt::issue_kmajor_x3<H / 8, MP, TR>(t_du + buf * (uint32_t)TR, od1, H / 8, id1, false);
       // dW^T += [u || agg]^T dz : M = 128 (j), N = H, K = 64 tile rows
-      rt::issue_mnmajor_x3(t_dw, uah, ual, dzmh, dzml, TR, id2, !first);
+      rt::issue_mnmajor_x3<TR>(t_dw, od2, id2, !first);
       tc::mma_commit(&mbar);
     }
     first = false;
     load_tile(t + gridDim.x);
-    tc::mbar_wait(&mbar, phase);
+    if (need_du && have_prev) store_du(prev_r0, buf ^ 1u);   // the previous tile's rows leave while this tile multiplies
+    tc::mbar_wait(&mbar, phase);                              // operand tiles may be rewritten after this
     phase ^= 1;
-    tc::fence_after_sync();
-    if (need_du) {
-      // (2) lane = output channel j, 16 tile rows per warp: every store instruction writes 32 consecutive channels
-      const int lq = warp & 3, cg = warp >> 2;
-      float v[16];
-      tc::tmem_ld_cols<16>(t_du + ((uint32_t)(32 * lq) << 16) + (uint32_t)(16 * cg), v);
-      const int j = 32 * lq + lane;
-      if (j < K2) {
-        float* dst = (j < C ? p.direct + j : p.nbr + (j - C)) + (r0 + 16 * cg) * C;
-#pragma unroll
-        for (int rr = 0; rr < 16; ++rr)
-          if (r0 + 16 * cg + rr < p.rows) dst[(long long)rr * C] = v[rr];
-      }
-    }
-    tc::fence_before_sync();
-    __syncthreads();   // operand tiles are rewritten by the next tile
+    have_prev = true;
+    prev_r0 = r0;
+    buf ^= 1u;
   }
+  tc::fence_after_sync();
+  if (need_du && have_prev) store_du(prev_r0, buf ^ 1u);
+  tc::fence_before_sync();
+  __syncthreads();
 
   // ---- per-CTA partial record: dW [H][2C] from the transposed accumulator, dbias from the column sums --------------
   float* part = p.partials + (size_t)blockIdx.x * p.part_stride;
@@ -819,7 +842,7 @@ int launch_sage_bwd_gemm(const float* du, const float* demb, const int32_t* row_
   a.direct = direct; a.nbr = nbr;
   a.partials = partials; a.part_stride = part_stride; a.o_pdb = o_pdb;
   a.tmem_cols = 32;
-  while (a.tmem_cols < (uint32_t)(64 + H)) a.tmem_cols <<= 1;
+  while (a.tmem_cols < (uint32_t)(2 * 64 + H)) a.tmem_cols <<= 1;
   const size_t total = (size_t)4 * HB * 64 * 128 + (size_t)2 * 4 * 64 * 128 + (size_t)2 * HB * 128 * 128 + (size_t)2 * 32 * CB * 4;
   const size_t smem = total + 1024;
   if (smem > (size_t)dev.smem_optin) return -1;

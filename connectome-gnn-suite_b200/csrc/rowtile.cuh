@@ -204,27 +204,40 @@ __device__ __forceinline__ void drain_rows_to_staging(uint32_t taddr, float4* st
 }
 
 // ---- MMA issue loops (one thread) -----------------------------------------------------------------------------------
-// D (+)= A B^T with K-major 128B-swizzled operands of a_rows / b_rows rows per 32-channel block, `ksteps` steps of 8
-__device__ __forceinline__ void issue_kmajor_x3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_rows, uint32_t b_hi,
-                                                uint32_t b_lo, int b_rows, int ksteps, uint32_t idesc, bool accumulate) {
-#pragma unroll 1
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const uint32_t kb = (uint32_t)(ks >> 2), ko = (uint32_t)((ks & 3) * 32);
-    const uint32_t ao = kb * (uint32_t)a_rows * 128u + ko, bo = kb * (uint32_t)b_rows * 128u + ko;
-    tc::mma_tf32x3_step(d_tmem, tc::smem_desc_sw128(a_hi + ao), tc::smem_desc_sw128(a_lo + ao), tc::smem_desc_sw128(b_hi + bo),
-                        tc::smem_desc_sw128(b_lo + bo), idesc, (accumulate || ks > 0) ? 1u : 0u);
+// The 64-bit shared-memory descriptors of the four operand tiles are formed once per kernel; per MMA the issuing
+// thread only adds a compile-time byte offset (>> 4) to the low word, so a whole K loop is a straight run of
+// tcgen05.mma instructions with immediate adds in between.
+struct OperandDescs {
+  uint64_t a_hi, a_lo, b_hi, b_lo;
+};
+__device__ __forceinline__ OperandDescs kmajor_descs(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+  return OperandDescs{tc::smem_desc_sw128(a_hi), tc::smem_desc_sw128(a_lo), tc::smem_desc_sw128(b_hi), tc::smem_desc_sw128(b_lo)};
+}
+__device__ __forceinline__ OperandDescs mnmajor_descs(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int krows) {
+  const uint32_t lbo = (uint32_t)krows * 128u;
+  return OperandDescs{tc::smem_desc_mn32(a_hi, lbo, 512u), tc::smem_desc_mn32(a_lo, lbo, 512u), tc::smem_desc_mn32(b_hi, lbo, 512u),
+                      tc::smem_desc_mn32(b_lo, lbo, 512u)};
+}
+// D (+)= A B^T with K-major 128B-swizzled operands of A_ROWS / B_ROWS rows per 32-channel block; KSTEPS steps of 8
+// channels are unrolled, `ksteps` (<= KSTEPS) of them are issued.
+template <int KSTEPS, int A_ROWS, int B_ROWS>
+__device__ __forceinline__ void issue_kmajor_x3(uint32_t d_tmem, const OperandDescs& od, int ksteps, uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    if (ks < ksteps) {
+      const uint64_t ao = (uint64_t)(((ks >> 2) * A_ROWS * 128 + (ks & 3) * 32) >> 4);
+      const uint64_t bo = (uint64_t)(((ks >> 2) * B_ROWS * 128 + (ks & 3) * 32) >> 4);
+      tc::mma_tf32x3_step(d_tmem, od.a_hi + ao, od.a_lo + ao, od.b_hi + bo, od.b_lo + bo, idesc, (accumulate || ks > 0) ? 1u : 0u);
+    }
   }
 }
-// D (+)= A^T B with MN-major operands whose contraction index is the tile row (`krows` rows, 8 per step)
-__device__ __forceinline__ void issue_mnmajor_x3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                                 int krows, uint32_t idesc, bool accumulate) {
-  const uint32_t lbo = (uint32_t)krows * 128u;
-#pragma unroll 1
-  for (int ks = 0; ks < krows / 8; ++ks) {
-    const uint32_t off = (uint32_t)ks * 1024u;
-    tc::mma_tf32x3_step(d_tmem, tc::smem_desc_mn32(a_hi + off, lbo, 512u), tc::smem_desc_mn32(a_lo + off, lbo, 512u),
-                        tc::smem_desc_mn32(b_hi + off, lbo, 512u), tc::smem_desc_mn32(b_lo + off, lbo, 512u), idesc,
-                        (accumulate || ks > 0) ? 1u : 0u);
+// D (+)= A^T B with MN-major operands whose contraction index is the tile row (KROWS rows, 8 per step)
+template <int KROWS>
+__device__ __forceinline__ void issue_mnmajor_x3(uint32_t d_tmem, const OperandDescs& od, uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < KROWS / 8; ++ks) {
+    const uint64_t off = (uint64_t)((ks * 1024) >> 4);
+    tc::mma_tf32x3_step(d_tmem, od.a_hi + off, od.a_lo + off, od.b_hi + off, od.b_lo + off, idesc, (accumulate || ks > 0) ? 1u : 0u);
   }
 }
 
