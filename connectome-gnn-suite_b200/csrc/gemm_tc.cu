@@ -27,9 +27,9 @@ __device__ __forceinline__ float f4_get(const float4& v, int j) { return j == 0 
 
 // W[n][k] (row stride ldw, zero beyond n_valid / k_valid) -> hi/lo K-major operand of `rows` rows, KP padded channels
 __device__ __forceinline__ void stage_weight_kmajor(const float* __restrict__ W, int ldw, int n_valid, int k_valid, int rows,
-                                                    int KP, unsigned char* hi, unsigned char* lo) {
+                                                    int KP, unsigned char* hi, unsigned char* lo, int nthreads = kThreads) {
   const int Q = KP >> 2;
-  for (int idx = threadIdx.x; idx < rows * Q; idx += kThreads) {
+  for (int idx = threadIdx.x; idx < rows * Q; idx += nthreads) {
     const int n = idx / Q, q = idx - n * Q;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < n_valid) v = rt::ld_quad<false>(W, n, ldw, 4 * q);
@@ -74,14 +74,14 @@ struct SageFwdGemmArgs {
 
 // KB = padded K / 32 (K = 2C), HB = H / 32.  WIDE: C = 16 KB is a multiple of 32 - the u and agg halves are two quad
 // maps with 16-byte loads; otherwise one element-wise map over the padded K (first layer, C = 5).
-template <int KB, int HB, bool WIDE>
-__global__ void __launch_bounds__(kThreads, 1) k_sage_fwd_gemm(SageFwdGemmArgs p) {
+template <int KB, int HB, bool WIDE, int NT>
+__global__ void __launch_bounds__(NT, 1) k_sage_fwd_gemm(SageFwdGemmArgs p) {
   constexpr int KP = 32 * KB, H = 32 * HB, TR = kRows;
   constexpr int A_HALF = KB * TR * 128, B_HALF = KB * H * 128;
   constexpr int QC = WIDE ? KP / 8 : KP / 4;           // quads per row of one loaded tensor (wide) / of the padded K
-  using MC = rt::QuadMap<QC, TR>;
+  using MC = rt::QuadMap<QC, TR, NT>;
   constexpr int QH = H / 4;
-  using MH = rt::QuadMap<QH, TR>;
+  using MH = rt::QuadMap<QH, TR, NT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
@@ -99,10 +99,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_fwd_gemm(SageFwdGemmArgs p
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, p.tmem_cols);
   if (tid == 0) tc::mbar_init(&mbar, 1);
-  stage_weight_kmajor(p.W, K, H, K, H, KP, b_hi, b_lo);
+  stage_weight_kmajor(p.W, K, H, K, H, KP, b_hi, b_lo, NT);
   if (!WIDE) {
-    stage_affine(p.act, C, KP, s_scale, s_shift);
-    for (int i = tid; i < 2 * A_HALF / 16; i += kThreads) reinterpret_cast<float4*>(a_hi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = tid; c < KP; c += NT) { s_scale[c] = (c < C && p.act.scale) ? p.act.scale[c] : (c < C ? 1.0f : 0.0f); s_shift[c] = (c < C && p.act.scale) ? p.act.shift[c] : 0.0f; }
+    for (int i = tid; i < 2 * A_HALF / 16; i += NT) reinterpret_cast<float4*>(a_hi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   // this thread's input quad(s) and output quad
   const int qc = tid % QC, rc = tid / QC;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_fwd_gemm(SageFwdGemmArgs p
 
   // accumulators of the tile starting at row r0 (TMEM buffer b) -> bias + ReLU -> z, BatchNorm statistics
   auto epilogue = [&](long long r0, uint32_t b) {
-    rt::drain_rows_to_staging<H>(taddr + b * (uint32_t)H, stage, warp, lane);
+    rt::drain_rows_to_staging<H, NT>(taddr + b * (uint32_t)H, stage, warp, lane);
     tc::fence_before_sync();
     __syncthreads();
 #pragma unroll
@@ -236,16 +236,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_fwd_gemm(SageFwdGemmArgs p
   __syncthreads();
 
   if (p.partials) {
-    float* rec = reinterpret_cast<float*>(stage);   // [kThreads][9]
+    float* rec = reinterpret_cast<float*>(base);   // [NT][9] over the operand tile (every MMA has completed)
     rec[tid * 9] = (float)cnt;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { rec[tid * 9 + 1 + j] = wf[j].mean; rec[tid * 9 + 5 + j] = wf[j].m2; }
     __syncthreads();
     double* out = p.partials + (size_t)blockIdx.x * (1 + 2 * H);
-    for (int c = tid; c < H; c += kThreads) {
+    for (int c = tid; c < H; c += NT) {
       const int q = c >> 2, j = c & 3;
       double n = 0.0, mean = 0.0, m2 = 0.0;
-      for (int th = q; th < kThreads; th += QH) {
+      for (int th = q; th < NT; th += QH) {
         const double nb = (double)rec[th * 9];
         if (nb <= 0.0) continue;
         const double mb = (double)rec[th * 9 + 1 + j], qb = (double)rec[th * 9 + 5 + j];
@@ -284,7 +284,6 @@ int launch_sage_fwd_gemm(const float* t_in, const cgnn_act_t* act, const float* 
   const size_t a_bytes = (size_t)2 * KB * kRows * 128, b_bytes = (size_t)2 * KB * H * 128;
   const size_t c_bytes = (size_t)2 * KP * 4;
   size_t stage_bytes = (size_t)kRows * H * 4;
-  if (stage_bytes < (size_t)kThreads * 9 * 4) stage_bytes = (size_t)kThreads * 9 * 4;
   size_t total = a_bytes + b_bytes + c_bytes;
   a.o_stage = (int)((total + 15) & ~(size_t)15);      // never aliases the operand: the epilogue of tile t-1 runs
   total = a.o_stage + stage_bytes;                      // while the MMAs of tile t read it
@@ -299,13 +298,14 @@ int launch_sage_fwd_gemm(const float* t_in, const cgnn_act_t* act, const float* 
   }
   if (grid < 1) return -1;
   *grid_out = (int)grid;
-#define CGNN_SF(KB_, HB_, W_)                                                                         \
+#define CGNN_SF(KB_, HB_, W_, NT_)                                                                    \
   {                                                                                                   \
-    auto kfn = k_sage_fwd_gemm<KB_, HB_, W_>;                                                         \
+    auto kfn = k_sage_fwd_gemm<KB_, HB_, W_, NT_>;                                                    \
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
-    CGNN_LAUNCH(kfn, (unsigned)grid, kThreads, smem, stream, a);                                      \
+    CGNN_LAUNCH(kfn, (unsigned)grid, NT_, smem, stream, a);                                           \
   }
-#define CGNN_SF_H(KB_, W_) { if (HB == 1) CGNN_SF(KB_, 1, W_) else if (HB == 2) CGNN_SF(KB_, 2, W_) else CGNN_SF(KB_, 4, W_) }
+#define CGNN_SF_H(KB_, W_) { if (HB == 1) CGNN_SF(KB_, 1, W_, 512) else if (HB == 2) CGNN_SF(KB_, 2, W_, 512) else CGNN_SF(KB_, 4, W_, 512) }
+  // (1024-thread CTAs were measured: no faster than 512 - the kernel is not occupancy-bound)
   if (wide) { if (KB == 2) CGNN_SF_H(2, true) else CGNN_SF_H(4, true) }
   else { if (KB == 1) CGNN_SF_H(1, false) else CGNN_SF_H(2, false) }
 #undef CGNN_SF_H

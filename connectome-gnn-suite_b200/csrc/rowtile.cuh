@@ -18,11 +18,11 @@ __device__ __forceinline__ float rcp_fast(float x) {
 }
 
 // thread <-> (quad column q, first row r) for a tile of TR rows x 4*Q channels; Q in {8, 16, 32}
-template <int Q, int TR>
+template <int Q, int TR, int NT = kThreads>
 struct QuadMap {
-  static constexpr int RS = kThreads / Q;    // rows between two quads of one thread
+  static constexpr int RS = NT / Q;          // rows between two quads of one thread
   static constexpr int NQ = TR / RS;         // quads per thread per tile
-  static_assert(kThreads % Q == 0 && RS % 8 == 0 && TR % RS == 0 && NQ >= 1, "unsupported tile shape");
+  static_assert(NT % Q == 0 && RS % 8 == 0 && TR % RS == 0 && NQ >= 1, "unsupported tile shape");
 };
 
 // byte offset of the quad (row, 4q) in a K-major 128B-swizzled operand of `rows` rows per 32-channel block
@@ -192,9 +192,9 @@ __device__ __forceinline__ float4 mask_quad(float4 v, int c0, int C) {   // zero
 // the quad-per-thread reads of the epilogues.
 __device__ __forceinline__ int stage_index(int row, int q, int QN) { return row * QN + (q ^ (row & 7)); }
 
-template <int NC>
+template <int NC, int NT = kThreads>
 __device__ __forceinline__ void drain_rows_to_staging(uint32_t taddr, float4* stage, int warp, int lane) {
-  constexpr int CW = NC / 4;   // columns per warp: 4 lane quarters x 4 column groups = 16 warps
+  constexpr int CW = NC / (NT / 128);   // columns per warp: 4 lane quarters x NT / 128 column groups
   const int lq = warp & 3, cg = warp >> 2, row = 32 * lq + lane;
   float v[CW];
   tc::tmem_ld_cols<CW>(taddr + ((uint32_t)(32 * lq) << 16) + (uint32_t)(cg * CW), v);
