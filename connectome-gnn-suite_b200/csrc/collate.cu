@@ -81,6 +81,7 @@ struct CollateArgs {
   const float* coo_w;
   long long B, total_rows, total_edges;
   int max_nodes;               // shared memory was sized for this many nodes per subject
+  int edge_cap;                // ... and for staging the sorted CSR of subjects with up to this many edges (0: none)
   // reference-visible outputs (FROM_STORE only)
   float* x; long long* edge_index; float* edge_weight; long long* batch; long long* labels;
   const long long* ptr; const long long* eptr;
@@ -144,34 +145,60 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
     for (int i = tid; i < n * F; i += kThreads) dx[i] = sx[i];
     for (int i = tid; i < n; i += kThreads) p.batch[nb + i] = g;
     if (tid == 0 && p.labels && p.store.label) p.labels[g] = p.store.label[sid];
-    for (int e = tid; e < m; e += kThreads) {
-      const uint32_t v = (uint32_t)lsrc[e];
-      const int s = ldst ? (int)v : (int)(v & 0xffffu), d = ldst ? ldst[e] : (int)(v >> 16);
-      p.edge_index[eb + e] = (long long)s + nb;
-      p.edge_index[p.total_edges + eb + e] = (long long)d + nb;
-      p.edge_weight[eb + e] = lw[e];
-    }
   } else {
     gsrc = p.coo + eb; gdst = p.coo + p.total_edges + eb; lw = p.coo_w + eb;
   }
-  // Local endpoints of edge e.  Endpoints outside the subject (malformed hand-built batches)
+  constexpr int kChunks = kWarps / 2;
+  int* cnt = reinterpret_cast<int*>(s_dinv + n);        // [2][kChunks][n]
+  // Subjects that fit are sorted entirely in shared memory: the raw COO list (src | dst << 16, w) is read from
+  // global memory once, both sorted lists live next to it, and the row sums, normalised weights and CSR arrays are
+  // produced from shared memory with coalesced stores.  Larger subjects re-read global memory (same results).
+  const bool staged = m <= p.edge_cap && n <= 65535;
+  uint32_t* pk = reinterpret_cast<uint32_t*>(cnt + 2 * kChunks * n);    // [2][m] sorted entries
+  float* cw = reinterpret_cast<float*>(pk + 2 * m);                      // [2][m]
+  uint32_t* raw_pk = reinterpret_cast<uint32_t*>(cw + 2 * m);            // [m] COO order
+  float* raw_w = reinterpret_cast<float*>(raw_pk + m);                   // [m]
+  // Local endpoints of edge e as stored.  Endpoints outside the subject (malformed hand-built batches)
   // are redirected to a zero-weight self edge on node 0 so the CSR stays consistent.
-  auto edge = [&](int e, int& s, int& d, float& w) {
+  auto load_edge = [&](int e, int& s, int& d, float& w) {
     if (FROM_STORE) {
       const uint32_t v = (uint32_t)lsrc[e];
       if (ldst) { s = (int)v; d = ldst[e]; } else { s = (int)(v & 0xffffu); d = (int)(v >> 16); }   // packed pairs
     }
     else { s = (int)(gsrc[e] - nb); d = (int)(gdst[e] - nb); }
     w = lw[e];
+  };
+  auto edge = [&](int e, int& s, int& d, float& w) {
+    if (staged) {
+      const uint32_t v = raw_pk[e];
+      s = (int)(v & 0xffffu); d = (int)(v >> 16); w = raw_w[e];
+      return;
+    }
+    load_edge(e, s, d, w);
     if ((unsigned)s >= (unsigned)n || (unsigned)d >= (unsigned)n) { s = 0; d = 0; w = 0.0f; }
   };
+  // one pass over the subject's COO list in global memory: reference-visible outputs and the shared-memory copy
+  if (FROM_STORE || staged) {
+    for (int e = tid; e < m; e += kThreads) {
+      int s, d; float w;
+      load_edge(e, s, d, w);
+      if (FROM_STORE) {
+        p.edge_index[eb + e] = (long long)s + nb;
+        p.edge_index[p.total_edges + eb + e] = (long long)d + nb;
+        p.edge_weight[eb + e] = w;
+      }
+      if (staged) {
+        if ((unsigned)s >= (unsigned)n || (unsigned)d >= (unsigned)n) { s = 0; d = 0; w = 0.0f; }
+        raw_pk[e] = (uint32_t)s | ((uint32_t)d << 16);
+        raw_w[e] = w;
+      }
+    }
+  }
 
   // Stable counting sort by destination (in-CSR) and by source (out-CSR), all 16 warps: the COO list is cut into
   // kChunks contiguous chunks; warp (dir, chunk) counts its chunk's keys, a scan over (key, chunk) turns the counts
   // into the first slot of every (chunk, key) pair, then every warp places its chunk 32 edges at a time - lanes that
   // share a key take consecutive slots in lane order, so the order inside a row is the COO order.
-  constexpr int kChunks = kWarps / 2;
-  int* cnt = reinterpret_cast<int*>(s_dinv + n);        // [2][kChunks][n]
   const int dir = warp / kChunks, chunk = warp % kChunks;
   const int clen = (((m + kChunks - 1) / kChunks) + 31) & ~31;
   const int e_lo = min(chunk * clen, m), e_hi = min(e_lo + clen, m);
@@ -224,9 +251,14 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
       if (live) start = my_cnt[key];
       __syncwarp();
       if (live) {
-        const long long pos = eb + start + rank;
-        col[pos] = (int32_t)(nb + (dir == 0 ? s : d));
-        wv[pos] = w;
+        if (staged) {
+          pk[dir * m + start + rank] = (uint32_t)s | ((uint32_t)d << 16);
+          cw[dir * m + start + rank] = w;
+        } else {
+          const long long pos = eb + start + rank;
+          col[pos] = (int32_t)(nb + (dir == 0 ? s : d));
+          wv[pos] = w;
+        }
         if (rank == 0) my_cnt[key] = start + __popc(peers);
       }
       __syncwarp();
@@ -241,6 +273,38 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   }
   __syncthreads();
 
+  if (staged) {
+    for (int i = tid; i < n; i += kThreads) {
+      const int o0 = i ? cur_out[i - 1] : 0, o1 = cur_out[i];
+      float deg = 0.0f;
+      for (int q = o0; q < o1; ++q) deg = __fadd_rn(deg, cw[m + q]);
+      deg = __fadd_rn(deg, 1.0f);
+      const int i0 = i ? cur_in[i - 1] : 0, i1 = cur_in[i];
+      float ws = 0.0f;
+      for (int q = i0; q < i1; ++q) ws = __fadd_rn(ws, cw[q]);
+      const float dinv = (float)(1.0 / sqrt((double)__fadd_rn(deg, 1e-8f)));
+      s_dinv[i] = dinv;
+      p.csr.deg[nb + i] = deg;
+      p.csr.dinv[nb + i] = dinv;
+      p.csr.wsum[nb + i] = ws;
+    }
+    __syncthreads();
+    for (int q = tid; q < m; q += kThreads) {
+      uint32_t v = pk[q];
+      int s = (int)(v & 0xffffu), d = (int)(v >> 16);
+      float w = cw[q];
+      p.csr.in_col[eb + q] = (int32_t)(nb + s);
+      p.csr.in_w[eb + q] = w;
+      p.csr.in_wn[eb + q] = __fmul_rn(__fmul_rn(s_dinv[s], w), s_dinv[d]);
+      v = pk[m + q];
+      s = (int)(v & 0xffffu); d = (int)(v >> 16);
+      w = cw[m + q];
+      p.csr.out_col[eb + q] = (int32_t)(nb + d);
+      p.csr.out_w[eb + q] = w;
+      p.csr.out_wn[eb + q] = __fmul_rn(__fmul_rn(s_dinv[s], w), s_dinv[d]);
+    }
+    return;
+  }
   // Row sums in COO order (fp32, sequential): D^ (by source, self-loop weight 1 last) and w_sum.
   for (int i = tid; i < n; i += kThreads) {
     const int o0 = i ? cur_out[i - 1] : 0, o1 = cur_out[i];
@@ -287,6 +351,16 @@ static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaSt
   if (max_nodes < 1) max_nodes = 1;
   size_t smem = (size_t)max_nodes * (12 + 4 * kWarps) + 16;   // cursors, dinv, per-chunk counters
   if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
+  // room for the raw and the two sorted edge lists of a typical subject (24 bytes per edge): an eighth above the batch average, as
+  // long as two CTAs still fit on an SM; larger subjects take the unstaged path inside the kernel
+  a.edge_cap = 0;
+  if (a.B > 0) {
+    const long long avg = a.total_edges / a.B;
+    long long cap = avg + avg / 8 + 32;
+    if (cap > a.total_edges) cap = a.total_edges;
+    const size_t want = smem + (size_t)cap * 24;
+    if (want + 1024 <= (size_t)(228 * 1024) / 2) { a.edge_cap = (int)cap; smem = want; }
+  }
   a.max_nodes = max_nodes;
   if (a.B <= 0) return CGNN_OK;
   if (from_store) {
