@@ -117,7 +117,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_fused(GcnFusedArgs p) {
 #pragma unroll
     for (int i = 0; i < NPF; ++i) {
       const int r = rl + i * RP;
-      if (r < m.y) s_tile[r * LPR + cl] = rt::mask_quad(rt::act_fwd4(p.act, cq, pre[i], rk, (uint32_t)(m.x + r)), c0, K);
+      if (r < m.y) {
+        float4 u = rt::act_fwd4(p.act, cq, pre[i], rk, (uint32_t)(m.x + r));
+        if (!VEC) u = rt::mask_quad(u, c0, K);
+        s_tile[r * LPR + cl] = u;
+      }
     }
     for (int r = rl + NPF * RP; r < m.y; r += RP) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGNN_ABI_VERSION 3
+#define CGNN_ABI_VERSION 4
 
 typedef void* cgnn_stream_t; /* cudaStream_t */
 
@@ -182,7 +182,9 @@ int cgnn_build_agg(const cgnn_csr_t* csr, int32_t kind, int64_t num_graphs, int6
 /* ---- K1/K2: layer forward ------------------------------------------------------------ */
 
 /* GCN layer (reference models.py:84-114):  z = A^ (u W^T) + bias,  u = act(t_in).
- * t_in [rows, d_in], W [H, d_in], bias [H], z [rows, H].
+ * t_in [rows, d_in], W [H, d_in], bias [H], z [rows, H].  With the GCN blobs of cgnn_build_agg attached to `csr` the
+ * layer runs as ONE kernel that evaluates the same product as (A^ u) W^T: the gather happens in the input width and
+ * the gathered rows feed the tensor cores from registers (fp32 round-off differs from the reference order by ~1e-7).
  * If bn_stats != NULL also returns the BatchNorm batch statistics of z as doubles
  * [1 + 2H] = {count, mean[H], M2[H]} (Welford/Chan merged, deterministic). */
 int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
@@ -192,9 +194,9 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
 
 /* GraphSAGE layer (reference models.py:136-152):
  *   agg_i = sum_{e: dst=i} w_e u_src / (wsum_i + 1e-8);  z = relu([u || agg] W^T + b)
- * W [H, 2*d_in], b [H].  agg [rows, d_in] (may be NULL) receives the aggregated neighbourhood: with it (and the
- * blobs of cgnn_build_agg) the layer runs as a gather kernel plus a tensor-core contraction, and backward reuses
- * it instead of gathering again. */
+ * W [H, 2*d_in], b [H].  agg [rows, d_in] (may be NULL) receives the aggregated neighbourhood (every code path fills
+ * it when given): with it and the blobs of cgnn_build_agg the layer runs as a gather kernel plus a tensor-core
+ * contraction, and backward reuses it instead of gathering again. */
 int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
                         const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
                         int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, double* bn_stats,
@@ -285,7 +287,9 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
 /* GraphSAGE layer backward (autograd of models.py:136-152 plus the BN/dropout that follows).
  * Same contract as cgnn_gcn_layer_bwd; W [H, 2*d_in].  scratch [2, rows, d_in] fp32 holds the
  * direct and neighbour parts of the input gradient between the two kernels of this call.  agg [rows, d_in] is the
- * aggregate cgnn_sage_layer_fwd stored (NULL: it is gathered again by the generic kernel). */
+ * aggregate cgnn_sage_layer_fwd stored: with it, the blobs of cgnn_build_agg and row_graph the call runs as tensor-core
+ * contractions (dz on load, [d_u || d_agg] = dz W, dW, dbias) followed by the transposed gather kernel; NULL: the
+ * generic kernels gather again. */
 int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
                         const cgnn_bn_bwd_t* bn, const float* t_in, const float* agg, const cgnn_act_t* act_in,
                         const float* W, const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs,
