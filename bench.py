@@ -231,7 +231,7 @@ def run_b200(a):
         kind, mode = name.split("_")
         tr = trainers[kind]
         ids = torch.randperm(a.batch, generator=order_gen).numpy()
-        batch = st.collate(ids, **meta)
+        batch = st.collate(ids, prepare_for=kind, **meta)
         if mode == "train":
             tr.model.train()
             return tr.train_step(batch)

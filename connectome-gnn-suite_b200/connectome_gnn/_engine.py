@@ -119,7 +119,9 @@ class Engine:
         return csr.agg[kind]
 
     def collate_csr(self, store: StoreT, ids: torch.Tensor, num_graphs: int, rows: int, edges: int, max_nodes: int,
-                    num_features: int, with_labels: bool):
+                    num_features: int, with_labels: bool, agg_kind: Optional[str] = None):
+        """Returns (fields, csr arrays, blobs): ``blobs`` = (agg_in, agg_out, row_graph) of ``agg_kind`` when the
+        collate kernel was asked to emit that model family's aggregation blobs in the same pass, else None."""
         e = self.empty
         out = dict(
             node_features=e((rows, num_features)), edge_index=e((2, edges), torch.int64), edge_weight=e(edges),
@@ -127,10 +129,16 @@ class Engine:
             ptr=e(num_graphs + 1, torch.int64), eptr=e(num_graphs + 1, torch.int64))
         csr = self.new_csr(rows, edges, num_graphs)
         cs = self.csr_struct(csr)
+        blobs = None
+        if agg_kind is not None and num_graphs > 0 and rows > 0:
+            words = int(self.lib.cgnn_agg_words(rows, edges, num_graphs))
+            blobs = (e(words, torch.int32), e(words, torch.int32), e(max(rows, 1), torch.int32))
+            cs.agg_in, cs.agg_out, cs.row_graph = _p(blobs[0]), _p(blobs[1]), _p(blobs[2])
+            cs.agg_kind = Engine.KINDS[agg_kind]
         self._call("cgnn_collate_csr", C.byref(store), _p(ids), num_graphs, rows, edges, max_nodes,
                    _p(out["node_features"]), _p(out["edge_index"]), _p(out["edge_weight"]), _p(out["batch"]),
                    _p(out["labels"]), _p(out["ptr"]), _p(out["eptr"]), C.byref(cs), self.stream())
-        return out, csr
+        return out, csr, blobs
 
     def csr_from_coo(self, edge_index, edge_weight, ptr, num_graphs: int, rows: int, edges: int, max_nodes: int):
         csr = self.new_csr(rows, edges, num_graphs)

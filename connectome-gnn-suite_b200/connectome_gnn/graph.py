@@ -271,8 +271,11 @@ class SubjectStore:
                                                           self.edge_ptr, self.label))
 
     def collate(self, ids, *, row_base: int = 0, graph_base: int = 0, global_num_graphs: Optional[int] = None,
-                global_num_nodes: Optional[int] = None, ids_device: Optional[torch.Tensor] = None) -> ConnectomeBatch:
-        """Device collate of subjects ``ids`` (host int sequence / array, in batch order)."""
+                global_num_nodes: Optional[int] = None, ids_device: Optional[torch.Tensor] = None,
+                prepare_for: Optional[str] = None) -> ConnectomeBatch:
+        """Device collate of subjects ``ids`` (host int sequence / array, in batch order).  ``prepare_for`` ("gcn" /
+        "sage") makes the collate kernel emit that model family's packed aggregation structure in the same pass
+        instead of a separate launch at the first layer (same bits either way)."""
         ids_np = np.asarray(ids, dtype=np.int64).reshape(-1)
         n_sel = self.node_ptr_host[ids_np + 1] - self.node_ptr_host[ids_np]
         e_sel = self.edge_ptr_host[ids_np + 1] - self.edge_ptr_host[ids_np]
@@ -287,17 +290,19 @@ class SubjectStore:
         if ready is not None:      # an upload enqueued on another stream (reload): order this stream after it
             torch.cuda.current_stream(self.device).wait_event(ready)
         eng = _engine.engine_for(self.x)
-        out, csr = eng.collate_csr(self._struct, ids_device, int(ids_np.size), rows, edges, max_nodes,
-                                   self.num_features, all_labelled)
+        out, csr, blobs = eng.collate_csr(self._struct, ids_device, int(ids_np.size), rows, edges, max_nodes,
+                                          self.num_features, all_labelled, prepare_for)
         labels = out["labels"]
         if not all_labelled and labelled.any():
             # reference quirk (graph.py:155-156,165): only labelled subjects contribute, so the
             # stack is shorter than B
             labels = self.label[torch.from_numpy(ids_np[labelled]).to(self.device)]
+        bcsr = BatchCSR(**csr, eptr=out["eptr"], max_nodes=max_nodes, max_edges=max_edges)
+        if blobs is not None:
+            bcsr.agg = {prepare_for: blobs}
         return ConnectomeBatch(
             out["node_features"], out["edge_index"], out["edge_weight"], out["batch"], labels, out["ptr"],
-            BatchCSR(**csr, eptr=out["eptr"], max_nodes=max_nodes, max_edges=max_edges), row_base, graph_base,
-            global_num_graphs, global_num_nodes)
+            bcsr, row_base, graph_base, global_num_graphs, global_num_nodes)
 
 
 class StreamingStore:
@@ -367,8 +372,9 @@ class ConnectomeDataLoader:
     single-process batch."""
 
     def __init__(self, dataset, batch_size: int = 16, shuffle: bool = True, *, rank: Optional[int] = None,
-                 world_size: Optional[int] = None, device=None):
+                 world_size: Optional[int] = None, device=None, prepare_for: Optional[str] = None):
         self.dataset = dataset
+        self.prepare_for = prepare_for   # "gcn" / "sage": collate also emits that family's aggregation structure
         self.batch_size = batch_size
         self.shuffle = shuffle
         self.device = device
@@ -427,6 +433,6 @@ class ConnectomeDataLoader:
         order = self.epoch_order()
         store = self.store()
         for step in self.plan(order):
-            yield store.collate(step["ids"], row_base=step.get("row_base", 0), graph_base=step["graph_base"],
+            yield store.collate(step["ids"], prepare_for=self.prepare_for, row_base=step.get("row_base", 0), graph_base=step["graph_base"],
                                 global_num_graphs=step["global_num_graphs"],
                                 global_num_nodes=step.get("global_num_nodes"))

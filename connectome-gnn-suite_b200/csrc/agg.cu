@@ -21,7 +21,7 @@ struct BuildAggArgs {
   const int32_t* in_rowptr; const int32_t* in_col; const float* in_w; const float* in_wn;
   const int32_t* out_rowptr; const int32_t* out_col; const float* out_w; const float* out_wn;
   const float* dinv; const float* wsum; const int32_t* meta;
-  int kind, max_nodes;
+  int kind, max_nodes, skip_edge_cap;
   int32_t* agg_in; int32_t* agg_out; int32_t* row_graph;
 };
 
@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) k_build_agg(BuildAggArgs p) {
   const long long nb = m.x, eb = m.z;
   const int n = m.y;
   if (n > p.max_nodes) return;
+  if (p.skip_edge_cap >= 0 && m.w <= p.skip_edge_cap && n <= 65535) return;   // the collate kernel already emitted this one
   const int self = p.kind == AGG_GCN ? 1 : 0;
   for (int dir = 0; dir < 2; ++dir) {
     const int32_t* rp = dir == 0 ? p.in_rowptr : p.out_rowptr;
@@ -295,6 +296,24 @@ int launch_gather(int mode, GatherArgs& a, int* grid_out, cudaStream_t stream) {
 #endif
 }
 
+int launch_build_agg(const cgnn_csr_t* csr, int32_t kind, int64_t num_graphs, int32_t max_nodes, int32_t* agg_in, int32_t* agg_out,
+                     int32_t* row_graph, int skip_edge_cap, cudaStream_t stream) {
+  BuildAggArgs a;
+  a.in_rowptr = csr->in_rowptr; a.in_col = csr->in_col; a.in_w = csr->in_w; a.in_wn = csr->in_wn;
+  a.out_rowptr = csr->out_rowptr; a.out_col = csr->out_col; a.out_w = csr->out_w; a.out_wn = csr->out_wn;
+  a.dinv = csr->dinv; a.wsum = csr->wsum; a.meta = csr->graph_meta;
+  a.kind = kind; a.max_nodes = max_nodes < 1 ? 1 : max_nodes; a.skip_edge_cap = skip_edge_cap;
+  a.agg_in = agg_in; a.agg_out = agg_out; a.row_graph = row_graph;
+  const size_t smem = (size_t)2 * a.max_nodes * sizeof(int) + 16;
+  const DeviceInfo dev = device_info();
+  if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
+  auto kfn = k_build_agg;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  CGNN_LAUNCH(kfn, (unsigned)num_graphs, 256, smem, stream, a);
+  CGNN_CHECK_LAUNCH();
+  return CGNN_OK;
+}
+
 }  // namespace cgnn
 
 using namespace cgnn;
@@ -315,20 +334,7 @@ int cgnn_build_agg(const cgnn_csr_t* csr, int32_t kind, int64_t num_graphs, int6
   if (!agg_in || !agg_out || !row_graph || !csr->in_rowptr || !csr->in_col || !csr->in_w || !csr->in_wn ||
       !csr->out_rowptr || !csr->out_col || !csr->out_w || !csr->out_wn || !csr->dinv || !csr->wsum || !csr->graph_meta)
     return CGNN_ERR_INVALID_ARG;
-  BuildAggArgs a;
-  a.in_rowptr = csr->in_rowptr; a.in_col = csr->in_col; a.in_w = csr->in_w; a.in_wn = csr->in_wn;
-  a.out_rowptr = csr->out_rowptr; a.out_col = csr->out_col; a.out_w = csr->out_w; a.out_wn = csr->out_wn;
-  a.dinv = csr->dinv; a.wsum = csr->wsum; a.meta = csr->graph_meta;
-  a.kind = kind; a.max_nodes = max_nodes < 1 ? 1 : max_nodes;
-  a.agg_in = agg_in; a.agg_out = agg_out; a.row_graph = row_graph;
-  const size_t smem = (size_t)2 * a.max_nodes * sizeof(int) + 16;
-  const DeviceInfo dev = device_info();
-  if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
-  auto kfn = k_build_agg;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  CGNN_LAUNCH(kfn, (unsigned)num_graphs, 256, smem, stream, a);
-  CGNN_CHECK_LAUNCH();
-  return CGNN_OK;
+  return launch_build_agg(csr, kind, num_graphs, max_nodes, agg_in, agg_out, row_graph, -1, stream);
 }
 
 }  // extern "C"

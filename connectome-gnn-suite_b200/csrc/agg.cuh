@@ -117,6 +117,9 @@ int launch_gcn_fwd_fused(const float* t_in, const cgnn_act_t* act, const float* 
                          int64_t num_graphs, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
                          double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream);
 #endif
+// agg.cu: blob builder; subjects with <= skip_edge_cap edges (and < 65536 rows) are skipped (built by the collate kernel)
+int launch_build_agg(const cgnn_csr_t* csr, int32_t kind, int64_t num_graphs, int32_t max_nodes, int32_t* agg_in, int32_t* agg_out,
+                     int32_t* row_graph, int skip_edge_cap, cudaStream_t stream);
 // true when launch_gather covers C channels (checked before a tensor-core contraction commits to the gather that follows)
 bool gather_supported(int C, int max_nodes, int max_edges);
 

@@ -8,6 +8,7 @@
 // inside a row = COO order) so that the sequential fp32 row sums below reproduce the CPU
 // scatter_add_ of the reference bit for bit.
 #include "common.cuh"
+#include "agg.cuh"
 
 namespace cgnn {
 
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   int* cur_in = reinterpret_cast<int*>(cgnn_smem);   // [n] counts -> row starts -> cursors
   int* cur_out = cur_in + n;                          // [n]
   float* s_dinv = reinterpret_cast<float*>(cur_out + n);  // [n]
+  float* s_wsum = s_dinv + n;                             // [n]
 
   const int32_t* lsrc = nullptr; const int32_t* ldst = nullptr; const float* lw = nullptr;
   const long long* gsrc = nullptr; const long long* gdst = nullptr;
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
     gsrc = p.coo + eb; gdst = p.coo + p.total_edges + eb; lw = p.coo_w + eb;
   }
   constexpr int kChunks = kWarps / 2;
-  int* cnt = reinterpret_cast<int*>(s_dinv + n);        // [2][kChunks][n]
+  int* cnt = reinterpret_cast<int*>(s_wsum + n);        // [2][kChunks][n]
   // Subjects that fit are sorted entirely in shared memory: the raw COO list (src | dst << 16, w) is read from
   // global memory once, both sorted lists live next to it, and the row sums, normalised weights and CSR arrays are
   // produced from shared memory with coalesced stores.  Larger subjects re-read global memory (same results).
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   float* cw = reinterpret_cast<float*>(pk + 2 * m);                      // [2][m]
   uint32_t* raw_pk = reinterpret_cast<uint32_t*>(cw + 2 * m);            // [m] COO order
   float* raw_w = reinterpret_cast<float*>(raw_pk + m);                   // [m]
+  const bool want_agg = staged && p.csr.agg_kind >= 0 && p.csr.agg_in && p.csr.agg_out && p.csr.row_graph;
   // Local endpoints of edge e as stored.  Endpoints outside the subject (malformed hand-built batches)
   // are redirected to a zero-weight self edge on node 0 so the CSR stays consistent.
   auto load_edge = [&](int e, int& s, int& d, float& w) {
@@ -284,11 +287,48 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
       for (int q = i0; q < i1; ++q) ws = __fadd_rn(ws, cw[q]);
       const float dinv = (float)(1.0 / sqrt((double)__fadd_rn(deg, 1e-8f)));
       s_dinv[i] = dinv;
+      s_wsum[i] = ws;
       p.csr.deg[nb + i] = deg;
       p.csr.dinv[nb + i] = dinv;
       p.csr.wsum[nb + i] = ws;
     }
     __syncthreads();
+    if (want_agg) {
+      // packed aggregation blobs of the requested family, straight from the sorted lists (same bits as k_build_agg)
+      const int self = p.csr.agg_kind == AGG_GCN ? 1 : 0;
+      int* pos = cnt;                                   // [2][n] padded record counts -> first record of every row
+      for (int idx = tid; idx < 2 * n; idx += kThreads) {
+        const int dd = idx / n, i = idx - dd * n;
+        const int* ce = dd == 0 ? cur_in : cur_out;
+        pos[idx] = ((ce[i] - (i ? ce[i - 1] : 0)) + self + 1) & ~1;
+      }
+      __syncthreads();
+      block_excl_scan(pos, n, s_warp);
+      block_excl_scan(pos + n, n, s_warp);
+      for (int i = tid; i < n; i += kThreads) p.csr.row_graph[nb + i] = (int32_t)g;
+      for (int idx = tid; idx < 2 * n; idx += kThreads) {
+        const int dd = idx / n, i = idx - dd * n;
+        const int* ce = dd == 0 ? cur_in : cur_out;
+        const int q0 = i ? ce[i - 1] : 0, q1 = ce[i];
+        int32_t* blob = (dd == 0 ? p.csr.agg_in : p.csr.agg_out) + agg_base_words(nb, eb, g);
+        int2* rec = reinterpret_cast<int2*>(blob + 4 * (long long)n);
+        int at = pos[idx];
+        const int begin = at;
+        for (int q = q0; q < q1; ++q) {
+          const uint32_t v = pk[dd * m + q];
+          const int s = (int)(v & 0xffffu), d = (int)(v >> 16);
+          const float w = cw[dd * m + q];
+          float wr;
+          if (p.csr.agg_kind == AGG_GCN) wr = __fmul_rn(__fmul_rn(s_dinv[s], w), s_dinv[d]);
+          else wr = dd == 0 ? w : w / (s_wsum[d] + 1e-8f);      // adjoint of the weighted mean
+          rec[at++] = make_int2(dd == 0 ? s : d, __float_as_int(wr));
+        }
+        if (self) { const float dv = s_dinv[i]; rec[at++] = make_int2(i, __float_as_int(__fmul_rn(dv, dv))); }
+        if (at & 1) rec[at++] = make_int2(i, 0);
+        const float aux = p.csr.agg_kind == AGG_SAGE ? s_wsum[i] : s_dinv[i];
+        reinterpret_cast<int4*>(blob)[i] = make_int4(begin, at, __float_as_int(aux), 0);
+      }
+    }
     for (int q = tid; q < m; q += kThreads) {
       uint32_t v = pk[q];
       int s = (int)(v & 0xffffu), d = (int)(v >> 16);
@@ -349,7 +389,7 @@ static bool csr_out_ok(const cgnn_csr_out_t* c) {
 static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaStream_t stream) {
   const DeviceInfo dev = device_info();
   if (max_nodes < 1) max_nodes = 1;
-  size_t smem = (size_t)max_nodes * (12 + 4 * kWarps) + 16;   // cursors, dinv, per-chunk counters
+  size_t smem = (size_t)max_nodes * (16 + 4 * kWarps) + 16;   // cursors, dinv, wsum, per-chunk counters
   if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   // room for the raw and the two sorted edge lists of a typical subject (24 bytes per edge): an eighth above the batch average, as
   // long as two CTAs still fit on an SM; larger subjects take the unstaged path inside the kernel
@@ -373,6 +413,15 @@ static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaSt
     CGNN_LAUNCH(kfn, (unsigned)a.B, kThreads, smem, stream, a);
   }
   CGNN_CHECK_LAUNCH();
+  if (a.csr.agg_kind >= 0 && a.csr.agg_in && a.csr.agg_out && a.csr.row_graph && a.edge_cap < a.total_edges) {
+    // subjects the kernel could not stage (more edges than edge_cap) get their blobs from the stand-alone builder,
+    // which skips the ones already done
+    cgnn_csr_t c{};
+    c.in_rowptr = a.csr.in_rowptr; c.in_col = a.csr.in_col; c.in_w = a.csr.in_w; c.in_wn = a.csr.in_wn;
+    c.out_rowptr = a.csr.out_rowptr; c.out_col = a.csr.out_col; c.out_w = a.csr.out_w; c.out_wn = a.csr.out_wn;
+    c.deg = a.csr.deg; c.dinv = a.csr.dinv; c.wsum = a.csr.wsum; c.graph_meta = a.csr.graph_meta;
+    return launch_build_agg(&c, a.csr.agg_kind, a.B, max_nodes, a.csr.agg_in, a.csr.agg_out, a.csr.row_graph, a.edge_cap, stream);
+  }
   return CGNN_OK;
 }
 

@@ -143,12 +143,17 @@ typedef struct {
   int32_t num_features;
 } cgnn_store_t;
 
-/* Mutable view of the CSR arrays the collate kernels fill (same layout as cgnn_csr_t). */
+/* Mutable view of the CSR arrays the collate kernels fill (same field order as cgnn_csr_t). */
 typedef struct {
   int32_t* in_rowptr;  int32_t* in_col;  float* in_w;  float* in_wn;
   int32_t* out_rowptr; int32_t* out_col; float* out_w; float* out_wn;
   float* deg; float* dinv; float* wsum;
   int32_t* graph_meta;
+  /* optional: have the collate kernel also emit the packed aggregation blobs of one model family (what
+   * cgnn_build_agg would produce from the arrays above, bit for bit) while the sorted lists are still in shared
+   * memory.  agg_kind = -1 (or NULL pointers): not requested. */
+  int32_t* agg_in; int32_t* agg_out; int32_t* row_graph;
+  int32_t agg_kind;
 } cgnn_csr_out_t;
 
 /* Gather `num_graphs` subjects (ids into the store, device int64) into one batch.

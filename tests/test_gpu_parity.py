@@ -304,3 +304,33 @@ def test_compact_store_collates_identically():
         assert torch.equal(getattr(a, f), getattr(b, f)), f
     for f in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn", "deg", "dinv", "wsum"):
         assert torch.equal(getattr(a.csr, f), getattr(b.csr, f)), f
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_collate_emits_the_same_aggregation_structure(kind):
+    """`prepare_for` (blobs written by the collate kernel) and the lazy `cgnn_build_agg` path feed the layer kernels
+    identical structure: forward outputs and backward gradients are bit-identical."""
+    from connectome_gnn import _engine
+    from connectome_gnn._engine import Act
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    graphs = generate_dataset(num_subjects=7, num_regions=84, seed=31) + generate_dataset(num_subjects=3, num_regions=50, seed=32)
+    store = SubjectStore(pack_graphs(graphs), DEV)
+    ids = np.array([9, 0, 4, 7, 2, 2, 8])
+    a = store.collate(ids, prepare_for=kind)
+    b = store.collate(ids)
+    assert a.csr.agg is not None and kind in a.csr.agg and b.csr.agg is None
+    eng = _engine.engine_for(a.node_features)
+    g = torch.Generator().manual_seed(5)
+    t_in = torch.randn(a.num_nodes, 64, generator=g).to(DEV)
+    W = (torch.randn(64, 64 if kind == "gcn" else 128, generator=g) * 0.2).to(DEV)
+    bias = (torch.randn(64, generator=g) * 0.1).to(DEV)
+    act = Act()
+    za, _, agg_a = eng.layer_fwd(kind, t_in, act, W, bias, a.csr, a.ptr, a.num_graphs, False)
+    zb, _, agg_b = eng.layer_fwd(kind, t_in, act, W, bias, b.csr, b.ptr, b.num_graphs, False)
+    assert torch.equal(za, zb)
+    du = torch.randn(a.num_nodes, 64, generator=g).to(DEV)
+    oa = eng.layer_bwd(kind, du, None, za, Act(), None, t_in, act, W, a.csr, a.ptr, a.num_graphs, True, None, None, agg_a)
+    ob = eng.layer_bwd(kind, du, None, zb, Act(), None, t_in, act, W, b.csr, b.ptr, b.num_graphs, True, None, None, agg_b)
+    for x, y in zip(oa[:3], ob[:3]):
+        assert torch.equal(x, y)
