@@ -112,6 +112,14 @@ int launch_sage_bwd_gemm(const float* du, const float* demb, const int32_t* row_
                          const cgnn_act_t* act_in, const float* W, int64_t rows, int32_t C, int32_t H, float* direct,
                          float* nbr, float* partials, int part_stride, int o_pdb, int* grid_out, size_t partial_bytes,
                          cudaStream_t stream);
+// first_layer.cu: narrow-input (d_in <= 8) layers without tensor cores; kind = AGG_GCN / AGG_SAGE
+int launch_first_fwd(int kind, const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+                     int64_t num_graphs, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, float* agg_out,
+                     double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream);
+int launch_first_bwd(int kind, const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
+                     const cgnn_bn_bwd_t* bn, const float* t_in, const float* agg, const cgnn_act_t* act_in, const cgnn_csr_t* csr,
+                     int64_t num_graphs, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* partials,
+                     int* grid_out, size_t partial_bytes, cudaStream_t stream);
 // gcn_fused.cu: the whole GCN forward layer (gather -> tensor-core projection) in one kernel
 int launch_gcn_fwd_fused(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
                          int64_t num_graphs, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,

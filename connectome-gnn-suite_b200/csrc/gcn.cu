@@ -506,7 +506,11 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
 #ifndef CGNN_EMU
   if (tensor_cores_enabled()) {   // tcgen05 / TMEM editions for the shapes they cover
     int tc_grid = 0;
-    int rc = launch_gcn_fwd_fused(t_in, act, W, bias, csr, num_graphs, d_in, H, max_nodes, max_edges, z,
+    int rc = launch_first_fwd(AGG_GCN, t_in, act, W, bias, csr, num_graphs, d_in, H, max_nodes, max_edges, z, nullptr,
+                              bn_stats ? (double*)workspace : nullptr, &tc_grid, workspace_bytes, stream);
+    if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;
+    if (rc > 0) return rc;
+    rc = launch_gcn_fwd_fused(t_in, act, W, bias, csr, num_graphs, d_in, H, max_nodes, max_edges, z,
                                   bn_stats ? (double*)workspace : nullptr, &tc_grid, workspace_bytes, stream);
     if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;
     if (rc > 0) return rc;
@@ -584,6 +588,19 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
   if (prev_sums && (!du_in || !prev_mean || !prev_rstd)) return CGNN_ERR_INVALID_ARG;
   if (bn && (!bn->scale || !bn->mean || !bn->rstd || (bn->train && (!bn->s1 || !bn->s2)))) return CGNN_ERR_INVALID_ARG;
 #ifndef CGNN_EMU
+  // Narrow first layer whose input needs no gradient: dW = dz^T (A^ u), dbias in one pass, no tensor cores.
+  if (tensor_cores_enabled() && !du_in && d_in <= 8) {
+    int g0 = 0;
+    const int rc0 = launch_first_bwd(AGG_GCN, du, demb, z, act_out, bn, t_in, nullptr, act_in, csr, num_graphs, d_in, H, max_nodes,
+                                     max_edges, (float*)workspace, &g0, workspace_bytes, stream);
+    if (rc0 > 0) return rc0;
+    if (rc0 == CGNN_OK) {
+      const int stride = H * d_in + H;
+      int rc1 = launch_reduce_partials((const float*)workspace, g0, stride, H, d_in, d_in, dW, stream);
+      if (rc1) return rc1;
+      return launch_reduce_partials((const float*)workspace + H * d_in, g0, stride, 1, H, H, dbias, stream);
+    }
+  }
   // Tensor-core generation: gather kernel (dz on load, dP = A^^T dz, dbias) + tcgen05 contractions (du_in, dW).
   if (tensor_cores_enabled() && scratch && csr->agg_out && csr->agg_kind == AGG_GCN && (H == 32 || H == 64 || H == 128) &&
       d_in <= 128 && (d_in + 31) / 32 != 3 && aligned16(scratch) && aligned16(z) && (!du || aligned16(du)) &&

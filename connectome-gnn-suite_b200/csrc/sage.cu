@@ -534,6 +534,14 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
   if (d_in % 4 == 0 && !aligned16(t_in)) return CGNN_ERR_INVALID_ARG;
   if (bn_stats && (!workspace || workspace_bytes < (size_t)(1 + 2 * H) * sizeof(double))) return CGNN_ERR_WORKSPACE;
 #ifndef CGNN_EMU
+  // Narrow first layer: gather + projection in one kernel, no tensor cores.
+  if (tensor_cores_enabled() && agg && d_in <= 8) {
+    int g0 = 0;
+    const int rc0 = launch_first_fwd(AGG_SAGE, t_in, act, W, bias, csr, num_graphs, d_in, H, max_nodes, max_edges, z, agg,
+                                     bn_stats ? (double*)workspace : nullptr, &g0, workspace_bytes, stream);
+    if (rc0 == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, g0, H, bn_stats, stream) : CGNN_OK;
+    if (rc0 > 0) return rc0;
+  }
   // Tensor-core generation: gather kernel (weighted mean of the neighbours) + tcgen05 contraction.
   if (tensor_cores_enabled() && agg && csr->agg_in && csr->agg_kind == AGG_SAGE && (H == 32 || H == 64 || H == 128) &&
       2 * d_in <= 128 && (2 * d_in + 31) / 32 != 3 && (d_in <= 32 || d_in % 32 == 0) && aligned16(agg) && aligned16(z)) {
@@ -626,6 +634,19 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
   if (prev_sums && (!du_in || !prev_mean || !prev_rstd)) return CGNN_ERR_INVALID_ARG;
   if (bn && (!bn->scale || !bn->mean || !bn->rstd || (bn->train && (!bn->s1 || !bn->s2)))) return CGNN_ERR_INVALID_ARG;
 #ifndef CGNN_EMU
+  // Narrow first layer whose input needs no gradient: dW = dz^T [u || agg], dbias in one pass, no tensor cores.
+  if (tensor_cores_enabled() && !du_in && agg && d_in <= 8) {
+    int g0 = 0;
+    const int rc0 = launch_first_bwd(AGG_SAGE, du, demb, z, act_out, bn, t_in, agg, act_in, csr, num_graphs, d_in, H, max_nodes,
+                                     max_edges, (float*)workspace, &g0, workspace_bytes, stream);
+    if (rc0 > 0) return rc0;
+    if (rc0 == CGNN_OK) {
+      const int stride = H * 2 * d_in + H;
+      int rc1 = launch_reduce_partials((const float*)workspace, g0, stride, H, 2 * d_in, 2 * d_in, dW, stream);
+      if (rc1) return rc1;
+      return launch_reduce_partials((const float*)workspace + H * 2 * d_in, g0, stride, 1, H, H, dbias, stream);
+    }
+  }
   // Tensor-core generation: tcgen05 contractions (dz on load, [d_u || d_agg], dW, dbias) + transposed gather kernel.
   if (tensor_cores_enabled() && agg && csr->agg_out && csr->row_graph && csr->agg_kind == AGG_SAGE &&
       (H == 32 || H == 64 || H == 128) && 2 * d_in <= 128 && (2 * d_in + 31) / 32 != 3 && (d_in <= 32 || d_in % 32 == 0) &&

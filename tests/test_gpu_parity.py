@@ -334,3 +334,53 @@ def test_collate_emits_the_same_aggregation_structure(kind):
     ob = eng.layer_bwd(kind, du, None, zb, Act(), None, t_in, act, W, b.csr, b.ptr, b.num_graphs, True, None, None, agg_b)
     for x, y in zip(oa[:3], ob[:3]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+@pytest.mark.parametrize("shape", [(6, 360, 5, 64), (9, 84, 5, 64), (5, 100, 8, 32), (4, 77, 3, 128)])
+@pytest.mark.parametrize("top", [False, True])
+def test_first_layer_kernels_match_the_generic_kernels(kind, shape, top):
+    """Narrow-input layer (no tensor cores, no input gradient): forward z / BatchNorm statistics and backward dW / dbias
+    against the generic SIMT kernels, with an activation on the input, dropout after the layer and a ragged batch."""
+    from connectome_gnn import _engine
+    from connectome_gnn._engine import Act, BnBwd
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    subjects, regions, d_in, H = shape
+    eng = _engine.engine_for(torch.zeros(1, device=DEV))
+    b = collate_graphs(generate_dataset(num_subjects=subjects, num_regions=regions, seed=8) +
+                       generate_dataset(num_subjects=2, num_regions=max(8, regions // 2), seed=9))
+    g = torch.Generator().manual_seed(4)
+    rows, B = b.num_nodes, b.num_graphs
+    rn = lambda *s: torch.randn(*s, generator=g)
+    t_in = rn(rows, d_in).to(DEV)
+    W = (rn(H, d_in if kind == "gcn" else 2 * d_in) * 0.3).to(DEV)
+    bias = (rn(H) * 0.1).to(DEV)
+    act_in = Act()
+    fwd = {}
+    for use_tc in (1, 0):
+        assert eng.lib.cgnn_set_option(1, use_tc) == 0
+        try:
+            fwd[use_tc] = eng.layer_fwd(kind, t_in, act_in, W, bias, b.csr, b.ptr, B, True)
+        finally:
+            eng.lib.cgnn_set_option(1, 1)
+    helpers.assert_close(fwd[1][0], fwd[0][0], f"{kind} first layer z", tol=2e-6)
+    helpers.assert_close(fwd[1][1][1:1 + H], fwd[0][1][1:1 + H], "BN mean", tol=2e-6, atol=1e-6)
+    helpers.assert_close(fwd[1][1][1 + H:], fwd[0][1][1 + H:], "BN M2", tol=2e-5)
+    if kind == "sage":
+        helpers.assert_close(fwd[1][2], fwd[0][2], "stored aggregate", tol=2e-6)
+    z, agg = fwd[0][0], fwd[0][2]
+    act_out = Act((1 + 0.1 * rn(H)).to(DEV), (0.1 * rn(H)).to(DEV), kind == "gcn", 0.3, seed=80, site=1, row_base=32)
+    mean, rstd = (0.1 * rn(H)).to(DEV), (1 + 0.1 * rn(H)).abs().to(DEV)
+    bn = BnBwd(act_out.scale, mean, rstd, (rn(2, H) * 0.5).to(DEV), float(rows), True)
+    du = None if top else rn(rows, H).to(DEV)
+    demb = rn(B, H).to(DEV) if top else None
+    out = {}
+    for use_tc in (1, 0):
+        assert eng.lib.cgnn_set_option(1, use_tc) == 0
+        try:
+            out[use_tc] = eng.layer_bwd(kind, du, demb, z, act_out, bn, t_in, act_in, W, b.csr, b.ptr, B, False, None, None, agg)
+        finally:
+            eng.lib.cgnn_set_option(1, 1)
+    for name, got, ref in zip(("dW", "dbias"), out[1], out[0]):
+        helpers.assert_close(got, ref, f"{kind} first layer bwd {name}", tol=5e-6)
