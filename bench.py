@@ -247,14 +247,15 @@ def run_b200(a):
 
     def step_e2e():
         """Every leg's subjects travel pinned host -> device on the loader's copy stream while the previous leg
-        computes; a step consumes four uploads and issues four (the last one is the next step's first leg), and every
-        leg ends with its loss read back to the host."""
-        out = None
+        computes; a step consumes four uploads and issues four (the last one is the next step's first leg) and ends
+        with its four losses read back to the host."""
+        losses = []
         for name in LEGS:
             st = streaming.next()
             streaming.prefetch(pinned)
-            out = float(leg(name, st))               # loss read back to the host
-        return out
+            losses.append(leg(name, st).reshape(()))
+            st.release()                             # the arena may be refilled once this leg's kernels have run
+        return torch.stack(losses).cpu().tolist()    # the step's four losses read back to the host
 
     def barrier():
         if world > 1:

@@ -239,6 +239,12 @@ class SubjectStore:
                               self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), self.label.data_ptr(),
                               self.num_features)
 
+    def release(self) -> None:
+        """Mark the work enqueued so far on the current stream as the last use of this arena's contents: a later
+        ``reload`` on another stream waits for it on the device, so the host never has to synchronise."""
+        self._free = torch.cuda.Event()
+        self._free.record(torch.cuda.current_stream(self.device))
+
     @classmethod
     def from_graphs(cls, graphs: Sequence[ConnectomeGraph], device=None) -> "SubjectStore":
         return cls(pack_graphs(graphs), device)
@@ -257,6 +263,9 @@ class SubjectStore:
         self.has_label = np.asarray(packed["has_label"], dtype=bool)
         ctx = torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
         with ctx:
+            free = getattr(self, "_free", None)
+            if free is not None:       # the previous consumer of this arena (release()) must have finished with it
+                torch.cuda.current_stream(self.device).wait_event(free)
             for k in names:
                 getattr(self, k).copy_(packed[k], non_blocking=True)
             self._ready = torch.cuda.Event()
@@ -319,8 +328,9 @@ class StreamingStore:
             batch = store.collate(ids)
             ...
 
-    All sets must have the shapes of the first one (same subjects-per-set layout); the caller must have finished
-    using arena k-2 (e.g. by reading a result back to the host) before ``prefetch`` reuses it."""
+    All sets must have the shapes of the first one (same subjects-per-set layout).  Call ``store.release()`` after the
+    last kernel that reads a set has been enqueued (or synchronise with the host): ``prefetch`` into that arena then
+    waits for it on the device."""
 
     def __init__(self, packed: dict, device=None):
         self.device = torch.device(device) if device is not None else _engine.default_device()

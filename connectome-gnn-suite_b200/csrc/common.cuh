@@ -99,13 +99,20 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
   return h;
 }
-// One hash per row, one per channel pair: 16 random bits per element.
+// Dropout stream: one mix per row (cheap, no avalanche of its own), one full-avalanche hash per channel QUAD, from
+// which the four 16-bit fields of the quad are cut - the second pair from a multiply / xor-shift of the first word.
+// (The row-tile kernels evaluate the same function a quad at a time, rowtile.cuh::drop_keep4.)
 __device__ __forceinline__ uint32_t drop_row_hash(const Act& a, long long grow) {
   uint32_t lo = (uint32_t)grow, hi = (uint32_t)((unsigned long long)grow >> 32);
-  return fmix32((lo * 0x9E3779B1u) ^ a.k0 ^ fmix32(hi + a.k1));
+  return (lo * 0x9E3779B1u) ^ a.k0 ^ fmix32(hi + a.k1);
+}
+__device__ __forceinline__ uint32_t drop_second_word(uint32_t y) {
+  uint32_t w = y * 0x9E3779B1u + 0x7F4A7C15u;
+  return w ^ (w >> 15);
 }
 __device__ __forceinline__ bool drop_keep(const Act& a, uint32_t row_hash, int c) {
-  uint32_t w = fmix32(row_hash + (uint32_t)(c >> 1) * 0x632BE5ABu + a.k1);
+  const uint32_t y = fmix32(row_hash + (uint32_t)(c >> 2) * 0x632BE5ABu + a.k1);
+  const uint32_t w = (c & 2) ? drop_second_word(y) : y;
   uint32_t bits = (c & 1) ? (w >> 16) : (w & 0xffffu);
   return bits >= a.thresh;
 }

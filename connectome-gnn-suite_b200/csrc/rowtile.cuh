@@ -45,7 +45,7 @@ __device__ __forceinline__ void sts4(unsigned char* p, float4 v) { *reinterpret_
 // ---- per-thread constants of one channel quad of an Act ---------------------------------------------------------
 struct ChanQuad {
   float sc[4], sh[4];
-  uint32_t ck0, ck1;   // dropout: (c >> 1) * 0x632BE5AB + k1 for the two channel pairs of the quad
+  uint32_t ck;         // dropout: (c >> 2) * 0x632BE5AB + k1 of this quad
 };
 __device__ __forceinline__ void chan_quad_init(ChanQuad& cq, const Act& a, int c0, int C) {
 #pragma unroll
@@ -54,8 +54,7 @@ __device__ __forceinline__ void chan_quad_init(ChanQuad& cq, const Act& a, int c
     cq.sc[j] = ok ? a.scale[c0 + j] : 1.0f;
     cq.sh[j] = ok ? a.shift[c0 + j] : 0.0f;
   }
-  cq.ck0 = (uint32_t)(c0 >> 1) * 0x632BE5ABu + a.k1;
-  cq.ck1 = (uint32_t)((c0 >> 1) + 1) * 0x632BE5ABu + a.k1;
+  cq.ck = (uint32_t)(c0 >> 2) * 0x632BE5ABu + a.k1;
 }
 // Dropout row key: the per-row hash of common.cuh::drop_row_hash for global row ids (row_base + row) computed from
 // 32-bit pieces - the high word's hash is formed once per kernel (and once more for rows behind a 2^32 boundary).
@@ -74,12 +73,12 @@ __device__ __forceinline__ RowKey row_key(const Act& a) {
 __device__ __forceinline__ uint32_t row_hash_at(const Act& a, const RowKey& k, uint32_t row) {
   const uint32_t lo = k.lo0 + row;
   const uint32_t hh = lo >= k.lo0 ? k.hh0 : k.hh1;
-  return fmix32((lo * 0x9E3779B1u) ^ a.k0 ^ hh);
+  return (lo * 0x9E3779B1u) ^ a.k0 ^ hh;
 }
 // keep masks of the quad's 4 channels at row `row` of the batch (bit j = channel c0 + j kept); same stream as drop_keep()
 __device__ __forceinline__ uint32_t drop_keep4(const Act& a, const ChanQuad& cq, const RowKey& rk, uint32_t row) {
   const uint32_t rh = row_hash_at(a, rk, row);
-  const uint32_t w0 = fmix32(rh + cq.ck0), w1 = fmix32(rh + cq.ck1);
+  const uint32_t w0 = fmix32(rh + cq.ck), w1 = drop_second_word(w0);
   return ((w0 & 0xffffu) >= a.thresh ? 1u : 0u) | ((w0 >> 16) >= a.thresh ? 2u : 0u) |
          ((w1 & 0xffffu) >= a.thresh ? 4u : 0u) | ((w1 >> 16) >= a.thresh ? 8u : 0u);
 }

@@ -63,7 +63,7 @@ def test_dropout_masks_regenerate_and_gradients_are_consistent(on_emu):
         params = [p for p in m.parameters()]
         direction = [torch.randn(p.shape, generator=torch.Generator().manual_seed(i)) for i, p in enumerate(params)]
         analytic = sum(float((p.grad * d).sum()) for p, d in zip(params, direction))
-        eps = 2e-3
+        eps = 2e-4   # small enough that ReLU kinks crossed by the probe stay below the tolerance (checked: converges to analytic)
         with torch.no_grad():
             for p, d in zip(params, direction): p.add_(eps * d)
             lp = float(loss_at())
