@@ -53,6 +53,16 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   int k = 0;
 #pragma unroll 1
+  for (; k + 4 <= lmin; k += 4, rp += 2) {   // four records per step: half the loop overhead, four tile loads in flight
+    const int4 r = rp[0], s = rp[1];
+    const float4 v0 = t4[r.x * PITCH], v1 = t4[r.z * PITCH], v2 = t4[s.x * PITCH], v3 = t4[s.z * PITCH];
+    const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w), w2 = __int_as_float(s.y), w3 = __int_as_float(s.w);
+    a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
+    a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
+    a.x = fmaf(v2.x, w2, a.x); a.y = fmaf(v2.y, w2, a.y); a.z = fmaf(v2.z, w2, a.z); a.w = fmaf(v2.w, w2, a.w);
+    a.x = fmaf(v3.x, w3, a.x); a.y = fmaf(v3.y, w3, a.y); a.z = fmaf(v3.z, w3, a.z); a.w = fmaf(v3.w, w3, a.w);
+  }
+#pragma unroll 1
   for (; k < lmin; k += 2, ++rp) {        // every row of the group has these records
     const int4 r = *rp;
     const float4 v0 = t4[r.x * PITCH], v1 = t4[r.z * PITCH];

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
     }
   __syncthreads();
   for (int idx = tid; idx < 2 * n; idx += kThreads) {
-    const int dd = idx / n, i = idx - dd * n;
+    const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
     int t = 0;
     for (int c = 0; c < kChunks; ++c) t += cnt[(size_t)(dd * kChunks + c) * n + i];
     (dd == 0 ? cur_in : cur_out)[i] = t;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   block_excl_scan(cur_in, n, s_warp);
   block_excl_scan(cur_out, n, s_warp);
   for (int idx = tid; idx < 2 * n; idx += kThreads) {
-    const int dd = idx / n, i = idx - dd * n;
+    const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
     int run = (dd == 0 ? cur_in : cur_out)[i];
     (dd == 0 ? p.csr.in_rowptr : p.csr.out_rowptr)[nb + i] = (int32_t)(eb + run);
     for (int c = 0; c < kChunks; ++c) {
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   __syncthreads();
   // cur_in / cur_out hold the exclusive row starts; the passes below want the inclusive ends (start of row i + 1)
   for (int idx = tid; idx < 2 * n; idx += kThreads) {
-    const int dd = idx / n, i = idx - dd * n;
+    const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
     const int* c = cnt + (size_t)(dd * kChunks + kChunks - 1) * n;
     (dd == 0 ? cur_in : cur_out)[i] = c[i];     // the last chunk's cursor of row i ended at the row's end
   }
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
       const int self = p.csr.agg_kind == AGG_GCN ? 1 : 0;
       int* pos = cnt;                                   // [2][n] padded record counts -> first record of every row
       for (int idx = tid; idx < 2 * n; idx += kThreads) {
-        const int dd = idx / n, i = idx - dd * n;
+        const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
         const int* ce = dd == 0 ? cur_in : cur_out;
         pos[idx] = ((ce[i] - (i ? ce[i - 1] : 0)) + self + 1) & ~1;
       }
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
       block_excl_scan(pos + n, n, s_warp);
       for (int i = tid; i < n; i += kThreads) p.csr.row_graph[nb + i] = (int32_t)g;
       for (int idx = tid; idx < 2 * n; idx += kThreads) {
-        const int dd = idx / n, i = idx - dd * n;
+        const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
         const int* ce = dd == 0 ? cur_in : cur_out;
         const int q0 = i ? ce[i - 1] : 0, q1 = ce[i];
         int32_t* blob = (dd == 0 ? p.csr.agg_in : p.csr.agg_out) + agg_base_words(nb, eb, g);

@@ -32,5 +32,8 @@ for SPEC in ${SPECS:-"89:5" "98:2"}; do
   timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KREGEX" -s $S -c $C \
       -f -o $OUT/prof_${TAG}_$i $CMD > $OUT/ncu_full_${TAG}_$i.log 2>&1
   echo "full capture $i ($SPEC) rc=$?"
+  # the summary always travels; the report itself only while the whole directory stays under the 64 MiB that come back
+  ncu -i $OUT/prof_${TAG}_$i.ncu-rep --page raw --csv > $OUT/prof_${TAG}_$i.raw.csv 2>/dev/null
+  if [ $(du -sm $OUT | cut -f1) -gt 56 ]; then rm -f $OUT/prof_${TAG}_$i.ncu-rep; echo "dropped prof_${TAG}_$i.ncu-rep (size)"; fi
 done
 du -sh $OUT; ls -la $OUT | tail -14
