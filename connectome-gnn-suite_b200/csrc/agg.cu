@@ -145,26 +145,28 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
       pooled = rt::ld_quad<VEC>(p.demb, g, C, c0);
       pooled = make_float4(pooled.x * inv_n, pooled.y * inv_n, pooled.z * inv_n, pooled.w * inv_n);
     }
-    for (int r = rl; r < n; r += 2 * RP) {
-      float4 a[2], b[2];
+    // UL rows per thread are loaded before any is processed: one exposed memory latency per batch of UL
+    constexpr int UL = MODE == GATHER_GCN_BWD ? 2 : 6;
+    for (int r = rl; r < n; r += UL * RP) {
+      float4 a[UL], b[MODE == GATHER_GCN_BWD ? UL : 1];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < UL; ++u) {
         const int rr = r + u * RP;
         a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        b[u] = pooled;
+        if (MODE == GATHER_GCN_BWD) b[u] = pooled;
         if (rr < n && live_quad) {
           a[u] = rt::ld_quad<VEC>(p.src, nb + rr, C, c0);
           if (MODE == GATHER_GCN_BWD && p.du) b[u] = rt::ld_quad<VEC>(p.du, nb + rr, C, c0);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < UL; ++u) {
         const int rr = r + u * RP;
         if (rr < n) {
           float4 o = a[u];
           if (MODE == GATHER_SAGE_FWD) o = rt::act_fwd4(p.act, cq, a[u], rk, (uint32_t)(nb + rr));
           if (MODE == GATHER_GCN_BWD) {
-            o = rt::bn_bwd4(bn, bq, a[u], rt::act_bwd4(p.act, cq, a[u], b[u], rk, (uint32_t)(nb + rr)));
+            o = rt::bn_bwd4(bn, bq, a[u], rt::act_bwd4(p.act, cq, a[u], b[MODE == GATHER_GCN_BWD ? u : 0], rk, (uint32_t)(nb + rr)));
             if (!VEC) o = rt::mask_quad(o, c0, C);
             s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
           }
@@ -182,6 +184,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
       float4 acc;
       float aux;
       int row;
+      float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f), rpre = dpre;
+      if (MODE == GATHER_SAGE_BWD) {   // the row's direct gradient and stored input: loads fly during the gather
+        const int rowp = i0 + (tid & 31) / LPR;
+        if (rowp < n && live_quad) {
+          dpre = rt::ld_quad<VEC>(p.direct, nb + rowp, C, c0);
+          if (p.want_prev) rpre = rt::ld_quad<VEC>(p.t_raw, nb + rowp, C, c0);
+        }
+      }
       const bool valid = agg_gather_group<LPR>(s_desc, s_rec2, s_tile, i0, n, acc, aux, row);
       if (!valid || !live_quad) continue;
       const long long grow = nb + row;
@@ -190,10 +200,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
         acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
       }
       if (MODE == GATHER_SAGE_BWD) {
-        const float4 d = rt::ld_quad<VEC>(p.direct, grow, C, c0);
+        const float4 d = dpre;
         acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
         if (p.want_prev) {
-          const float4 raw = rt::ld_quad<VEC>(p.t_raw, grow, C, c0);
+          const float4 raw = rpre;
           const float4 dyp = rt::act_bwd4(p.act, cq, raw, acc, rk, (uint32_t)grow);
           const float rv[4] = {raw.x, raw.y, raw.z, raw.w}, dv[4] = {dyp.x, dyp.y, dyp.z, dyp.w};
 #pragma unroll

@@ -43,16 +43,29 @@ __device__ __forceinline__ void stage_subject(const FirstArgs& p, const int4& m,
   }
   cp_async_commit();
   const bool affine = p.act_in.scale != nullptr;
-  for (int idx = tid; idx < 8 * n; idx += NT) {
-    const int r = idx >> 3, k = idx & 7;
-    float v = 0.0f;
-    if (k < K) {
-      v = p.t_in[(nb + r) * K + k];
-      const uint32_t rh = p.act_in.drop ? drop_row_hash(p.act_in, p.act_in.row_base + nb + r) : 0u;
-      v = act_fwd(p.act_in, affine, v, affine ? p.act_in.scale[k] : 1.0f, affine ? p.act_in.shift[k] : 0.0f, rh, k);
+  for (int base = tid; base < 8 * n; base += 4 * NT) {     // four independent loads in flight per thread
+    float v[4], g2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * NT, r = idx >> 3, k = idx & 7;
+      v[u] = 0.0f; g2[u] = 0.0f;
+      if (idx < 8 * n && k < K) {
+        v[u] = p.t_in[(nb + r) * K + k];
+        if (!need_gather) g2[u] = p.agg_in[(nb + r) * K + k];
+      }
     }
-    reinterpret_cast<float*>(s_x)[idx] = v;
-    if (!need_gather) reinterpret_cast<float*>(s_a)[idx] = k < K ? p.agg_in[(nb + r) * K + k] : 0.0f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * NT, r = idx >> 3, k = idx & 7;
+      if (idx >= 8 * n) continue;
+      float x = v[u];
+      if (k < K) {
+        const uint32_t rh = p.act_in.drop ? drop_row_hash(p.act_in, p.act_in.row_base + nb + r) : 0u;
+        x = act_fwd(p.act_in, affine, x, affine ? p.act_in.scale[k] : 1.0f, affine ? p.act_in.shift[k] : 0.0f, rh, k);
+      }
+      reinterpret_cast<float*>(s_x)[idx] = x;
+      if (!need_gather) reinterpret_cast<float*>(s_a)[idx] = g2[u];
+    }
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -197,10 +210,11 @@ __global__ void __launch_bounds__(NT, 2) k_first_bwd(FirstArgs p) {
       pooled = rt::ld_quad<true>(p.demb, g, H, 4 * q);
       pooled = make_float4(pooled.x * inv_n, pooled.y * inv_n, pooled.z * inv_n, pooled.w * inv_n);
     }
-    for (int r = rsub; r < m.y; r += 2 * RS) {
-      float4 zv[2], uv[2];
+    constexpr int UB = 4;     // rows in flight per thread
+    for (int r = rsub; r < m.y; r += UB * RS) {
+      float4 zv[UB], uv[UB];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < UB; ++u) {
         uv[u] = pooled;
         if (r + u * RS < m.y) {
           zv[u] = rt::ld_quad<true>(p.zin, nb + r + u * RS, H, 4 * q);
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(NT, 2) k_first_bwd(FirstArgs p) {
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < UB; ++u) {
         const int rr = r + u * RS;
         if (rr >= m.y) continue;
         float4 dz = rt::bn_bwd4(p.bn, bq, zv[u], rt::act_bwd4(p.act_out, cq, zv[u], uv[u], rk, (uint32_t)(nb + rr)));
