@@ -144,7 +144,14 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
     const int F = p.store.num_features;
     const float* sx = p.store.x + sn * F;
     float* dx = p.x + nb * F;
-    for (int i = tid; i < n * F; i += kThreads) dx[i] = sx[i];
+    for (int i0 = tid; i0 < n * F; i0 += 4 * kThreads) {     // four loads in flight per thread
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = i0 + u * kThreads < n * F ? sx[i0 + u * kThreads] : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * kThreads < n * F) dx[i0 + u * kThreads] = v[u];
+    }
     for (int i = tid; i < n; i += kThreads) p.batch[nb + i] = g;
     if (tid == 0 && p.labels && p.store.label) p.labels[g] = p.store.label[sid];
   } else {
@@ -182,18 +189,28 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   };
   // one pass over the subject's COO list in global memory: reference-visible outputs and the shared-memory copy
   if (FROM_STORE || staged) {
-    for (int e = tid; e < m; e += kThreads) {
-      int s, d; float w;
-      load_edge(e, s, d, w);
-      if (FROM_STORE) {
-        p.edge_index[eb + e] = (long long)s + nb;
-        p.edge_index[p.total_edges + eb + e] = (long long)d + nb;
-        p.edge_weight[eb + e] = w;
+    for (int e0 = tid; e0 < m; e0 += 3 * kThreads) {           // three edges in flight per thread
+      int es[3], ed[3]; float ew[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        es[u] = 0; ed[u] = 0; ew[u] = 0.0f;
+        if (e0 + u * kThreads < m) load_edge(e0 + u * kThreads, es[u], ed[u], ew[u]);
       }
-      if (staged) {
-        if ((unsigned)s >= (unsigned)n || (unsigned)d >= (unsigned)n) { s = 0; d = 0; w = 0.0f; }
-        raw_pk[e] = (uint32_t)s | ((uint32_t)d << 16);
-        raw_w[e] = w;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int e = e0 + u * kThreads;
+        if (e >= m) continue;
+        int s = es[u], d = ed[u]; float w = ew[u];
+        if (FROM_STORE) {
+          p.edge_index[eb + e] = (long long)s + nb;
+          p.edge_index[p.total_edges + eb + e] = (long long)d + nb;
+          p.edge_weight[eb + e] = w;
+        }
+        if (staged) {
+          if ((unsigned)s >= (unsigned)n || (unsigned)d >= (unsigned)n) { s = 0; d = 0; w = 0.0f; }
+          raw_pk[e] = (uint32_t)s | ((uint32_t)d << 16);
+          raw_w[e] = w;
+        }
       }
     }
   }
