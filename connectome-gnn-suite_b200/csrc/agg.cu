@@ -127,8 +127,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
 
   const int4* meta = reinterpret_cast<const int4*>(p.meta);
   const long long gstep = gridDim.x / nslab;
+  int4 m_next = make_int4(0, 0, 0, 0);
+  if ((long long)(blockIdx.x / nslab) < p.B) m_next = meta[blockIdx.x / nslab];
   for (long long g = blockIdx.x / nslab; g < p.B; g += gstep) {
-    const int4 m = meta[g];
+    const int4 m = m_next;                       // loaded one unit ahead: no exposed latency at the top of a unit
+    if (g + gstep < p.B) m_next = meta[g + gstep];
     const long long nb = m.x, eb = m.z;
     const int n = min(m.y, p.max_nodes), me = min(m.w, p.max_edges);
     // ---- the subject's blob: one asynchronous burst ------------------------------------------------------------

@@ -117,8 +117,11 @@ __global__ void __launch_bounds__(NT, 2) k_first_fwd(FirstArgs p) {
   for (int j = 0; j < 4; ++j) wf[j].init();
 
   const int4* meta = reinterpret_cast<const int4*>(p.meta);
+  int4 m_next = make_int4(0, 0, 0, 0);
+  if ((long long)blockIdx.x < p.B) m_next = meta[blockIdx.x];
   for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
-    int4 m = meta[g];
+    int4 m = m_next;                               // loaded one subject ahead
+    if (g + gridDim.x < p.B) m_next = meta[g + gridDim.x];
     m.y = min(m.y, p.max_nodes); m.w = min(m.w, p.max_edges);
     stage_subject<SAGE, false, NT>(p, m, g, s_x, s_a, s_blob);
     const long long nb = m.x;
@@ -199,8 +202,11 @@ __global__ void __launch_bounds__(NT, 2) k_first_bwd(FirstArgs p) {
   float db[4] = {0.f, 0.f, 0.f, 0.f};
 
   const int4* meta = reinterpret_cast<const int4*>(p.meta);
+  int4 m_next = make_int4(0, 0, 0, 0);
+  if ((long long)blockIdx.x < p.B) m_next = meta[blockIdx.x];
   for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
-    int4 m = meta[g];
+    int4 m = m_next;                               // loaded one subject ahead
+    if (g + gridDim.x < p.B) m_next = meta[g + gridDim.x];
     m.y = min(m.y, p.max_nodes); m.w = min(m.w, p.max_edges);
     stage_subject<SAGE, true, NT>(p, m, g, s_x, s_a, s_blob);
     const long long nb = m.x;

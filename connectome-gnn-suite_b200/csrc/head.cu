@@ -73,9 +73,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_pool_fwd_quad(PoolArgs p) {
   rt::ChanQuad cq;
   rt::chan_quad_init(cq, p.act, 4 * q, C);
   const rt::RowKey rk = rt::row_key(p.act);
+  long long nb_next = 0, ne_next = 0;
+  if ((long long)blockIdx.x < p.B) { nb_next = p.ptr[blockIdx.x]; ne_next = p.ptr[blockIdx.x + 1]; }
   for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
-    const long long nb = p.ptr[g];
-    const int n = (int)(p.ptr[g + 1] - nb);
+    const long long nb = nb_next;                  // row range loaded one subject ahead
+    const int n = (int)(ne_next - nb);
+    if (g + gridDim.x < p.B) { nb_next = p.ptr[g + gridDim.x]; ne_next = p.ptr[g + gridDim.x + 1]; }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = r; i < n; i += 4 * RS) {
       float4 v[4];

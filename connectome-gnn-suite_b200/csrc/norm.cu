@@ -122,9 +122,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_bn_bwd_sums_quad(BnSumsArgs p) 
 #pragma unroll
   for (int j = 0; j < 4; ++j) { mean[j] = p.mean[4 * q + j]; rstd[j] = p.rstd[4 * q + j]; }
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  long long nb_next = 0, ne_next = 0;
+  if ((long long)blockIdx.x < p.B) { nb_next = p.ptr[blockIdx.x]; ne_next = p.ptr[blockIdx.x + 1]; }
   for (long long g = blockIdx.x; g < p.B; g += gridDim.x) {
-    const long long nb = p.ptr[g];
-    const int n = (int)(p.ptr[g + 1] - nb);
+    const long long nb = nb_next;                  // row range loaded one subject ahead
+    const int n = (int)(ne_next - nb);
+    if (g + gridDim.x < p.B) { nb_next = p.ptr[g + gridDim.x]; ne_next = p.ptr[g + gridDim.x + 1]; }
     float4 pooled = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!p.du) {
       const float inv_n = 1.0f / ((float)n + 1e-8f);
