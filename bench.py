@@ -315,7 +315,7 @@ def run_b200(a):
         e2e = {"value": graphs_per_step * e2e_steps / (ms_e / 1e3), "unit": "graphs/s",
                "h2d_bytes_per_step": int(h2d_bytes * len(LEGS)), "d2h_bytes_per_step": 4 * len(LEGS),
                "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
-               "path": "pinned host arena -> StreamingStore (H2D on a copy stream, double-buffered) -> collate -> Trainer.train_step/eval_step -> float(loss)"}
+               "path": "pinned host arena (compact store) -> StreamingStore (H2D on a copy stream, double-buffered) -> collate -> Trainer.train_step/eval_step -> the step's four losses read back to the host"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------------
     cpu = None
@@ -391,9 +391,19 @@ def profile_calls(a, eng, step_fn, peak, peak_src):
     top = max(agg, key=lambda k: agg[k]["ms"])
     r = agg[top]
     achieved = r["bytes"] / (r["ms"] / 1e3) / 1e9 if r["ms"] > 0 else 0.0
+    # DRAM bytes per launch of the same entry point from the committed ncu --set full capture of this workload
+    # (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of its kernels, averaged over a step's calls)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    same_workload = (a.batch, a.regions, a.hidden, a.layers) == (4096, 360, 64, 3)
+    if os.path.exists(tpath) and same_workload:
+        t = json.load(open(tpath))
+        if top in t.get("entries", {}):
+            traffic, traffic_src = t["entries"][top]["dram_bytes_per_launch"], t.get("source")
     return {
         "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src, "avg_launch_ms": r["ms"] / r["calls"], "launches_timed": r["calls"],
+        "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)", "traffic_source": traffic_src,
+        "peak_source": peak_src, "avg_launch_ms": r["ms"] / r["calls"], "launches_timed": r["calls"],
         "algorithmic_bytes_per_launch": r["bytes"] / r["calls"], "share_of_step": r["ms"] / total if total else None,
         "per_entry_point": {k: {"ms_per_step": v["ms"] / 3, "calls_per_step": v["calls"] / 3,
                                 "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["bytes"] else None}

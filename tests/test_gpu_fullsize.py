@@ -1,0 +1,143 @@
+"""GPU parity at BASELINE.json's full single-GPU size (360-node subjects, batch 4096, hidden 64, 3 layers).
+
+The oracle cannot chew 4096 x 360-node subjects in seconds, so this file checks
+  * size-independent properties at the full size: the CSR is the stable sort of the COO (numpy stable argsort on
+    1.2e7 edges), D^ / w_sum are the sequential sums of the sorted weights, identical subjects get identical
+    structure; evaluation logits do not depend on how subjects are split into batches (bit for bit) and identical
+    subjects get identical logits; a permuted training batch gives the same loss and gradients within the fp32
+    tolerance of the north star (only the reduction order differs);
+  * a direct comparison with the oracle (oracle/port.py, the reference's op sequence) at a quarter of the batch
+    (1024 subjects, a few seconds of CPU): logits, loss and every gradient within 1e-5 max-norm relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from helpers import REL_TOL
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+UNIQUE, BATCH, REGIONS, HIDDEN, LAYERS = 64, 4096, 360, 64, 3
+
+
+@pytest.fixture(scope="module")
+def dataset():
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    pool = generate_dataset(num_subjects=UNIQUE, num_regions=REGIONS, k=8, beta=0.15, trait_idx=0, seed=42)
+    graphs = (pool * (BATCH // UNIQUE))[:BATCH]
+    return pool, graphs, SubjectStore(pack_graphs(graphs), DEV)
+
+
+def _model(kind, dropout=0.0, seed=0):
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    torch.manual_seed(seed)
+    cls = GCNConnectome if kind == "gcn" else GraphSAGEConnectome
+    return cls(in_channels=5, hidden_dim=HIDDEN, num_classes=2, num_layers=LAYERS, dropout=dropout).to(DEV)
+
+
+def test_collate_full_size_is_the_stable_sort_with_sequential_sums(dataset):
+    pool, graphs, store = dataset
+    ids = np.random.default_rng(1).permutation(BATCH)
+    b = store.collate(ids, prepare_for="gcn")
+    rows, edges = BATCH * REGIONS, BATCH * 8 * REGIONS
+    assert b.num_nodes == rows and b.edge_index.shape == (2, edges)
+    np_ = lambda t: t.detach().cpu().numpy()
+    ptr = np_(b.ptr)
+    assert np.array_equal(ptr, np.arange(BATCH + 1) * REGIONS)
+    assert np.array_equal(np_(b.batch), np.repeat(np.arange(BATCH), REGIONS))
+    src, dst = np_(b.edge_index)
+    w = np_(b.edge_weight)
+    # every subject's edges stay inside its node range, offsets are integer-exact
+    assert np.array_equal(src // REGIONS, np.repeat(np.arange(BATCH), 8 * REGIONS))
+    assert np.array_equal(dst // REGIONS, src // REGIONS)
+    c = b.csr
+    for key, other, rowptr, col, cw in ((dst, src, c.in_rowptr, c.in_col, c.in_w), (src, dst, c.out_rowptr, c.out_col, c.out_w)):
+        order = np.argsort(key, kind="stable")
+        assert np.array_equal(np_(col), other[order].astype(np.int32))
+        assert np.array_equal(np_(cw), w[order])
+        assert np.array_equal(np_(rowptr), np.searchsorted(key[order], np.arange(rows + 1)).astype(np.int32))
+    # sequential fp32 sums in sorted order (self loop last): replay with a cumulative loop over the (small) max degree
+    for rowptr, cw, got, plus_one in ((c.out_rowptr, c.out_w, c.deg, True), (c.in_rowptr, c.in_w, c.wsum, False)):
+        rp, ww = np_(rowptr).astype(np.int64), np_(cw)
+        acc = np.zeros(rows, dtype=np.float32)
+        deg = rp[1:] - rp[:-1]
+        for k in range(int(deg.max())):
+            live = deg > k
+            acc[live] = acc[live] + ww[rp[:-1][live] + k]
+        if plus_one:
+            acc = acc + np.float32(1.0)
+        assert np.array_equal(np_(got), acc)
+    # identical subjects (the pool is tiled) have identical structure: a checksum per subject, compared across copies
+    sub = ids % UNIQUE
+    deg_sum = np_(c.deg).reshape(BATCH, REGIONS)
+    first = {}
+    for g, s in enumerate(sub):
+        if s in first:
+            assert np.array_equal(deg_sum[g], deg_sum[first[s]])
+        else:
+            first[s] = g
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_eval_logits_do_not_depend_on_the_batch_split(dataset, kind):
+    pool, graphs, store = dataset
+    model = _model(kind)
+    model.eval()
+    ids = np.random.default_rng(2).permutation(BATCH)
+    with torch.no_grad():
+        full = model(store.collate(ids, prepare_for=kind))
+        parts = torch.cat([model(store.collate(ids[lo:hi])) for lo, hi in ((0, 1000), (1000, 1001), (1001, BATCH))])
+    assert torch.isfinite(full).all()
+    assert torch.equal(full, parts), "eval-mode logits changed with the batch split"
+    sub = torch.from_numpy(ids % UNIQUE).to(DEV)
+    rep = torch.zeros(UNIQUE, 2, device=DEV).index_copy_(0, sub, full)      # one copy per unique subject
+    assert torch.equal(rep[sub], full), "identical subjects produced different logits"
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_training_step_is_invariant_to_batch_order(dataset, kind):
+    from connectome_gnn.train import CrossEntropyLoss
+    pool, graphs, store = dataset
+    model = _model(kind)
+    model.train()
+    ids = np.arange(BATCH)
+    perm = np.random.default_rng(3).permutation(BATCH)
+    out = []
+    for order in (ids, perm):
+        for bn in model.batch_norms:
+            bn.reset_running_stats()
+        model.zero_grad()
+        batch = store.collate(order, prepare_for=kind)
+        loss = CrossEntropyLoss()(model(batch), batch.labels)
+        loss.backward()
+        out.append((float(loss), torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone(),
+                    torch.cat([bn.running_var for bn in model.batch_norms]).clone()))
+    assert out[0][0] == pytest.approx(out[1][0], rel=1e-6)
+    helpers.assert_close(out[1][1], out[0][1], f"{kind}: gradients under a batch permutation", tol=REL_TOL)
+    helpers.assert_close(out[1][2], out[0][2], f"{kind}: BatchNorm running variance under a batch permutation", tol=REL_TOL)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_quarter_batch_training_step_against_the_oracle(dataset, kind):
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.train import CrossEntropyLoss
+    from oracle import port      # the checker
+    pool, graphs, store = dataset
+    sample = graphs[:1024]
+    model = _model(kind, seed=5)
+    params = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    model.train()
+    batch = store.collate(np.arange(1024), prepare_for=kind)
+    logits = model(batch)
+    loss = CrossEntropyLoss()(logits, batch.labels)
+    loss.backward()
+    ref_batch = port.collate(sample)
+    assert torch.equal(batch.edge_index.cpu(), ref_batch["edge_index"])
+    ref_logits, ref_loss, ref_grads = port.loss_and_grads(kind, params, ref_batch, training=True, dropout=0.0)
+    helpers.assert_close(logits, ref_logits, f"{kind}: logits, 1024 x 360-node subjects", tol=REL_TOL)
+    assert float(loss) == pytest.approx(float(ref_loss), rel=1e-5)
+    got = torch.cat([p.grad.reshape(-1).cpu() for _, p in model.named_parameters()])
+    ref = torch.cat([ref_grads[k].reshape(-1) for k, _ in model.named_parameters()])
+    helpers.assert_close(got, ref, f"{kind}: all gradients, 1024 x 360-node subjects", tol=REL_TOL)

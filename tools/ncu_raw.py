@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""Key metrics per captured launch of an .ncu-rep: usage ncu_raw.py report.ncu-rep"""
+"""Key metrics per captured launch of an .ncu-rep (or of its `--page raw --csv` export): ncu_raw.py report.ncu-rep|raw.csv"""
 import csv, subprocess, sys, io
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = (open(sys.argv[1]).read() if sys.argv[1].endswith(".csv") else
+       subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
