@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(NT, 2) k_first_fwd(FirstArgs p) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) b4[j] = p.bias ? p.bias[4 * q + j] : 0.0f;
   int cnt = 0;
+  const bool want_stats = p.stats_partials != nullptr;
   Welford wf[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) wf[j].init();
@@ -146,10 +147,12 @@ __global__ void __launch_bounds__(NT, 2) k_first_fwd(FirstArgs p) {
         for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.0f);
       }
       *reinterpret_cast<float4*>(p.z + (nb + r) * H + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
-      cnt += 1;
-      const float inv = rt::rcp_fast((float)cnt);
+      if (want_stats) {        // BatchNorm batch statistics: training only
+        cnt += 1;
+        const float inv = rt::rcp_fast((float)cnt);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) wf[j].push(o[j], inv);
+        for (int j = 0; j < 4; ++j) wf[j].push(o[j], inv);
+      }
     }
     __syncthreads();   // tiles and blob are rewritten by the next subject
   }

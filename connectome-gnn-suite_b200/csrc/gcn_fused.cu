@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_fused(GcnFusedArgs p) {
   };
 
   int cnt = 0;
+  const bool want_stats = p.partials != nullptr;
   Welford wf[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) wf[j].init();
@@ -153,9 +154,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_fwd_fused(GcnFusedArgs p) {
         float4 v = stage[rt::stage_index(r, qh, QH)];
         v.x += bias4[0]; v.y += bias4[1]; v.z += bias4[2]; v.w += bias4[3];
         *reinterpret_cast<float4*>(p.z + (pend_row0 + r) * H + 4 * qh) = v;
-        cnt += 1;
-        const float inv = rt::rcp_fast((float)cnt);
-        wf[0].push(v.x, inv); wf[1].push(v.y, inv); wf[2].push(v.z, inv); wf[3].push(v.w, inv);
+        if (want_stats) {      // BatchNorm batch statistics: training only
+          cnt += 1;
+          const float inv = rt::rcp_fast((float)cnt);
+          wf[0].push(v.x, inv); wf[1].push(v.y, inv); wf[2].push(v.z, inv); wf[3].push(v.w, inv);
+        }
       }
     }
     __syncthreads();   // staging (= A operand) is rewritten next

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(NT, 1) k_sage_fwd_gemm(SageFwdGemmArgs p) {
   };
 
   int cnt = 0;
+  const bool want_stats = p.partials != nullptr;
   Welford wf[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) wf[j].init();
@@ -172,9 +173,11 @@ __global__ void __launch_bounds__(NT, 1) k_sage_fwd_gemm(SageFwdGemmArgs p) {
         v.z = fmaxf(v.z + bias4[2], 0.0f);
         v.w = fmaxf(v.w + bias4[3], 0.0f);
         *reinterpret_cast<float4*>(p.z + (r0 + r) * H + 4 * qh) = v;
-        cnt += 1;
-        const float inv = rt::rcp_fast((float)cnt);
-        wf[0].push(v.x, inv); wf[1].push(v.y, inv); wf[2].push(v.z, inv); wf[3].push(v.w, inv);
+        if (want_stats) {      // BatchNorm batch statistics: training only
+          cnt += 1;
+          const float inv = rt::rcp_fast((float)cnt);
+          wf[0].push(v.x, inv); wf[1].push(v.y, inv); wf[2].push(v.z, inv); wf[3].push(v.w, inv);
+        }
       }
     }
   };
