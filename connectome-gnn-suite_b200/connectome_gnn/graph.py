@@ -302,6 +302,8 @@ class SubjectStore:
         out, csr, blobs = eng.collate_csr(self._struct, ids_device, int(ids_np.size), rows, edges, max_nodes,
                                           self.num_features, all_labelled, prepare_for)
         labels = out["labels"]
+        if ids_np.size == 0:         # an empty slice of a data-parallel batch: no subjects, no labels (not "unlabelled")
+            labels = torch.empty(0, dtype=torch.int64, device=self.device)
         if not all_labelled and labelled.any():
             # reference quirk (graph.py:155-156,165): only labelled subjects contribute, so the
             # stack is shorter than B

@@ -53,9 +53,9 @@ def _merge_stats_across_ranks(eng, stats: torch.Tensor, channels: int, group=Non
     if world == 1:
         return stats
     import torch.distributed as dist
-    parts = torch.empty((world, stats.numel()), dtype=stats.dtype, device=stats.device)
-    dist.all_gather_into_tensor(parts, stats.contiguous(), group=group)
-    return eng.bn_merge_stats(parts, channels)
+    flat = torch.empty(world * stats.numel(), dtype=stats.dtype, device=stats.device)   # 1-D: gloo insists on it
+    dist.all_gather_into_tensor(flat, stats.contiguous().reshape(-1), group=group)
+    return eng.bn_merge_stats(flat.view(world, stats.numel()), channels)
 
 
 def _sum_across_ranks(t: Optional[torch.Tensor], group=None) -> Optional[torch.Tensor]:
@@ -136,7 +136,11 @@ class _EncodeFn(torch.autograd.Function):
             dW, db, du_in, prev_sums = eng.layer_bwd(kind, du, pooled, z, act_out, bn, t_in, act_in, W, csr, ptr, B,
                                                      need_du, prev_mean, prev_rstd, agg)
             grads[4 * l + 0], grads[4 * l + 1] = dW, db
-            grads[4 * l + 2], grads[4 * l + 3] = sums[1], sums[0]   # d gamma = sum dy*xhat, d beta = sum dy
+            # d gamma = sum dy*xhat, d beta = sum dy.  Under data parallelism `sums` is already the global sum while
+            # every other gradient is this rank's share and Trainer adds the ranks up: hand out 1/world of it.
+            share = 1.0 / _world(group)
+            grads[4 * l + 2] = sums[1] if share == 1.0 else sums[1] * share
+            grads[4 * l + 3] = sums[0] if share == 1.0 else sums[0] * share
             sums = _sum_across_ranks(prev_sums, group)
             du, pooled, act_out = du_in, None, act_in
             if l == 0:

@@ -449,6 +449,14 @@ int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int6
                      float* edge_weight, int64_t* batch, int64_t* labels, int64_t* ptr, int64_t* eptr,
                      const cgnn_csr_out_t* csr, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (num_graphs == 0) {   // a rank's slice of a short global batch may be empty: an empty batch is a valid batch
+    if (!ptr || !eptr || !csr || !csr->in_rowptr || !csr->out_rowptr) return CGNN_ERR_INVALID_ARG;
+    cudaMemsetAsync(ptr, 0, sizeof(int64_t), stream);
+    cudaMemsetAsync(eptr, 0, sizeof(int64_t), stream);
+    cudaMemsetAsync(csr->in_rowptr, 0, sizeof(int32_t), stream);
+    cudaMemsetAsync(csr->out_rowptr, 0, sizeof(int32_t), stream);
+    return CGNN_OK;
+  }
   if (!store || !subject_ids || num_graphs < 0 || total_rows < 0 || total_edges < 0 || !ptr || !eptr ||
       !csr_out_ok(csr) || !store->node_ptr || !store->edge_ptr || store->num_features <= 0)
     return CGNN_ERR_INVALID_ARG;
