@@ -3,6 +3,7 @@
 //   k_build_agg      CSR arrays -> packed per-subject aggregation blobs (agg.cuh), once per batch and model family
 //   k_gather<MODE>   one subject tile [n, C] in shared memory (two CTAs per SM), one warp per output row:
 //     GATHER_SAGE_FWD  agg_i = sum_{e: dst=i} w_e u_src / (w_sum_i + 1e-8), u = act(t_in)     (reference models.py:146-149)
+//     GATHER_GCN_FWD   a_i   = sum_{e: dst=i} w^_e u_src + dinv_i^2 u_i, u = act(t_in)  (wide layers, models.py:94-114)
 //     GATHER_GCN_BWD   dP_j  = sum_{e: src=j} w^_e dz_dst + dinv_j^2 dz_j, dz from z / upstream / BatchNorm backward
 //                      on load, plus dbias = column sums of dz                        (autograd of models.py:112-114)
 //     GATHER_SAGE_BWD  du_j  = d_u_j + sum_{e: src=j} w_e d_agg_dst / (w_sum_dst + 1e-8), plus the BatchNorm
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
         const int rr = r + u * RP;
         if (rr < n) {
           float4 o = a[u];
-          if (MODE == GATHER_SAGE_FWD) o = rt::act_fwd4(p.act, cq, a[u], rk, (uint32_t)(nb + rr));
+          if (MODE == GATHER_SAGE_FWD || MODE == GATHER_GCN_FWD) o = rt::act_fwd4(p.act, cq, a[u], rk, (uint32_t)(nb + rr));
           if (MODE == GATHER_GCN_BWD) {
             o = rt::bn_bwd4(bn, bq, a[u], rt::act_bwd4(p.act, cq, a[u], b[MODE == GATHER_GCN_BWD ? u : 0], rk, (uint32_t)(nb + rr)));
             if (!VEC) o = rt::mask_quad(o, c0, C);
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
 
 // ---- host side -------------------------------------------------------------------------------------------------
 static bool gather_shape(int C, int max_nodes, int max_edges, int* lpr, int* nslab, size_t* smem) {
-  if (C <= 0 || C > 128) return false;
+  if (C <= 0 || C > 256) return false;
   int L, S;
   if (C <= 8) { L = 2; S = 1; }
   else if (C <= 32) { L = 8; S = 1; }
@@ -301,6 +302,7 @@ int launch_gather(int mode, GatherArgs& a, int* grid_out, cudaStream_t stream) {
   }
   if (mode == GATHER_SAGE_FWD) CGNN_GATHER_L(GATHER_SAGE_FWD)
   else if (mode == GATHER_GCN_BWD) CGNN_GATHER_L(GATHER_GCN_BWD)
+  else if (mode == GATHER_GCN_FWD) CGNN_GATHER_L(GATHER_GCN_FWD)
   else CGNN_GATHER_L(GATHER_SAGE_BWD)
 #undef CGNN_GATHER_L
 #undef CGNN_GATHER

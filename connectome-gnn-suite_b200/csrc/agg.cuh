@@ -84,14 +84,14 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
   return valid;
 }
 
-enum { GATHER_SAGE_FWD = 0, GATHER_GCN_BWD = 1, GATHER_SAGE_BWD = 2 };
+enum { GATHER_SAGE_FWD = 0, GATHER_GCN_BWD = 1, GATHER_SAGE_BWD = 2, GATHER_GCN_FWD = 3 };
 enum { GC_SCALE = 0, GC_SHIFT, GC_BSC, GC_MEAN, GC_RSTD, GC_S1N, GC_S2N, GC_ROWS };   // per-channel constant rows
 
 struct GatherArgs {
   const int32_t* meta; long long B; const int32_t* blob;
   int C, max_nodes, max_edges, nslab;
   // tile source
-  const float* src;        // SAGE_FWD: t_in   GCN_BWD: z   SAGE_BWD: d_agg
+  const float* src;        // SAGE_FWD / GCN_FWD: t_in   GCN_BWD: z   SAGE_BWD: d_agg
   Act act;                 // SAGE_FWD: act on load   GCN_BWD: act_out (its backward)   SAGE_BWD: act_in (for the sums)
   const float* du; const float* demb;                                    // GCN_BWD upstream
   const float* bn_scale; const float* bn_mean; const float* bn_rstd; const float* bn_s1; const float* bn_s2;
@@ -131,6 +131,16 @@ int launch_first_bwd(int kind, const float* du, const float* demb, const float* 
                      int64_t num_graphs, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* partials,
                      int* grid_out, size_t partial_bytes, cudaStream_t stream);
 // gcn_fused.cu: the whole GCN forward layer (gather -> tensor-core projection) in one kernel
+// wide_tc.cu: H = d_in = 256 (gather + K-looped tcgen05 contraction; forward runs in place in z)
+bool wide_shape(int d_in, int H);
+int launch_gcn_fwd_wide(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+                        int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
+                        int want_stats, int* grid_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_gcn_bwd_wide(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out, const cgnn_bn_bwd_t* bn,
+                        const float* t_in, const cgnn_act_t* act_in, const float* W, const cgnn_csr_t* csr, const int64_t* ptr,
+                        int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
+                        float* dW, float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums,
+                        float* scratch, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_gcn_fwd_fused(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
                          int64_t num_graphs, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
                          double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream);

@@ -294,7 +294,7 @@ static size_t first_smem(int max_nodes, int max_edges) {
   return b;
 }
 static bool first_shape_ok(const cgnn_csr_t* csr, int kind, int d_in, int H, int max_nodes, int max_edges, size_t* smem) {
-  if (d_in < 1 || d_in > 8 || (H != 32 && H != 64 && H != 128)) return false;
+  if (d_in < 1 || d_in > 8 || (H != 32 && H != 64 && H != 128 && H != 256)) return false;
   if (!csr->agg_in || csr->agg_kind != kind) return false;
   *smem = first_smem(max_nodes < 1 ? 1 : max_nodes, max_edges);
   return *smem <= (size_t)device_info().smem_optin;
@@ -334,7 +334,7 @@ int launch_first_fwd(int kind, const float* t_in, const cgnn_act_t* act, const f
     if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     CGNN_LAUNCH(kfn, (unsigned)grid, (S_ ? 256 : 512), smem, stream, a);                                   \
   }
-#define CGNN_FF_H(S_, KX_) { if (H == 32) CGNN_FF(S_, 8, KX_) else if (H == 64) CGNN_FF(S_, 16, KX_) else CGNN_FF(S_, 32, KX_) }
+#define CGNN_FF_H(S_, KX_) { if (H == 32) CGNN_FF(S_, 8, KX_) else if (H == 64) CGNN_FF(S_, 16, KX_) else if (H == 128) CGNN_FF(S_, 32, KX_) else CGNN_FF(S_, 64, KX_) }
   if (d_in <= 5) { if (kind == AGG_SAGE) CGNN_FF_H(1, 5) else CGNN_FF_H(0, 5) }
   else { if (kind == AGG_SAGE) CGNN_FF_H(1, 8) else CGNN_FF_H(0, 8) }
 #undef CGNN_FF_H
@@ -375,7 +375,7 @@ int launch_first_bwd(int kind, const float* du, const float* demb, const float* 
     if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     CGNN_LAUNCH(kfn, (unsigned)grid, 256, smem, stream, a);                                                \
   }
-#define CGNN_FB_H(S_, KX_) { if (H == 32) CGNN_FB(S_, 8, KX_) else if (H == 64) CGNN_FB(S_, 16, KX_) else CGNN_FB(S_, 32, KX_) }
+#define CGNN_FB_H(S_, KX_) { if (H == 32) CGNN_FB(S_, 8, KX_) else if (H == 64) CGNN_FB(S_, 16, KX_) else if (H == 128) CGNN_FB(S_, 32, KX_) else CGNN_FB(S_, 64, KX_) }
   if (d_in <= 5) { if (kind == AGG_SAGE) CGNN_FB_H(1, 5) else CGNN_FB_H(0, 5) }
   else { if (kind == AGG_SAGE) CGNN_FB_H(1, 8) else CGNN_FB_H(0, 8) }
 #undef CGNN_FB_H

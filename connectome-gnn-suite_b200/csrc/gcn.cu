@@ -518,6 +518,10 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
                                      bn_stats ? (double*)workspace : nullptr, &tc_grid, workspace_bytes, stream);
     if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;
     if (rc > 0) return rc;
+    rc = launch_gcn_fwd_wide(t_in, act, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, z, bn_stats ? 1 : 0,
+                             &tc_grid, workspace, workspace_bytes, stream);
+    if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;
+    if (rc > 0) return rc;
   }
 #endif
   const DeviceInfo dev = device_info();
@@ -600,6 +604,13 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
       if (rc1) return rc1;
       return launch_reduce_partials((const float*)workspace + H * d_in, g0, stride, 1, H, H, dbias, stream);
     }
+  }
+  // Wide layers (H = d_in = 256): gather + K-looped contractions (wide_tc.cu).
+  if (tensor_cores_enabled() && wide_shape(d_in, H)) {
+    const int rcw = launch_gcn_bwd_wide(du, demb, z, act_out, bn, t_in, act_in, W, csr, ptr, num_graphs, rows, d_in, H, max_nodes,
+                                        max_edges, dW, dbias, du_in, prev_mean, prev_rstd, prev_sums, scratch, workspace,
+                                        workspace_bytes, stream);
+    if (rcw >= 0) return rcw;
   }
   // Tensor-core generation: gather kernel (dz on load, dP = A^^T dz, dbias) + tcgen05 contractions (du_in, dW).
   if (tensor_cores_enabled() && scratch && csr->agg_out && csr->agg_kind == AGG_GCN && (H == 32 || H == 64 || H == 128) &&

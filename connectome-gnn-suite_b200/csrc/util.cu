@@ -111,7 +111,7 @@ const char* cgnn_status_string(int status) {
 
 int cgnn_abi_version(void) { return CGNN_ABI_VERSION; }
 int cgnn_last_cuda_error(void) { return cgnn::g_last_cuda_error; }
-size_t cgnn_workspace_bytes(void) { return (size_t)32 << 20; }
+size_t cgnn_workspace_bytes(void) { return (size_t)64 << 20; }   // 148 CTAs x a 256 x 256 fp32 partial + the small records
 uint64_t cgnn_kernel_launches(void) { return (uint64_t)cgnn::launches(); }
 int cgnn_set_option(int32_t key, int32_t value) {
   if (key == CGNN_OPT_TENSOR_CORES) { cgnn::set_tensor_cores(value); return CGNN_OK; }

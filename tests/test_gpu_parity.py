@@ -50,6 +50,48 @@ def test_oracle_random_weights(kind, shape):
     parity.check_against_oracle(graphs, kind, DEV, hidden=hidden, layers=layers)
 
 
+@pytest.mark.parametrize("shape", [(4, 360, 256, 3), (7, 84, 256, 2), (3, 45, 256, 3)])
+def test_wide_gcn_hidden_256(shape):
+    """BASELINE configs[4] shape class (GCN, hidden 256): first-layer kernel at 256 outputs, then the wide layers
+    (slab gather + K-looped tcgen05 contractions, wide_tc.cu), forward, backward and BatchNorm statistics."""
+    from connectome_gnn.synthetic import generate_dataset
+    subjects, regions, hidden, layers = shape
+    graphs = generate_dataset(num_subjects=subjects, num_regions=regions, seed=5)
+    parity.check_against_oracle(graphs, "gcn", DEV, hidden=hidden, layers=layers)
+
+
+def test_wide_gcn_dropout_masks_are_consistent():
+    """Hidden 256 with dropout: the same seed gives the same loss twice, and the step is finite."""
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.models import GCNConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import CrossEntropyLoss
+    b = collate_graphs(generate_dataset(num_subjects=5, num_regions=84, seed=2))
+    torch.manual_seed(0)
+    m = GCNConnectome(in_channels=5, hidden_dim=256, num_classes=2, num_layers=3, dropout=0.3).cuda().train()
+    losses = []
+    for _ in range(2):
+        m.zero_grad()
+        torch.manual_seed(123)
+        loss = CrossEntropyLoss()(m(b), b.labels)
+        loss.backward()
+        losses.append(float(loss))
+        assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+    assert losses[0] == losses[1]
+
+
+def test_sage_hidden_256_fails_loudly():
+    """GraphSAGE at hidden 256 is not covered (K = 512 contraction): an error, never a silent fallback."""
+    from connectome_gnn import _lib
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.models import GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    b = collate_graphs(generate_dataset(num_subjects=2, num_regions=360, seed=1))
+    m = GraphSAGEConnectome(in_channels=5, hidden_dim=256).cuda().eval()
+    with pytest.raises(_lib.CgnnError), torch.no_grad():
+        m(b)
+
+
 def test_csr_from_coo_equals_collate():
     from connectome_gnn.graph import ConnectomeBatch, collate_graphs
     a = helpers.golden("ref_ragged.npz")
