@@ -48,20 +48,30 @@ def parse():
     ap.add_argument("--dropout", type=float, default=0.3)
     ap.add_argument("--pool", type=int, default=256, help="unique generated subjects, tiled to --batch")
     ap.add_argument("--cpu-sample", type=int, default=96, help="subjects per leg for the CPU baseline")
+    ap.add_argument("--legs", default=",".join(LEGS),
+                    help="comma-separated subset of the step's legs (other BASELINE configs, e.g. configs[4]: "
+                         "--hidden 256 --batch 8192 --legs gcn_train)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.legs = tuple(x for x in a.legs.split(",") if x)
+    if not a.legs or any(x not in LEGS for x in a.legs):
+        ap.error(f"--legs takes a subset of {LEGS}")
+    return a
 
 
 def workload_config(a, world):
     return {
-        "workload": f"BASELINE configs[2]: GCN+SAGE train & infer, {a.regions}-node synthetic Watts-Strogatz connectomes, "
-                    f"batch {a.batch}/GPU, hidden {a.hidden}, {a.layers} layers, dropout {a.dropout}, Adam",
+        "workload": (f"BASELINE configs[2]: GCN+SAGE train & infer, {a.regions}-node synthetic Watts-Strogatz connectomes, "
+                     f"batch {a.batch}/GPU, hidden {a.hidden}, {a.layers} layers, dropout {a.dropout}, Adam")
+                    if (a.legs == LEGS and a.hidden == 64) else
+                    (f"non-default workload: legs {','.join(a.legs)}, {a.regions}-node synthetic Watts-Strogatz connectomes, "
+                     f"batch {a.batch}/GPU, hidden {a.hidden}, {a.layers} layers, dropout {a.dropout}, Adam"),
         "per_gpu_batch": a.batch, "global_batch": a.batch * world, "regions": a.regions, "edges_per_subject": 8 * a.regions,
         "hidden": a.hidden, "layers": a.layers, "unique_subjects": a.pool,
         "parallelism": f"dp{world}" if world > 1 else "single",
         "cache": "inputs larger than L2 (one activation tensor = %.0f MB vs 126 MB L2)" % (a.batch * a.regions * a.hidden * 4 / 1e6),
-        "step": "4 legs x 1 batch: gcn_train, sage_train, gcn_infer, sage_infer",
+        "step": f"{len(a.legs)} legs x 1 batch: " + ", ".join(a.legs),
     }
 
 
@@ -147,16 +157,16 @@ def cpu_legs(a, graphs, steps, warmup):
         else:
             port.evaluate(mods[kind], sample, len(sample))
 
-    per_leg = {leg: [] for leg in LEGS}
+    per_leg = {leg: [] for leg in a.legs}
     for it in range(warmup + steps):
-        for leg in LEGS:
+        for leg in a.legs:
             t0 = time.perf_counter()
             run(leg)
             if it >= warmup:
                 per_leg[leg].append(time.perf_counter() - t0)
     leg_s = {leg: float(np.mean(v)) for leg, v in per_leg.items()}
     step_s = sum(leg_s.values())
-    return len(LEGS) * len(sample) / step_s, {leg: len(sample) / s for leg, s in leg_s.items()}, step_s
+    return len(a.legs) * len(sample) / step_s, {leg: len(sample) / s for leg, s in leg_s.items()}, step_s
 
 
 def run_reference(a):
@@ -239,7 +249,7 @@ def run_b200(a):
         return tr.eval_step(batch)[0]
 
     def step_resident():
-        for name in LEGS:
+        for name in a.legs:
             leg(name, store)
 
     streaming = StreamingStore(pinned, dev)
@@ -250,7 +260,7 @@ def run_b200(a):
         computes; a step consumes four uploads and issues four (the last one is the next step's first leg) and ends
         with its four losses read back to the host."""
         losses = []
-        for name in LEGS:
+        for name in a.legs:
             st = streaming.next()
             streaming.prefetch(pinned)
             losses.append(leg(name, st).reshape(()))
@@ -282,12 +292,12 @@ def run_b200(a):
     with ClockSampler(local) as clocks:
         ms = timed(step_resident, a.steps)
     launches = lib.cgnn_kernel_launches() - launches0
-    graphs_per_step = len(LEGS) * a.batch * world
+    graphs_per_step = len(a.legs) * a.batch * world
     value = graphs_per_step * a.steps / (ms / 1e3)
 
     # ---- per-leg device time (CUDA events on the launching stream) -------------------------------------
     leg_ms = {}
-    for name in LEGS:
+    for name in a.legs:
         leg_ms[name] = timed(lambda: leg(name, store), a.steps) / a.steps
     bpg = bytes_per_graph(a.regions, a.hidden, a.layers)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -296,7 +306,7 @@ def run_b200(a):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     legs = {}
-    for name in LEGS:
+    for name in a.legs:
         gps = a.batch / (leg_ms[name] / 1e3)
         b = bpg["train" if name.endswith("train") else "infer"]
         legs[name] = {"graphs_per_s_per_gpu": gps, "ms": leg_ms[name], "algorithmic_bytes_per_graph": b,
@@ -313,7 +323,7 @@ def run_b200(a):
         e2e_steps = max(2, min(a.steps, 5))
         ms_e = timed(step_e2e, e2e_steps)
         e2e = {"value": graphs_per_step * e2e_steps / (ms_e / 1e3), "unit": "graphs/s",
-               "h2d_bytes_per_step": int(h2d_bytes * len(LEGS)), "d2h_bytes_per_step": 4 * len(LEGS),
+               "h2d_bytes_per_step": int(h2d_bytes * len(a.legs)), "d2h_bytes_per_step": 4 * len(a.legs),
                "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
                "path": "pinned host arena (compact store) -> StreamingStore (H2D on a copy stream, double-buffered) -> collate -> Trainer.train_step/eval_step -> the step's four losses read back to the host"}
 

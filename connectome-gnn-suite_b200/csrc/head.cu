@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kThreads) k_pool_fwd(PoolArgs p) {
 }
 
 #ifndef CGNN_EMU
-// Channel-quad edition (C a multiple of 4 up to 128, 16-byte aligned rows): thread = one channel quad, four
+// Channel-quad edition (C = 32 / 64 / 128 / 256, 16-byte aligned rows): thread = one channel quad, four
 // independent 16-byte loads in flight per thread, two CTAs of 512 threads per SM.
 template <int Q>
 __global__ void __launch_bounds__(kThreads, 2) k_pool_fwd_quad(PoolArgs p) {
@@ -281,12 +281,13 @@ int cgnn_pool_fwd(const float* t_in, const cgnn_act_t* act, const int64_t* ptr, 
   a.emb = emb;
   if (a.C4 > 256) return CGNN_ERR_TILE_TOO_LARGE;
 #ifndef CGNN_EMU
-  if ((C == 32 || C == 64 || C == 128) && (((uintptr_t)t_in) & 15u) == 0) {
+  if ((C == 32 || C == 64 || C == 128 || C == 256) && (((uintptr_t)t_in) & 15u) == 0) {
     long long g2 = 2LL * dev.sm_count;
     if (g2 > num_graphs) g2 = num_graphs;
     if (C == 32) { auto kfn = k_pool_fwd_quad<8>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
     else if (C == 64) { auto kfn = k_pool_fwd_quad<16>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
-    else { auto kfn = k_pool_fwd_quad<32>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
+    else if (C == 128) { auto kfn = k_pool_fwd_quad<32>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
+    else { auto kfn = k_pool_fwd_quad<64>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
     CGNN_CHECK_LAUNCH();
     return CGNN_OK;
   }

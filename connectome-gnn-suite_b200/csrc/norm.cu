@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kThreads) k_bn_bwd_sums(BnSumsArgs p) {
 }
 
 #ifndef CGNN_EMU
-// Channel-quad edition of k_bn_bwd_sums (C = 32 / 64 / 128, 16-byte aligned rows).
+// Channel-quad edition of k_bn_bwd_sums (C = 32 / 64 / 128 / 256, 16-byte aligned rows).
 template <int Q>
 __global__ void __launch_bounds__(kThreads, 2) k_bn_bwd_sums_quad(BnSumsArgs p) {
   __shared__ float4 s_red[2 * kThreads];
@@ -225,14 +225,15 @@ int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, c
   if ((size_t)grid * rec > workspace_bytes) grid = (int)(workspace_bytes / rec);
   a.partials = (float*)workspace;
 #ifndef CGNN_EMU
-  if ((C == 32 || C == 64 || C == 128) && (((uintptr_t)z) & 15u) == 0 && (!du || (((uintptr_t)du) & 15u) == 0) &&
+  if ((C == 32 || C == 64 || C == 128 || C == 256) && (((uintptr_t)z) & 15u) == 0 && (!du || (((uintptr_t)du) & 15u) == 0) &&
       (!demb || (((uintptr_t)demb) & 15u) == 0)) {
     long long g2 = 2LL * dev.sm_count;
     if (g2 > num_graphs) g2 = num_graphs;
     if ((size_t)g2 * rec > workspace_bytes) g2 = (long long)(workspace_bytes / rec);
     if (C == 32) { auto kfn = k_bn_bwd_sums_quad<8>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
     else if (C == 64) { auto kfn = k_bn_bwd_sums_quad<16>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
-    else { auto kfn = k_bn_bwd_sums_quad<32>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
+    else if (C == 128) { auto kfn = k_bn_bwd_sums_quad<32>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
+    else { auto kfn = k_bn_bwd_sums_quad<64>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
     CGNN_CHECK_LAUNCH();
     return launch_reduce_partials(a.partials, (int)g2, 2 * a.C4, 2, C, a.C4, sums, stream);
   }

@@ -29,17 +29,33 @@ DeviceInfo device_info() {
   return cached;
 }
 
-// out[r*out_ld + c] = sum_g partials[g*stride + r*ld + c]; one thread per output, fp64, fixed order.
+// out[r*out_ld + c] = sum_g partials[g*stride + r*ld + c]; fp64, fixed order: a CTA owns 32 consecutive outputs
+// (128-byte coalesced loads), its 8 warps sum one eighth of the records each, warp 0 adds the eight slices in order.
+constexpr int kReduceSlices = 8;
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partials, int G, int stride,
                                                          int rows, int cols, int ld, float* __restrict__ out,
                                                          int out_ld) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * cols) return;
-  int r = i / cols, c = i - r * cols;
-  const float* p = partials + (size_t)r * ld + c;
+  __shared__ double s_part[kReduceSlices][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const bool live = i < rows * cols;
   double s = 0.0;
-  for (int g = 0; g < G; ++g) s += (double)p[(size_t)g * stride];
-  out[(size_t)r * out_ld + c] = (float)s;
+  int r = 0, c = 0;
+  if (live) {
+    r = i / cols; c = i - r * cols;
+    const float* p = partials + (size_t)r * ld + c;
+    const int per = (G + kReduceSlices - 1) / kReduceSlices;
+    const int g0 = slice * per, g1 = (g0 + per < G) ? g0 + per : G;
+#pragma unroll 4
+    for (int g = g0; g < g1; ++g) s += (double)p[(size_t)g * stride];
+  }
+  s_part[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && live) {
+    double t = 0.0;
+    for (int k = 0; k < kReduceSlices; ++k) t += s_part[k][lane];
+    out[(size_t)r * out_ld + c] = (float)t;
+  }
 }
 
 int launch_reduce_partials(const float* partials, int G, int stride, int rows, int cols, int ld, float* out,
@@ -48,7 +64,7 @@ int launch_reduce_partials(const float* partials, int G, int stride, int rows, i
   int n = rows * cols;
   if (n <= 0) return CGNN_OK;
   auto kfn = k_reduce_partials;
-  CGNN_LAUNCH(kfn, (n + 255) / 256, 256, 0, stream, partials, G, stride, rows, cols, ld, out, out_ld);
+  CGNN_LAUNCH(kfn, (n + 31) / 32, 256, 0, stream, partials, G, stride, rows, cols, ld, out, out_ld);
   CGNN_CHECK_LAUNCH();
   return CGNN_OK;
 }
