@@ -32,6 +32,44 @@ static inline __host__ __device__ int agg_smem_words(int max_nodes, int max_edge
 // returns acc = sum over that row's records of w * tile[nbr][quad] (tile rows are LPR float4 wide), the row's aux
 // word and whether the row exists.  Records are read two at a time (rows are padded to an even count); the rows of a
 // group run in lock step up to the shortest one, the remainder is predicated.
+// acc += w * v on a channel quad.  Device build: two packed fp32 FMAs (fma.rn.f32x2 -> FFMA2 with the weight as a
+// broadcast scalar) - the same IEEE fused multiply-adds as four FFMAs, half the issue slots.
+__device__ __forceinline__ void fma_quad(float4& a, const float4& v, float w) {
+#ifdef CGNN_EMU
+  a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
+#else
+  float2 a0 = make_float2(a.x, a.y), a1 = make_float2(a.z, a.w);
+  const float2 v0 = make_float2(v.x, v.y), v1 = make_float2(v.z, v.w), w2 = make_float2(w, w);
+  unsigned long long d0 = reinterpret_cast<unsigned long long&>(a0), d1 = reinterpret_cast<unsigned long long&>(a1);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d0) : "l"(reinterpret_cast<const unsigned long long&>(v0)), "l"(reinterpret_cast<const unsigned long long&>(w2)));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d1) : "l"(reinterpret_cast<const unsigned long long&>(v1)), "l"(reinterpret_cast<const unsigned long long&>(w2)));
+  a0 = reinterpret_cast<float2&>(d0); a1 = reinterpret_cast<float2&>(d1);
+  a = make_float4(a0.x, a0.y, a1.x, a1.y);
+#endif
+}
+
+// the channel quad of tile row `nbr` for this lane: one shared-space address = one multiply-add per record
+struct TileQuads {
+#ifdef CGNN_EMU
+  const float4* t4; int pitch;
+  __device__ __forceinline__ float4 at(int nbr) const { return t4[nbr * pitch]; }
+#else
+  uint32_t base, pitch_bytes;
+  __device__ __forceinline__ float4 at(int nbr) const {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base + (uint32_t)nbr * pitch_bytes));
+    return v;
+  }
+#endif
+};
+__device__ __forceinline__ TileQuads tile_quads(const float4* t4, int pitch) {
+#ifdef CGNN_EMU
+  return TileQuads{t4, pitch};
+#else
+  return TileQuads{(uint32_t)__cvta_generic_to_shared(t4), (uint32_t)pitch * 16u};
+#endif
+}
+
 template <int LPR, int PITCH = LPR>
 static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__ s_desc, const int4* __restrict__ s_rec2,
                                                         const float4* __restrict__ tile4, int i0, int n, float4& acc, float& aux,
@@ -48,36 +86,33 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
     lmin = min(lmin, __shfl_xor_sync(kFull, lmin, o));
     lmax = max(lmax, __shfl_xor_sync(kFull, lmax, o));
   }
-  const float4* t4 = tile4 + cl;
+  const TileQuads t = tile_quads(tile4 + cl, PITCH);
   const int4* rp = s_rec2 + (d.x >> 1);
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   int k = 0;
 #pragma unroll 1
   for (; k + 4 <= lmin; k += 4, rp += 2) {   // four records per step: half the loop overhead, four tile loads in flight
     const int4 r = rp[0], s = rp[1];
-    const float4 v0 = t4[r.x * PITCH], v1 = t4[r.z * PITCH], v2 = t4[s.x * PITCH], v3 = t4[s.z * PITCH];
-    const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w), w2 = __int_as_float(s.y), w3 = __int_as_float(s.w);
-    a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
-    a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
-    a.x = fmaf(v2.x, w2, a.x); a.y = fmaf(v2.y, w2, a.y); a.z = fmaf(v2.z, w2, a.z); a.w = fmaf(v2.w, w2, a.w);
-    a.x = fmaf(v3.x, w3, a.x); a.y = fmaf(v3.y, w3, a.y); a.z = fmaf(v3.z, w3, a.z); a.w = fmaf(v3.w, w3, a.w);
+    const float4 v0 = t.at(r.x), v1 = t.at(r.z), v2 = t.at(s.x), v3 = t.at(s.z);
+    fma_quad(a, v0, __int_as_float(r.y));
+    fma_quad(a, v1, __int_as_float(r.w));
+    fma_quad(a, v2, __int_as_float(s.y));
+    fma_quad(a, v3, __int_as_float(s.w));
   }
 #pragma unroll 1
   for (; k < lmin; k += 2, ++rp) {        // every row of the group has these records
     const int4 r = *rp;
-    const float4 v0 = t4[r.x * PITCH], v1 = t4[r.z * PITCH];
-    const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
-    a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
-    a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
+    const float4 v0 = t.at(r.x), v1 = t.at(r.z);
+    fma_quad(a, v0, __int_as_float(r.y));
+    fma_quad(a, v1, __int_as_float(r.w));
   }
 #pragma unroll 1
   for (; k < lmax; k += 2, ++rp) {        // rows that have ended contribute zero weights (and read row 0)
     int4 r = make_int4(0, 0, 0, 0);
     if (k < len) r = *rp;
-    const float4 v0 = t4[r.x * PITCH], v1 = t4[r.z * PITCH];
-    const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
-    a.x = fmaf(v0.x, w0, a.x); a.y = fmaf(v0.y, w0, a.y); a.z = fmaf(v0.z, w0, a.z); a.w = fmaf(v0.w, w0, a.w);
-    a.x = fmaf(v1.x, w1, a.x); a.y = fmaf(v1.y, w1, a.y); a.z = fmaf(v1.z, w1, a.z); a.w = fmaf(v1.w, w1, a.w);
+    const float4 v0 = t.at(r.x), v1 = t.at(r.z);
+    fma_quad(a, v0, __int_as_float(r.y));
+    fma_quad(a, v1, __int_as_float(r.w));
   }
   acc = a;
   aux = __int_as_float(d.z);

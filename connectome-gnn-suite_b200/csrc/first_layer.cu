@@ -129,19 +129,19 @@ __global__ void __launch_bounds__(NT, 2) k_first_fwd(FirstArgs p) {
     for (int r = rsub; r < m.y; r += RS) {
       const float4 a0 = s_a[2 * r], a1 = s_a[2 * r + 1];
       const float in_a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float o[4] = {b4[0], b4[1], b4[2], b4[3]};
+      float4 o4 = make_float4(b4[0], b4[1], b4[2], b4[3]);
       if (SAGE) {
         const float4 x0 = s_x[2 * r], x1 = s_x[2 * r + 1];
         const float in_x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-        for (int k = 0; k < KX; ++k)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = fmaf(in_x[k], wq[k][j], o[j]);
+        for (int k = 0; k < KX; ++k) fma_quad(o4, make_float4(wq[k][0], wq[k][1], wq[k][2], wq[k][3]), in_x[k]);
       }
 #pragma unroll
-      for (int k = 0; k < KX; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = fmaf(in_a[k], wq[SAGE ? KX + k : k][j], o[j]);
+      for (int k = 0; k < KX; ++k) {
+        constexpr int O = SAGE ? KX : 0;
+        fma_quad(o4, make_float4(wq[O + k][0], wq[O + k][1], wq[O + k][2], wq[O + k][3]), in_a[k]);
+      }
+      float o[4] = {o4.x, o4.y, o4.z, o4.w};
       if (SAGE) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.0f);
