@@ -118,8 +118,11 @@ __device__ __forceinline__ void block_excl_scan(int* a, int n, int* s_warp) {
   __syncthreads();
 }
 
-template <bool FROM_STORE>
-__global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
+// NT threads per CTA: 512 for 360-node subjects; 128 for small subjects (<= 128 nodes), where the per-row phases would
+// leave most of a 512-thread CTA waiting at barriers - four times as many CTAs are resident instead.
+template <bool FROM_STORE, int NT>
+__global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
+  constexpr int kNW = NT / 32;
   CGNN_SMEM_DECL;
   __shared__ int s_warp[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -144,20 +147,20 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
     const int F = p.store.num_features;
     const float* sx = p.store.x + sn * F;
     float* dx = p.x + nb * F;
-    for (int i0 = tid; i0 < n * F; i0 += 4 * kThreads) {     // four loads in flight per thread
+    for (int i0 = tid; i0 < n * F; i0 += 4 * NT) {     // four loads in flight per thread
       float v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = i0 + u * kThreads < n * F ? sx[i0 + u * kThreads] : 0.0f;
+      for (int u = 0; u < 4; ++u) v[u] = i0 + u * NT < n * F ? sx[i0 + u * NT] : 0.0f;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (i0 + u * kThreads < n * F) dx[i0 + u * kThreads] = v[u];
+        if (i0 + u * NT < n * F) dx[i0 + u * NT] = v[u];
     }
-    for (int i = tid; i < n; i += kThreads) p.batch[nb + i] = g;
+    for (int i = tid; i < n; i += NT) p.batch[nb + i] = g;
     if (tid == 0 && p.labels && p.store.label) p.labels[g] = p.store.label[sid];
   } else {
     gsrc = p.coo + eb; gdst = p.coo + p.total_edges + eb; lw = p.coo_w + eb;
   }
-  constexpr int kChunks = kWarps / 2;
+  constexpr int kChunks = kNW / 2;
   int* cnt = reinterpret_cast<int*>(s_wsum + n);        // [2][kChunks][n]
   // Subjects that fit are sorted entirely in shared memory: the raw COO list (src | dst << 16, w) is read from
   // global memory once, both sorted lists live next to it, and the row sums, normalised weights and CSR arrays are
@@ -189,16 +192,16 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   };
   // one pass over the subject's COO list in global memory: reference-visible outputs and the shared-memory copy
   if (FROM_STORE || staged) {
-    for (int e0 = tid; e0 < m; e0 += 3 * kThreads) {           // three edges in flight per thread
+    for (int e0 = tid; e0 < m; e0 += 3 * NT) {           // three edges in flight per thread
       int es[3], ed[3]; float ew[3];
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
         es[u] = 0; ed[u] = 0; ew[u] = 0.0f;
-        if (e0 + u * kThreads < m) load_edge(e0 + u * kThreads, es[u], ed[u], ew[u]);
+        if (e0 + u * NT < m) load_edge(e0 + u * NT, es[u], ed[u], ew[u]);
       }
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
-        const int e = e0 + u * kThreads;
+        const int e = e0 + u * NT;
         if (e >= m) continue;
         int s = es[u], d = ed[u]; float w = ew[u];
         if (FROM_STORE) {
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   const int clen = (((m + kChunks - 1) / kChunks) + 31) & ~31;
   const int e_lo = min(chunk * clen, m), e_hi = min(e_lo + clen, m);
   int* my_cnt = cnt + (size_t)(dir * kChunks + chunk) * n;
-  for (int i = tid; i < 2 * kChunks * n; i += kThreads) cnt[i] = 0;
+  for (int i = tid; i < 2 * kChunks * n; i += NT) cnt[i] = 0;
   __syncthreads();
   if (n > 0)
     for (int e = e_lo + lane; e < e_hi; e += 32) {
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
       atomicAdd(&my_cnt[dir == 0 ? d : s], 1);
     }
   __syncthreads();
-  for (int idx = tid; idx < 2 * n; idx += kThreads) {
+  for (int idx = tid; idx < 2 * n; idx += NT) {
     const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
     int t = 0;
     for (int c = 0; c < kChunks; ++c) t += cnt[(size_t)(dd * kChunks + c) * n + i];
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   __syncthreads();
   block_excl_scan(cur_in, n, s_warp);
   block_excl_scan(cur_out, n, s_warp);
-  for (int idx = tid; idx < 2 * n; idx += kThreads) {
+  for (int idx = tid; idx < 2 * n; idx += NT) {
     const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
     int run = (dd == 0 ? cur_in : cur_out)[i];
     (dd == 0 ? p.csr.in_rowptr : p.csr.out_rowptr)[nb + i] = (int32_t)(eb + run);
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   }
   __syncthreads();
   // cur_in / cur_out hold the exclusive row starts; the passes below want the inclusive ends (start of row i + 1)
-  for (int idx = tid; idx < 2 * n; idx += kThreads) {
+  for (int idx = tid; idx < 2 * n; idx += NT) {
     const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
     const int* c = cnt + (size_t)(dd * kChunks + kChunks - 1) * n;
     (dd == 0 ? cur_in : cur_out)[i] = c[i];     // the last chunk's cursor of row i ended at the row's end
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   __syncthreads();
 
   if (staged) {
-    for (int i = tid; i < n; i += kThreads) {
+    for (int i = tid; i < n; i += NT) {
       const int o0 = i ? cur_out[i - 1] : 0, o1 = cur_out[i];
       float deg = 0.0f;
       for (int q = o0; q < o1; ++q) deg = __fadd_rn(deg, cw[m + q]);
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
       // packed aggregation blobs of the requested family, straight from the sorted lists (same bits as k_build_agg)
       const int self = p.csr.agg_kind == AGG_GCN ? 1 : 0;
       int* pos = cnt;                                   // [2][n] padded record counts -> first record of every row
-      for (int idx = tid; idx < 2 * n; idx += kThreads) {
+      for (int idx = tid; idx < 2 * n; idx += NT) {
         const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
         const int* ce = dd == 0 ? cur_in : cur_out;
         pos[idx] = ((ce[i] - (i ? ce[i - 1] : 0)) + self + 1) & ~1;
@@ -322,8 +325,8 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
       __syncthreads();
       block_excl_scan(pos, n, s_warp);
       block_excl_scan(pos + n, n, s_warp);
-      for (int i = tid; i < n; i += kThreads) p.csr.row_graph[nb + i] = (int32_t)g;
-      for (int idx = tid; idx < 2 * n; idx += kThreads) {
+      for (int i = tid; i < n; i += NT) p.csr.row_graph[nb + i] = (int32_t)g;
+      for (int idx = tid; idx < 2 * n; idx += NT) {
         const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
         const int* ce = dd == 0 ? cur_in : cur_out;
         const int q0 = i ? ce[i - 1] : 0, q1 = ce[i];
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
         reinterpret_cast<int4*>(blob)[i] = make_int4(begin, at, __float_as_int(aux), 0);
       }
     }
-    for (int q = tid; q < m; q += kThreads) {
+    for (int q = tid; q < m; q += NT) {
       uint32_t v = pk[q];
       int s = (int)(v & 0xffffu), d = (int)(v >> 16);
       float w = cw[q];
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
     return;
   }
   // Row sums in COO order (fp32, sequential): D^ (by source, self-loop weight 1 last) and w_sum.
-  for (int i = tid; i < n; i += kThreads) {
+  for (int i = tid; i < n; i += NT) {
     const int o0 = i ? cur_out[i - 1] : 0, o1 = cur_out[i];
     float deg = 0.0f;
     for (int q = o0; q < o1; ++q) deg = __fadd_rn(deg, p.csr.out_w[eb + q]);
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(kThreads) k_collate_graph(CollateArgs p) {
   }
   __syncthreads();
   // w^_e = (dinv[src] * w) * dinv[dst]   (reference models.py:108 evaluation order)
-  for (int i = tid; i < n; i += kThreads) {
+  for (int i = tid; i < n; i += NT) {
     const int i0 = i ? cur_in[i - 1] : 0, i1 = cur_in[i];
     for (int q = i0; q < i1; ++q) {
       const int s = (int)(p.csr.in_col[eb + q] - nb);
@@ -406,7 +409,8 @@ static bool csr_out_ok(const cgnn_csr_out_t* c) {
 static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaStream_t stream) {
   const DeviceInfo dev = device_info();
   if (max_nodes < 1) max_nodes = 1;
-  size_t smem = (size_t)max_nodes * (16 + 4 * kWarps) + 16;   // cursors, dinv, wsum, per-chunk counters
+  const int nt = (max_nodes <= 128 && a.B > 0 && a.total_edges / a.B <= 2048) ? 128 : kThreads;
+  size_t smem = (size_t)max_nodes * (16 + 4 * (nt / 32)) + 16;   // cursors, dinv, wsum, per-chunk counters
   if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   // room for the raw and the two sorted edge lists of a typical subject (24 bytes per edge): an eighth above the batch average, as
   // long as two CTAs still fit on an SM; larger subjects take the unstaged path inside the kernel
@@ -420,15 +424,15 @@ static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaSt
   }
   a.max_nodes = max_nodes;
   if (a.B <= 0) return CGNN_OK;
-  if (from_store) {
-    auto kfn = k_collate_graph<true>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    CGNN_LAUNCH(kfn, (unsigned)a.B, kThreads, smem, stream, a);
-  } else {
-    auto kfn = k_collate_graph<false>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    CGNN_LAUNCH(kfn, (unsigned)a.B, kThreads, smem, stream, a);
+#define CGNN_COLLATE(FS_, NT_)                                                                              \
+  {                                                                                                         \
+    auto kfn = k_collate_graph<FS_, NT_>;                                                                   \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    CGNN_LAUNCH(kfn, (unsigned)a.B, NT_, smem, stream, a);                                                  \
   }
+  if (from_store) { if (nt == 128) CGNN_COLLATE(true, 128) else CGNN_COLLATE(true, kThreads) }
+  else { if (nt == 128) CGNN_COLLATE(false, 128) else CGNN_COLLATE(false, kThreads) }
+#undef CGNN_COLLATE
   CGNN_CHECK_LAUNCH();
   if (a.csr.agg_kind >= 0 && a.csr.agg_in && a.csr.agg_out && a.csr.row_graph && a.edge_cap < a.total_edges) {
     // subjects the kernel could not stage (more edges than edge_cap) get their blobs from the stand-alone builder,

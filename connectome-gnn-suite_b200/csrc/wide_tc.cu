@@ -9,8 +9,8 @@
 //                                 both have 256 channels, so the aggregate never needs a buffer of its own
 //   backward   k_gather<GCN_BWD>  dz on load, dP = A^^T dz, dbias                        (agg.cu)
 //              k_wide_xw          du_in = dP W                                           (autograd of models.py:111)
-//              k_wide_xty         dW = dP^T act(t_in), accumulated in tensor memory over all of a CTA's rows
-//              cgnn_bn_bwd_sums   BatchNorm-backward sums of the layer below (stand-alone pass)
+//              k_wide_xty         dW = dP^T act(t_in), accumulated in tensor memory over all of a CTA's rows; the
+//                                 BatchNorm-backward sums of the layer below ride along (t_in is in registers there)
 //
 // k_wide_xw streams the weight, pre-split into TF32 hi/lo parts and laid out as swizzled K-major blocks by
 // k_wide_prep_w (512 KB, L2 resident), one 32-channel block per pipeline stage; the accumulator of a 128-row tile is
@@ -253,6 +253,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_xw(WideXwArgs p) {
 // ---- partial dW[h][k] = sum_r dP[r][h] act(t_in)[r][k] over this CTA's rows --------------------------------------------
 struct WideXtyArgs {
   const float* dP; const float* t_in; Act act_in; long long rows; float* partials;
+  // optional: BatchNorm-backward sums of the layer below from du_in (the layer input is in registers here anyway)
+  const float* du_in; const float* prev_mean; const float* prev_rstd; float* prev_partials;   // per CTA [2][256]
 };
 
 __global__ void __launch_bounds__(kThreads, 1) k_wide_xty(WideXtyArgs p) {
@@ -285,8 +287,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_xty(WideXtyArgs p) {
   rt::chan_quad_init(cq, p.act_in, 4 * q, WN);
   const rt::RowKey rk = rt::row_key(p.act_in);
 
+  const bool want_prev = p.prev_partials != nullptr;
+  float pmean[4], prstd[4], ps1[4] = {0.f, 0.f, 0.f, 0.f}, ps2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    pmean[j] = want_prev ? p.prev_mean[4 * q + j] : 0.0f;
+    prstd[j] = want_prev ? p.prev_rstd[4 * q + j] : 0.0f;
+  }
+
   const long long nchunks = (p.rows + XR - 1) / XR;
-  float4 dp[2], tu[2];
+  float4 dp[2], tu[2], dd[2];
   auto load_chunk = [&](long long c) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -294,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_xty(WideXtyArgs p) {
       const bool live = c < nchunks && row < p.rows;
       dp[i] = live ? rt::ld_quad<true>(p.dP, row, WN, 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
       tu[i] = live ? rt::ld_quad<true>(p.t_in, row, WN, 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dd[i] = (live && want_prev) ? rt::ld_quad<true>(p.du_in, row, WN, 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   long long c = blockIdx.x;
@@ -311,7 +322,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_xty(WideXtyArgs p) {
       rt::sts4(a_hi + moff + i * 8 * rt::kRowBytes, h);
       rt::sts4(a_hi + X_HALF + moff + i * 8 * rt::kRowBytes, l);
       float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < p.rows) u = rt::act_fwd4(p.act_in, cq, tu[i], rk, (uint32_t)row);
+      if (row < p.rows) {
+        u = rt::act_fwd4(p.act_in, cq, tu[i], rk, (uint32_t)row);
+        if (want_prev) {
+          const float4 dy = rt::act_bwd4(p.act_in, cq, tu[i], dd[i], rk, (uint32_t)row);
+          const float tv[4] = {tu[i].x, tu[i].y, tu[i].z, tu[i].w}, dv[4] = {dy.x, dy.y, dy.z, dy.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ps1[j] += dv[j];
+            ps2[j] = fmaf(dv[j], (tv[j] - pmean[j]) * prstd[j], ps2[j]);
+          }
+        }
+      }
       rt::split4(u, h, l);
       rt::sts4(a_hi + 2 * X_HALF + moff + i * 8 * rt::kRowBytes, h);
       rt::sts4(a_hi + 3 * X_HALF + moff + i * 8 * rt::kRowBytes, l);
@@ -358,6 +380,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_xty(WideXtyArgs p) {
       }
     }
   }
+  if (want_prev) {
+    float* red = reinterpret_cast<float*>(base);   // [kThreads][8] over stage 0 (every MMA has completed)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[tid * 8 + j] = ps1[j]; red[tid * 8 + 4 + j] = ps2[j]; }
+    __syncthreads();
+    for (int c2 = tid; c2 < 2 * WN; c2 += kThreads) {
+      const int which = c2 / WN, ch = c2 - which * WN;
+      const int qq = ch >> 2, j = ch & 3;
+      float sacc = 0.0f;
+      for (int th = qq; th < kThreads; th += WN / 4) sacc += red[th * 8 + which * 4 + j];
+      p.prev_partials[(size_t)blockIdx.x * 2 * WN + c2] = sacc;
+    }
+  }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(taddr, 512);
@@ -395,16 +430,19 @@ int launch_wide_xw(const float* A, long long rows, int K, const unsigned char* i
 }
 
 int launch_wide_xty(const float* dP, const float* t_in, const cgnn_act_t* act_in, long long rows, float* partials,
-                    size_t partial_bytes, int* grid_out, cudaStream_t stream) {
+                    size_t partial_bytes, const float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_partials,
+                    size_t prev_bytes, int* grid_out, cudaStream_t stream) {
   const DeviceInfo dev = device_info();
   if (W_XTY_SMEM > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   WideXtyArgs a;
   a.dP = dP; a.t_in = t_in; a.act_in = make_act(act_in); a.rows = rows; a.partials = partials;
+  a.du_in = du_in; a.prev_mean = prev_mean; a.prev_rstd = prev_rstd; a.prev_partials = prev_partials;
   const long long nchunks = (rows + XR - 1) / XR;
   long long grid = dev.sm_count;
   if (grid > nchunks) grid = nchunks;
   const size_t rec = (size_t)WN * WN * sizeof(float);
   if ((size_t)grid * rec > partial_bytes) grid = (long long)(partial_bytes / rec);
+  if (prev_partials && (size_t)grid * 2 * WN * sizeof(float) > prev_bytes) grid = (long long)(prev_bytes / (2 * WN * sizeof(float)));
   if (grid < 1) return CGNN_ERR_WORKSPACE;
   *grid_out = (int)grid;
   auto kfn = k_wide_xty;
@@ -457,10 +495,13 @@ int launch_gcn_bwd_wide(const float* du, const float* demb, const float* z, cons
     return -1;
   const DeviceInfo dev = device_info();
   const size_t region_a = (((size_t)2 * dev.sm_count * WN * sizeof(float)) + 1023) & ~(size_t)1023;   // dbias partials
-  if (workspace_bytes < region_a + kImgBytes + (size_t)WN * WN * sizeof(float)) return CGNN_ERR_WORKSPACE;
-  unsigned char* img = (unsigned char*)workspace + region_a;
+  const size_t region_p = (((size_t)dev.sm_count * 2 * WN * sizeof(float)) + 1023) & ~(size_t)1023;      // prev-sum partials
+  if (workspace_bytes < region_a + region_p + kImgBytes + (size_t)WN * WN * sizeof(float)) return CGNN_ERR_WORKSPACE;
+  float* prev_parts = (float*)((unsigned char*)workspace + region_a);
+  unsigned char* img = (unsigned char*)workspace + region_a + region_p;
   float* parts = (float*)(img + kImgBytes);
-  const size_t parts_bytes = workspace_bytes - region_a - kImgBytes;
+  const size_t parts_bytes = workspace_bytes - region_a - region_p - kImgBytes;
+  const bool fuse_prev = prev_sums != nullptr && du_in != nullptr;
 
   GatherArgs ga{};
   ga.meta = csr->graph_meta; ga.B = num_graphs; ga.blob = csr->agg_out;
@@ -482,16 +523,15 @@ int launch_gcn_bwd_wide(const float* du, const float* demb, const float* z, cons
     rc = launch_wide_xw(scratch, rows, H, img, nullptr, du_in, nullptr, 0, &g2, stream);
     if (rc != CGNN_OK) return rc;
   }
-  rc = launch_wide_xty(scratch, t_in, act_in, rows, parts, parts_bytes, &g3, stream);
+  rc = launch_wide_xty(scratch, t_in, act_in, rows, parts, parts_bytes, fuse_prev ? du_in : nullptr, prev_mean, prev_rstd,
+                       fuse_prev ? prev_parts : nullptr, region_p, &g3, stream);
   if (rc != CGNN_OK) return rc;
   rc = launch_reduce_partials((const float*)workspace, g1, WN, 1, WN, WN, dbias, stream);
   if (rc) return rc;
   rc = launch_reduce_partials(parts, g3, WN * WN, WN, WN, WN, dW, stream);
   if (rc) return rc;
-  if (prev_sums) {   // sums of dy = d act_in / dy * du_in and dy * xhat over the batch (stream-ordered after the reductions)
-    rc = cgnn_bn_bwd_sums(t_in, act_in, prev_mean, prev_rstd, du_in, nullptr, ptr, num_graphs, rows, d_in, prev_sums, workspace,
-                          workspace_bytes, (cgnn_stream_t)stream);
-  }
+  if (fuse_prev) rc = launch_reduce_partials(prev_parts, g3, 2 * WN, 2, WN, WN, prev_sums, stream);
+  (void)ptr;
   return rc;
 }
 #endif  // CGNN_EMU
