@@ -421,8 +421,32 @@ def profile_calls(a, eng, step_fn, peak, peak_src):
     }
 
 
+def _claim_stdout():
+    """Only the JSON line may reach stdout: libraries that print there (NCCL's version banner under torchrun) are
+    sent to stderr by pointing fd 1 at fd 2 for the run; the line itself goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, text):
+    sys.stdout.flush()
+    os.write(saved_fd, (text + "\n").encode())
+
+
 if __name__ == "__main__":
     args = parse()
+    _OUT = _claim_stdout()
+    import builtins
+    _print = builtins.print
+
+    def _json_print(*a, **k):     # the single print(json.dumps(line)) of either arm
+        if len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{") and "file" not in k:
+            _emit(_OUT, a[0])
+        else:
+            _print(*a, **k)
+    builtins.print = _json_print
     if args.impl == "reference":
         run_reference(args)
     else:
