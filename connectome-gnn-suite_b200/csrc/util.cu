@@ -1,6 +1,8 @@
 // util.cu - status strings, device query, deterministic partial reductions.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace cgnn {
 
 static thread_local int g_last_cuda_error = 0;
@@ -10,6 +12,15 @@ unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_REL
 static int g_use_tensor_cores = 1;
 bool tensor_cores_enabled() { return g_use_tensor_cores != 0; }
 void set_tensor_cores(int on) { g_use_tensor_cores = on; }
+static int g_gather_pipe = -1;   // -1: not set yet (environment CGNN_GATHER_PIPE=0/1, default 0: measured 1 % slower per step)
+bool gather_pipe_enabled() {
+  if (g_gather_pipe < 0) {
+    const char* e = getenv("CGNN_GATHER_PIPE");
+    g_gather_pipe = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_gather_pipe != 0;
+}
+void set_gather_pipe(int on) { g_gather_pipe = on; }
 void set_cuda_error(int err) { g_last_cuda_error = err; }
 void set_tensor_cores(int on);
 
@@ -131,6 +142,7 @@ size_t cgnn_workspace_bytes(void) { return (size_t)64 << 20; }   // 148 CTAs x a
 uint64_t cgnn_kernel_launches(void) { return (uint64_t)cgnn::launches(); }
 int cgnn_set_option(int32_t key, int32_t value) {
   if (key == CGNN_OPT_TENSOR_CORES) { cgnn::set_tensor_cores(value); return CGNN_OK; }
+  if (key == CGNN_OPT_GATHER_PIPE) { cgnn::set_gather_pipe(value); return CGNN_OK; }
   return CGNN_ERR_INVALID_ARG;
 }
 

@@ -51,6 +51,10 @@ uint64_t cgnn_kernel_launches(void);
  * kernels, 0 = every shape runs the generic SIMT kernels (same results to fp32 round-off; used to
  * cross-check the two paths on the device). */
 #define CGNN_OPT_TENSOR_CORES 1
+/* CGNN_OPT_GATHER_PIPE: 1 = the packed-blob gathers run the pipelined kernel (one 1024-thread CTA per SM, double-
+ * buffered tiles filled by cp.async) where its shared memory fits; 0 (default) = the two-CTA-per-SM kernel, which
+ * measured 1 % faster per step on B200.  Same results bit for bit. */
+#define CGNN_OPT_GATHER_PIPE 2
 int cgnn_set_option(int32_t key, int32_t value);
 
 /* ---------------------------------------------------------------------------------------

@@ -80,6 +80,35 @@ def test_wide_gcn_dropout_masks_are_consistent():
     assert losses[0] == losses[1]
 
 
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_pipelined_gather_option_gives_identical_results(kind):
+    """CGNN_OPT_GATHER_PIPE switches the gather kernels to the one-CTA-per-SM pipelined edition: same bits."""
+    from connectome_gnn import _engine
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import CrossEntropyLoss
+    b = collate_graphs(generate_dataset(num_subjects=9, num_regions=360, seed=4))
+    eng = _engine.engine_for(b.node_features)
+    torch.manual_seed(0)
+    cls = GCNConnectome if kind == "gcn" else GraphSAGEConnectome
+    m = cls(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.2).cuda().train()
+    out = []
+    try:
+        for pipe in (0, 1):
+            assert eng.lib.cgnn_set_option(2, pipe) == 0
+            m.zero_grad()
+            torch.manual_seed(7)
+            loss = CrossEntropyLoss()(m(b), b.labels)
+            loss.backward()
+            out.append((loss.detach().clone(), [p.grad.clone() for p in m.parameters()]))
+    finally:
+        eng.lib.cgnn_set_option(2, 0)
+    assert torch.equal(out[0][0], out[1][0])
+    for g0, g1 in zip(out[0][1], out[1][1]):
+        helpers.assert_close(g1, g0, "gradient under the pipelined gather", tol=1e-6, atol=1e-9)
+
+
 def test_sage_hidden_256_fails_loudly():
     """GraphSAGE at hidden 256 is not covered (K = 512 contraction): an error, never a silent fallback."""
     from connectome_gnn import _lib
