@@ -110,6 +110,50 @@ def test_pipelined_gather_option_gives_identical_results(kind):
     helpers.assert_close(flat[1], flat[0], "gradients under the pipelined gather", tol=1e-6)
 
 
+@pytest.mark.parametrize("kind,hidden,regions", [("gcn", 64, 77), ("sage", 64, 77), ("gcn", 256, 45), ("gcn", 64, 360), ("sage", 64, 360)])
+def test_no_writes_outside_the_output_tensors(kind, hidden, regions, monkeypatch):
+    """Every tensor the engine allocates for a call is placed between two guard bands; after a full training step and
+    an eval forward over ragged row counts (not multiples of the 128-row / 16-row tiles) the bands must be untouched."""
+    from connectome_gnn import _engine
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import CrossEntropyLoss
+    PAD = 256                                     # elements on either side (keeps 16-byte alignment for every dtype)
+    guards = []
+
+    def guarded_empty(self, shape, dtype=torch.float32):
+        shape = tuple(shape) if isinstance(shape, (tuple, list, torch.Size)) else (int(shape),)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        raw = torch.empty(n + 2 * PAD, dtype=dtype, device=self.device)
+        fill = 0x5A if not dtype.is_floating_point else None
+        if fill is None:
+            raw.fill_(float("nan"))
+        else:
+            raw.fill_(fill)
+        guards.append((raw, n, dtype))
+        return raw[PAD:PAD + n].view(shape)
+
+    monkeypatch.setattr(_engine.Engine, "empty", guarded_empty)
+    graphs = generate_dataset(num_subjects=5, num_regions=regions, seed=3) + generate_dataset(num_subjects=2, num_regions=max(8, regions // 3), seed=4)
+    b = collate_graphs(graphs)
+    torch.manual_seed(0)
+    cls = GCNConnectome if kind == "gcn" else GraphSAGEConnectome
+    m = cls(in_channels=5, hidden_dim=hidden, num_classes=2, num_layers=3, dropout=0.1).cuda().train()
+    CrossEntropyLoss()(m(b), b.labels).backward()
+    m.eval()
+    with torch.no_grad():
+        m(b)
+    torch.cuda.synchronize()
+    assert len(guards) > 20
+    for raw, n, dtype in guards:
+        for band in (raw[:PAD], raw[PAD + n:]):
+            ok = torch.isnan(band).all() if dtype.is_floating_point else (band == 0x5A).all()
+            assert bool(ok), f"guard band of a {dtype} tensor with {n} elements was written"
+
+
 def test_sage_hidden_256_fails_loudly():
     """GraphSAGE at hidden 256 is not covered (K = 512 contraction): an error, never a silent fallback."""
     from connectome_gnn import _lib
