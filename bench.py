@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--dropout", type=float, default=0.3)
     ap.add_argument("--pool", type=int, default=256, help="unique generated subjects, tiled to --batch")
     ap.add_argument("--cpu-sample", type=int, default=96, help="subjects per leg for the CPU baseline")
+    ap.add_argument("--eager-sample", type=int, default=256, help="subjects per leg for the PyTorch-eager-on-GPU baseline")
     ap.add_argument("--legs", default=",".join(LEGS),
                     help="comma-separated subset of the step's legs (other BASELINE configs, e.g. configs[4]: "
                          "--hidden 256 --batch 8192 --legs gcn_train)")
@@ -139,23 +140,30 @@ class ClockSampler:
 # CPU baseline / reference arm: the oracle port (the reference's own op sequence) on the host cores
 # ---------------------------------------------------------------------------------------------
 
-def cpu_legs(a, graphs, steps, warmup):
+def cpu_legs(a, graphs, steps, warmup, device=None, sample_size=None):
     """Times the reference algorithm (oracle/port.py: collate + forward (+ backward + Adam)) per leg on a
-    bounded sample of the same workload.  Returns (graphs/s combined, per-leg graphs/s, seconds/step)."""
+    bounded sample of the same workload.  Returns (graphs/s combined, per-leg graphs/s, seconds/step).
+    `device` = None: the host cores (the reference's own arm).  A CUDA device: the same op sequence as PyTorch eager
+    kernels on the GPU (host-side collate + batch.to(device) as the reference Trainer does) - SURVEY 8d's optional
+    second baseline, reported inside cpu_baseline as `eager_cuda`."""
     from oracle import port   # bench.py is allowed to execute the oracle ONLY here (cpu_baseline / --impl reference)
-    sample = graphs[: a.cpu_sample]
+    sample = graphs[: (sample_size or a.cpu_sample)]
     torch.manual_seed(0)
     mods, opts = {}, {}
     for kind in ("gcn", "sage"):
         mods[kind] = port.Module(kind, port.init_params(kind, 5, a.hidden, 2, a.layers), dropout=a.dropout)
+        if device is not None:
+            mods[kind] = mods[kind].to(device)
         opts[kind] = torch.optim.Adam(mods[kind].parameters(), lr=1e-3, weight_decay=1e-4)
 
     def run(leg):
         kind, mode = leg.split("_")
         if mode == "train":
-            port.train_epoch(mods[kind], opts[kind], sample, len(sample), shuffle=True)
+            port.train_epoch(mods[kind], opts[kind], sample, len(sample), shuffle=True, device=device)
         else:
-            port.evaluate(mods[kind], sample, len(sample))
+            port.evaluate(mods[kind], sample, len(sample), device=device)
+        if device is not None:
+            torch.cuda.synchronize(device)
 
     per_leg = {leg: [] for leg in a.legs}
     for it in range(warmup + steps):
@@ -334,6 +342,13 @@ def run_b200(a):
         cpu = {"value": v, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port", "legs": cl,
                "sample": f"{a.cpu_sample} subjects per leg per step (2 steps after 1 warm-up) of the same shapes",
                "host_cpus": os.cpu_count()}
+        try:     # the reference's op sequence as PyTorch eager kernels on this GPU (informational second baseline)
+            n_eager = min(a.eager_sample, len(pool))
+            ve, cle, _ = cpu_legs(a, pool, steps=2, warmup=1, device=dev, sample_size=n_eager)
+            cpu["eager_cuda"] = {"value": ve, "unit": "graphs/s", "legs": cle,
+                                 "sample": f"{n_eager} subjects per leg per step, host collate + .to(device) as the reference Trainer does"}
+        except Exception as exc:   # never fail the bench line over the informational leg
+            cpu["eager_cuda"] = {"unavailable": repr(exc)[:200]}
 
     if rank == 0:
         line = {

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_bwd_gemm(GcnBwdGemmArgs p) 
   // MN groups of the A view run into the neighbouring operand tiles and fill accumulator rows that are never read.
   constexpr int MM = 128;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint64_t mbar;
+  __shared__ uint64_t mbar, mbar_dw;   // du_in MMAs / dW MMAs of a tile complete
   __shared__ uint32_t tmem_base_s;
   unsigned char* base = tc::smem_align1024(smem_raw);
   unsigned char* a1k_hi = base;                 // dP [128 rows][H], K-major (for du_in = dP W)
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_bwd_gemm(GcnBwdGemmArgs p) 
   const bool aff_in = p.act_in.scale != nullptr;
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, p.tmem_cols);
-  if (tid == 0) tc::mbar_init(&mbar, 1);
+  if (tid == 0) { tc::mbar_init(&mbar, 1); tc::mbar_init(&mbar_dw, 1); }
   stage_weight_transposed(p.W, Kin, Kin, H, KP, H, b1_hi, b1_lo);   // operand row n = input channel, k = h: W[h][n]
   stage_affine(p.act_in, Kin, KP, s_ci, s_ci + KP);
   if (!WIDE) {   // padded channels of the u operand stay zero
@@ -443,17 +443,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_bwd_gemm(GcnBwdGemmArgs p) 
     __syncthreads();
     tc::fence_after_sync();
     if (tid == 0) {
-      if (p.du_in) rt::issue_kmajor_x3<H / 8, TR, KP>(taddr, od1, H / 8, id1, false);   // du_in tile = dP W
+      // two commits: the du_in product (a third of the tensor work) is waited for first, its epilogue - staged over the
+      // K-major dP operand only that product reads - then runs while the dW product is still multiplying
+      if (p.du_in) {
+        rt::issue_kmajor_x3<H / 8, TR, KP>(taddr, od1, H / 8, id1, false);   // du_in tile = dP W
+        tc::mma_commit(&mbar);
+      }
       // dW += dP^T u : M = H (MN-major view of the dP tile), N = KP (MN-major view of the u tile), K = 128 rows
       rt::issue_mnmajor_x3<TR>(taddr + (uint32_t)KP, od2, id2, !first);
-      tc::mma_commit(&mbar);
+      tc::mma_commit(&mbar_dw);
     }
     first = false;
     load_tile(t + gridDim.x);
-    tc::mbar_wait(&mbar, phase);
-    phase ^= 1;
-    tc::fence_after_sync();
     if (p.du_in) {
+      tc::mbar_wait(&mbar, phase);
+      tc::fence_after_sync();
       rt::drain_rows_to_staging<KP>(taddr, stage, warp, lane);
       tc::fence_before_sync();
       __syncthreads();
@@ -481,6 +485,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gcn_bwd_gemm(GcnBwdGemmArgs p) 
         }
       }
     }
+    tc::mbar_wait(&mbar_dw, phase);   // the MN-major operands may be rewritten once the dW product has read them
+    phase ^= 1;
+    tc::fence_after_sync();
     __syncthreads();   // operand tiles / staging are rewritten by the next tile
   }
   (void)aff_in;
@@ -532,6 +539,7 @@ int launch_gcn_bwd_gemm(const float* dP, const float* t_in, const cgnn_act_t* ac
   if ((((uintptr_t)dP) & 15u) != 0) return -1;
   const bool wide = (d_in % 32 == 0) && ((((uintptr_t)t_in) & 15u) == 0) && (!du_in || (((uintptr_t)du_in) & 15u) == 0);
   if (!wide && KB > 2) return -1;
+  if (du_in && 32 * KB > 2 * H) return -1;   // the du_in staging must stay inside the K-major dP operand (see the two commits)
   const DeviceInfo dev = device_info();
   GcnBwdGemmArgs a;
   a.dP = dP; a.t_in = t_in; a.act_in = make_act(act_in); a.W = W;
@@ -647,6 +655,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p
   const long long ntiles = (p.rows + TR - 1) / TR;
   float4 zq[MHq::NQ], uq[MHq::NQ], tq[MCq::NQ], aq[WIDE ? MCq::NQ : 1];
   const int4* meta = reinterpret_cast<const int4*>(p.meta);
+  // pooled upstream (top layer): the subject of a row is needed before its pooled gradient can be addressed - that
+  // index is loaded one tile further ahead than the data, so no load in load_tile waits for another
+  int rg[MHq::NQ];
+  auto load_rg = [&](long long t) {
+#pragma unroll
+    for (int i = 0; i < MHq::NQ; ++i) {
+      const long long row = t * TR + rh + i * MHq::RS;
+      rg[i] = (!p.du && t < ntiles && row < p.rows) ? p.row_graph[row] : 0;
+    }
+  };
   auto load_tile = [&](long long t) {
     const long long r0 = t * TR;
 #pragma unroll
@@ -657,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p
         zv = rt::ld_quad<true>(p.z, row, H, 4 * qh);
         if (p.du) uv = rt::ld_quad<true>(p.du, row, H, 4 * qh);
         else {
-          const int g = p.row_graph[row];
+          const int g = rg[i];
           const float inv_n = 1.0f / ((float)meta[g].y + 1e-8f);
           const float4 e = rt::ld_quad<true>(p.demb, g, H, 4 * qh);
           uv = make_float4(e.x * inv_n, e.y * inv_n, e.z * inv_n, e.w * inv_n);
@@ -686,6 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p
       tq[i] = tv;
       if constexpr (WIDE) aq[i] = av;
     }
+    load_rg(t + gridDim.x);
   };
 
   // [d_u || d_agg] rows of the tile at r0 (accumulator buffer b): lane = output channel j, 16 tile rows per warp -
@@ -705,6 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p
 
   float colsum[4] = {0.f, 0.f, 0.f, 0.f};
   long long t = blockIdx.x;
+  load_rg(t);
   load_tile(t);
   uint32_t phase = 0, buf = 0;
   bool first = true, have_prev = false;

@@ -235,17 +235,21 @@ class Module(torch.nn.Module):
         return forward(self.kind, self.tensors(), batch, self.training, self.p)
 
 
-def batches(dataset: Sequence, batch_size: int, shuffle: bool):
-    """Epoch iterator with the reference's shuffling contract (graph.py:190-197)."""
+def batches(dataset: Sequence, batch_size: int, shuffle: bool, device=None):
+    """Epoch iterator with the reference's shuffling contract (graph.py:190-197); `device` = the reference Trainer's
+    `batch.to(self.device)` (train.py:47,62)."""
     order = torch.randperm(len(dataset)).tolist() if shuffle else list(range(len(dataset)))
     for s in range(0, len(order), batch_size):
-        yield collate([dataset[i] for i in order[s:s + batch_size]])
+        b = collate([dataset[i] for i in order[s:s + batch_size]])
+        if device is not None:
+            b = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in b.items()}
+        yield b
 
 
-def train_epoch(module: Module, optimizer, dataset, batch_size: int, shuffle: bool = True) -> float:
+def train_epoch(module: Module, optimizer, dataset, batch_size: int, shuffle: bool = True, device=None) -> float:
     module.train()
     total, seen = 0.0, 0
-    for b in batches(dataset, batch_size, shuffle):
+    for b in batches(dataset, batch_size, shuffle, device):
         optimizer.zero_grad()
         loss = F.cross_entropy(module(b), b["labels"])
         loss.backward()
@@ -257,10 +261,10 @@ def train_epoch(module: Module, optimizer, dataset, batch_size: int, shuffle: bo
 
 
 @torch.no_grad()
-def evaluate(module: Module, dataset, batch_size: int) -> dict:
+def evaluate(module: Module, dataset, batch_size: int, device=None) -> dict:
     module.eval()
     total, correct, seen = 0.0, 0, 0
-    for b in batches(dataset, batch_size, False):
+    for b in batches(dataset, batch_size, False, device):
         logits = module(b)
         nb = int(b["ptr"].shape[0]) - 1
         total += float(F.cross_entropy(logits, b["labels"])) * nb
