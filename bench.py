@@ -230,7 +230,8 @@ def run_b200(a):
     packed = pack_graphs(graphs)
     gen_s = time.time() - t0
     store = SubjectStore(packed, dev)
-    packed_c = pack_graphs(graphs, compact=True)     # host format of the e2e path: both endpoints of an edge in one int32
+    packed_c = pack_graphs(graphs, compact=True, pairs=True)   # host format of the e2e path: both endpoints of an edge in
+                                                               # one int32, one entry per undirected edge (lossless)
     pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in packed_c.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in packed_c.values() if isinstance(v, torch.Tensor))
     n_per = a.regions
@@ -333,7 +334,7 @@ def run_b200(a):
         e2e = {"value": graphs_per_step * e2e_steps / (ms_e / 1e3), "unit": "graphs/s",
                "h2d_bytes_per_step": int(h2d_bytes * len(a.legs)), "d2h_bytes_per_step": 4 * len(a.legs),
                "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
-               "path": "pinned host arena (compact store) -> StreamingStore (H2D on a copy stream, double-buffered) -> collate -> Trainer.train_step/eval_step -> the step's four losses read back to the host"}
+               "path": "pinned host arena (compact pair store: " + ("one entry per undirected edge" if packed_c.get("edge_pairs") else "one entry per directed edge") + ") -> StreamingStore (H2D on a copy stream, double-buffered) -> collate -> Trainer.train_step/eval_step -> the step's four losses read back to the host"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------------
     cpu = None

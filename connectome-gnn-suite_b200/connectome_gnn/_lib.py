@@ -14,7 +14,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcgnn.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_f32p = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 c_ptr = C.c_void_p
@@ -50,7 +50,7 @@ class StoreT(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("src", C.c_void_p), ("dst", C.c_void_p), ("w", C.c_void_p),
         ("node_ptr", C.c_void_p), ("edge_ptr", C.c_void_p), ("label", C.c_void_p),
-        ("num_features", C.c_int32),
+        ("num_features", C.c_int32), ("edge_pairs", C.c_int32),
     ]
 
 

@@ -168,12 +168,22 @@ class ConnectomeBatch:
 # Subject store: the dataset packed once
 # ---------------------------------------------------------------------------
 
-def pack_graphs(graphs: Sequence[ConnectomeGraph], compact: bool = False) -> dict:
+def _is_pair_list(ei: torch.Tensor, w: torch.Tensor, n_edges: np.ndarray) -> bool:
+    """True when every subject's COO list is a sequence of adjacent (s -> d), (d -> s) pairs of equal weight."""
+    if ei.shape[1] == 0 or bool((n_edges % 2).any()):
+        return False
+    a, b = ei[:, 0::2], ei[:, 1::2]
+    return bool(torch.equal(a[0], b[1]) and torch.equal(a[1], b[0]) and torch.equal(w[0::2], w[1::2]))
+
+
+def pack_graphs(graphs: Sequence[ConnectomeGraph], compact: bool = False, pairs: bool = False) -> dict:
     """Host packing of a list of subjects into arena arrays (pure indexing, no arithmetic).
 
     Returns CPU tensors: ``x [sum N, F]`` f32, ``src/dst [sum E]`` int32 subject-local ids,
     ``w [sum E]`` f32, ``node_ptr/edge_ptr [S+1]`` int64, ``label [S]`` int64 (0 where absent)
-    and ``has_label [S]`` bool.  Raises ``ValueError`` on ragged feature widths or edge
+    and ``has_label [S]`` bool.  ``compact`` packs both endpoints into one int32; ``pairs`` (with ``compact``)
+    additionally stores one entry per undirected edge when every subject's list allows it (``edge_pairs`` = 1 in the
+    result, else 0 and the plain compact form).  Raises ``ValueError`` on ragged feature widths or edge
     endpoints outside ``[0, N_s)`` - the kernels index shared-memory tiles with them."""
     if len(graphs) == 0:
         raise ValueError("cannot pack an empty list of ConnectomeGraph")
@@ -200,6 +210,7 @@ def pack_graphs(graphs: Sequence[ConnectomeGraph], compact: bool = False) -> dic
     if has_label.any():
         vals = torch.stack([cpu(g.label).reshape(()).to(torch.int64) for g in graphs if g.label is not None])
         label[torch.from_numpy(np.nonzero(has_label)[0])] = vals
+    edge_pairs = 0
     if compact:
         # both endpoints of an edge in one int32 (src | dst << 16): 4 bytes less per edge over PCIe
         if n_nodes.size and int(n_nodes.max()) > 65535:
@@ -207,12 +218,16 @@ def pack_graphs(graphs: Sequence[ConnectomeGraph], compact: bool = False) -> dic
         src = (ei[0] | (ei[1] << 16)).to(torch.int64)
         src = torch.where(src >= 2 ** 31, src - 2 ** 32, src).to(torch.int32).contiguous()
         dst = torch.zeros(0, dtype=torch.int32)
+        # undirected connectomes list every edge as two adjacent directed edges of equal weight (the reference
+        # generator and its real-data recipe both do): one entry per pair then carries the same information
+        if pairs and _is_pair_list(ei, w, n_edges):
+            src, w, edge_pairs = src[0::2].contiguous(), w[0::2].contiguous(), 1
     else:
         src, dst = ei[0].to(torch.int32).contiguous(), ei[1].to(torch.int32).contiguous()
     return dict(
         x=x, src=src, dst=dst, w=w,
         node_ptr=torch.from_numpy(node_ptr), edge_ptr=torch.from_numpy(edge_ptr), label=label,
-        has_label=has_label, num_features=feat)
+        has_label=has_label, num_features=feat, edge_pairs=edge_pairs)
 
 
 class SubjectStore:
@@ -235,9 +250,10 @@ class SubjectStore:
         self.node_ptr, self.edge_ptr = nb(packed["node_ptr"]), nb(packed["edge_ptr"])
         self.label = nb(packed["label"])
         compact = self.dst.numel() == 0 and self.src.numel() > 0     # pack_graphs(compact=True): src | dst << 16
+        self.edge_pairs = int(packed.get("edge_pairs", 0))
         self._struct = StoreT(self.x.data_ptr(), self.src.data_ptr(), None if compact else self.dst.data_ptr(), self.w.data_ptr(),
                               self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), self.label.data_ptr(),
-                              self.num_features)
+                              self.num_features, self.edge_pairs)
 
     def release(self) -> None:
         """Mark the work enqueued so far on the current stream as the last use of this arena's contents: a later
@@ -258,6 +274,8 @@ class SubjectStore:
         for k in names:
             if tuple(packed[k].shape) != tuple(getattr(self, k).shape) or packed[k].dtype != getattr(self, k).dtype:
                 raise ValueError(f"reload: '{k}' differs in shape or dtype from the resident arena")
+        if int(packed.get("edge_pairs", 0)) != self.edge_pairs:
+            raise ValueError("reload: the packed set and the resident arena differ in their edge layout (edge_pairs)")
         self.node_ptr_host = packed["node_ptr"].numpy()
         self.edge_ptr_host = packed["edge_ptr"].numpy()
         self.has_label = np.asarray(packed["has_label"], dtype=bool)

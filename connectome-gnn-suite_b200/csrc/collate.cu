@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
   if (FROM_STORE) {
     const long long sid = p.ids[g];
     const long long sn = p.store.node_ptr[sid], se = p.store.edge_ptr[sid];
-    lsrc = p.store.src + se; ldst = p.store.dst ? p.store.dst + se : nullptr; lw = p.store.w + se;
+    const long long so = p.store.edge_pairs ? (se >> 1) : se;     // pair store: one entry per undirected edge
+    lsrc = p.store.src + so; ldst = p.store.dst ? p.store.dst + so : nullptr; lw = p.store.w + so;
     const int F = p.store.num_features;
     const float* sx = p.store.x + sn * F;
     float* dx = p.x + nb * F;
@@ -173,13 +174,16 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
   const bool want_agg = staged && p.csr.agg_kind >= 0 && p.csr.agg_in && p.csr.agg_out && p.csr.row_graph;
   // Local endpoints of edge e as stored.  Endpoints outside the subject (malformed hand-built batches)
   // are redirected to a zero-weight self edge on node 0 so the CSR stays consistent.
+  const bool pair_store = FROM_STORE && p.store.edge_pairs != 0;
   auto load_edge = [&](int e, int& s, int& d, float& w) {
     if (FROM_STORE) {
-      const uint32_t v = (uint32_t)lsrc[e];
-      if (ldst) { s = (int)v; d = ldst[e]; } else { s = (int)(v & 0xffffu); d = (int)(v >> 16); }   // packed pairs
+      const int ee = pair_store ? (e >> 1) : e;
+      const uint32_t v = (uint32_t)lsrc[ee];
+      if (ldst) { s = (int)v; d = ldst[ee]; } else { s = (int)(v & 0xffffu); d = (int)(v >> 16); }   // both endpoints in one word
+      if (pair_store && (e & 1)) { const int t = s; s = d; d = t; }                                 // the reverse edge of the pair
+      w = lw[ee];
     }
-    else { s = (int)(gsrc[e] - nb); d = (int)(gdst[e] - nb); }
-    w = lw[e];
+    else { s = (int)(gsrc[e] - nb); d = (int)(gdst[e] - nb); w = lw[e]; }
   };
   auto edge = [&](int e, int& s, int& d, float& w) {
     if (staged) {
@@ -468,6 +472,7 @@ int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int6
   if (total_edges > 0 && (!edge_index || !edge_weight || !store->src || !store->w))
     return CGNN_ERR_INVALID_ARG;
   if (total_edges >= ((int64_t)1 << 31) || total_rows >= ((int64_t)1 << 31)) return CGNN_ERR_INVALID_ARG;
+  if (store->edge_pairs && store->dst) return CGNN_ERR_INVALID_ARG;   // the pair layout exists for the compact store only
   {
     auto kfn = k_scan_ptrs;
     CGNN_LAUNCH(kfn, 1, 1024, 0, stream, (const long long*)store->node_ptr, (const long long*)store->edge_ptr,

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGNN_ABI_VERSION 4
+#define CGNN_ABI_VERSION 5
 
 typedef void* cgnn_stream_t; /* cudaStream_t */
 
@@ -145,6 +145,11 @@ typedef struct {
   const int64_t* edge_ptr;  /* [S+1] */
   const int64_t* label;     /* [S] or NULL */
   int32_t num_features;
+  int32_t edge_pairs;       /* 1 (compact store only, dst == NULL): src / w hold one entry per UNDIRECTED edge; entry k of a
+                             * subject stands for the two adjacent COO edges 2k = (s -> d) and 2k + 1 = (d -> s) of equal
+                             * weight - the layout the reference generator (synthetic.py:137-158) and its real-data recipe
+                             * (README.md:145-179) emit.  edge_ptr keeps counting directed edges (even per subject); the
+                             * entries of subject s start at edge_ptr[s] / 2.  Halves the edge bytes that cross PCIe. */
 } cgnn_store_t;
 
 /* Mutable view of the CSR arrays the collate kernels fill (same field order as cgnn_csr_t). */

@@ -110,3 +110,20 @@ def test_oracle_random_weights(on_emu):
     graphs = generate_dataset(num_subjects=5, num_regions=70, seed=11)   # 70 rows: chunk boundary (64) inside a subject
     parity.check_against_oracle(graphs, "gcn", "cpu", hidden=20, layers=2)  # hidden not a multiple of 32
     parity.check_against_oracle(graphs, "sage", "cpu", hidden=12, layers=2)
+
+
+def test_pair_store_collates_identically(on_emu):
+    """One entry per undirected edge (cgnn_store_t.edge_pairs) expands to the same batch and CSR bit for bit."""
+    import numpy as np
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    graphs = generate_dataset(num_subjects=5, num_regions=20, seed=21)
+    ids = np.array([3, 0, 4, 4, 1])
+    packed = pack_graphs(graphs, compact=True, pairs=True)
+    assert packed["edge_pairs"] == 1 and packed["src"].numel() * 2 == int(packed["edge_ptr"][-1])
+    a = SubjectStore(pack_graphs(graphs), "cpu").collate(ids, prepare_for="gcn")
+    b = SubjectStore(packed, "cpu").collate(ids, prepare_for="gcn")
+    for f in ("node_features", "edge_index", "edge_weight", "batch", "labels", "ptr"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+    for f in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn", "deg", "dinv", "wsum"):
+        assert torch.equal(getattr(a.csr, f), getattr(b.csr, f)), f

@@ -422,6 +422,37 @@ def test_compact_store_collates_identically():
         assert torch.equal(getattr(a.csr, f), getattr(b.csr, f)), f
 
 
+def test_pair_store_collates_identically():
+    """pack_graphs(compact=True, pairs=True): one entry per undirected edge (edge_pairs = 1) expands to the same batch,
+    CSR and aggregation blobs bit for bit; a list that is not made of reversed pairs keeps the plain compact form."""
+    from connectome_gnn.graph import ConnectomeGraph, SubjectStore, pack_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    graphs = generate_dataset(num_subjects=6, num_regions=84, seed=21) + generate_dataset(num_subjects=3, num_regions=360, seed=22)
+    ids = np.array([3, 0, 8, 5, 5, 1, 7])
+    packed = pack_graphs(graphs, compact=True, pairs=True)
+    assert packed["edge_pairs"] == 1 and packed["src"].numel() * 2 == int(packed["edge_ptr"][-1])
+    for kind in ("gcn", "sage"):
+        a = SubjectStore(pack_graphs(graphs), DEV).collate(ids, prepare_for=kind)
+        b = SubjectStore(packed, DEV).collate(ids, prepare_for=kind)
+        for f in ("node_features", "edge_index", "edge_weight", "batch", "labels", "ptr"):
+            assert torch.equal(getattr(a, f), getattr(b, f)), f
+        for f in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn", "deg", "dinv", "wsum"):
+            assert torch.equal(getattr(a.csr, f), getattr(b.csr, f)), f
+        # the aggregation blobs (uninitialised slack between subjects, so not comparable as buffers): same logits
+        from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+        torch.manual_seed(0)
+        m = (GCNConnectome if kind == "gcn" else GraphSAGEConnectome)(in_channels=5, hidden_dim=64).cuda().eval()
+        with torch.no_grad():
+            assert torch.equal(m(a), m(b))
+    g0 = graphs[0]
+    odd = ConnectomeGraph(g0.node_features, g0.edge_index[:, :-1], g0.edge_weight[:-1], g0.label)   # one edge without its reverse
+    plain = pack_graphs([odd] + graphs[1:], compact=True, pairs=True)
+    assert plain["edge_pairs"] == 0 and plain["src"].numel() == int(plain["edge_ptr"][-1])
+    c = SubjectStore(plain, DEV).collate(np.array([0, 2]))
+    d = SubjectStore(pack_graphs([odd] + graphs[1:]), DEV).collate(np.array([0, 2]))
+    assert torch.equal(c.edge_index, d.edge_index) and torch.equal(c.csr.in_wn, d.csr.in_wn)
+
+
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_collate_emits_the_same_aggregation_structure(kind):
     """`prepare_for` (blobs written by the collate kernel) and the lazy `cgnn_build_agg` path feed the layer kernels
