@@ -74,11 +74,12 @@ def collate(graphs: Sequence) -> dict:
 def gcn_structure(edge_index: torch.Tensor, edge_weight: torch.Tensor, n: int):
     """Self-loops (weight 1) appended AFTER the real edges; D^ = row (source) sums; d^-1/2;
     w^ = d[src] * w * d[dst]   (models.py:94-108)."""
-    loops = torch.arange(n)
+    dev = edge_weight.device   # temporaries live where the batch lives, as in the reference (models.py:95-103)
+    loops = torch.arange(n, device=dev)
     src = torch.cat([edge_index[0], loops])
     dst = torch.cat([edge_index[1], loops])
-    w = torch.cat([edge_weight, torch.ones(n)])
-    deg = torch.zeros(n).scatter_add_(0, src, w)
+    w = torch.cat([edge_weight, torch.ones(n, device=dev)])
+    deg = torch.zeros(n, device=dev).scatter_add_(0, src, w)
     dinv = (deg + 1e-8).pow(-0.5)
     w_hat = dinv[src] * w * dinv[dst]
     return src, dst, w_hat, deg, dinv
@@ -86,11 +87,11 @@ def gcn_structure(edge_index: torch.Tensor, edge_weight: torch.Tensor, n: int):
 
 def sage_wsum(edge_index: torch.Tensor, edge_weight: torch.Tensor, n: int) -> torch.Tensor:
     """w_sum[i] = sum of weights of edges arriving at i (models.py:147-148)."""
-    return torch.zeros(n, 1).scatter_add_(0, edge_index[1].unsqueeze(1), edge_weight.unsqueeze(1))
+    return torch.zeros(n, 1, device=edge_weight.device).scatter_add_(0, edge_index[1].unsqueeze(1), edge_weight.unsqueeze(1))
 
 
 def _segment_sum(values: torch.Tensor, index: torch.Tensor, size: int) -> torch.Tensor:
-    out = torch.zeros(size, values.shape[1], dtype=values.dtype)
+    out = torch.zeros(size, values.shape[1], dtype=values.dtype, device=values.device)
     return out.scatter_add_(0, index.unsqueeze(1).expand_as(values), values)
 
 
@@ -114,7 +115,7 @@ def sage_conv(x, edge_index, edge_weight, weight, bias):
 def mean_pool(h: torch.Tensor, batch: torch.Tensor, num_graphs: int) -> torch.Tensor:
     """Per-subject mean with the reference's fp32 count and +1e-8 (models.py:40-47)."""
     total = _segment_sum(h, batch, num_graphs)
-    count = torch.zeros(num_graphs, 1).scatter_add_(0, batch.unsqueeze(1), torch.ones(batch.shape[0], 1))
+    count = torch.zeros(num_graphs, 1, device=h.device).scatter_add_(0, batch.unsqueeze(1), torch.ones(batch.shape[0], 1, device=h.device))
     return total / (count + 1e-8)
 
 
