@@ -260,8 +260,9 @@ class Engine:
                  _p(dW), _p(db),
                  _p(du_in), _p(prev_mean) if want_prev else None, _p(prev_rstd) if want_prev else None,
                  _p(prev_sums)]
-        # scratch between the two kernels of one call: GCN dP [rows, H]; GraphSAGE [2, rows, d_in]
-        scratch = self.empty((rows, H)) if kind == "gcn" else self.empty((2, rows, d_in))
+        # scratch between the kernels of one call: GCN dP [rows, H]; GraphSAGE [2, rows, d_in] (d_u, d_agg), and a third
+        # [rows, H] plane (dz) for the wide layers (H = d_in = 256)
+        scratch = self.empty((rows, H)) if kind == "gcn" else self.empty((3 if (H == 256 and d_in == 256) else 2, rows, d_in))
         args += [_p(scratch), _p(self.workspace), self.workspace_bytes, self.stream()]
         self._call(f"cgnn_{kind}_layer_bwd", *args)
         return dW, db, du_in, prev_sums

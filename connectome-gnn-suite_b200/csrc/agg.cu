@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
           }
           if (!VEC) o = rt::mask_quad(o, c0, C);
           s_tile[rr * LPR + cl] = o;
+          if (MODE == GATHER_SAGE_FWD && p.out_u && live_quad) rt::st_quad<VEC>(p.out_u, nb + rr, C, c0, o);
         }
       }
     }
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_gather_pipe(GatherArgs p) {
           o = rt::act_fwd4(p.act, cq, a, rk, grow);
         }
         tile[idx] = o;
+        if (MODE == GATHER_SAGE_FWD && p.out_u) rt::st_quad<true>(p.out_u, nb + (idx >> 3), C, c0, o);
       }
     }
     __syncthreads();     // tile / blob of unit g complete; everybody has left the gather of the previous unit

@@ -136,6 +136,7 @@ struct GatherArgs {
   const float* t_raw;      // this layer's stored input (for the sums of the layer below)
   const float* prev_mean; const float* prev_rstd; int want_prev;
   float* out;              // [rows, C]
+  float* out_u;            // SAGE_FWD, optional: the transformed input rows act(t_in) are also written here (wide layers)
   float* partials; int part_stride;   // GCN_BWD: dbias [C]; SAGE_BWD: prev sums [2C]
 };
 
@@ -171,6 +172,15 @@ bool wide_shape(int d_in, int H);
 int launch_gcn_fwd_wide(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
                         int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
                         int want_stats, int* grid_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_sage_fwd_wide(const float* t_in, const cgnn_act_t* act, float* agg, const float* W, const float* bias,
+                         const cgnn_csr_t* csr, int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes,
+                         int32_t max_edges, float* z, int want_stats, int* grid_out, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream);
+int launch_sage_bwd_wide(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out, const cgnn_bn_bwd_t* bn,
+                         const float* t_in, const float* agg, const cgnn_act_t* act_in, const float* W, const cgnn_csr_t* csr,
+                         int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* dW,
+                         float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_gcn_bwd_wide(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out, const cgnn_bn_bwd_t* bn,
                         const float* t_in, const cgnn_act_t* act_in, const float* W, const cgnn_csr_t* csr, const int64_t* ptr,
                         int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,

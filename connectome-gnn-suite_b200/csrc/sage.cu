@@ -542,6 +542,14 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
     if (rc0 == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, g0, H, bn_stats, stream) : CGNN_OK;
     if (rc0 > 0) return rc0;
   }
+  // Wide layers (H = d_in = 256): gather + K-looped contraction (wide_tc.cu).
+  if (tensor_cores_enabled() && wide_shape(d_in, H)) {
+    int gw = 0;
+    const int rcw = launch_sage_fwd_wide(t_in, act, agg, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, z,
+                                         bn_stats ? 1 : 0, &gw, workspace, workspace_bytes, stream);
+    if (rcw == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, gw, H, bn_stats, stream) : CGNN_OK;
+    if (rcw > 0) return rcw;
+  }
   // Tensor-core generation: gather kernel (weighted mean of the neighbours) + tcgen05 contraction.
   if (tensor_cores_enabled() && agg && csr->agg_in && csr->agg_kind == AGG_SAGE && (H == 32 || H == 64 || H == 128) &&
       2 * d_in <= 128 && (2 * d_in + 31) / 32 != 3 && (d_in <= 32 || d_in % 32 == 0) && aligned16(agg) && aligned16(z)) {
@@ -646,6 +654,13 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
       if (rc1) return rc1;
       return launch_reduce_partials((const float*)workspace + H * 2 * d_in, g0, stride, 1, H, H, dbias, stream);
     }
+  }
+  // Wide layers (H = d_in = 256): dz pass, K-looped contractions, transposed gather (wide_tc.cu; scratch = 3 x [rows, 256]).
+  if (tensor_cores_enabled() && wide_shape(d_in, H)) {
+    const int rcw = launch_sage_bwd_wide(du, demb, z, act_out, bn, t_in, agg, act_in, W, csr, num_graphs, rows, d_in, H, max_nodes,
+                                         max_edges, dW, dbias, du_in, prev_mean, prev_rstd, prev_sums, scratch, workspace,
+                                         workspace_bytes, stream);
+    if (rcw >= 0) return rcw;
   }
   // Tensor-core generation: tcgen05 contractions (dz on load, [d_u || d_agg], dW, dbias) + transposed gather kernel.
   if (tensor_cores_enabled() && agg && csr->agg_out && csr->row_graph && csr->agg_kind == AGG_SAGE &&

@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(256) k_wide_prep_w(const float* __restrict__ W
 // ---- out = A B^T (+ bias), 128-row tiles, K streamed in 32-channel blocks ----------------------------------------------
 struct WideXwArgs {
   const float* A; long long rows; int K;
+  const float* A2; int KB1, lda;     // K blocks >= KB1 come from A2 (GraphSAGE: [u || agg]); both have row stride lda
+  int relu;                          // epilogue: max(. + bias, 0)
   const unsigned char* Bimg; const float* bias; float* out; double* partials;
 };
 
@@ -119,7 +121,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_xw(WideXwArgs p) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const long long row = tt * WTR + ra + 64 * i;
-      pa[i] = (tt < ntiles && row < p.rows) ? rt::ld_quad<true>(p.A, row, p.K, 32 * kk + 4 * qa) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool second = kk >= p.KB1;
+      pa[i] = (tt < ntiles && row < p.rows)
+                  ? rt::ld_quad<true>(second ? p.A2 : p.A, row, p.lda, 32 * (second ? kk - p.KB1 : kk) + 4 * qa)
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   auto copy_b = [&](int kk, uint32_t s) {
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_xw(WideXwArgs p) {
       if (pend_r0 + r < p.rows) {
         float4 x = staging[rt::stage_index(r, qs, W_SLAB / 4)];
         x.x += bias4[J][0]; x.y += bias4[J][1]; x.z += bias4[J][2]; x.w += bias4[J][3];
+        if (p.relu) { x.x = fmaxf(x.x, 0.0f); x.y = fmaxf(x.y, 0.0f); x.z = fmaxf(x.z, 0.0f); x.w = fmaxf(x.w, 0.0f); }
         *reinterpret_cast<float4*>(p.out + (pend_r0 + r) * WN + J * W_SLAB + 4 * qs) = x;
         if (want_stats) {
           cnt[J] += 1;
@@ -398,6 +404,64 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_xty(WideXtyArgs p) {
   if (warp == 0) tc::tmem_dealloc(taddr, 512);
 }
 
+// ---- dz = relu'(z) * BatchNorm-backward(dropout-backward(upstream)) materialised, plus its column sums (GraphSAGE) ------
+struct WideDzArgs {
+  const float* z; const float* du; const float* demb; const int32_t* row_graph; const int32_t* meta;
+  Act act_out; rt::BnBwdDev bn; long long rows; float* dz; float* partials;   // per CTA [256]
+};
+
+__global__ void __launch_bounds__(kThreads, 2) k_wide_dz(WideDzArgs p) {
+  __shared__ float4 s_red[kThreads];
+  const int tid = threadIdx.x, q = tid & 63, r = tid >> 6;
+  rt::ChanQuad cq;
+  rt::chan_quad_init(cq, p.act_out, 4 * q, WN);
+  const rt::RowKey rk = rt::row_key(p.act_out);
+  rt::BnQuad bq;
+  rt::bn_quad_init(bq, p.bn, 4 * q, WN);
+  const int4* meta = reinterpret_cast<const int4*>(p.meta);
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long step = (long long)gridDim.x * 16;
+  for (long long row0 = (long long)blockIdx.x * 16 + r; row0 < p.rows; row0 += step) {
+    float4 zv[2], uv[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {          // two rows in flight per thread
+      const long long row = row0 + 8 * i;
+      zv[i] = make_float4(0.f, 0.f, 0.f, 0.f); uv[i] = zv[i];
+      if (row < p.rows) {
+        zv[i] = rt::ld_quad<true>(p.z, row, WN, 4 * q);
+        if (p.du) uv[i] = rt::ld_quad<true>(p.du, row, WN, 4 * q);
+        else {
+          const int g = p.row_graph[row];
+          const float inv_n = 1.0f / ((float)meta[g].y + 1e-8f);
+          const float4 e = rt::ld_quad<true>(p.demb, g, WN, 4 * q);
+          uv[i] = make_float4(e.x * inv_n, e.y * inv_n, e.z * inv_n, e.w * inv_n);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long row = row0 + 8 * i;
+      if (row >= p.rows) continue;
+      const float4 dy = rt::act_bwd4(p.act_out, cq, zv[i], uv[i], rk, (uint32_t)row);
+      float4 dz = rt::bn_bwd4(p.bn, bq, zv[i], dy);
+      if (!(zv[i].x > 0.0f)) dz.x = 0.0f;
+      if (!(zv[i].y > 0.0f)) dz.y = 0.0f;
+      if (!(zv[i].z > 0.0f)) dz.z = 0.0f;
+      if (!(zv[i].w > 0.0f)) dz.w = 0.0f;
+      cs[0] += dz.x; cs[1] += dz.y; cs[2] += dz.z; cs[3] += dz.w;
+      rt::st_quad<true>(p.dz, row, WN, 4 * q, dz);
+    }
+  }
+  s_red[tid] = make_float4(cs[0], cs[1], cs[2], cs[3]);
+  __syncthreads();
+  if (tid < WN) {
+    const int qq = tid >> 2, j = tid & 3;
+    float s = 0.0f;
+    for (int t = qq; t < kThreads; t += WN / 4) s += reinterpret_cast<const float*>(&s_red[t])[j];
+    p.partials[(size_t)blockIdx.x * WN + tid] = s;
+  }
+}
+
 bool al16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 int launch_prep_w(const float* W, int ldw, int K, int transposed, unsigned char* img, cudaStream_t stream) {
@@ -408,11 +472,13 @@ int launch_prep_w(const float* W, int ldw, int K, int transposed, unsigned char*
 }
 
 int launch_wide_xw(const float* A, long long rows, int K, const unsigned char* img, const float* bias, float* out,
-                   double* partials, size_t partial_bytes, int* grid_out, cudaStream_t stream) {
+                   double* partials, size_t partial_bytes, int* grid_out, cudaStream_t stream, const float* A2 = nullptr,
+                   int KB1 = -1, int relu = 0) {
   const DeviceInfo dev = device_info();
   if (W_XW_SMEM > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   WideXwArgs a;
   a.A = A; a.rows = rows; a.K = K; a.Bimg = img; a.bias = bias; a.out = out; a.partials = partials;
+  a.A2 = A2; a.KB1 = KB1 < 0 ? K / 32 : KB1; a.lda = A2 ? 32 * a.KB1 : K; a.relu = relu;
   const long long ntiles = (rows + WTR - 1) / WTR;
   long long grid = dev.sm_count;
   if (grid > ntiles) grid = ntiles;
@@ -533,6 +599,109 @@ int launch_gcn_bwd_wide(const float* du, const float* demb, const float* z, cons
   if (fuse_prev) rc = launch_reduce_partials(prev_parts, g3, 2 * WN, 2, WN, WN, prev_sums, stream);
   (void)ptr;
   return rc;
+}
+// GraphSAGE, H = d_in = 256:  z = relu([u || agg] W^T + b).  The gather writes the weighted mean into `agg` and, from the same
+// staged rows, u = act(t_in) into z; the contraction then reads its K = 512 operand from z and agg and writes z in place.
+int launch_sage_fwd_wide(const float* t_in, const cgnn_act_t* act, float* agg, const float* W, const float* bias,
+                         const cgnn_csr_t* csr, int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes,
+                         int32_t max_edges, float* z, int want_stats, int* grid_out, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream) {
+  if (!wide_shape(d_in, H)) return -1;
+  if (!agg || !csr->agg_in || csr->agg_kind != AGG_SAGE || !gather_supported(WN, max_nodes, max_edges)) return -1;
+  if (!al16(t_in) || !al16(z) || !al16(agg) || !al16(W) || !al16(workspace)) return -1;
+  const DeviceInfo dev = device_info();
+  const size_t stats_bytes = (((size_t)dev.sm_count * (1 + 2 * WN) * sizeof(double)) + 1023) & ~(size_t)1023;
+  if (!workspace || workspace_bytes < stats_bytes + 2 * kImgBytes) return CGNN_ERR_WORKSPACE;
+  unsigned char* img = (unsigned char*)workspace + stats_bytes;
+  GatherArgs ga{};
+  ga.meta = csr->graph_meta; ga.B = num_graphs; ga.blob = csr->agg_in;
+  ga.C = WN; ga.max_nodes = max_nodes; ga.max_edges = max_edges;
+  ga.src = t_in; ga.act = make_act(act); ga.out = agg; ga.out_u = z;
+  int g0 = 0;
+  int rc = launch_gather(GATHER_SAGE_FWD, ga, &g0, stream);
+  if (rc != CGNN_OK) return rc;
+  rc = launch_prep_w(W, 2 * d_in, 2 * d_in, 0, img, stream);
+  if (rc != CGNN_OK) return rc;
+  return launch_wide_xw(z, rows, 2 * d_in, img, bias, z, want_stats ? (double*)workspace : nullptr, stats_bytes, grid_out, stream,
+                        agg, d_in / 32, 1);
+}
+
+// Backward of the same layer; `scratch` = [3][rows, 256] floats: d_u, d_agg, dz.
+int launch_sage_bwd_wide(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out, const cgnn_bn_bwd_t* bn,
+                         const float* t_in, const float* agg, const cgnn_act_t* act_in, const float* W, const cgnn_csr_t* csr,
+                         int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* dW,
+                         float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!wide_shape(d_in, H)) return -1;
+  if (!scratch || !agg || !csr->agg_out || !csr->row_graph || csr->agg_kind != AGG_SAGE || !gather_supported(WN, max_nodes, max_edges))
+    return -1;
+  if (!al16(scratch) || !al16(z) || !al16(t_in) || !al16(agg) || !al16(W) || !al16(workspace) || (du && !al16(du)) ||
+      (demb && !al16(demb)) || (du_in && !al16(du_in)))
+    return -1;
+  const DeviceInfo dev = device_info();
+  const size_t region_a = (((size_t)2 * dev.sm_count * 2 * WN * sizeof(float)) + 1023) & ~(size_t)1023;   // dbias / prev-sum partials
+  if (workspace_bytes < region_a + kImgBytes + (size_t)WN * WN * sizeof(float)) return CGNN_ERR_WORKSPACE;
+  unsigned char* img = (unsigned char*)workspace + region_a;
+  float* parts = (float*)(img + kImgBytes);
+  const size_t parts_bytes = workspace_bytes - region_a - kImgBytes;
+  float* direct = scratch;
+  float* nbr = scratch + (size_t)rows * WN;
+  float* dz = scratch + (size_t)2 * rows * WN;
+
+  // (1) dz and dbias
+  WideDzArgs a{};
+  a.z = z; a.du = du; a.demb = demb; a.row_graph = csr->row_graph; a.meta = csr->graph_meta;
+  a.act_out = make_act(act_out);
+  a.bn.has = bn ? 1 : 0;
+  a.bn.scale = bn ? bn->scale : nullptr; a.bn.mean = bn ? bn->mean : nullptr; a.bn.rstd = bn ? bn->rstd : nullptr;
+  a.bn.s1 = bn ? bn->s1 : nullptr; a.bn.s2 = bn ? bn->s2 : nullptr;
+  a.bn.train = bn ? bn->train : 0;
+  a.bn.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
+  a.rows = rows; a.dz = dz; a.partials = (float*)workspace;
+  long long gdz = 2LL * dev.sm_count;
+  if (gdz > (rows + 15) / 16) gdz = (rows + 15) / 16;
+  {
+    auto kfn = k_wide_dz;
+    CGNN_LAUNCH(kfn, (unsigned)gdz, kThreads, 0, stream, a);
+    CGNN_CHECK_LAUNCH();
+  }
+  int rc = launch_reduce_partials((const float*)workspace, (int)gdz, WN, 1, WN, WN, dbias, stream);
+  if (rc) return rc;
+  // (2) dW = dz^T [u || agg]: two 256 x 256 halves through the same partial buffer
+  int g3 = 0;
+  rc = launch_wide_xty(dz, t_in, act_in, rows, parts, parts_bytes, nullptr, nullptr, nullptr, nullptr, 0, &g3, stream);
+  if (rc != CGNN_OK) return rc;
+  rc = launch_reduce_partials(parts, g3, WN * WN, WN, WN, WN, dW, stream, 2 * WN);
+  if (rc) return rc;
+  rc = launch_wide_xty(dz, agg, nullptr, rows, parts, parts_bytes, nullptr, nullptr, nullptr, nullptr, 0, &g3, stream);
+  if (rc != CGNN_OK) return rc;
+  rc = launch_reduce_partials(parts, g3, WN * WN, WN, WN, WN, dW + WN, stream, 2 * WN);
+  if (rc) return rc;
+  if (!du_in) return CGNN_OK;
+  // (3) [d_u || d_agg] = dz W: the two column halves of W as transposed operand images
+  int g2 = 0;
+  rc = launch_prep_w(W, 2 * d_in, H, 1, img, stream);
+  if (rc != CGNN_OK) return rc;
+  rc = launch_wide_xw(dz, rows, H, img, nullptr, direct, nullptr, 0, &g2, stream);
+  if (rc != CGNN_OK) return rc;
+  rc = launch_prep_w(W + d_in, 2 * d_in, H, 1, img, stream);
+  if (rc != CGNN_OK) return rc;
+  rc = launch_wide_xw(dz, rows, H, img, nullptr, nbr, nullptr, 0, &g2, stream);
+  if (rc != CGNN_OK) return rc;
+  // (4) du_in = d_u + A~^T d_agg, BatchNorm-backward sums of the layer below
+  GatherArgs ga{};
+  ga.meta = csr->graph_meta; ga.B = num_graphs; ga.blob = csr->agg_out;
+  ga.C = WN; ga.max_nodes = max_nodes; ga.max_edges = max_edges;
+  ga.src = nbr; ga.act = make_act(act_in); ga.direct = direct; ga.t_raw = t_in;
+  ga.prev_mean = prev_mean; ga.prev_rstd = prev_rstd; ga.want_prev = prev_sums ? 1 : 0;
+  ga.out = du_in;
+  ga.partials = (float*)workspace; ga.part_stride = 2 * WN;
+  int g4 = 0;
+  rc = launch_gather(GATHER_SAGE_BWD, ga, &g4, stream);
+  if (rc != CGNN_OK) return rc > 0 ? rc : CGNN_ERR_TILE_TOO_LARGE;
+  if ((size_t)g4 * 2 * WN * sizeof(float) > region_a) return CGNN_ERR_WORKSPACE;
+  if (prev_sums) return launch_reduce_partials(ga.partials, g4, 2 * WN, 2, WN, WN, prev_sums, stream);
+  return CGNN_OK;
 }
 #endif  // CGNN_EMU
 }  // namespace cgnn

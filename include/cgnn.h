@@ -299,7 +299,8 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
                        float* scratch, void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
 
 /* GraphSAGE layer backward (autograd of models.py:136-152 plus the BN/dropout that follows).
- * Same contract as cgnn_gcn_layer_bwd; W [H, 2*d_in].  scratch [2, rows, d_in] fp32 holds the
+ * Same contract as cgnn_gcn_layer_bwd; W [H, 2*d_in].  scratch [2, rows, d_in] fp32 ([3, rows, 256] for the wide
+ * layers, H = d_in = 256: the third plane carries dz) holds the
  * direct and neighbour parts of the input gradient between the two kernels of this call.  agg [rows, d_in] is the
  * aggregate cgnn_sage_layer_fwd stored: with it, the blobs of cgnn_build_agg and row_graph the call runs as tensor-core
  * contractions (dz on load, [d_u || d_agg] = dz W, dW, dbias) followed by the transposed gather kernel; NULL: the

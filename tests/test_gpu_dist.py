@@ -14,7 +14,7 @@ import helpers
 
 pytestmark = pytest.mark.gpu
 ROOT = helpers.ROOT
-CASES = (("gcn", 64, 84), ("sage", 64, 84), ("gcn", 256, 45))
+CASES = (("gcn", 64, 84), ("sage", 64, 84), ("gcn", 256, 45), ("sage", 256, 45))
 
 
 def _run_case(kind, hidden, graphs, batch_size, rank, world):

@@ -110,7 +110,7 @@ def test_pipelined_gather_option_gives_identical_results(kind):
     helpers.assert_close(flat[1], flat[0], "gradients under the pipelined gather", tol=1e-6)
 
 
-@pytest.mark.parametrize("kind,hidden,regions", [("gcn", 64, 77), ("sage", 64, 77), ("gcn", 256, 45), ("gcn", 64, 360), ("sage", 64, 360)])
+@pytest.mark.parametrize("kind,hidden,regions", [("gcn", 64, 77), ("sage", 64, 77), ("gcn", 256, 45), ("sage", 256, 45), ("gcn", 64, 360), ("sage", 64, 360)])
 def test_no_writes_outside_the_output_tensors(kind, hidden, regions, monkeypatch):
     """Every tensor the engine allocates for a call is placed between two guard bands; after a full training step and
     an eval forward over ragged row counts (not multiples of the 128-row / 16-row tiles) the bands must be untouched."""
@@ -154,14 +154,24 @@ def test_no_writes_outside_the_output_tensors(kind, hidden, regions, monkeypatch
             assert bool(ok), f"guard band of a {dtype} tensor with {n} elements was written"
 
 
-def test_sage_hidden_256_fails_loudly():
-    """GraphSAGE at hidden 256 is not covered (K = 512 contraction): an error, never a silent fallback."""
+@pytest.mark.parametrize("shape", [(4, 360, 256, 3), (7, 84, 256, 2)])
+def test_wide_sage_hidden_256(shape):
+    """GraphSAGE at hidden 256: gather (+ transformed rows) -> K = 512 contraction in place; backward through the dz
+    pass, the two weight-gradient halves, the two input-gradient halves and the transposed gather."""
+    from connectome_gnn.synthetic import generate_dataset
+    subjects, regions, hidden, layers = shape
+    graphs = generate_dataset(num_subjects=subjects, num_regions=regions, seed=6)
+    parity.check_against_oracle(graphs, "sage", DEV, hidden=hidden, layers=layers)
+
+
+def test_hidden_192_fails_loudly_for_large_subjects():
+    """Widths the kernels do not cover (here 192 with 360-node subjects) are an error, never a silent fallback."""
     from connectome_gnn import _lib
     from connectome_gnn.graph import collate_graphs
     from connectome_gnn.models import GraphSAGEConnectome
     from connectome_gnn.synthetic import generate_dataset
     b = collate_graphs(generate_dataset(num_subjects=2, num_regions=360, seed=1))
-    m = GraphSAGEConnectome(in_channels=5, hidden_dim=256).cuda().eval()
+    m = GraphSAGEConnectome(in_channels=5, hidden_dim=192).cuda().eval()
     with pytest.raises(_lib.CgnnError), torch.no_grad():
         m(b)
 
