@@ -289,6 +289,7 @@ int launch_stats_merge(const double* parts, int parts_n, int C, double* stats, c
 // Process-wide switch (cgnn_set_option): 1 = eligible shapes run on the tcgen05 kernels (default),
 // 0 = everything on the generic SIMT kernels (used to cross-check the two on the device).
 bool tensor_cores_enabled();
+bool project_a_in_tmem();     // CGNN_OPT_PROJECT_A_TMEM / environment CGNN_PROJECT_TS=1 (default 0)
 bool gather_pipe_enabled();   // CGNN_OPT_GATHER_PIPE: 1 = pipelined one-CTA-per-SM gather kernel where it fits (default 0)
 #ifndef CGNN_EMU
 // gcn_tc.cu: returns CGNN_OK when launched, -1 when the shape is not eligible, else an error status.

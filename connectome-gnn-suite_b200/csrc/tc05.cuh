@@ -196,6 +196,23 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[N]) {
   }
 }
 
+// ---- A operand in tensor memory ("ts" form) -----------------------------------------------------------------------
+// D[tmem] (+)= A[tmem] * B[smem]^T, one K = 8 step: A is read from tensor memory (lane = row of the tile, one 32-bit
+// column per K element), so the instruction takes no shared-memory bandwidth for A.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 8 consecutive 32-bit columns of this thread's lane (lane = 32 * (warp % 4) + laneid)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // One K = 8 step of the three-term product with explicit descriptors (hi/lo operand pairs).
 __device__ __forceinline__ void mma_tf32x3_step(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
                                                 uint32_t idesc, uint32_t accumulate) {

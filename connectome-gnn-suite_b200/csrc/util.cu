@@ -21,6 +21,15 @@ bool gather_pipe_enabled() {
   return g_gather_pipe != 0;
 }
 void set_gather_pipe(int on) { g_gather_pipe = on; }
+static int g_project_ts = -1;
+bool project_a_in_tmem() {
+  if (g_project_ts < 0) {
+    const char* e = getenv("CGNN_PROJECT_TS");
+    g_project_ts = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_project_ts != 0;
+}
+void set_project_ts(int on) { g_project_ts = on; }
 void set_cuda_error(int err) { g_last_cuda_error = err; }
 void set_tensor_cores(int on);
 
@@ -143,6 +152,7 @@ uint64_t cgnn_kernel_launches(void) { return (uint64_t)cgnn::launches(); }
 int cgnn_set_option(int32_t key, int32_t value) {
   if (key == CGNN_OPT_TENSOR_CORES) { cgnn::set_tensor_cores(value); return CGNN_OK; }
   if (key == CGNN_OPT_GATHER_PIPE) { cgnn::set_gather_pipe(value); return CGNN_OK; }
+  if (key == CGNN_OPT_PROJECT_A_TMEM) { cgnn::set_project_ts(value); return CGNN_OK; }
   return CGNN_ERR_INVALID_ARG;
 }
 

@@ -55,6 +55,10 @@ uint64_t cgnn_kernel_launches(void);
  * buffered tiles filled by cp.async) where its shared memory fits; 0 (default) = the two-CTA-per-SM kernel, which
  * measured 1 % faster per step on B200.  Same results bit for bit. */
 #define CGNN_OPT_GATHER_PIPE 2
+/* CGNN_OPT_PROJECT_A_TMEM: 1 = cgnn_project_tf32x3 keeps its A operand in tensor memory (tcgen05.st + the [a_tmem] form of
+ * tcgen05.mma) instead of shared memory: same fp32-grade result, a third of the shared-memory wavefronts, 27 - 36 % less time
+ * (profiles/r01d_summary.md, addendum 3).  Default 0; the proving ground for the next generation of row-tile kernels. */
+#define CGNN_OPT_PROJECT_A_TMEM 3
 int cgnn_set_option(int32_t key, int32_t value);
 
 /* ---------------------------------------------------------------------------------------

@@ -272,16 +272,22 @@ def test_unsupported_shapes_fail_loudly():
         m(b)
 
 
+@pytest.mark.parametrize("a_in_tmem", [0, 1])
 @pytest.mark.parametrize("rows,K,N", [(128, 64, 64), (360, 64, 64), (1000, 64, 64), (77, 32, 32), (300, 128, 64), (256, 64, 128)])
-def test_tensor_core_projection_is_fp32_grade(rows, K, N):
+def test_tensor_core_projection_is_fp32_grade(rows, K, N, a_in_tmem):
     """cgnn_project_tf32x3 (tcgen05 3xTF32, accumulators in TMEM) against an fp64 matmul: error at the level of
-    an fp32 FMA chain, far inside the 1e-5 budget (plain TF32 would sit at ~5e-4)."""
+    an fp32 FMA chain, far inside the 1e-5 budget (plain TF32 would sit at ~5e-4).  a_in_tmem = 1: the A operand is
+    written to tensor memory with tcgen05.st and read by the [a_tmem] form of tcgen05.mma (CGNN_OPT_PROJECT_A_TMEM)."""
     from connectome_gnn import _engine
     eng = _engine.engine_for(torch.zeros(1, device=DEV))
     g = torch.Generator().manual_seed(rows + K + N)
     X = torch.randn(rows, K, generator=g)
     W = torch.randn(N, K, generator=g) * 0.2
-    P = eng.project_tf32x3(X.to(DEV), W.to(DEV)).cpu()
+    assert eng.lib.cgnn_set_option(3, a_in_tmem) == 0
+    try:
+        P = eng.project_tf32x3(X.to(DEV), W.to(DEV)).cpu()
+    finally:
+        eng.lib.cgnn_set_option(3, 0)
     ref = (X.double() @ W.double().T)
     err = helpers.max_rel(P, ref)
     fp32 = helpers.max_rel(X @ W.T, ref)
