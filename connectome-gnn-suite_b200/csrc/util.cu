@@ -30,6 +30,15 @@ bool project_a_in_tmem() {
   return g_project_ts != 0;
 }
 void set_project_ts(int on) { g_project_ts = on; }
+static int g_sage_fwd_ts = -1;
+bool sage_fwd_ts_enabled() {
+  if (g_sage_fwd_ts < 0) {
+    const char* e = getenv("CGNN_SAGE_FWD_TS");
+    g_sage_fwd_ts = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_sage_fwd_ts != 0;
+}
+void set_sage_fwd_ts(int on) { g_sage_fwd_ts = on; }
 void set_cuda_error(int err) { g_last_cuda_error = err; }
 void set_tensor_cores(int on);
 
@@ -153,6 +162,7 @@ int cgnn_set_option(int32_t key, int32_t value) {
   if (key == CGNN_OPT_TENSOR_CORES) { cgnn::set_tensor_cores(value); return CGNN_OK; }
   if (key == CGNN_OPT_GATHER_PIPE) { cgnn::set_gather_pipe(value); return CGNN_OK; }
   if (key == CGNN_OPT_PROJECT_A_TMEM) { cgnn::set_project_ts(value); return CGNN_OK; }
+  if (key == CGNN_OPT_SAGE_FWD_A_TMEM) { cgnn::set_sage_fwd_ts(value); return CGNN_OK; }
   return CGNN_ERR_INVALID_ARG;
 }
 

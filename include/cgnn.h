@@ -59,6 +59,9 @@ uint64_t cgnn_kernel_launches(void);
  * tcgen05.mma) instead of shared memory: same fp32-grade result, a third of the shared-memory wavefronts, 27 - 36 % less time
  * (profiles/r01d_summary.md, addendum 3).  Default 0; the proving ground for the next generation of row-tile kernels. */
 #define CGNN_OPT_PROJECT_A_TMEM 3
+/* CGNN_OPT_SAGE_FWD_A_TMEM: 1 = the GraphSAGE forward contraction of the 32- / 64-channel layers keeps [u || agg] in tensor
+ * memory (k_sage_fwd_gemm_ts).  Same results to fp32 round-off. */
+#define CGNN_OPT_SAGE_FWD_A_TMEM 4
 int cgnn_set_option(int32_t key, int32_t value);
 
 /* ---------------------------------------------------------------------------------------

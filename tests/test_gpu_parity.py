@@ -154,6 +154,38 @@ def test_no_writes_outside_the_output_tensors(kind, hidden, regions, monkeypatch
             assert bool(ok), f"guard band of a {dtype} tensor with {n} elements was written"
 
 
+@pytest.mark.parametrize("hidden", [32, 64])
+def test_sage_forward_contraction_with_the_activations_in_tensor_memory(hidden):
+    """CGNN_OPT_SAGE_FWD_A_TMEM: [u || agg] goes to tensor memory (tcgen05.st, [a_tmem] MMA form) instead of shared
+    memory.  Same 3 x TF32 arithmetic, only the accumulation order inside the tensor core may differ: logits and
+    gradients within 1e-6 of the shared-memory edition, and within the usual bar of the oracle."""
+    from connectome_gnn import _engine
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.models import GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import CrossEntropyLoss
+    graphs = generate_dataset(num_subjects=7, num_regions=360, seed=8)
+    b = collate_graphs(graphs)
+    eng = _engine.engine_for(b.node_features)
+    torch.manual_seed(0)
+    m = GraphSAGEConnectome(in_channels=5, hidden_dim=hidden, num_classes=2, num_layers=3, dropout=0.2).cuda().train()
+    out = []
+    try:
+        for ts in (0, 1):
+            assert eng.lib.cgnn_set_option(4, ts) == 0
+            m.zero_grad()
+            torch.manual_seed(7)
+            logits = m(b)
+            CrossEntropyLoss()(logits, b.labels).backward()
+            out.append((logits.detach().clone(), torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()))
+        helpers.assert_close(out[1][0], out[0][0], "logits, activations in tensor memory", tol=1e-6)
+        helpers.assert_close(out[1][1], out[0][1], "gradients, activations in tensor memory", tol=2e-6)
+        if hidden == 64:
+            parity.check_against_oracle(graphs[:4], "sage", DEV, hidden=64, layers=3)
+    finally:
+        eng.lib.cgnn_set_option(4, 0)
+
+
 @pytest.mark.parametrize("shape", [(4, 360, 256, 3), (7, 84, 256, 2)])
 def test_wide_sage_hidden_256(shape):
     """GraphSAGE at hidden 256: gather (+ transformed rows) -> K = 512 contraction in place; backward through the dz
