@@ -67,6 +67,9 @@ class Engine:
     def __init__(self, lib: C.CDLL, device: torch.device):
         self.lib = lib
         self.device = torch.device(device)
+        # CUDA ordinal the C side must see as current (None: the test-only simulator engine, host pointers)
+        self._index = None if self.device.type != "cuda" else (
+            self.device.index if self.device.index is not None else torch.cuda.current_device())
         self.workspace_bytes = int(lib.cgnn_workspace_bytes())
         self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
         self.launches = 0  # C-ABI calls issued (each enqueues >= 1 kernel); bench reports kernel counts separately
@@ -76,8 +79,14 @@ class Engine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _call(self, name: str, *args) -> None:
+        """One ABI call with this engine's device current: the C side launches on the *current* device and sizes its
+        grids from it, so a batch on cuda:1 while cuda:0 is current must switch first (no-op when already current)."""
         self.launches += 1
-        _lib.check(self.lib, getattr(self.lib, name)(*args), name)
+        if self._index is not None and torch.cuda.current_device() != self._index:
+            with torch.cuda.device(self._index):
+                _lib.check(self.lib, getattr(self.lib, name)(*args), name)
+        else:
+            _lib.check(self.lib, getattr(self.lib, name)(*args), name)
 
     def empty(self, shape, dtype=torch.float32) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -153,6 +162,8 @@ class Engine:
         """Returns (z, stats, agg): ``agg`` is GraphSAGE's aggregated neighbourhood [rows, d_in] (kept for backward)."""
         rows, d_in = t_in.shape
         H = W.shape[0]
+        if W.shape[1] != (2 * d_in if kind == "sage" else d_in):
+            raise RuntimeError(f"{kind} layer: input has {d_in} channels but the weight is {tuple(W.shape)}")
         z = self.empty((rows, H))
         stats = self.empty(1 + 2 * H, torch.float64) if want_stats else None
         self.ensure_agg(csr, kind, num_graphs, rows, int(csr.in_col.shape[0]))

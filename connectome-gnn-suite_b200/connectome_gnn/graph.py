@@ -157,6 +157,13 @@ class ConnectomeBatch:
             counts = (self.ptr[1:] - self.ptr[:-1])
             max_nodes = int(counts.max().item()) if counts.numel() else 0
             ei = self.edge_index.contiguous()
+            if ei.shape[1] > 0:
+                # the CSR builder walks the COO list subject by subject: edges must be grouped by subject (as
+                # collate_graphs emits them) and stay inside their subject - anything else would silently drop edges
+                gs, gd = self.batch[ei[0]], self.batch[ei[1]]
+                if not bool((gs == gd).all()) or not bool((gs[1:] >= gs[:-1]).all()):
+                    raise ValueError("ConnectomeBatch.edge_index must list edges grouped by subject, both endpoints in "
+                                     "the same subject (sort the COO list by batch[edge_index[0]] first)")
             csr, eptr = eng.csr_from_coo(ei, self.edge_weight.contiguous(), self.ptr.contiguous(), self.num_graphs,
                                          self.num_nodes, int(ei.shape[1]), max_nodes)
             max_edges = int((eptr[1:] - eptr[:-1]).max().item()) if self.num_graphs else 0

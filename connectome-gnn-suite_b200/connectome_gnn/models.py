@@ -65,10 +65,21 @@ def _sum_across_ranks(t: Optional[torch.Tensor], group=None) -> Optional[torch.T
     return t
 
 
+_SEED_GEN: Optional[torch.Generator] = None
+_SEED_ROOT: Optional[int] = None
+
+
 def _draw_seed() -> int:
-    """Dropout stream seed from torch's global CPU generator (so ``torch.manual_seed`` governs it
-    and every data-parallel rank, seeded alike, draws the same value)."""
-    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    """Dropout stream seed from a dedicated generator that is (re)seeded from ``torch.initial_seed()``: ``torch.manual_seed``
+    still governs the masks and every data-parallel rank, seeded alike, draws the same sequence, but the global CPU
+    generator is left alone - ``ConnectomeDataLoader``'s ``randperm`` (reference ``graph.py:193``) sees exactly the stream
+    it sees in the reference, whose CUDA dropout never touches the CPU generator either."""
+    global _SEED_GEN, _SEED_ROOT
+    root = int(torch.initial_seed())
+    if _SEED_GEN is None or _SEED_ROOT != root:
+        _SEED_GEN, _SEED_ROOT = torch.Generator(), root
+        _SEED_GEN.manual_seed((root ^ 0x5DEECE66D) & 0x7FFFFFFFFFFFFFFF)
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, generator=_SEED_GEN).item())
 
 
 # ---------------------------------------------------------------------------
@@ -95,7 +106,10 @@ class _EncodeFn(torch.autograd.Function):
             z, stats, agg = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, want_stats=training)
             if training:
                 stats = _merge_stats_across_ranks(eng, stats, W.shape[0], cfg["group"])
-                momentum = 0.1 if bn.momentum is None else bn.momentum
+                if bn.momentum is None:    # torch: cumulative moving average, factor 1 / num_batches_tracked (after increment)
+                    momentum = 1.0 / float(int(bn.num_batches_tracked) + 1)
+                else:
+                    momentum = bn.momentum
                 scale, shift, mean, rstd = eng.bn_finalize(stats, gamma, beta, bn.eps, momentum, bn.running_mean,
                                                            bn.running_var, bn.num_batches_tracked)
             else:

@@ -57,6 +57,11 @@ class CrossEntropyLoss(nn.CrossEntropyLoss):
     def forward(self, logits: torch.Tensor, labels: torch.Tensor, denominator: int | None = None) -> torch.Tensor:
         if logits.dim() != 2:
             raise ValueError("expected logits of shape [num_graphs, num_classes]")
+        if labels is None or labels.dim() != 1 or labels.shape[0] != logits.shape[0]:
+            # a partially labelled batch stacks fewer labels than subjects (reference graph.py:155-156,165); the
+            # reference's nn.CrossEntropyLoss raises on that shape mismatch - so do we, instead of reading past the buffer
+            got = "None" if labels is None else tuple(labels.shape)
+            raise ValueError(f"expected one label per graph: logits {tuple(logits.shape)} but labels {got}")
         count = logits.shape[0] if denominator is None else denominator
         loss, correct = _CrossEntropyFn.apply(logits.float(), labels.to(torch.int64), 1.0 / max(count, 1))
         self.last_correct = correct

@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(256) k_ce_fwd(const float* __restrict__ logits
     const float lse = mx + logf(se);
     long long y = labels[g];
     const bool ok = y >= 0 && y < K;
-    const float v = ok ? lse - l[y] : 0.0f;
+    // a label outside [0, K) is a caller error (torch's CrossEntropyLoss raises): poison the loss instead of
+    // silently dropping the graph from the numerator
+    const float v = ok ? lse - l[y] : __int_as_float(0x7fc00000);
     if (nll) nll[g] = v;
     acc += (double)v;
     corr += (ok && arg == (int)y) ? 1 : 0;

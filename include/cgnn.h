@@ -262,7 +262,9 @@ int cgnn_head_fwd(const float* emb, const float* W0, const float* b0, const floa
                   int64_t graph_base, float* hidden, float* logits, cgnn_stream_t stream);
 
 /* Cross entropy over graphs: loss_sum[0] = sum_g nll_g * inv_count (inv_count = 1/B_global gives
- * nn.CrossEntropyLoss()'s mean), correct[0] = #argmax == label (int64), nll [B] per graph. */
+ * nn.CrossEntropyLoss()'s mean), correct[0] = #argmax == label (int64), nll [B] per graph.
+ * labels [B] int64, one per graph (the host wrapper rejects shorter label vectors); a label outside
+ * [0, K) - where the reference's nn.CrossEntropyLoss raises - makes nll_g and the loss NaN. */
 int cgnn_ce_fwd(const float* logits, const int64_t* labels, int64_t num_graphs, int32_t K,
                 float inv_count, float* nll, float* loss, int64_t* correct, cgnn_stream_t stream);
 
