@@ -65,21 +65,23 @@ def _sum_across_ranks(t: Optional[torch.Tensor], group=None) -> Optional[torch.T
     return t
 
 
-_SEED_GEN: Optional[torch.Generator] = None
-_SEED_ROOT: Optional[int] = None
-
-
-def _draw_seed() -> int:
-    """Dropout stream seed from a dedicated generator that is (re)seeded from ``torch.initial_seed()``: ``torch.manual_seed``
-    still governs the masks and every data-parallel rank, seeded alike, draws the same sequence, but the global CPU
-    generator is left alone - ``ConnectomeDataLoader``'s ``randperm`` (reference ``graph.py:193``) sees exactly the stream
-    it sees in the reference, whose CUDA dropout never touches the CPU generator either."""
-    global _SEED_GEN, _SEED_ROOT
-    root = int(torch.initial_seed())
-    if _SEED_GEN is None or _SEED_ROOT != root:
-        _SEED_GEN, _SEED_ROOT = torch.Generator(), root
-        _SEED_GEN.manual_seed((root ^ 0x5DEECE66D) & 0x7FFFFFFFFFFFFFFF)
-    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, generator=_SEED_GEN).item())
+def _draw_seed(device=None) -> int:
+    """Dropout stream seed.  On a CUDA device it is cut from that device's default CUDA generator exactly the way
+    torch's own CUDA dropout consumes it: (seed, philox offset) is read on the host and the offset advanced - so
+    ``torch.manual_seed`` governs the masks, successive forwards differ, every data-parallel rank seeded alike draws
+    alike, and the global CPU generator (whose ``randperm`` stream defines batch membership, reference ``graph.py:193``)
+    is never touched, as in the reference running on CUDA.  Without CUDA (test-only simulator) the CPU generator is used."""
+    if device is not None and torch.device(device).type == "cuda" and torch.cuda.is_available():
+        dev = torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        gen = torch.cuda.default_generators[idx]
+        seed, off = int(gen.initial_seed()), int(gen.get_offset())
+        gen.set_offset(off + 4)
+        x = (seed * 0x9E3779B97F4A7C15 + (off // 4 + 1) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        x ^= x >> 31
+        x = (x * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return (x ^ (x >> 29)) & 0x3FFFFFFFFFFFFFFF
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
 
 # ---------------------------------------------------------------------------
@@ -274,7 +276,7 @@ class _ConnectomeClassifier(nn.Module):
         training = self.training
         need_seed = training and self.dropout > 0.0
         return dict(engine=_engine.engine_for(batch.node_features), batch=batch, kind=self.kind, training=training,
-                    dropout=float(self.dropout), seed=_draw_seed() if need_seed else 0,
+                    dropout=float(self.dropout), seed=_draw_seed(batch.node_features.device) if need_seed else 0,
                     bns=list(self.batch_norms), group=self.process_group, graph_base=batch.graph_base)
 
     def _encode(self, batch: ConnectomeBatch, cfg: dict) -> torch.Tensor:

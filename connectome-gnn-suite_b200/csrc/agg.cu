@@ -79,10 +79,11 @@ __global__ void __launch_bounds__(256) k_build_agg(BuildAggArgs p) {
         const int nbr = (int)(col[e] - nb);
         float w = wv[e];
         if (p.kind == AGG_SAGE && dir == 1) w = w / (p.wsum[nb + nbr] + 1e-8f);   // adjoint of the weighted mean
-        rec[pos++] = make_int2(nbr, __float_as_int(w));
+        rec[pos++] = make_int2(dir == 0 ? agg_rec_x(nbr) : nbr, __float_as_int(w));
       }
-      if (self) { const float d = p.dinv[nb + i]; rec[pos++] = make_int2(i, __float_as_int(__fmul_rn(d, d))); }
-      if (pos & 1) rec[pos++] = make_int2(i, 0);
+      const int self_x = dir == 0 ? agg_rec_x(i) : i;
+      if (self) { const float d = p.dinv[nb + i]; rec[pos++] = make_int2(self_x, __float_as_int(__fmul_rn(d, d))); }
+      if (pos & 1) rec[pos++] = make_int2(self_x, 0);
       const float aux = p.kind == AGG_SAGE ? p.wsum[nb + i] : p.dinv[nb + i];
       desc[i] = make_int4(begin, pos, __float_as_int(aux), 0);
     }
@@ -197,7 +198,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
           if (p.want_prev) rpre = rt::ld_quad<VEC>(p.t_raw, nb + rowp, C, c0);
         }
       }
-      const bool valid = agg_gather_group<LPR>(s_desc, s_rec2, s_tile, i0, n, acc, aux, row);
+      constexpr bool kPre = MODE == GATHER_SAGE_FWD || MODE == GATHER_GCN_FWD;   // by-destination blob
+      const bool valid = agg_gather_group<LPR, LPR, kPre>(s_desc, s_rec2, s_tile, i0, n, acc, aux, row);
       if (!valid || !live_quad) continue;
       const long long grow = nb + row;
       if (MODE == GATHER_SAGE_FWD) {
@@ -362,7 +364,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_gather_pipe(GatherArgs p) {
           if (p.want_prev) rpre = rt::ld_quad<true>(p.t_raw, nb + rowp, C, c0);
         }
       }
-      const bool valid = agg_gather_group<LPR>(s_desc, s_rec2, tile, i0, n, acc, aux, row);
+      constexpr bool kPre = MODE == GATHER_SAGE_FWD || MODE == GATHER_GCN_FWD;
+      const bool valid = agg_gather_group<LPR, LPR, kPre>(s_desc, s_rec2, tile, i0, n, acc, aux, row);
       if (!valid) continue;
       const long long grow = nb + row;
       if (MODE == GATHER_SAGE_FWD) {

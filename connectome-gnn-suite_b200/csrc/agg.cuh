@@ -6,12 +6,19 @@
 //   row descriptor  int4 {rec_begin, rec_end, aux bits, 0}          one broadcast load per row
 //   record pair     int4 {nbr0, w0 bits, nbr1, w1 bits}             one broadcast load per two edges
 // Rows are padded to an even number of records (zero weight), GCN rows end with their self-loop record.
+// The neighbour word of the by-destination blob (agg_in) is stored as agg_rec_x(nbr) = the byte offset of the
+// neighbour's row in a 256-byte-pitch tile with its XOR-swizzle key (row & 7) in the 16-byte-chunk bits: the
+// warp-specialised forward kernels (engine.cu) turn it into a shared-memory address with one XOR.  Everybody else
+// takes agg_rec_row().  The by-source blob (agg_out) carries plain row indices.
 #pragma once
 #include "common.cuh"
 
 namespace cgnn {
 
 enum { AGG_GCN = 0, AGG_SAGE = 1 };
+
+static inline __host__ __device__ int agg_rec_x(int nbr) { return (nbr << 8) | ((nbr & 7) << 4); }
+static inline __host__ __device__ int agg_rec_row(int x) { return x >> 8; }
 
 // word offset of subject g's blob: 8 words per row + 2 per edge (edge base rounded up to even) + 4 per subject;
 // a blob uses at most 4n (descriptors) + 2(m + 2n) (records incl. self-loop and padding) words.
@@ -70,7 +77,8 @@ __device__ __forceinline__ TileQuads tile_quads(const float4* t4, int pitch) {
 #endif
 }
 
-template <int LPR, int PITCH = LPR>
+// PRE: the records' neighbour words are agg_rec_x() encoded (agg_in); false: plain row indices (agg_out)
+template <int LPR, int PITCH = LPR, bool PRE = true>
 static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__ s_desc, const int4* __restrict__ s_rec2,
                                                         const float4* __restrict__ tile4, int i0, int n, float4& acc, float& aux,
                                                         int& row) {
@@ -93,7 +101,8 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
 #pragma unroll 1
   for (; k + 4 <= lmin; k += 4, rp += 2) {   // four records per step: half the loop overhead, four tile loads in flight
     const int4 r = rp[0], s = rp[1];
-    const float4 v0 = t.at(r.x), v1 = t.at(r.z), v2 = t.at(s.x), v3 = t.at(s.z);
+    const float4 v0 = t.at(PRE ? agg_rec_row(r.x) : r.x), v1 = t.at(PRE ? agg_rec_row(r.z) : r.z);
+    const float4 v2 = t.at(PRE ? agg_rec_row(s.x) : s.x), v3 = t.at(PRE ? agg_rec_row(s.z) : s.z);
     fma_quad(a, v0, __int_as_float(r.y));
     fma_quad(a, v1, __int_as_float(r.w));
     fma_quad(a, v2, __int_as_float(s.y));
@@ -102,7 +111,7 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
 #pragma unroll 1
   for (; k < lmin; k += 2, ++rp) {        // every row of the group has these records
     const int4 r = *rp;
-    const float4 v0 = t.at(r.x), v1 = t.at(r.z);
+    const float4 v0 = t.at(PRE ? agg_rec_row(r.x) : r.x), v1 = t.at(PRE ? agg_rec_row(r.z) : r.z);
     fma_quad(a, v0, __int_as_float(r.y));
     fma_quad(a, v1, __int_as_float(r.w));
   }
@@ -110,7 +119,7 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
   for (; k < lmax; k += 2, ++rp) {        // rows that have ended contribute zero weights (and read row 0)
     int4 r = make_int4(0, 0, 0, 0);
     if (k < len) r = *rp;
-    const float4 v0 = t.at(r.x), v1 = t.at(r.z);
+    const float4 v0 = t.at(PRE ? agg_rec_row(r.x) : r.x), v1 = t.at(PRE ? agg_rec_row(r.z) : r.z);
     fma_quad(a, v0, __int_as_float(r.y));
     fma_quad(a, v1, __int_as_float(r.w));
   }
@@ -144,6 +153,10 @@ struct GatherArgs {
 // agg.cu: one gather kernel; CGNN_OK when launched (grid in *grid_out: the caller reduces `partials` over it),
 // -1 when the shape is not covered.
 int launch_gather(int mode, GatherArgs& a, int* grid_out, cudaStream_t stream);
+// engine.cu: warp-specialised hidden-layer forward (64 -> 64 channels; also built for the simulator)
+int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+                      int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
+                      double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream);
 #ifndef CGNN_EMU
 // gemm_tc.cu: tensor-core contractions; same return convention.
 int launch_sage_fwd_gemm(const float* t_in, const cgnn_act_t* act, const float* agg, const float* W, const float* bias,

@@ -345,10 +345,11 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
           float wr;
           if (p.csr.agg_kind == AGG_GCN) wr = __fmul_rn(__fmul_rn(s_dinv[s], w), s_dinv[d]);
           else wr = dd == 0 ? w : w / (s_wsum[d] + 1e-8f);      // adjoint of the weighted mean
-          rec[at++] = make_int2(dd == 0 ? s : d, __float_as_int(wr));
+          rec[at++] = make_int2(dd == 0 ? agg_rec_x(s) : d, __float_as_int(wr));
         }
-        if (self) { const float dv = s_dinv[i]; rec[at++] = make_int2(i, __float_as_int(__fmul_rn(dv, dv))); }
-        if (at & 1) rec[at++] = make_int2(i, 0);
+        const int self_x = dd == 0 ? agg_rec_x(i) : i;
+        if (self) { const float dv = s_dinv[i]; rec[at++] = make_int2(self_x, __float_as_int(__fmul_rn(dv, dv))); }
+        if (at & 1) rec[at++] = make_int2(self_x, 0);
         const float aux = p.csr.agg_kind == AGG_SAGE ? s_wsum[i] : s_dinv[i];
         reinterpret_cast<int4*>(blob)[i] = make_int4(begin, at, __float_as_int(aux), 0);
       }

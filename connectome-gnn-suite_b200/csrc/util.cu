@@ -39,6 +39,9 @@ bool sage_fwd_ts_enabled() {
   return g_sage_fwd_ts != 0;
 }
 void set_sage_fwd_ts(int on) { g_sage_fwd_ts = on; }
+static int g_ws_engine = 1;
+bool ws_engine_enabled() { return g_ws_engine != 0; }
+void set_ws_engine(int on) { g_ws_engine = on; }
 void set_cuda_error(int err) { g_last_cuda_error = err; }
 void set_tensor_cores(int on);
 
@@ -163,6 +166,7 @@ int cgnn_set_option(int32_t key, int32_t value) {
   if (key == CGNN_OPT_GATHER_PIPE) { cgnn::set_gather_pipe(value); return CGNN_OK; }
   if (key == CGNN_OPT_PROJECT_A_TMEM) { cgnn::set_project_ts(value); return CGNN_OK; }
   if (key == CGNN_OPT_SAGE_FWD_A_TMEM) { cgnn::set_sage_fwd_ts(value); return CGNN_OK; }
+  if (key == CGNN_OPT_WS_ENGINE) { cgnn::set_ws_engine(value); return CGNN_OK; }
   return CGNN_ERR_INVALID_ARG;
 }
 

@@ -62,6 +62,9 @@ uint64_t cgnn_kernel_launches(void);
 /* CGNN_OPT_SAGE_FWD_A_TMEM: 1 = the GraphSAGE forward contraction of the 32- / 64-channel layers keeps [u || agg] in tensor
  * memory (k_sage_fwd_gemm_ts).  Same results to fp32 round-off. */
 #define CGNN_OPT_SAGE_FWD_A_TMEM 4
+/* CGNN_OPT_WS_ENGINE: 1 (default) = 64-channel hidden layers run the warp-specialised kernels (engine.cu: TMA loads, A operand in
+ * tensor memory, gather overlapped with the tensor core); 0 = the previous generation, kept for on-device A/B runs. */
+#define CGNN_OPT_WS_ENGINE 5
 int cgnn_set_option(int32_t key, int32_t value);
 
 /* ---------------------------------------------------------------------------------------

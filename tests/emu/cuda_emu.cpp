@@ -17,8 +17,12 @@ constexpr size_t kGuard = 256;
 struct Fiber {
   ucontext_t ctx;
   bool done = true;
-  int wait = 0;  // 0 runnable, 1 at block barrier, 2 at warp barrier
+  int wait = 0;  // 0 runnable, 1 at block barrier, 2 at warp barrier, 3 polling (runnable, but proves no progress)
 };
+uint64_t g_events = 0;                  // bumped by note_event()
+std::vector<float> g_tmem;              // 128 x 512 tensor-memory words of the running block
+int g_named_cnt[16];
+uint64_t g_named_gen[16];
 
 std::vector<Fiber> fibers;
 std::vector<char*> stacks;
@@ -50,6 +54,9 @@ void run_block(size_t smem_bytes) {
   g_dyn_smem = smem.data();
 
   for (auto& w : warp_slots) for (auto& s : w) s = kDead;
+  g_tmem.assign(128 * 512, 0.0f);
+  for (int i = 0; i < 16; ++i) { g_named_cnt[i] = 0; g_named_gen[i] = 0; }
+  int idle_sweeps = 0;
   for (int t = 0; t < nthreads; ++t) {
     Fiber& f = fibers[t];
     f.done = false;
@@ -64,14 +71,18 @@ void run_block(size_t smem_bytes) {
   int alive = nthreads;
   while (alive > 0) {
     bool progressed = false;
+    const uint64_t events0 = g_events;
     for (int t = 0; t < nthreads; ++t) {
       Fiber& f = fibers[t];
-      if (f.done || f.wait != 0) continue;
+      if (f.done || (f.wait != 0 && f.wait != 3)) continue;
+      const bool polling = f.wait == 3;
+      f.wait = 0;
       cur = t;
       set_thread_index(t);
       swapcontext(&main_ctx, &f.ctx);
-      progressed = true;
+      if (!polling || f.done || f.wait != 3) progressed = true;   // a poller that only polled again proves nothing
     }
+    if (g_events != events0) progressed = true;
     alive = 0;
     int at_block = 0;
     for (int t = 0; t < nthreads; ++t)
@@ -93,12 +104,13 @@ void run_block(size_t smem_bytes) {
         released = true;
       }
     }
-    if (alive > 0 && !progressed && !released) {
+    if (progressed || released) idle_sweeps = 0; else ++idle_sweeps;
+    if (alive > 0 && idle_sweeps >= 3) {
       fprintf(stderr, "[cuda_emu] DEADLOCK in block (%u,%u,%u): %d live threads;", g_blockIdx.x,
               g_blockIdx.y, g_blockIdx.z, alive);
       int shown = 0;
       for (int t = 0; t < nthreads && shown < 16; ++t)
-        if (!fibers[t].done) { fprintf(stderr, " t%d:%s", t, fibers[t].wait == 1 ? "block" : "warp"); ++shown; }
+        if (!fibers[t].done) { fprintf(stderr, " t%d:%s", t, fibers[t].wait == 1 ? "block" : fibers[t].wait == 2 ? "warp" : "poll"); ++shown; }
       fprintf(stderr, "\n");
       abort();
     }
@@ -149,6 +161,27 @@ const uint64_t* warp_gather(uint64_t v) {
 void warp_release() {
   fibers[cur].wait = 2;
   yield();
+}
+
+void poll_yield() {
+  fibers[cur].wait = 3;
+  yield();
+}
+
+void note_event() { ++g_events; }
+
+float* tmem() { return g_tmem.data(); }
+
+void named_barrier(int id, int count) {
+  if (id < 0 || id >= 16) { fprintf(stderr, "[cuda_emu] named barrier id %d\n", id); abort(); }
+  const uint64_t gen = g_named_gen[id];
+  if (++g_named_cnt[id] == count) {
+    g_named_cnt[id] = 0;
+    ++g_named_gen[id];
+    note_event();
+    return;
+  }
+  while (g_named_gen[id] == gen) poll_yield();
 }
 
 }  // namespace cgnn_emu

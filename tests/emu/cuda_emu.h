@@ -33,6 +33,7 @@
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 #define __constant__ static
+#define __grid_constant__
 
 struct uint3_ { unsigned x, y, z; };
 struct dim3 {
@@ -70,6 +71,13 @@ void sync_threads();
 const uint64_t* warp_gather(uint64_t v);
 void warp_release();
 int lane_id();
+// ---- warp-specialised kernels: polling waits (mbarrier / named barriers) and tensor memory -------------------
+// A fiber that spins on shared state calls poll_yield() inside its loop; whoever changes state that a poller may be
+// waiting for calls note_event().  A sweep in which only pollers ran and no event was noted is a deadlock.
+void poll_yield();
+void note_event();
+float* tmem();                 // [128 lanes][512 columns] of the running block, zeroed at block start
+void named_barrier(int id, int nthreads);   // bar.sync id, nthreads
 
 }  // namespace cgnn_emu
 

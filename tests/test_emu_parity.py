@@ -127,3 +127,53 @@ def test_pair_store_collates_identically(on_emu):
         assert torch.equal(getattr(a, f), getattr(b, f)), f
     for f in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn", "deg", "dinv", "wsum"):
         assert torch.equal(getattr(a.csr, f), getattr(b.csr, f)), f
+
+
+# ---- warp-specialised forward engine (csrc/engine.cu) on the simulator: mbarrier protocol, TMA box layout, tensor-memory
+# ---- lane quadrants, unit tables and the XOR-swizzled gather, against the reference fixtures and the oracle ----------
+
+def test_ws_engine_reference_fixture_c1(on_emu):
+    """16 x 84-node subjects, hidden 64: four subjects per unit, a CTA walks several units."""
+    parity.check_model(helpers.golden("ref_c1.npz"), "gcn", "cpu")
+
+
+@pytest.mark.parametrize("shape", [(2, 360, 3), (5, 70, 2), (3, 130, 2)])
+def test_ws_engine_oracle_shapes(on_emu, shape):
+    """360-node subjects (three tiles, one subject per unit), 70-node (five per unit, short last unit) and 130-node
+    (two per unit, a subject straddling a tile boundary) against oracle/port.py, hidden 64."""
+    from connectome_gnn.synthetic import generate_dataset
+    subjects, regions, layers = shape
+    graphs = generate_dataset(num_subjects=subjects, num_regions=regions, seed=11)
+    parity.check_against_oracle(graphs, "gcn", "cpu", hidden=64, layers=layers)
+
+
+def test_ws_engine_mixed_sizes_and_empty_subject(on_emu):
+    """Subjects of different sizes in one unit, one of them with no nodes at all."""
+    from connectome_gnn.graph import ConnectomeGraph
+    from connectome_gnn.synthetic import generate_connectome
+    graphs = [generate_connectome(num_regions=n, seed=s) for s, n in enumerate((33, 90, 12, 57, 101, 64))]
+    empty = ConnectomeGraph(torch.zeros(0, 5), torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0), torch.tensor(1), "sub-empty")
+    graphs.insert(2, empty)
+    parity.check_against_oracle(graphs, "gcn", "cpu", hidden=64, layers=2)
+
+
+def test_ws_engine_dropout_matches_generic_kernels(on_emu):
+    """With dropout on, the engine (converters apply the mask thread-per-row) and the generic kernels regenerate the
+    same masks from (seed, site, row, channel): identical outputs up to fp32 summation order."""
+    from connectome_gnn.graph import collate_graphs
+    from connectome_gnn.models import GCNConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    b = collate_graphs(generate_dataset(num_subjects=3, num_regions=84, seed=4))
+    torch.manual_seed(0)
+    m = GCNConnectome(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.4).train()
+    for bn in m.batch_norms:
+        bn.momentum = 0.0
+    outs = []
+    for tc in (1, 0):
+        assert on_emu.lib.cgnn_set_option(1, tc) == 0
+        try:
+            torch.manual_seed(7)
+            outs.append(m(b).detach().clone())
+        finally:
+            on_emu.lib.cgnn_set_option(1, 1)
+    assert float((outs[0] - outs[1]).abs().max()) <= 1e-5 * float(outs[1].abs().max())
