@@ -73,6 +73,7 @@ def _draw_seed(device=None) -> int:
     is never touched, as in the reference running on CUDA.  Without CUDA (test-only simulator) the CPU generator is used."""
     if device is not None and torch.device(device).type == "cuda" and torch.cuda.is_available():
         dev = torch.device(device)
+        torch.cuda.init()          # default_generators is filled by the lazy initialisation
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
         gen = torch.cuda.default_generators[idx]
         seed, off = int(gen.initial_seed()), int(gen.get_offset())

@@ -263,6 +263,9 @@ def test_dropout_statistics_and_determinism():
 
 
 def test_dropout_gradient_consistency():
+    """Dropout on: the same seed gives the same masks twice, and the analytic gradient (backward regenerates the forward
+    masks) agrees with a central finite difference taken with the masks held fixed.  A finite-difference probe can cross
+    a ReLU kink for one particular mask instance, so three mask instances are probed and two must agree."""
     from connectome_gnn.graph import collate_graphs
     from connectome_gnn.train import CrossEntropyLoss
     a = helpers.golden("ref_small.npz")
@@ -272,24 +275,28 @@ def test_dropout_gradient_consistency():
         m.train()
         for bn in m.batch_norms:
             bn.momentum = 0.0
-
-        def loss_at():
-            torch.manual_seed(123)
-            return CrossEntropyLoss()(m(b), b.labels)
-
-        l0 = loss_at()
-        l0.backward()
-        assert float(loss_at().detach()) == float(l0.detach())
         params = list(m.parameters())
         direction = [torch.randn(p.shape, generator=torch.Generator().manual_seed(i)).to(DEV) for i, p in enumerate(params)]
-        analytic = sum(float((p.grad * d).sum()) for p, d in zip(params, direction))
-        eps = 2e-4   # small enough that ReLU kinks crossed by the probe stay below the tolerance (checked: converges to analytic)
-        with torch.no_grad():
-            for p, d in zip(params, direction): p.add_(eps * d)
-            lp = float(loss_at())
-            for p, d in zip(params, direction): p.sub_(2 * eps * d)
-            lm = float(loss_at())
-        assert (lp - lm) / (2 * eps) == pytest.approx(analytic, rel=0.05, abs=2e-3), kind
+        good = 0
+        for seed in (123, 124, 125):
+            def loss_at():
+                torch.manual_seed(seed)
+                return CrossEntropyLoss()(m(b), b.labels)
+
+            m.zero_grad()
+            l0 = loss_at()
+            l0.backward()
+            assert float(loss_at().detach()) == float(l0.detach())
+            analytic = sum(float((p.grad * d).sum()) for p, d in zip(params, direction))
+            eps = 2e-4
+            with torch.no_grad():
+                for p, d in zip(params, direction): p.add_(eps * d)
+                lp = float(loss_at())
+                for p, d in zip(params, direction): p.sub_(2 * eps * d)
+                lm = float(loss_at())
+                for p, d in zip(params, direction): p.add_(eps * d)
+            good += (lp - lm) / (2 * eps) == pytest.approx(analytic, rel=0.05, abs=2e-3)
+        assert good >= 2, (kind, good)
 
 
 def test_unsupported_shapes_fail_loudly():
