@@ -249,166 +249,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
   (void)RP;
 }
 
-// ---- pipelined edition ---------------------------------------------------------------------------------------------
-// k_gather alternates an HBM-bound phase (tile load) and a shared-memory-bound phase (gather) per CTA, and two CTAs per
-// SM only overlap the two by chance (ncu: every phase near its own roofline, the sum twice the larger one).  Here one
-// 1024-thread CTA per SM keeps TWO tile / blob buffers: the raw rows and the blob of unit g + 1 arrive by cp.async
-// while unit g is gathered; each thread then transforms, in place, exactly the quads it copied itself, so a unit costs
-// one barrier.  GCN_BWD stages its second input (du) through a third, single buffer that only the transform reads.
-// Measured on B200 (profiles/r01d_summary.md): each launch 3 % faster under ncu, the whole step 1 % slower - the gather
-// phase is bound by shared-memory wavefronts either way - so this edition is opt-in (CGNN_OPT_GATHER_PIPE).
-constexpr int kPipeThreads = 1024;
-template <int MODE>
-__global__ void __launch_bounds__(kPipeThreads, 1) k_gather_pipe(GatherArgs p) {
-  CGNN_SMEM_DECL;
-  constexpr int NT = kPipeThreads, LPR = 8, RPW = 32 / LPR, NW = NT / 32;
-  const int tile_quads_n = p.max_nodes * LPR;                                   // float4 per tile buffer
-  const int blob_words = (agg_smem_words(p.max_nodes, p.max_edges) + 3) & ~3;   // keeps the second buffer 16-byte aligned
-  float4* s_tile0 = reinterpret_cast<float4*>(cgnn_smem);
-  float4* s_up = s_tile0 + 2 * (size_t)tile_quads_n;                           // GCN_BWD with du only
-  int32_t* s_blob0 = reinterpret_cast<int32_t*>(s_up + (MODE == GATHER_GCN_BWD ? (size_t)tile_quads_n : 0));
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int cl = tid & (LPR - 1);
-  const int C = p.C, nslab = p.nslab;
-  const int slab = blockIdx.x % nslab;
-  const int c0 = slab * 4 * LPR + 4 * cl;
-
-  rt::ChanQuad cq;
-  rt::chan_quad_init(cq, p.act, c0, C);
-  const rt::RowKey rk = rt::row_key(p.act);
-  rt::BnBwdDev bn;
-  bn.scale = p.bn_scale; bn.mean = p.bn_mean; bn.rstd = p.bn_rstd; bn.s1 = p.bn_s1; bn.s2 = p.bn_s2;
-  bn.inv_count = p.inv_count; bn.train = p.bn_train; bn.has = p.has_bn;
-  rt::BnQuad bq;
-  if (MODE == GATHER_GCN_BWD) rt::bn_quad_init(bq, bn, c0, C);
-  float pmean[4] = {0.f, 0.f, 0.f, 0.f}, prstd[4] = {0.f, 0.f, 0.f, 0.f};
-  if (MODE == GATHER_SAGE_BWD && p.want_prev) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { pmean[j] = p.prev_mean[c0 + j]; prstd[j] = p.prev_rstd[c0 + j]; }
-  }
-  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-
-  const int4* meta = reinterpret_cast<const int4*>(p.meta);
-  const long long gstep = gridDim.x / nslab;
-  const bool has_up = MODE == GATHER_GCN_BWD && p.du != nullptr;
-  // asynchronous copies of subject g: blob, this thread's quads of the raw tile (and of du)
-  auto issue = [&](const int4& m, long long g, int buf) {
-    const long long nb = m.x, eb = m.z;
-    const int n = min(m.y, p.max_nodes), me = min(m.w, p.max_edges);
-    const int32_t* gb = p.blob + agg_base_words(nb, eb, g);
-    int32_t* sb = s_blob0 + (size_t)buf * blob_words;
-    const int n16 = (agg_copy_words(n, me) + 3) >> 2;
-    for (int i = tid; i < n16; i += NT) cp_async_16(sb + 4 * i, gb + 4 * i);
-    float4* st = s_tile0 + (size_t)buf * tile_quads_n;
-    for (int idx = tid; idx < n * LPR; idx += NT) {
-      const long long off = (nb + (idx >> 3)) * C + c0;
-      cp_async_16(st + idx, p.src + off);
-      if (has_up) cp_async_16(s_up + idx, p.du + off);
-    }
-    cp_async_commit();
-  };
-
-  long long g = blockIdx.x / nslab;
-  int4 m_cur = make_int4(0, 0, 0, 0), m_next = m_cur;
-  if (g < p.B) { m_cur = meta[g]; issue(m_cur, g, 0); }
-  if (g + gstep < p.B) m_next = meta[g + gstep];
-  int buf = 0;
-  for (; g < p.B; g += gstep) {
-    const int4 m = m_cur;
-    const long long nb = m.x;
-    const int n = min(m.y, p.max_nodes);
-    float4* tile = s_tile0 + (size_t)buf * tile_quads_n;
-    float4 pooled = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (MODE == GATHER_GCN_BWD && !p.du) {
-      const float inv_n = 1.0f / ((float)n + 1e-8f);
-      pooled = rt::ld_quad<true>(p.demb, g, C, c0);
-      pooled = make_float4(pooled.x * inv_n, pooled.y * inv_n, pooled.z * inv_n, pooled.w * inv_n);
-    }
-    cp_async_wait<0>();                       // this thread's copies of unit g have landed
-    if (MODE != GATHER_SAGE_BWD) {            // transform in place the quads this thread copied
-      for (int idx = tid; idx < n * LPR; idx += NT) {
-        const uint32_t grow = (uint32_t)(nb + (idx >> 3));
-        const float4 a = tile[idx];
-        float4 o;
-        if (MODE == GATHER_GCN_BWD) {
-          const float4 b = has_up ? s_up[idx] : pooled;
-          o = rt::bn_bwd4(bn, bq, a, rt::act_bwd4(p.act, cq, a, b, rk, grow));
-          s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
-        } else {
-          o = rt::act_fwd4(p.act, cq, a, rk, grow);
-        }
-        tile[idx] = o;
-        if (MODE == GATHER_SAGE_FWD && p.out_u) rt::st_quad<true>(p.out_u, nb + (idx >> 3), C, c0, o);
-      }
-    }
-    __syncthreads();     // tile / blob of unit g complete; everybody has left the gather of the previous unit
-    const long long gn = g + gstep;
-    if (gn < p.B) {
-      m_cur = m_next;
-      issue(m_cur, gn, buf ^ 1);
-      if (gn + gstep < p.B) m_next = meta[gn + gstep];
-    }
-    // ---- gather unit g -------------------------------------------------------------------------------------------
-    const int32_t* s_blob = s_blob0 + (size_t)buf * blob_words;
-    const int4* s_desc = reinterpret_cast<const int4*>(s_blob);
-    const int4* s_rec2 = reinterpret_cast<const int4*>(s_blob + 4 * n);
-    for (int i0 = warp * RPW; i0 < n; i0 += NW * RPW) {
-      float4 acc;
-      float aux;
-      int row;
-      float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f), rpre = dpre;
-      if (MODE == GATHER_SAGE_BWD) {   // the row's direct gradient and stored input: loads fly during the gather
-        const int rowp = i0 + (tid & 31) / LPR;
-        if (rowp < n) {
-          dpre = rt::ld_quad<true>(p.direct, nb + rowp, C, c0);
-          if (p.want_prev) rpre = rt::ld_quad<true>(p.t_raw, nb + rowp, C, c0);
-        }
-      }
-      constexpr bool kPre = MODE == GATHER_SAGE_FWD || MODE == GATHER_GCN_FWD;
-      const bool valid = agg_gather_group<LPR, LPR, kPre>(s_desc, s_rec2, tile, i0, n, acc, aux, row);
-      if (!valid) continue;
-      const long long grow = nb + row;
-      if (MODE == GATHER_SAGE_FWD) {
-        const float inv = rt::rcp_fast(aux + 1e-8f);
-        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-      }
-      if (MODE == GATHER_SAGE_BWD) {
-        acc.x += dpre.x; acc.y += dpre.y; acc.z += dpre.z; acc.w += dpre.w;
-        if (p.want_prev) {
-          const float4 dyp = rt::act_bwd4(p.act, cq, rpre, acc, rk, (uint32_t)grow);
-          const float rv[4] = {rpre.x, rpre.y, rpre.z, rpre.w}, dv[4] = {dyp.x, dyp.y, dyp.z, dyp.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float xh = (rv[j] - pmean[j]) * prstd[j];
-            s1[j] += dv[j];
-            s2[j] = fmaf(dv[j], xh, s2[j]);
-          }
-        }
-      }
-      rt::st_quad<true>(p.out, grow, C, c0, acc);
-    }
-    buf ^= 1;
-  }
-
-  const bool want = (MODE == GATHER_GCN_BWD && p.partials) || (MODE == GATHER_SAGE_BWD && p.partials && p.want_prev);
-  if (want) {
-    __syncthreads();     // the last gather has finished reading the tiles
-    float* red = reinterpret_cast<float*>(s_tile0);   // [NT][8]
-    *reinterpret_cast<float4*>(red + 8 * tid) = make_float4(s1[0], s1[1], s1[2], s1[3]);
-    *reinterpret_cast<float4*>(red + 8 * tid + 4) = make_float4(s2[0], s2[1], s2[2], s2[3]);
-    __syncthreads();
-    const int nrec = MODE == GATHER_GCN_BWD ? 1 : 2;
-    for (int idx = tid; idx < nrec * C; idx += NT) {
-      const int which = idx / C, c = idx - which * C;
-      float s = 0.0f;
-      if (c / (4 * LPR) == slab) {
-        const int q = (c % (4 * LPR)) >> 2, j = c & 3;
-        for (int t = q; t < NT; t += LPR) s += red[8 * t + 4 * which + j];
-      }
-      p.partials[(size_t)blockIdx.x * p.part_stride + idx] = s;
-    }
-  }
-}
 #endif  // CGNN_EMU
 
 // ---- host side -------------------------------------------------------------------------------------------------
@@ -445,31 +285,6 @@ int launch_gather(int mode, GatherArgs& a, int* grid_out, cudaStream_t stream) {
   const int C = a.C;
   auto al16 = [](const void* p) { return p == nullptr || (((uintptr_t)p) & 15u) == 0; };
   const int vec = (C % 4 == 0) && al16(a.src) && al16(a.du) && al16(a.demb) && al16(a.direct) && al16(a.t_raw) && al16(a.out);
-  if (vec && LPR == 8 && C % 32 == 0 && gather_pipe_enabled()) {
-    const size_t tile_b = (size_t)a.max_nodes * LPR * 16, blob_b = (size_t)((agg_smem_words(a.max_nodes, a.max_edges) + 3) & ~3) * 4;
-    size_t pipe = (mode == GATHER_GCN_BWD ? 3 : 2) * tile_b + 2 * blob_b;
-    if (pipe < (size_t)kPipeThreads * 8 * 4) pipe = (size_t)kPipeThreads * 8 * 4;
-    if (pipe <= (size_t)dev.smem_optin) {
-      long long grid = dev.sm_count;
-      grid -= grid % nslab;
-      if (grid > a.B * nslab) grid = a.B * nslab;
-      if (grid < nslab) grid = nslab;
-      *grid_out = (int)grid;
-#define CGNN_GATHER_PIPE(MODE_)                                                                          \
-  {                                                                                                      \
-    auto kfn = k_gather_pipe<MODE_>;                                                                     \
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe);                   \
-    CGNN_LAUNCH(kfn, (unsigned)grid, kPipeThreads, pipe, stream, a);                                     \
-  }
-      if (mode == GATHER_SAGE_FWD) CGNN_GATHER_PIPE(GATHER_SAGE_FWD)
-      else if (mode == GATHER_GCN_BWD) CGNN_GATHER_PIPE(GATHER_GCN_BWD)
-      else if (mode == GATHER_GCN_FWD) CGNN_GATHER_PIPE(GATHER_GCN_FWD)
-      else CGNN_GATHER_PIPE(GATHER_SAGE_BWD)
-#undef CGNN_GATHER_PIPE
-      CGNN_CHECK_LAUNCH();
-      return CGNN_OK;
-    }
-  }
   int per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;

@@ -289,14 +289,6 @@ int launch_stats_merge(const double* parts, int parts_n, int C, double* stats, c
 // Process-wide switch (cgnn_set_option): 1 = eligible shapes run on the tcgen05 kernels (default),
 // 0 = everything on the generic SIMT kernels (used to cross-check the two on the device).
 bool tensor_cores_enabled();
-bool project_a_in_tmem();     // CGNN_OPT_PROJECT_A_TMEM / environment CGNN_PROJECT_TS=1 (default 0)
 bool ws_engine_enabled();     // CGNN_OPT_WS_ENGINE: 1 (default) = hidden layers run the warp-specialised kernels of engine.cu
-bool gather_pipe_enabled();   // CGNN_OPT_GATHER_PIPE: 1 = pipelined one-CTA-per-SM gather kernel where it fits (default 0)
-#ifndef CGNN_EMU
-// gcn_tc.cu: returns CGNN_OK when launched, -1 when the shape is not eligible, else an error status.
-int launch_gcn_fwd_tc(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
-                      int64_t num_graphs, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
-                      double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream);
-#endif
 
 }  // namespace cgnn

@@ -521,10 +521,6 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
                                   bn_stats ? (double*)workspace : nullptr, &tc_grid, workspace_bytes, stream);
     if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;
     if (rc > 0) return rc;
-    rc = launch_gcn_fwd_tc(t_in, act, W, bias, csr, num_graphs, d_in, H, max_nodes, max_edges, z,
-                                     bn_stats ? (double*)workspace : nullptr, &tc_grid, workspace_bytes, stream);
-    if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;
-    if (rc > 0) return rc;
     rc = launch_gcn_fwd_wide(t_in, act, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, z, bn_stats ? 1 : 0,
                              &tc_grid, workspace, workspace_bytes, stream);
     if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;

@@ -267,206 +267,6 @@ __global__ void __launch_bounds__(NT, 1) k_sage_fwd_gemm(SageFwdGemmArgs p) {
   if (warp == 0) tc::tmem_dealloc(taddr, p.tmem_cols);
 }
 
-// ---- the same contraction with the activations operand in TENSOR MEMORY ----------------------------------------------
-// An SS-mode MMA re-reads its A tile from shared memory three times per K step of the 3 x TF32 product, and the hi / lo
-// operand stores go through the same pipe - the kernel above is bound by shared-memory wavefronts (profiles/
-// r01d_summary.md, addenda 2 and 3).  Here thread = (row, quarter of the K columns): warp w owns TMEM lanes 32 (w % 4) ..
-// + 31 (rows of the tile) and the K columns [(w / 4) K/4, (w / 4 + 1) K/4) - the u half for w < 8, the agg half for w >= 8.
-// A row's slice goes from registers straight into the thread's TMEM lane (tcgen05.st), the MMA takes [a_tmem]; only the
-// weight operand and the epilogue staging remain in shared memory.  TMEM columns: [0, 2H) two accumulators,
-// [2H, 2H + K) A hi, [2H + K, 2H + 2K) A lo.
-template <int KB, int HB>
-__global__ void __launch_bounds__(kThreads, 1) k_sage_fwd_gemm_ts(SageFwdGemmArgs p) {
-  constexpr int KP = 32 * KB, H = 32 * HB, TR = kRows, NT = kThreads;
-  constexpr int CW = KP / 4;                 // K columns per thread (all from one of the two tensors)
-  constexpr int NQ = CW / 4;                 // quads per thread per tile
-  constexpr int B_HALF = KB * H * 128;
-  constexpr int QH = H / 4;
-  using MH = rt::QuadMap<QH, TR, NT>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint64_t mbar;
-  __shared__ uint32_t tmem_base_s;
-  unsigned char* base = tc::smem_align1024(smem_raw);
-  unsigned char* b_hi = base;
-  unsigned char* b_lo = b_hi + B_HALF;
-  float4* s_sc = reinterpret_cast<float4*>(b_lo + B_HALF);      // [C / 4] scale quads of the activation
-  float4* s_sh = s_sc + KP / 8;                                  // [C / 4] shift quads
-  constexpr int PITCH = KP + 4;                                  // floats per staged row: 16-byte lanes of 8 rows cover all banks
-  float* raw = reinterpret_cast<float*>(s_sh + KP / 8);          // [TR][PITCH] raw [t_in || agg] rows, filled by cp.async
-  float4* stage = reinterpret_cast<float4*>(base + p.o_stage);   // [TR][H] swizzled
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int C = p.C;
-  const bool affine = p.act.scale != nullptr;
-
-  if (warp == 0) tc::tmem_alloc(&tmem_base_s, p.tmem_cols);
-  if (tid == 0) tc::mbar_init(&mbar, 1);
-  stage_weight_kmajor(p.W, 2 * C, H, 2 * C, H, KP, b_hi, b_lo, NT);
-  for (int c = tid; c < C; c += NT) {
-    reinterpret_cast<float*>(s_sc)[c] = affine ? p.act.scale[c] : 1.0f;
-    reinterpret_cast<float*>(s_sh)[c] = affine ? p.act.shift[c] : 0.0f;
-  }
-  const int lq = warp & 3, cg = warp >> 2;
-  const bool u_half = cg < 2;
-  const int ch0 = (cg & 1) * CW;                                  // first channel of this thread's slice in its tensor
-  const int rrow = 32 * lq + lane;                                // row of the tile = TMEM lane
-  const rt::RowKey rk = rt::row_key(p.act);
-  const int qh = tid % QH, rh = tid / QH;
-  float bias4[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) bias4[j] = p.bias ? p.bias[4 * qh + j] : 0.0f;
-  tc::fence_proxy_async();
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t taddr = tmem_base_s;
-  const uint32_t lane_base = taddr + ((uint32_t)(32 * lq) << 16);
-  const uint32_t a_hi_col = (uint32_t)(2 * H), a_lo_col = (uint32_t)(2 * H + KP);
-  const uint32_t b_hi_u = tc::smem_u32(b_hi), b_lo_u = tc::smem_u32(b_lo);
-  const uint64_t bd_hi = tc::smem_desc_sw128(b_hi_u), bd_lo = tc::smem_desc_sw128(b_lo_u);
-  const uint32_t idesc = tc::idesc_tf32(TR, H);
-
-  const long long ntiles = (p.rows + TR - 1) / TR;
-  // coalesced asynchronous copy of a tile's raw rows (consecutive threads = consecutive 16-byte chunks of a row)
-  auto load_tile = [&](long long t) {
-    if (t < ntiles) {
-      constexpr int QR = KP / 4;
-      for (int idx = tid; idx < TR * QR; idx += NT) {
-        const int r = idx / QR, qq = idx - r * QR;
-        const long long row = t * TR + r;
-        float* dst = raw + r * PITCH + 4 * qq;
-        if (row < p.rows) cp_async_16(dst, (4 * qq < C ? p.t_in + row * C + 4 * qq : p.agg + row * C + (4 * qq - C)));
-        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    cp_async_commit();
-  };
-
-  int cnt = 0;
-  const bool want_stats = p.partials != nullptr;
-  Welford wf[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) wf[j].init();
-  auto epilogue = [&](long long r0, uint32_t b) {
-    rt::drain_rows_to_staging<H, NT>(taddr + b * (uint32_t)H, stage, warp, lane);
-    tc::fence_before_sync();
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < MH::NQ; ++i) {
-      const int r = rh + i * MH::RS;
-      if (r0 + r < p.rows) {
-        float4 v = stage[rt::stage_index(r, qh, QH)];
-        v.x = fmaxf(v.x + bias4[0], 0.0f);
-        v.y = fmaxf(v.y + bias4[1], 0.0f);
-        v.z = fmaxf(v.z + bias4[2], 0.0f);
-        v.w = fmaxf(v.w + bias4[3], 0.0f);
-        *reinterpret_cast<float4*>(p.z + (r0 + r) * H + 4 * qh) = v;
-        if (want_stats) {
-          cnt += 1;
-          const float inv = rt::rcp_fast((float)cnt);
-          wf[0].push(v.x, inv); wf[1].push(v.y, inv); wf[2].push(v.z, inv); wf[3].push(v.w, inv);
-        }
-      }
-    }
-  };
-
-  long long t = blockIdx.x;
-  load_tile(t);
-  uint32_t phase = 0, buf = 0;
-  bool have_prev = false;
-  long long prev_r0 = 0;
-  for (; t < ntiles; t += gridDim.x) {
-    const long long r0 = t * TR;
-    const long long row = r0 + rrow;
-    const bool live = row < p.rows;
-    cp_async_wait<0>();
-    __syncthreads();                   // the tile's raw rows have landed (everybody's copies)
-    // (1) this thread's slice of its row: activation of the u half, hi / lo split, straight into tensor memory
-    const float* my = raw + rrow * PITCH + cg * CW;
-#pragma unroll
-    for (int i = 0; i < NQ; i += 2) {
-      float hi8[8], lo8[8];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        float4 v = *reinterpret_cast<const float4*>(my + 4 * (i + k));
-        if (u_half && live) {
-          rt::ChanQuad cq;
-          const float4 sc = s_sc[(ch0 >> 2) + i + k], sh = s_sh[(ch0 >> 2) + i + k];
-          cq.sc[0] = sc.x; cq.sc[1] = sc.y; cq.sc[2] = sc.z; cq.sc[3] = sc.w;
-          cq.sh[0] = sh.x; cq.sh[1] = sh.y; cq.sh[2] = sh.z; cq.sh[3] = sh.w;
-          cq.ck = (uint32_t)((ch0 >> 2) + i + k) * 0x632BE5ABu + p.act.k1;
-          v = rt::act_fwd4(p.act, cq, v, rk, (uint32_t)row);
-        }
-        float4 h, l;
-        rt::split4(v, h, l);
-        hi8[4 * k] = h.x; hi8[4 * k + 1] = h.y; hi8[4 * k + 2] = h.z; hi8[4 * k + 3] = h.w;
-        lo8[4 * k] = l.x; lo8[4 * k + 1] = l.y; lo8[4 * k + 2] = l.z; lo8[4 * k + 3] = l.w;
-      }
-      const uint32_t col = (uint32_t)(cg * CW + 4 * i);
-      tc::tmem_st8(lane_base + a_hi_col + col, hi8);
-      tc::tmem_st8(lane_base + a_lo_col + col, lo8);
-    }
-    tc::tmem_st_wait();
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    if (tid == 0) {
-      const uint32_t d = taddr + buf * (uint32_t)H;
-#pragma unroll
-      for (int ks = 0; ks < KP / 8; ++ks) {
-        const uint64_t bo = (uint64_t)(((ks >> 2) * H * 128 + (ks & 3) * 32) >> 4);
-        tc::mma_tf32_ts(d, taddr + a_lo_col + 8u * ks, bd_hi + bo, idesc, ks > 0 ? 1u : 0u);   // small terms first
-        tc::mma_tf32_ts(d, taddr + a_hi_col + 8u * ks, bd_lo + bo, idesc, 1u);
-        tc::mma_tf32_ts(d, taddr + a_hi_col + 8u * ks, bd_hi + bo, idesc, 1u);
-      }
-      tc::mma_commit(&mbar);
-    }
-    load_tile(t + gridDim.x);          // next tile's rows fly during the MMA and the epilogue (the barrier above
-                                       // made sure everybody is done reading this tile's)
-    if (have_prev) epilogue(prev_r0, buf ^ 1u);
-    tc::mbar_wait(&mbar, phase);       // the A columns may be rewritten once this tile's MMAs have read them
-    tc::fence_after_sync();
-    phase ^= 1;
-    have_prev = true;
-    prev_r0 = r0;
-    buf ^= 1u;
-  }
-  if (have_prev) {
-    tc::fence_after_sync();
-    epilogue(prev_r0, buf ^ 1u);
-  }
-  __syncthreads();
-
-  if (p.partials) {
-    float* rec = reinterpret_cast<float*>(base);   // [NT][9] over the weight operand (every MMA has completed)
-    rec[tid * 9] = (float)cnt;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { rec[tid * 9 + 1 + j] = wf[j].mean; rec[tid * 9 + 5 + j] = wf[j].m2; }
-    __syncthreads();
-    double* out = p.partials + (size_t)blockIdx.x * (1 + 2 * H);
-    for (int c = tid; c < H; c += NT) {
-      const int q = c >> 2, j = c & 3;
-      double n = 0.0, mean = 0.0, m2 = 0.0;
-      for (int th = q; th < NT; th += QH) {
-        const double nb = (double)rec[th * 9];
-        if (nb <= 0.0) continue;
-        const double mb = (double)rec[th * 9 + 1 + j], qb = (double)rec[th * 9 + 5 + j];
-        const double nt = n + nb, delta = mb - mean;
-        mean += delta * (nb / nt);
-        m2 += qb + delta * delta * (n * nb / nt);
-        n = nt;
-      }
-      out[1 + c] = mean;
-      out[1 + H + c] = m2;
-      if (c == 0) out[0] = n;
-    }
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(taddr, p.tmem_cols);
-}
-
-bool sage_fwd_ts_enabled();   // util.cu: CGNN_OPT_SAGE_FWD_A_TMEM / environment CGNN_SAGE_FWD_TS; default 0 - measured 331 us against the
-                              // 301 us of k_sage_fwd_gemm: a third fewer instructions, but 34 % barrier stalls (profiles/r01d_summary.md)
 
 int launch_sage_fwd_gemm(const float* t_in, const cgnn_act_t* act, const float* agg, const float* W, const float* bias,
                          int64_t rows, int32_t C, int32_t H, float* z, double* partials, int* grid_out,
@@ -485,42 +285,6 @@ int launch_sage_fwd_gemm(const float* t_in, const cgnn_act_t* act, const float* 
   a.tmem_cols = 32;
   while (a.tmem_cols < (uint32_t)(2 * H)) a.tmem_cols <<= 1;   // two accumulator buffers
   const int KP = 32 * KB;
-  // activations operand in tensor memory: K = 2C a multiple of 64 (a quarter of the K columns per thread, in whole octets)
-  if (wide && sage_fwd_ts_enabled() && (KB == 2 || KB == 4) && 2 * H + 2 * KP <= 512) {
-    const size_t b_bytes_ts = (size_t)2 * KB * H * 128, c_bytes_ts = (size_t)2 * (KP / 2) * 4;
-    const size_t raw_bytes_ts = (size_t)kRows * (KP + 4) * 4;
-    a.o_stage = (int)((b_bytes_ts + c_bytes_ts + raw_bytes_ts + 15) & ~(size_t)15);
-    const size_t smem_ts = a.o_stage + (size_t)kRows * H * 4 + 1024;
-    size_t need = smem_ts < (size_t)kThreads * 9 * 4 + 1024 ? (size_t)kThreads * 9 * 4 + 1024 : smem_ts;
-    a.tmem_cols = 32;
-    while (a.tmem_cols < (uint32_t)(2 * H + 2 * KP)) a.tmem_cols <<= 1;
-    if (need <= (size_t)dev.smem_optin) {
-      const long long ntiles_ts = (rows + kRows - 1) / kRows;
-      long long grid_ts = dev.sm_count;
-      if (grid_ts > ntiles_ts) grid_ts = ntiles_ts;
-      if (partials) {
-        const size_t rec = (size_t)(1 + 2 * H) * sizeof(double);
-        if ((size_t)grid_ts * rec > workspace_bytes) grid_ts = (long long)(workspace_bytes / rec);
-      }
-      if (grid_ts >= 1) {
-        *grid_out = (int)grid_ts;
-#define CGNN_SFT(KB_, HB_)                                                                            \
-  {                                                                                                   \
-    auto kfn = k_sage_fwd_gemm_ts<KB_, HB_>;                                                          \
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);                \
-    CGNN_LAUNCH(kfn, (unsigned)grid_ts, kThreads, need, stream, a);                                   \
-  }
-#define CGNN_SFT_H(KB_) { if (HB == 1) CGNN_SFT(KB_, 1) else if (HB == 2) CGNN_SFT(KB_, 2) else CGNN_SFT(KB_, 4) }
-        if (KB == 2) CGNN_SFT_H(2) else CGNN_SFT_H(4)
-#undef CGNN_SFT_H
-#undef CGNN_SFT
-        CGNN_CHECK_LAUNCH();
-        return CGNN_OK;
-      }
-    }
-    a.tmem_cols = 32;
-    while (a.tmem_cols < (uint32_t)(2 * H)) a.tmem_cols <<= 1;
-  }
   const size_t a_bytes = (size_t)2 * KB * kRows * 128, b_bytes = (size_t)2 * KB * H * 128;
   const size_t c_bytes = (size_t)2 * KP * 4;
   size_t stage_bytes = (size_t)kRows * H * 4;

@@ -161,7 +161,7 @@ extern "C" int cgnn_project_tf32x3(const float* X, const float* W, int64_t rows,
   const size_t smem = (size_t)(K / 32) * (2 * kTcRows + 2 * N) * 128 + 1024;
   const DeviceInfo dev = device_info();
   if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
-  if (project_a_in_tmem() && N + 2 * K <= 512) {   // CGNN_OPT_PROJECT_A_TMEM: A operand in tensor memory
+  if (N + 2 * K <= 512) {   // A operand in tensor memory whenever its columns fit next to the accumulators (27 - 36 % faster, profiles/r01d_summary.md)
     uint32_t tcols = 32;
     while (tcols < (uint32_t)(N + 2 * K)) tcols <<= 1;
     const size_t smem_ts = (size_t)(K / 32) * (2 * N) * 128 + 1024;

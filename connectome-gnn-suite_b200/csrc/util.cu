@@ -1,7 +1,6 @@
 // util.cu - status strings, device query, deterministic partial reductions.
 #include "common.cuh"
 
-#include <cstdlib>
 
 namespace cgnn {
 
@@ -12,33 +11,6 @@ unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_REL
 static int g_use_tensor_cores = 1;
 bool tensor_cores_enabled() { return g_use_tensor_cores != 0; }
 void set_tensor_cores(int on) { g_use_tensor_cores = on; }
-static int g_gather_pipe = -1;   // -1: not set yet (environment CGNN_GATHER_PIPE=0/1, default 0: measured 1 % slower per step)
-bool gather_pipe_enabled() {
-  if (g_gather_pipe < 0) {
-    const char* e = getenv("CGNN_GATHER_PIPE");
-    g_gather_pipe = (e && e[0] == '1') ? 1 : 0;
-  }
-  return g_gather_pipe != 0;
-}
-void set_gather_pipe(int on) { g_gather_pipe = on; }
-static int g_project_ts = -1;
-bool project_a_in_tmem() {
-  if (g_project_ts < 0) {
-    const char* e = getenv("CGNN_PROJECT_TS");
-    g_project_ts = (e && e[0] == '1') ? 1 : 0;
-  }
-  return g_project_ts != 0;
-}
-void set_project_ts(int on) { g_project_ts = on; }
-static int g_sage_fwd_ts = -1;
-bool sage_fwd_ts_enabled() {
-  if (g_sage_fwd_ts < 0) {
-    const char* e = getenv("CGNN_SAGE_FWD_TS");
-    g_sage_fwd_ts = (e && e[0] == '1') ? 1 : 0;
-  }
-  return g_sage_fwd_ts != 0;
-}
-void set_sage_fwd_ts(int on) { g_sage_fwd_ts = on; }
 static int g_ws_engine = 1;
 bool ws_engine_enabled() { return g_ws_engine != 0; }
 void set_ws_engine(int on) { g_ws_engine = on; }
@@ -163,9 +135,6 @@ size_t cgnn_workspace_bytes(void) { return (size_t)64 << 20; }   // 148 CTAs x a
 uint64_t cgnn_kernel_launches(void) { return (uint64_t)cgnn::launches(); }
 int cgnn_set_option(int32_t key, int32_t value) {
   if (key == CGNN_OPT_TENSOR_CORES) { cgnn::set_tensor_cores(value); return CGNN_OK; }
-  if (key == CGNN_OPT_GATHER_PIPE) { cgnn::set_gather_pipe(value); return CGNN_OK; }
-  if (key == CGNN_OPT_PROJECT_A_TMEM) { cgnn::set_project_ts(value); return CGNN_OK; }
-  if (key == CGNN_OPT_SAGE_FWD_A_TMEM) { cgnn::set_sage_fwd_ts(value); return CGNN_OK; }
   if (key == CGNN_OPT_WS_ENGINE) { cgnn::set_ws_engine(value); return CGNN_OK; }
   return CGNN_ERR_INVALID_ARG;
 }

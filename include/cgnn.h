@@ -51,17 +51,6 @@ uint64_t cgnn_kernel_launches(void);
  * kernels, 0 = every shape runs the generic SIMT kernels (same results to fp32 round-off; used to
  * cross-check the two paths on the device). */
 #define CGNN_OPT_TENSOR_CORES 1
-/* CGNN_OPT_GATHER_PIPE: 1 = the packed-blob gathers run the pipelined kernel (one 1024-thread CTA per SM, double-
- * buffered tiles filled by cp.async) where its shared memory fits; 0 (default) = the two-CTA-per-SM kernel, which
- * measured 1 % faster per step on B200.  Same results bit for bit. */
-#define CGNN_OPT_GATHER_PIPE 2
-/* CGNN_OPT_PROJECT_A_TMEM: 1 = cgnn_project_tf32x3 keeps its A operand in tensor memory (tcgen05.st + the [a_tmem] form of
- * tcgen05.mma) instead of shared memory: same fp32-grade result, a third of the shared-memory wavefronts, 27 - 36 % less time
- * (profiles/r01d_summary.md, addendum 3).  Default 0; the proving ground for the next generation of row-tile kernels. */
-#define CGNN_OPT_PROJECT_A_TMEM 3
-/* CGNN_OPT_SAGE_FWD_A_TMEM: 1 = the GraphSAGE forward contraction of the 32- / 64-channel layers keeps [u || agg] in tensor
- * memory (k_sage_fwd_gemm_ts).  Same results to fp32 round-off. */
-#define CGNN_OPT_SAGE_FWD_A_TMEM 4
 /* CGNN_OPT_WS_ENGINE: 1 (default) = 64-channel hidden layers run the warp-specialised kernels (engine.cu: TMA loads, A operand in
  * tensor memory, gather overlapped with the tensor core); 0 = the previous generation, kept for on-device A/B runs. */
 #define CGNN_OPT_WS_ENGINE 5

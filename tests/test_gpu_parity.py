@@ -80,36 +80,6 @@ def test_wide_gcn_dropout_masks_are_consistent():
     assert losses[0] == losses[1]
 
 
-@pytest.mark.parametrize("kind", ["gcn", "sage"])
-def test_pipelined_gather_option_gives_identical_results(kind):
-    """CGNN_OPT_GATHER_PIPE switches the gather kernels to the one-CTA-per-SM pipelined edition: same bits."""
-    from connectome_gnn import _engine
-    from connectome_gnn.graph import collate_graphs
-    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
-    from connectome_gnn.synthetic import generate_dataset
-    from connectome_gnn.train import CrossEntropyLoss
-    b = collate_graphs(generate_dataset(num_subjects=9, num_regions=360, seed=4))
-    eng = _engine.engine_for(b.node_features)
-    torch.manual_seed(0)
-    cls = GCNConnectome if kind == "gcn" else GraphSAGEConnectome
-    m = cls(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.2).cuda().train()
-    out = []
-    try:
-        for pipe in (0, 1):
-            assert eng.lib.cgnn_set_option(2, pipe) == 0
-            m.zero_grad()
-            torch.manual_seed(7)
-            loss = CrossEntropyLoss()(m(b), b.labels)
-            loss.backward()
-            out.append((loss.detach().clone(), [p.grad.clone() for p in m.parameters()]))
-    finally:
-        eng.lib.cgnn_set_option(2, 0)
-    assert torch.equal(out[0][0], out[1][0])
-    # per-CTA partial sums are reduced over a different grid: same values to summation-order round-off
-    flat = [torch.cat([g.reshape(-1) for g in o[1]]) for o in out]
-    helpers.assert_close(flat[1], flat[0], "gradients under the pipelined gather", tol=1e-6)
-
-
 @pytest.mark.parametrize("kind,hidden,regions", [("gcn", 64, 77), ("sage", 64, 77), ("gcn", 256, 45), ("sage", 256, 45), ("gcn", 64, 360), ("sage", 64, 360)])
 def test_no_writes_outside_the_output_tensors(kind, hidden, regions, monkeypatch):
     """Every tensor the engine allocates for a call is placed between two guard bands; after a full training step and
@@ -152,38 +122,6 @@ def test_no_writes_outside_the_output_tensors(kind, hidden, regions, monkeypatch
         for band in (raw[:PAD], raw[PAD + n:]):
             ok = torch.isnan(band).all() if dtype.is_floating_point else (band == 0x5A).all()
             assert bool(ok), f"guard band of a {dtype} tensor with {n} elements was written"
-
-
-@pytest.mark.parametrize("hidden", [32, 64])
-def test_sage_forward_contraction_with_the_activations_in_tensor_memory(hidden):
-    """CGNN_OPT_SAGE_FWD_A_TMEM: [u || agg] goes to tensor memory (tcgen05.st, [a_tmem] MMA form) instead of shared
-    memory.  Same 3 x TF32 arithmetic, only the accumulation order inside the tensor core may differ: logits and
-    gradients within 1e-6 of the shared-memory edition, and within the usual bar of the oracle."""
-    from connectome_gnn import _engine
-    from connectome_gnn.graph import collate_graphs
-    from connectome_gnn.models import GraphSAGEConnectome
-    from connectome_gnn.synthetic import generate_dataset
-    from connectome_gnn.train import CrossEntropyLoss
-    graphs = generate_dataset(num_subjects=7, num_regions=360, seed=8)
-    b = collate_graphs(graphs)
-    eng = _engine.engine_for(b.node_features)
-    torch.manual_seed(0)
-    m = GraphSAGEConnectome(in_channels=5, hidden_dim=hidden, num_classes=2, num_layers=3, dropout=0.2).cuda().train()
-    out = []
-    try:
-        for ts in (0, 1):
-            assert eng.lib.cgnn_set_option(4, ts) == 0
-            m.zero_grad()
-            torch.manual_seed(7)
-            logits = m(b)
-            CrossEntropyLoss()(logits, b.labels).backward()
-            out.append((logits.detach().clone(), torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()))
-        helpers.assert_close(out[1][0], out[0][0], "logits, activations in tensor memory", tol=1e-6)
-        helpers.assert_close(out[1][1], out[0][1], "gradients, activations in tensor memory", tol=2e-6)
-        if hidden == 64:
-            parity.check_against_oracle(graphs[:4], "sage", DEV, hidden=64, layers=3)
-    finally:
-        eng.lib.cgnn_set_option(4, 0)
 
 
 @pytest.mark.parametrize("shape", [(4, 360, 256, 3), (7, 84, 256, 2)])
@@ -311,22 +249,17 @@ def test_unsupported_shapes_fail_loudly():
         m(b)
 
 
-@pytest.mark.parametrize("a_in_tmem", [0, 1])
-@pytest.mark.parametrize("rows,K,N", [(128, 64, 64), (360, 64, 64), (1000, 64, 64), (77, 32, 32), (300, 128, 64), (256, 64, 128)])
-def test_tensor_core_projection_is_fp32_grade(rows, K, N, a_in_tmem):
+@pytest.mark.parametrize("rows,K,N", [(128, 64, 64), (360, 64, 64), (1000, 64, 64), (77, 32, 32), (300, 128, 64), (256, 64, 128), (200, 256, 64)])
+def test_tensor_core_projection_is_fp32_grade(rows, K, N):
     """cgnn_project_tf32x3 (tcgen05 3xTF32, accumulators in TMEM) against an fp64 matmul: error at the level of
-    an fp32 FMA chain, far inside the 1e-5 budget (plain TF32 would sit at ~5e-4).  a_in_tmem = 1: the A operand is
-    written to tensor memory with tcgen05.st and read by the [a_tmem] form of tcgen05.mma (CGNN_OPT_PROJECT_A_TMEM)."""
+    an fp32 FMA chain, far inside the 1e-5 budget (plain TF32 would sit at ~5e-4).  The A operand goes to tensor memory
+    (tcgen05.st + the [a_tmem] form of tcgen05.mma) whenever its columns fit; K = 256 takes the shared-memory form."""
     from connectome_gnn import _engine
     eng = _engine.engine_for(torch.zeros(1, device=DEV))
     g = torch.Generator().manual_seed(rows + K + N)
     X = torch.randn(rows, K, generator=g)
     W = torch.randn(N, K, generator=g) * 0.2
-    assert eng.lib.cgnn_set_option(3, a_in_tmem) == 0
-    try:
-        P = eng.project_tf32x3(X.to(DEV), W.to(DEV)).cpu()
-    finally:
-        eng.lib.cgnn_set_option(3, 0)
+    P = eng.project_tf32x3(X.to(DEV), W.to(DEV)).cpu()
     ref = (X.double() @ W.double().T)
     err = helpers.max_rel(P, ref)
     fp32 = helpers.max_rel(X @ W.T, ref)
