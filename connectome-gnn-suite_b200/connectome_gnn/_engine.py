@@ -102,22 +102,27 @@ class Engine:
 
     KINDS = {"gcn": 0, "sage": 1}
 
+    ARRAYS = ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn", "deg", "dinv", "wsum")
+
     @staticmethod
     def csr_struct(c, kind: Optional[str] = None) -> CsrT:
-        """``cgnn_csr_t`` of a CSR (dict or BatchCSR); ``kind`` attaches that model family's aggregation blobs."""
-        g = (lambda k: c[k]) if isinstance(c, dict) else (lambda k: getattr(c, k))
-        base = [_p(g(k)) for k in ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col",
-                                   "out_w", "out_wn", "deg", "dinv", "wsum", "graph_meta")]
+        """``cgnn_csr_t`` of a CSR (dict or BatchCSR); ``kind`` attaches that model family's aggregation blobs.
+        A lean BatchCSR passes NULL for every array it has not materialised (``peek`` never triggers the lazy collate)."""
+        g = (lambda k: c[k]) if isinstance(c, dict) else c.peek
+        base = [_p(g(k)) for k in Engine.ARRAYS + ("graph_meta",)]
         blobs = None if (kind is None or isinstance(c, dict)) else (getattr(c, "agg", None) or {}).get(kind)
         if blobs is None:
             return CsrT(*base, None, None, None, -1)
         return CsrT(*base, _p(blobs[0]), _p(blobs[1]), _p(blobs[2]), Engine.KINDS[kind])
 
-    def ensure_agg(self, csr, kind: str, num_graphs: int, rows: int, edges: int):
-        """Packed aggregation blobs of one model family for this batch (built once, cached on the CSR)."""
+    def ensure_agg(self, csr, kind: str, num_graphs: int, rows: int, edges: int, need_out: bool = True):
+        """Packed aggregation blobs of one model family for this batch (built once, cached on the CSR).  ``need_out``:
+        the by-source blob (backward) is wanted too - a forward-only batch carries the by-destination blob alone."""
         if getattr(csr, "agg", None) is None:
             csr.agg = {}
-        if kind not in csr.agg:
+        have = csr.agg.get(kind)
+        if have is None or (need_out and have[1] is None):
+            csr.materialize()            # the stand-alone builder reads the CSR arrays (no-op for a full batch)
             words = int(self.lib.cgnn_agg_words(rows, edges, num_graphs))
             agg_in, agg_out = self.empty(words, torch.int32), self.empty(words, torch.int32)
             row_graph = self.empty(max(rows, 1), torch.int32)
@@ -127,26 +132,56 @@ class Engine:
             csr.agg[kind] = (agg_in, agg_out, row_graph)
         return csr.agg[kind]
 
+    def _call_csr(self, name: str, csr, build_args) -> None:
+        """An ABI call that takes a ``cgnn_csr_t``: a lean batch that hits a code path reading the CSR arrays
+        (CGNN_ERR_NEED_CSR) materialises them once and the call is repeated."""
+        try:
+            self._call(name, *build_args())
+        except _lib.CgnnError as e:
+            if e.status != _lib.ERR_NEED_CSR or csr.is_full():
+                raise
+            csr.materialize()
+            self._call(name, *build_args())
+
     def collate_csr(self, store: StoreT, ids: torch.Tensor, num_graphs: int, rows: int, edges: int, max_nodes: int,
-                    num_features: int, with_labels: bool, agg_kind: Optional[str] = None):
+                    max_edges: int, num_features: int, with_labels: bool, agg_kind: Optional[str] = None,
+                    lean: bool = False, need_out: bool = True):
         """Returns (fields, csr arrays, blobs): ``blobs`` = (agg_in, agg_out, row_graph) of ``agg_kind`` when the
-        collate kernel was asked to emit that model family's aggregation blobs in the same pass, else None."""
+        collate kernel was asked to emit that model family's aggregation blobs in the same pass, else None.
+        ``lean`` (with ``agg_kind``): only node_features, labels, ptr / eptr, graph_meta and the blobs are written -
+        the COO fields, ``batch`` and every CSR array come back as None; ``need_out`` = False drops the by-source blob
+        (forward-only batches).  Falls back to a full collate when the kernel cannot stage the largest subject."""
         e = self.empty
-        out = dict(
-            node_features=e((rows, num_features)), edge_index=e((2, edges), torch.int64), edge_weight=e(edges),
-            batch=e(rows, torch.int64), labels=e(num_graphs, torch.int64) if with_labels else None,
-            ptr=e(num_graphs + 1, torch.int64), eptr=e(num_graphs + 1, torch.int64))
-        csr = self.new_csr(rows, edges, num_graphs)
+        lean = lean and agg_kind is not None and num_graphs > 0 and rows > 0
+        if lean:
+            out = dict(node_features=e((rows, num_features)), edge_index=None, edge_weight=None, batch=None,
+                       labels=e(num_graphs, torch.int64) if with_labels else None,
+                       ptr=e(num_graphs + 1, torch.int64), eptr=e(num_graphs + 1, torch.int64))
+            csr = {k: None for k in Engine.ARRAYS}
+            csr["graph_meta"] = e((num_graphs, 4), torch.int32)
+        else:
+            out = dict(
+                node_features=e((rows, num_features)), edge_index=e((2, edges), torch.int64), edge_weight=e(edges),
+                batch=e(rows, torch.int64), labels=e(num_graphs, torch.int64) if with_labels else None,
+                ptr=e(num_graphs + 1, torch.int64), eptr=e(num_graphs + 1, torch.int64))
+            csr = self.new_csr(rows, edges, num_graphs)
         cs = self.csr_struct(csr)
         blobs = None
         if agg_kind is not None and num_graphs > 0 and rows > 0:
             words = int(self.lib.cgnn_agg_words(rows, edges, num_graphs))
-            blobs = (e(words, torch.int32), e(words, torch.int32), e(max(rows, 1), torch.int32))
+            blobs = (e(words, torch.int32), e(words, torch.int32) if (need_out or not lean) else None,
+                     e(max(rows, 1), torch.int32))
             cs.agg_in, cs.agg_out, cs.row_graph = _p(blobs[0]), _p(blobs[1]), _p(blobs[2])
             cs.agg_kind = Engine.KINDS[agg_kind]
-        self._call("cgnn_collate_csr", C.byref(store), _p(ids), num_graphs, rows, edges, max_nodes,
-                   _p(out["node_features"]), _p(out["edge_index"]), _p(out["edge_weight"]), _p(out["batch"]),
-                   _p(out["labels"]), _p(out["ptr"]), _p(out["eptr"]), C.byref(cs), self.stream())
+        try:
+            self._call("cgnn_collate_csr", C.byref(store), _p(ids), num_graphs, rows, edges, max_nodes, max_edges,
+                       _p(out["node_features"]), _p(out["edge_index"]), _p(out["edge_weight"]), _p(out["batch"]),
+                       _p(out["labels"]), _p(out["ptr"]), _p(out["eptr"]), C.byref(cs), self.stream())
+        except _lib.CgnnError as err:
+            if not lean or err.status != _lib.ERR_NEED_CSR:
+                raise
+            return self.collate_csr(store, ids, num_graphs, rows, edges, max_nodes, max_edges, num_features, with_labels,
+                                    agg_kind, lean=False)
         return out, csr, blobs
 
     def csr_from_coo(self, edge_index, edge_weight, ptr, num_graphs: int, rows: int, edges: int, max_nodes: int):
@@ -166,15 +201,21 @@ class Engine:
             raise RuntimeError(f"{kind} layer: input has {d_in} channels but the weight is {tuple(W.shape)}")
         z = self.empty((rows, H))
         stats = self.empty(1 + 2 * H, torch.float64) if want_stats else None
-        self.ensure_agg(csr, kind, num_graphs, rows, int(csr.in_col.shape[0]))
-        a, cs = act.struct(), self.csr_struct(csr, kind)
-        args = [_p(t_in), C.byref(a), _p(W), _p(bias), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, csr.max_nodes,
-                csr.max_edges, _p(z), _p(stats)]
-        agg = None
-        if kind == "sage":
-            agg = self.empty((rows, d_in))
-            args.append(_p(agg))
-        self._call(f"cgnn_{kind}_layer_fwd", *args, _p(self.workspace), self.workspace_bytes, self.stream())
+        self.ensure_agg(csr, kind, num_graphs, rows, csr.num_edges, need_out=False)
+        a = act.struct()
+        agg = self.empty((rows, d_in)) if kind == "sage" else None
+
+        def build():
+            cs = self.csr_struct(csr, kind)
+            keep.append(cs)
+            args = [_p(t_in), C.byref(a), _p(W), _p(bias), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, csr.max_nodes,
+                    csr.max_edges, _p(z), _p(stats)]
+            if kind == "sage":
+                args.append(_p(agg))
+            return args + [_p(self.workspace), self.workspace_bytes, self.stream()]
+
+        keep: list = []
+        self._call_csr(f"cgnn_{kind}_layer_fwd", csr, build)
         return z, stats, agg
 
     def project_tf32x3(self, X, W):
@@ -261,21 +302,27 @@ class Engine:
         du_in = self.empty((rows, d_in)) if need_du else None
         want_prev = need_du and prev_mean is not None
         prev_sums = self.empty((2, d_in)) if want_prev else None
-        self.ensure_agg(csr, kind, num_graphs, rows, int(csr.in_col.shape[0]))
-        ao, ai, cs = act_out.struct(), act_in.struct(), self.csr_struct(csr, kind)
+        self.ensure_agg(csr, kind, num_graphs, rows, csr.num_edges, need_out=True)
+        ao, ai = act_out.struct(), act_in.struct()
         bs = bn.struct() if bn is not None else None
-        args = [_p(du), _p(demb), _p(z), C.byref(ao), C.byref(bs) if bs is not None else None, _p(t_in)]
-        if kind == "sage":
-            args.append(_p(agg))
-        args += [C.byref(ai), _p(W), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, csr.max_nodes, csr.max_edges,
-                 _p(dW), _p(db),
-                 _p(du_in), _p(prev_mean) if want_prev else None, _p(prev_rstd) if want_prev else None,
-                 _p(prev_sums)]
         # scratch between the kernels of one call: GCN dP [rows, H]; GraphSAGE [2, rows, d_in] (d_u, d_agg), and a third
         # [rows, H] plane (dz) for the wide layers (H = d_in = 256)
         scratch = self.empty((rows, H)) if kind == "gcn" else self.empty((3 if (H == 256 and d_in == 256) else 2, rows, d_in))
-        args += [_p(scratch), _p(self.workspace), self.workspace_bytes, self.stream()]
-        self._call(f"cgnn_{kind}_layer_bwd", *args)
+
+        def build():
+            cs = self.csr_struct(csr, kind)
+            keep.append(cs)
+            args = [_p(du), _p(demb), _p(z), C.byref(ao), C.byref(bs) if bs is not None else None, _p(t_in)]
+            if kind == "sage":
+                args.append(_p(agg))
+            args += [C.byref(ai), _p(W), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, csr.max_nodes, csr.max_edges,
+                     _p(dW), _p(db),
+                     _p(du_in), _p(prev_mean) if want_prev else None, _p(prev_rstd) if want_prev else None,
+                     _p(prev_sums)]
+            return args + [_p(scratch), _p(self.workspace), self.workspace_bytes, self.stream()]
+
+        keep: list = []
+        self._call_csr(f"cgnn_{kind}_layer_bwd", csr, build)
         return dW, db, du_in, prev_sums
 
 

@@ -14,7 +14,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcgnn.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_f32p = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 c_ptr = C.c_void_p
@@ -65,7 +65,7 @@ PROTOTYPES = {
     "cgnn_workspace_bytes": (_sz, []),
     "cgnn_kernel_launches": (C.c_uint64, []),
     "cgnn_set_option": (C.c_int, [_i32, _i32]),
-    "cgnn_collate_csr": (C.c_int, [_P(StoreT), _p, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p,
+    "cgnn_collate_csr": (C.c_int, [_P(StoreT), _p, _i64, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p,
                                    _P(CsrT), _p]),
     "cgnn_csr_from_coo": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i32, _p, _P(CsrT), _p]),
     "cgnn_agg_words": (_sz, [_i64, _i64, _i64]),
@@ -93,7 +93,14 @@ PROTOTYPES = {
 
 
 class CgnnError(RuntimeError):
-    """A C-ABI call returned a non-zero ``cgnn_status``."""
+    """A C-ABI call returned a non-zero ``cgnn_status`` (``.status``)."""
+
+    def __init__(self, message: str, status: int = -1):
+        super().__init__(message)
+        self.status = status
+
+
+ERR_NEED_CSR = 5   # a lean batch met a code path that reads the CSR arrays
 
 
 def bind(path: str) -> C.CDLL:
@@ -129,4 +136,4 @@ def check(lib: C.CDLL, status: int, what: str) -> None:
     if status != 0:
         msg = lib.cgnn_status_string(status).decode()
         extra = f" (cudaError {lib.cgnn_last_cuda_error()})" if status == 4 else ""
-        raise CgnnError(f"{what}: {msg}{extra}")
+        raise CgnnError(f"{what}: {msg}{extra}", status)

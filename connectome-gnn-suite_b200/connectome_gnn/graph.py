@@ -77,34 +77,66 @@ class ConnectomeGraph:
 # Batch
 # ---------------------------------------------------------------------------
 
-@dataclass
 class BatchCSR:
     """Device CSR of a batch (``cgnn_csr_t``): by-destination and by-source rows in stable COO
-    order, raw and GCN-normalised weights, D^ / d^-1/2 / w_sum.  See include/cgnn.h."""
+    order, raw and GCN-normalised weights, D^ / d^-1/2 / w_sum.  See include/cgnn.h.
 
-    in_rowptr: torch.Tensor
-    in_col: torch.Tensor
-    in_w: torch.Tensor
-    in_wn: torch.Tensor
-    out_rowptr: torch.Tensor
-    out_col: torch.Tensor
-    out_w: torch.Tensor
-    out_wn: torch.Tensor
-    deg: torch.Tensor
-    dinv: torch.Tensor
-    wsum: torch.Tensor
-    graph_meta: torch.Tensor  # [B, 4] int32 {first row, rows, first edge, edges} per subject
-    eptr: torch.Tensor        # [B+1] int64 edge prefix sums
-    max_nodes: int            # largest subject of the batch (sizes shared-memory tiles)
-    max_edges: int            # most edges in one subject
-    agg: Optional[dict] = None  # model family -> (agg_in, agg_out, row_graph) packed blobs, built lazily by the engine
+    A LEAN instance (what ``SubjectStore.collate(prepare_for=...)`` returns) carries only ``graph_meta``, ``eptr`` and
+    the packed aggregation blobs in ``agg`` - all the tensor-core layer kernels read.  The eleven arrays are
+    materialised on first attribute access by collating the same subjects again with every output requested
+    (``materialize``); ``peek`` looks without triggering that."""
 
-    _FIELDS = ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn",
-               "deg", "dinv", "wsum", "graph_meta", "eptr")
+    _ARRAYS = ("in_rowptr", "in_col", "in_w", "in_wn", "out_rowptr", "out_col", "out_w", "out_wn", "deg", "dinv", "wsum")
+    _FIELDS = _ARRAYS + ("graph_meta", "eptr")
+
+    def __init__(self, in_rowptr=None, in_col=None, in_w=None, in_wn=None, out_rowptr=None, out_col=None, out_w=None,
+                 out_wn=None, deg=None, dinv=None, wsum=None, graph_meta=None, eptr=None, max_nodes: int = 0,
+                 max_edges: int = 0, agg: Optional[dict] = None, num_edges: Optional[int] = None, fill=None):
+        d = self.__dict__
+        for k, v in zip(self._ARRAYS, (in_rowptr, in_col, in_w, in_wn, out_rowptr, out_col, out_w, out_wn, deg, dinv, wsum)):
+            d["_" + k] = v
+        self.graph_meta = graph_meta     # [B, 4] int32 {first row, rows, first edge, edges} per subject
+        self.eptr = eptr                 # [B+1] int64 edge prefix sums
+        self.max_nodes = max_nodes       # largest subject of the batch (sizes shared-memory tiles)
+        self.max_edges = max_edges       # most edges in one subject
+        self.agg = agg                   # model family -> (agg_in, agg_out | None, row_graph) packed blobs
+        self.num_edges = int(num_edges) if num_edges is not None else (int(in_col.shape[0]) if in_col is not None else 0)
+        self._fill = fill                # callable returning a full BatchCSR of the same batch (lean instances)
+
+    def peek(self, name: str):
+        """The array if it exists on the device, else None (never materialises)."""
+        if name in self._ARRAYS:
+            return self.__dict__["_" + name]
+        return getattr(self, name)
+
+    def is_full(self) -> bool:
+        return self.__dict__["_in_col"] is not None
+
+    def materialize(self) -> "BatchCSR":
+        """Make sure the CSR arrays exist (a lean batch collates its subjects again with every output requested)."""
+        if not self.is_full():
+            if self._fill is None:
+                raise RuntimeError("this BatchCSR has no CSR arrays and no way to build them")
+            self._fill()
+        return self
+
+    def _adopt(self, full: "BatchCSR") -> None:
+        for k in self._ARRAYS:
+            self.__dict__["_" + k] = full.peek(k)
+        self._fill = None
+
+    def __getattr__(self, name: str):
+        # only reached for names that are not instance attributes: the lazily materialised arrays
+        if name in BatchCSR._ARRAYS:
+            self.materialize()
+            return self.__dict__["_" + name]
+        raise AttributeError(name)
 
     def to(self, device) -> "BatchCSR":
-        return BatchCSR(*[getattr(self, f).to(device) for f in self._FIELDS], max_nodes=self.max_nodes,
-                        max_edges=self.max_edges)
+        self.materialize()
+        mv = lambda t: None if t is None else t.to(device)
+        return BatchCSR(*[mv(self.peek(f)) for f in self._FIELDS], max_nodes=self.max_nodes, max_edges=self.max_edges,
+                        num_edges=self.num_edges)
 
 
 @dataclass
@@ -124,6 +156,20 @@ class ConnectomeBatch:
     graph_base: int = 0
     global_num_graphs: Optional[int] = None
     global_num_nodes: Optional[int] = None
+    # lean batches (SubjectStore.collate(prepare_for=...)): edge_index / edge_weight / batch are None until somebody
+    # reads them; `_fill` then collates the same subjects again with every reference field requested
+    _fill: Optional[object] = None
+
+    _LAZY = ("edge_index", "edge_weight", "batch")
+
+    def __getattribute__(self, name):
+        v = object.__getattribute__(self, name)
+        if v is None and name in ConnectomeBatch._LAZY:
+            fill = object.__getattribute__(self, "_fill")
+            if fill is not None:
+                fill()
+                v = object.__getattribute__(self, name)
+        return v
 
     @property
     def num_graphs(self) -> int:
@@ -144,7 +190,7 @@ class ConnectomeBatch:
         if device == self.node_features.device:
             return self
         move = lambda t: None if t is None else t.to(device)
-        return ConnectomeBatch(
+        return ConnectomeBatch(   # reading the lazy fields materialises them: a moved batch is a full batch
             move(self.node_features), move(self.edge_index), move(self.edge_weight), move(self.batch),
             move(self.labels), move(self.ptr), None if self.csr is None else self.csr.to(device),
             self.row_base, self.graph_base, self.global_num_graphs, self.global_num_nodes)
@@ -306,10 +352,14 @@ class SubjectStore:
 
     def collate(self, ids, *, row_base: int = 0, graph_base: int = 0, global_num_graphs: Optional[int] = None,
                 global_num_nodes: Optional[int] = None, ids_device: Optional[torch.Tensor] = None,
-                prepare_for: Optional[str] = None) -> ConnectomeBatch:
+                prepare_for: Optional[str] = None, lean: Optional[bool] = None, backward: bool = True) -> ConnectomeBatch:
         """Device collate of subjects ``ids`` (host int sequence / array, in batch order).  ``prepare_for`` ("gcn" /
         "sage") makes the collate kernel emit that model family's packed aggregation structure in the same pass
-        instead of a separate launch at the first layer (same bits either way)."""
+        instead of a separate launch at the first layer (same bits either way) - and, unless ``lean=False``, makes
+        the batch LEAN: the kernel writes only what that model's kernels read (node features, labels, ``ptr``, the
+        packed structure); ``edge_index`` / ``edge_weight`` / ``batch`` and the CSR arrays are filled in - bit for bit
+        what a full collate writes - the first time they are read.  ``backward=False`` (inference) also skips the
+        by-source half of the structure."""
         ids_np = np.asarray(ids, dtype=np.int64).reshape(-1)
         n_sel = self.node_ptr_host[ids_np + 1] - self.node_ptr_host[ids_np]
         e_sel = self.edge_ptr_host[ids_np + 1] - self.edge_ptr_host[ids_np]
@@ -324,8 +374,10 @@ class SubjectStore:
         if ready is not None:      # an upload enqueued on another stream (reload): order this stream after it
             torch.cuda.current_stream(self.device).wait_event(ready)
         eng = _engine.engine_for(self.x)
-        out, csr, blobs = eng.collate_csr(self._struct, ids_device, int(ids_np.size), rows, edges, max_nodes,
-                                          self.num_features, all_labelled, prepare_for)
+        want_lean = (prepare_for is not None) if lean is None else (bool(lean) and prepare_for is not None)
+        out, csr, blobs = eng.collate_csr(self._struct, ids_device, int(ids_np.size), rows, edges, max_nodes, max_edges,
+                                          self.num_features, all_labelled, prepare_for, lean=want_lean,
+                                          need_out=backward)
         labels = out["labels"]
         if ids_np.size == 0:         # an empty slice of a data-parallel batch: no subjects, no labels (not "unlabelled")
             labels = torch.empty(0, dtype=torch.int64, device=self.device)
@@ -333,12 +385,24 @@ class SubjectStore:
             # reference quirk (graph.py:155-156,165): only labelled subjects contribute, so the
             # stack is shorter than B
             labels = self.label[torch.from_numpy(ids_np[labelled]).to(self.device)]
-        bcsr = BatchCSR(**csr, eptr=out["eptr"], max_nodes=max_nodes, max_edges=max_edges)
+        bcsr = BatchCSR(**csr, eptr=out["eptr"], max_nodes=max_nodes, max_edges=max_edges, num_edges=edges)
         if blobs is not None:
             bcsr.agg = {prepare_for: blobs}
-        return ConnectomeBatch(
+        batch = ConnectomeBatch(
             out["node_features"], out["edge_index"], out["edge_weight"], out["batch"], labels, out["ptr"],
             bcsr, row_base, graph_base, global_num_graphs, global_num_nodes)
+        if out["edge_index"] is None:          # lean: the missing fields are one full collate of the same subjects away
+            def fill(batch=batch, bcsr=bcsr, ids_np=ids_np, ids_device=ids_device):
+                if object.__getattribute__(batch, "_fill") is None:
+                    return
+                full = self.collate(ids_np, ids_device=ids_device)
+                for k in ConnectomeBatch._LAZY:
+                    object.__setattr__(batch, k, object.__getattribute__(full, k))
+                bcsr._adopt(full.csr)
+                object.__setattr__(batch, "_fill", None)
+            object.__setattr__(batch, "_fill", fill)
+            bcsr._fill = fill
+        return batch
 
 
 class StreamingStore:

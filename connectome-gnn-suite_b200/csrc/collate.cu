@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
   constexpr int kNW = NT / 32;
   CGNN_SMEM_DECL;
   __shared__ int s_warp[32];
+  __shared__ int s_bk[kNW * kAggBuckets];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long g = blockIdx.x;
   const long long nb = p.ptr[g], eb = p.eptr[g];
@@ -156,7 +157,8 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
       for (int u = 0; u < 4; ++u)
         if (i0 + u * NT < n * F) dx[i0 + u * NT] = v[u];
     }
-    for (int i = tid; i < n; i += NT) p.batch[nb + i] = g;
+    if (p.batch)
+      for (int i = tid; i < n; i += NT) p.batch[nb + i] = g;
     if (tid == 0 && p.labels && p.store.label) p.labels[g] = p.store.label[sid];
   } else {
     gsrc = p.coo + eb; gdst = p.coo + p.total_edges + eb; lw = p.coo_w + eb;
@@ -171,7 +173,10 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
   float* cw = reinterpret_cast<float*>(pk + 2 * m);                      // [2][m]
   uint32_t* raw_pk = reinterpret_cast<uint32_t*>(cw + 2 * m);            // [m] COO order
   float* raw_w = reinterpret_cast<float*>(raw_pk + m);                   // [m]
-  const bool want_agg = staged && p.csr.agg_kind >= 0 && p.csr.agg_in && p.csr.agg_out && p.csr.row_graph;
+  const bool want_agg = staged && p.csr.agg_kind >= 0 && p.csr.agg_in && p.csr.row_graph;   // agg_out is optional
+  // lean batch: none of the CSR arrays is wanted (the layer kernels read the blobs only); needs the staged path
+  const bool lean = p.csr.in_col == nullptr;
+  if (lean && !staged) return;
   // Local endpoints of edge e as stored.  Endpoints outside the subject (malformed hand-built batches)
   // are redirected to a zero-weight self edge on node 0 so the CSR stays consistent.
   const bool pair_store = FROM_STORE && p.store.edge_pairs != 0;
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
         const int e = e0 + u * NT;
         if (e >= m) continue;
         int s = es[u], d = ed[u]; float w = ew[u];
-        if (FROM_STORE) {
+        if (FROM_STORE && p.edge_index) {
           p.edge_index[eb + e] = (long long)s + nb;
           p.edge_index[p.total_edges + eb + e] = (long long)d + nb;
           p.edge_weight[eb + e] = w;
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
   for (int idx = tid; idx < 2 * n; idx += NT) {
     const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
     int run = (dd == 0 ? cur_in : cur_out)[i];
-    (dd == 0 ? p.csr.in_rowptr : p.csr.out_rowptr)[nb + i] = (int32_t)(eb + run);
+    if (!lean) (dd == 0 ? p.csr.in_rowptr : p.csr.out_rowptr)[nb + i] = (int32_t)(eb + run);
     for (int c = 0; c < kChunks; ++c) {
       int* q = &cnt[(size_t)(dd * kChunks + c) * n + i];
       const int t = *q;
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
       run += t;
     }
   }
-  if (g == p.B - 1 && tid == 0) {
+  if (g == p.B - 1 && tid == 0 && !lean) {
     p.csr.in_rowptr[p.total_rows] = (int32_t)p.total_edges;
     p.csr.out_rowptr[p.total_rows] = (int32_t)p.total_edges;
   }
@@ -312,26 +317,30 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
       const float dinv = (float)(1.0 / sqrt((double)__fadd_rn(deg, 1e-8f)));
       s_dinv[i] = dinv;
       s_wsum[i] = ws;
-      p.csr.deg[nb + i] = deg;
-      p.csr.dinv[nb + i] = dinv;
-      p.csr.wsum[nb + i] = ws;
+      if (!lean) {
+        p.csr.deg[nb + i] = deg;
+        p.csr.dinv[nb + i] = dinv;
+        p.csr.wsum[nb + i] = ws;
+      }
     }
     __syncthreads();
     if (want_agg) {
       // packed aggregation blobs of the requested family, straight from the sorted lists (same bits as k_build_agg)
       const int self = p.csr.agg_kind == AGG_GCN ? 1 : 0;
+      const int ndir = p.csr.agg_out ? 2 : 1;           // inference batches ask for the by-destination blob only
       int* pos = cnt;                                   // [2][n] padded record counts -> first record of every row
-      for (int idx = tid; idx < 2 * n; idx += NT) {
-        const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
+      int* slot = cnt + 2 * n;                          // [2][n] descriptor position of every row (ascending length)
+      for (int idx = tid; idx < ndir * n; idx += NT) {
+        const int dd = idx >= n ? 1 : 0, i = idx - dd * n;
         const int* ce = dd == 0 ? cur_in : cur_out;
         pos[idx] = ((ce[i] - (i ? ce[i - 1] : 0)) + self + 1) & ~1;
       }
       __syncthreads();
-      block_excl_scan(pos, n, s_warp);
-      block_excl_scan(pos + n, n, s_warp);
+      for (int dd = 0; dd < ndir; ++dd) agg_rank_rows(pos + dd * n, n, slot + dd * n, s_bk);
+      for (int dd = 0; dd < ndir; ++dd) block_excl_scan(pos + dd * n, n, s_warp);
       for (int i = tid; i < n; i += NT) p.csr.row_graph[nb + i] = (int32_t)g;
-      for (int idx = tid; idx < 2 * n; idx += NT) {
-        const int dd = idx >= n ? 1 : 0, i = idx - dd * n;   // idx < 2n
+      for (int idx = tid; idx < ndir * n; idx += NT) {
+        const int dd = idx >= n ? 1 : 0, i = idx - dd * n;
         const int* ce = dd == 0 ? cur_in : cur_out;
         const int q0 = i ? ce[i - 1] : 0, q1 = ce[i];
         int32_t* blob = (dd == 0 ? p.csr.agg_in : p.csr.agg_out) + agg_base_words(nb, eb, g);
@@ -351,9 +360,10 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
         if (self) { const float dv = s_dinv[i]; rec[at++] = make_int2(self_x, __float_as_int(__fmul_rn(dv, dv))); }
         if (at & 1) rec[at++] = make_int2(self_x, 0);
         const float aux = p.csr.agg_kind == AGG_SAGE ? s_wsum[i] : s_dinv[i];
-        reinterpret_cast<int4*>(blob)[i] = make_int4(begin, at, __float_as_int(aux), 0);
+        reinterpret_cast<int4*>(blob)[slot[idx]] = make_int4(begin, at, __float_as_int(aux), i);
       }
     }
+    if (lean) return;
     for (int q = tid; q < m; q += NT) {
       uint32_t v = pk[q];
       int s = (int)(v & 0xffffu), d = (int)(v >> 16);
@@ -405,13 +415,19 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
 
 using namespace cgnn;
 
-static bool csr_out_ok(const cgnn_csr_out_t* c) {
+// all CSR arrays, or none of them (a lean batch: graph_meta + the aggregation blobs only)
+static bool csr_out_full(const cgnn_csr_out_t* c) {
   return c && c->in_rowptr && c->in_col && c->in_w && c->in_wn && c->out_rowptr && c->out_col && c->out_w &&
          c->out_wn && c->deg && c->dinv && c->wsum && c->graph_meta;
 }
+static bool csr_out_lean(const cgnn_csr_out_t* c) {
+  return c && !c->in_rowptr && !c->in_col && !c->in_w && !c->in_wn && !c->out_rowptr && !c->out_col && !c->out_w &&
+         !c->out_wn && !c->deg && !c->dinv && !c->wsum && c->graph_meta && c->agg_in && c->row_graph && c->agg_kind >= 0;
+}
+static bool csr_out_ok(const cgnn_csr_out_t* c) { return csr_out_full(c) || csr_out_lean(c); }
 
 // Dynamic shared memory (two cursor arrays + dinv) is sized for the largest subject of the batch.
-static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaStream_t stream) {
+static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, int max_edges, cudaStream_t stream) {
   const DeviceInfo dev = device_info();
   if (max_nodes < 1) max_nodes = 1;
   const int nt = (max_nodes <= 128 && a.B > 0 && a.total_edges / a.B <= 2048) ? 128 : kThreads;
@@ -420,12 +436,23 @@ static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaSt
   // room for the raw and the two sorted edge lists of a typical subject (24 bytes per edge): an eighth above the batch average, as
   // long as two CTAs still fit on an SM; larger subjects take the unstaged path inside the kernel
   a.edge_cap = 0;
+  const bool lean = a.csr.in_col == nullptr;
   if (a.B > 0) {
     const long long avg = a.total_edges / a.B;
     long long cap = avg + avg / 8 + 32;
+    if (max_edges >= 0 && max_edges <= cap) cap = max_edges;         // every subject staged
     if (cap > a.total_edges) cap = a.total_edges;
-    const size_t want = smem + (size_t)cap * 24;
+    size_t want = smem + (size_t)cap * 24;
     if (want + 1024 <= (size_t)(228 * 1024) / 2) { a.edge_cap = (int)cap; smem = want; }
+    if (lean) {
+      // a lean batch has nowhere to spill: every subject must be sorted in shared memory (one CTA per SM if need be)
+      if (max_edges < 0) return CGNN_ERR_NEED_CSR;
+      if (a.edge_cap < max_edges) {
+        want = (size_t)max_nodes * (16 + 4 * (nt / 32)) + 16 + (size_t)max_edges * 24;
+        if (want > (size_t)dev.smem_optin || max_nodes > 65535) return CGNN_ERR_NEED_CSR;
+        a.edge_cap = max_edges; smem = want;
+      }
+    }
   }
   a.max_nodes = max_nodes;
   if (a.B <= 0) return CGNN_OK;
@@ -439,7 +466,8 @@ static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaSt
   else { if (nt == 128) CGNN_COLLATE(false, 128) else CGNN_COLLATE(false, kThreads) }
 #undef CGNN_COLLATE
   CGNN_CHECK_LAUNCH();
-  if (a.csr.agg_kind >= 0 && a.csr.agg_in && a.csr.agg_out && a.csr.row_graph && a.edge_cap < a.total_edges) {
+  if (!lean && a.csr.agg_kind >= 0 && a.csr.agg_in && a.csr.agg_out && a.csr.row_graph && a.edge_cap < a.total_edges &&
+      (max_edges < 0 || a.edge_cap < max_edges)) {
     // subjects the kernel could not stage (more edges than edge_cap) get their blobs from the stand-alone builder,
     // which skips the ones already done
     cgnn_csr_t c{};
@@ -454,24 +482,24 @@ static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, cudaSt
 extern "C" {
 
 int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int64_t num_graphs,
-                     int64_t total_rows, int64_t total_edges, int32_t max_nodes, float* node_features, int64_t* edge_index,
-                     float* edge_weight, int64_t* batch, int64_t* labels, int64_t* ptr, int64_t* eptr,
+                     int64_t total_rows, int64_t total_edges, int32_t max_nodes, int32_t max_edges, float* node_features,
+                     int64_t* edge_index, float* edge_weight, int64_t* batch, int64_t* labels, int64_t* ptr, int64_t* eptr,
                      const cgnn_csr_out_t* csr, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (num_graphs == 0) {   // a rank's slice of a short global batch may be empty: an empty batch is a valid batch
-    if (!ptr || !eptr || !csr || !csr->in_rowptr || !csr->out_rowptr) return CGNN_ERR_INVALID_ARG;
+    if (!ptr || !eptr || !csr) return CGNN_ERR_INVALID_ARG;
     cudaMemsetAsync(ptr, 0, sizeof(int64_t), stream);
     cudaMemsetAsync(eptr, 0, sizeof(int64_t), stream);
-    cudaMemsetAsync(csr->in_rowptr, 0, sizeof(int32_t), stream);
-    cudaMemsetAsync(csr->out_rowptr, 0, sizeof(int32_t), stream);
+    if (csr->in_rowptr) cudaMemsetAsync(csr->in_rowptr, 0, sizeof(int32_t), stream);
+    if (csr->out_rowptr) cudaMemsetAsync(csr->out_rowptr, 0, sizeof(int32_t), stream);
     return CGNN_OK;
   }
   if (!store || !subject_ids || num_graphs < 0 || total_rows < 0 || total_edges < 0 || !ptr || !eptr ||
       !csr_out_ok(csr) || !store->node_ptr || !store->edge_ptr || store->num_features <= 0)
     return CGNN_ERR_INVALID_ARG;
-  if (total_rows > 0 && (!node_features || !batch || !store->x)) return CGNN_ERR_INVALID_ARG;
-  if (total_edges > 0 && (!edge_index || !edge_weight || !store->src || !store->w))
-    return CGNN_ERR_INVALID_ARG;
+  if (total_rows > 0 && (!node_features || !store->x)) return CGNN_ERR_INVALID_ARG;
+  if (total_edges > 0 && (!store->src || !store->w)) return CGNN_ERR_INVALID_ARG;
+  if ((edge_index == nullptr) != (edge_weight == nullptr)) return CGNN_ERR_INVALID_ARG;   // the COO fields come together
   if (total_edges >= ((int64_t)1 << 31) || total_rows >= ((int64_t)1 << 31)) return CGNN_ERR_INVALID_ARG;
   if (store->edge_pairs && store->dst) return CGNN_ERR_INVALID_ARG;   // the pair layout exists for the compact store only
   {
@@ -489,14 +517,14 @@ int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int6
   a.batch = (long long*)batch; a.labels = (long long*)labels;
   a.ptr = (const long long*)ptr; a.eptr = (const long long*)eptr;
   a.csr = *csr;
-  return collate_launch(a, true, max_nodes, stream);
+  return collate_launch(a, true, max_nodes, max_edges, stream);
 }
 
 int cgnn_csr_from_coo(const int64_t* edge_index, const float* edge_weight, const int64_t* ptr,
                       int64_t num_graphs, int64_t total_rows, int64_t total_edges, int32_t max_nodes,
                       int64_t* eptr, const cgnn_csr_out_t* csr, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!ptr || !eptr || num_graphs < 0 || total_rows < 0 || total_edges < 0 || !csr_out_ok(csr))
+  if (!ptr || !eptr || num_graphs < 0 || total_rows < 0 || total_edges < 0 || !csr_out_full(csr))
     return CGNN_ERR_INVALID_ARG;
   if (total_edges > 0 && (!edge_index || !edge_weight)) return CGNN_ERR_INVALID_ARG;
   if (total_edges >= ((int64_t)1 << 31) || total_rows >= ((int64_t)1 << 31)) return CGNN_ERR_INVALID_ARG;
@@ -515,7 +543,7 @@ int cgnn_csr_from_coo(const int64_t* edge_index, const float* edge_weight, const
   a.x = nullptr; a.edge_index = nullptr; a.edge_weight = nullptr; a.batch = nullptr; a.labels = nullptr;
   a.ptr = (const long long*)ptr; a.eptr = (const long long*)eptr;
   a.csr = *csr;
-  return collate_launch(a, false, max_nodes, stream);
+  return collate_launch(a, false, max_nodes, -1, stream);
 }
 
 }  // extern "C"

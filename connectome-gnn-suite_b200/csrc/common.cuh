@@ -289,6 +289,5 @@ int launch_stats_merge(const double* parts, int parts_n, int C, double* stats, c
 // Process-wide switch (cgnn_set_option): 1 = eligible shapes run on the tcgen05 kernels (default),
 // 0 = everything on the generic SIMT kernels (used to cross-check the two on the device).
 bool tensor_cores_enabled();
-bool ws_engine_enabled();     // CGNN_OPT_WS_ENGINE: 1 (default) = hidden layers run the warp-specialised kernels of engine.cu
 
 }  // namespace cgnn

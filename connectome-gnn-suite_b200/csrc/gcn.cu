@@ -487,6 +487,8 @@ using namespace cgnn;
 
 static bool csr_in_ok(const cgnn_csr_t* c) { return c && c->in_rowptr && c->in_col && c->in_wn && c->dinv && c->graph_meta; }
 static bool csr_out_ok_(const cgnn_csr_t* c) { return c && c->out_rowptr && c->out_col && c->out_wn && c->dinv && c->graph_meta; }
+// a lean batch: graph_meta + this family's blobs, no arrays (the tensor-core kernels read nothing else)
+static bool csr_lean_gcn(const cgnn_csr_t* c) { return c && c->graph_meta && c->agg_in && c->agg_kind == AGG_GCN && !c->in_col; }
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 extern "C" {
@@ -501,9 +503,9 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
     if (bn_stats) cudaMemsetAsync(bn_stats, 0, (size_t)(1 + 2 * H) * sizeof(double), stream);
     return CGNN_OK;
   }
-  if (!t_in || !W || !csr_in_ok(csr) || !ptr || !z) return CGNN_ERR_INVALID_ARG;
+  if (!t_in || !W || !(csr_in_ok(csr) || csr_lean_gcn(csr)) || !ptr || !z) return CGNN_ERR_INVALID_ARG;
   if (bn_stats && (!workspace || workspace_bytes < (size_t)(1 + 2 * H) * sizeof(double))) return CGNN_ERR_WORKSPACE;
-  if (tensor_cores_enabled() && ws_engine_enabled()) {   // warp-specialised hidden layer (TMA + tensor memory); also runs on the simulator
+  if (tensor_cores_enabled()) {   // warp-specialised hidden layer (TMA + tensor memory); also runs on the simulator
     int ws_grid = 0;
     const int rc = launch_gcn_fwd_ws(t_in, act, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, z,
                                      bn_stats ? (double*)workspace : nullptr, &ws_grid, workspace_bytes, stream);
@@ -517,16 +519,13 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
                               bn_stats ? (double*)workspace : nullptr, &tc_grid, workspace_bytes, stream);
     if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;
     if (rc > 0) return rc;
-    rc = launch_gcn_fwd_fused(t_in, act, W, bias, csr, num_graphs, d_in, H, max_nodes, max_edges, z,
-                                  bn_stats ? (double*)workspace : nullptr, &tc_grid, workspace_bytes, stream);
-    if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;
-    if (rc > 0) return rc;
     rc = launch_gcn_fwd_wide(t_in, act, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, z, bn_stats ? 1 : 0,
                              &tc_grid, workspace, workspace_bytes, stream);
     if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, tc_grid, H, bn_stats, stream) : CGNN_OK;
     if (rc > 0) return rc;
   }
 #endif
+  if (!csr_in_ok(csr)) return CGNN_ERR_NEED_CSR;     // the generic kernel walks the CSR arrays
   const DeviceInfo dev = device_info();
   GcnFwdArgs a;
   a.t_in = t_in; a.act = make_act(act); a.W = W; a.bias = bias;
@@ -591,7 +590,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
     return CGNN_OK;
   }
   if ((du == nullptr) == (demb == nullptr)) return CGNN_ERR_INVALID_ARG;
-  if (!z || !t_in || !W || !csr_out_ok_(csr) || !ptr || !workspace) return CGNN_ERR_INVALID_ARG;
+  if (!z || !t_in || !W || !(csr_out_ok_(csr) || csr_lean_gcn(csr)) || !ptr || !workspace) return CGNN_ERR_INVALID_ARG;
   if (prev_sums && (!du_in || !prev_mean || !prev_rstd)) return CGNN_ERR_INVALID_ARG;
   if (bn && (!bn->scale || !bn->mean || !bn->rstd || (bn->train && (!bn->s1 || !bn->s2)))) return CGNN_ERR_INVALID_ARG;
 #ifndef CGNN_EMU
@@ -652,6 +651,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
     }
   }
 #endif
+  if (!csr_out_ok_(csr)) return CGNN_ERR_NEED_CSR;   // the generic kernel walks the CSR arrays
   const DeviceInfo dev = device_info();
   GcnBwdArgs a;
   a.du = du; a.demb = demb; a.z = z; a.act_out = make_act(act_out);

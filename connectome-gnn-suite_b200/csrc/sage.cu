@@ -529,8 +529,10 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
     if (bn_stats) cudaMemsetAsync(bn_stats, 0, (size_t)(1 + 2 * H) * sizeof(double), stream);
     return CGNN_OK;
   }
-  if (!t_in || !W || !csr || !csr->in_rowptr || !csr->in_col || !csr->in_w || !csr->wsum || !csr->graph_meta || !ptr || !z)
-    return CGNN_ERR_INVALID_ARG;
+  // full CSR arrays, or a lean batch (graph_meta + this family's blobs; the tensor-core kernels read nothing else)
+  const bool arrays_fwd = csr && csr->in_rowptr && csr->in_col && csr->in_w && csr->wsum;
+  const bool lean = csr && !csr->in_col && csr->agg_in && csr->agg_kind == AGG_SAGE;
+  if (!t_in || !W || !csr || !csr->graph_meta || !(arrays_fwd || lean) || !ptr || !z) return CGNN_ERR_INVALID_ARG;
   if (d_in % 4 == 0 && !aligned16(t_in)) return CGNN_ERR_INVALID_ARG;
   if (bn_stats && (!workspace || workspace_bytes < (size_t)(1 + 2 * H) * sizeof(double))) return CGNN_ERR_WORKSPACE;
 #ifndef CGNN_EMU
@@ -568,6 +570,7 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
     }
   }
 #endif
+  if (!arrays_fwd) return CGNN_ERR_NEED_CSR;       // the generic kernel walks the CSR arrays
   const DeviceInfo dev = device_info();
   SageFwdArgs a;
   a.t_in = t_in; a.act = make_act(act); a.W = W; a.bias = bias;
@@ -634,11 +637,12 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
     return CGNN_OK;
   }
   if ((du == nullptr) == (demb == nullptr)) return CGNN_ERR_INVALID_ARG;
-  if (!z || !t_in || !W || !csr || !csr->in_rowptr || !csr->in_col || !csr->in_w || !csr->wsum || !csr->graph_meta ||
-      !ptr || !workspace)
-    return CGNN_ERR_INVALID_ARG;
+  const bool arrays_bwd = csr && csr->in_rowptr && csr->in_col && csr->in_w && csr->wsum &&
+                          (!du_in || (csr->out_rowptr && csr->out_col && csr->out_w));
+  const bool lean = csr && !csr->in_col && csr->agg_in && csr->agg_kind == AGG_SAGE;
+  if (!z || !t_in || !W || !csr || !csr->graph_meta || !(arrays_bwd || lean) || !ptr || !workspace) return CGNN_ERR_INVALID_ARG;
   if (d_in % 4 == 0 && (!aligned16(t_in) || (scratch && !aligned16(scratch)))) return CGNN_ERR_INVALID_ARG;
-  if (du_in && (!scratch || !csr->out_rowptr || !csr->out_col || !csr->out_w)) return CGNN_ERR_INVALID_ARG;
+  if (du_in && !scratch) return CGNN_ERR_INVALID_ARG;
   if (prev_sums && (!du_in || !prev_mean || !prev_rstd)) return CGNN_ERR_INVALID_ARG;
   if (bn && (!bn->scale || !bn->mean || !bn->rstd || (bn->train && (!bn->s1 || !bn->s2)))) return CGNN_ERR_INVALID_ARG;
 #ifndef CGNN_EMU
@@ -697,6 +701,7 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
     }
   }
 #endif
+  if (!arrays_bwd) return CGNN_ERR_NEED_CSR;       // the generic kernels walk the CSR arrays
   const DeviceInfo dev = device_info();
   SageBwdArgs a;
   a.du = du; a.demb = demb; a.z = z; a.act_out = make_act(act_out);

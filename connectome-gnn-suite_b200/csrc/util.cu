@@ -11,9 +11,6 @@ unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_REL
 static int g_use_tensor_cores = 1;
 bool tensor_cores_enabled() { return g_use_tensor_cores != 0; }
 void set_tensor_cores(int on) { g_use_tensor_cores = on; }
-static int g_ws_engine = 1;
-bool ws_engine_enabled() { return g_ws_engine != 0; }
-void set_ws_engine(int on) { g_ws_engine = on; }
 void set_cuda_error(int err) { g_last_cuda_error = err; }
 void set_tensor_cores(int on);
 
@@ -125,6 +122,7 @@ const char* cgnn_status_string(int status) {
     case CGNN_ERR_TILE_TOO_LARGE: return "subject tile or weight matrix does not fit in shared memory";
     case CGNN_ERR_WORKSPACE: return "workspace too small";
     case CGNN_ERR_CUDA: return "CUDA runtime error";
+    case CGNN_ERR_NEED_CSR: return "lean batch: this code path needs the CSR arrays";
     default: return "unknown status";
   }
 }
@@ -135,7 +133,6 @@ size_t cgnn_workspace_bytes(void) { return (size_t)64 << 20; }   // 148 CTAs x a
 uint64_t cgnn_kernel_launches(void) { return (uint64_t)cgnn::launches(); }
 int cgnn_set_option(int32_t key, int32_t value) {
   if (key == CGNN_OPT_TENSOR_CORES) { cgnn::set_tensor_cores(value); return CGNN_OK; }
-  if (key == CGNN_OPT_WS_ENGINE) { cgnn::set_ws_engine(value); return CGNN_OK; }
   return CGNN_ERR_INVALID_ARG;
 }
 

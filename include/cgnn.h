@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGNN_ABI_VERSION 5
+#define CGNN_ABI_VERSION 6
 
 typedef void* cgnn_stream_t; /* cudaStream_t */
 
@@ -36,7 +36,9 @@ typedef enum {
   CGNN_ERR_INVALID_ARG = 1,     /* null pointer / negative size / unsupported combination */
   CGNN_ERR_TILE_TOO_LARGE = 2,  /* one subject's [N_g, C] fp32 tile (or W) exceeds shared memory */
   CGNN_ERR_WORKSPACE = 3,       /* workspace too small: call cgnn_workspace_bytes()          */
-  CGNN_ERR_CUDA = 4             /* a CUDA runtime call failed: see cgnn_last_cuda_error()     */
+  CGNN_ERR_CUDA = 4,            /* a CUDA runtime call failed: see cgnn_last_cuda_error()     */
+  CGNN_ERR_NEED_CSR = 5         /* a lean batch (blobs only) met a code path that reads the CSR arrays: materialise
+                                 * them (full cgnn_collate_csr / cgnn_csr_from_coo) and call again                */
 } cgnn_status;
 
 const char* cgnn_status_string(int status);
@@ -51,9 +53,6 @@ uint64_t cgnn_kernel_launches(void);
  * kernels, 0 = every shape runs the generic SIMT kernels (same results to fp32 round-off; used to
  * cross-check the two paths on the device). */
 #define CGNN_OPT_TENSOR_CORES 1
-/* CGNN_OPT_WS_ENGINE: 1 (default) = 64-channel hidden layers run the warp-specialised kernels (engine.cu: TMA loads, A operand in
- * tensor memory, gather overlapped with the tensor core); 0 = the previous generation, kept for on-device A/B runs. */
-#define CGNN_OPT_WS_ENGINE 5
 int cgnn_set_option(int32_t key, int32_t value);
 
 /* ---------------------------------------------------------------------------------------
@@ -85,16 +84,21 @@ typedef struct {
   const float*   dinv;       /* [rows] */
   const float*   wsum;       /* [rows] */
   const int32_t* graph_meta; /* [B][4] per subject {first row, rows, first edge, edges}: one 16-byte load per subject */
-  /* Optional packed aggregation blobs built by cgnn_build_agg (NULL = not built: the layer entry points then run
-   * their generic kernels).  One 16-byte aligned blob per subject and direction, at word offset
-   * 8*first_row + 2*(first_edge rounded up to even) + 4*subject inside the buffer:
-   *   [rows x int4 {rec_begin, rec_end, aux bits, 0}] [records int2 {neighbour's local row, weight bits}]
-   * Every row's record list is padded to an even length with zero-weight records; agg_kind 0 (GCN) carries the
-   * normalised weights w^ and ends every row with the self-loop record {row, dinv^2} (reference models.py:98-100
-   * puts self-loops last); agg_kind 1 (GraphSAGE) carries w with aux = w_sum by destination, and
-   * w / (w_sum[dst] + 1e-8) by source (the adjoint of models.py:146-149). */
+  /* Optional packed aggregation blobs built by cgnn_build_agg or by cgnn_collate_csr itself (NULL = not built: the
+   * layer entry points then run their generic kernels).  One 16-byte aligned blob per subject and direction, at
+   * word offset 8*first_row + 2*(first_edge rounded up to even) + 4*subject inside the buffer:
+   *   [rows x int4 {rec_begin, rec_end, aux bits, row}] [records int2 {neighbour, weight bits}]
+   * Descriptors are sorted by ascending record count (ties by row; `row` says which row a descriptor stands for) so
+   * that rows walked in lock step have equal lengths.  Every row's record list is padded to an even length with
+   * zero-weight records; agg_kind 0 (GCN) carries the normalised weights w^ and ends every row with the self-loop
+   * record {row, dinv^2} (reference models.py:98-100 puts self-loops last); agg_kind 1 (GraphSAGE) carries w with
+   * aux = w_sum by destination, and w / (w_sum[dst] + 1e-8) by source (the adjoint of models.py:146-149).
+   * `neighbour` is the local row index in agg_out and (row << 8) | ((row & 7) << 4) in agg_in (the byte offset of the
+   * row in a 256-byte-pitch shared-memory tile with its swizzle key).
+   * A LEAN batch carries graph_meta, row_graph and the blobs only - every array pointer above is NULL: all the
+   * tensor-core layer kernels read nothing else.  Entry points that would need the arrays return CGNN_ERR_NEED_CSR. */
   const int32_t* agg_in;     /* rows = destination nodes, neighbours = sources       */
-  const int32_t* agg_out;    /* rows = source nodes,      neighbours = destinations  */
+  const int32_t* agg_out;    /* rows = source nodes,      neighbours = destinations (NULL on inference-only batches) */
   const int32_t* row_graph;  /* [rows] subject index of every row (ConnectomeBatch.batch as int32) */
   int32_t agg_kind;          /* 0 = GCN, 1 = GraphSAGE, -1 = none */
 } cgnn_csr_t;
@@ -159,7 +163,9 @@ typedef struct {
   int32_t* graph_meta;
   /* optional: have the collate kernel also emit the packed aggregation blobs of one model family (what
    * cgnn_build_agg would produce from the arrays above, bit for bit) while the sorted lists are still in shared
-   * memory.  agg_kind = -1 (or NULL pointers): not requested. */
+   * memory.  agg_kind = -1 (or NULL pointers): not requested; agg_out alone may be NULL (forward-only batches).
+   * LEAN request: every array pointer above except graph_meta is NULL and the blobs are requested - the kernel then
+   * writes nothing but node_features, labels, graph_meta, row_graph and the blobs (a quarter of the bytes). */
   int32_t* agg_in; int32_t* agg_out; int32_t* row_graph;
   int32_t agg_kind;
 } cgnn_csr_out_t;
@@ -170,10 +176,13 @@ typedef struct {
  * (graph.py:152), edge_weight [E], batch [rows] int64 (graph.py:154), labels [B] int64
  * (NULL to skip), ptr [B+1] int64 (graph.py:158,166) - plus eptr [B+1] int64 (edge prefix
  * sums) and the device CSR.  total_rows / total_edges are the host-computed sums used to
- * size the outputs; max_nodes is the largest N_s among the selected subjects (sizes the
- * per-CTA shared memory). */
+ * size the outputs; max_nodes / max_edges are the largest N_s / E_s among the selected subjects
+ * (they size the per-CTA shared memory; max_edges < 0 = unknown).  edge_index + edge_weight and
+ * batch may be NULL: the field is then not materialised (the host mirror fills it on first access
+ * by collating again).  A lean request whose largest subject cannot be sorted in shared memory
+ * returns CGNN_ERR_NEED_CSR. */
 int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int64_t num_graphs,
-                     int64_t total_rows, int64_t total_edges, int32_t max_nodes,
+                     int64_t total_rows, int64_t total_edges, int32_t max_nodes, int32_t max_edges,
                      float* node_features, int64_t* edge_index, float* edge_weight,
                      int64_t* batch, int64_t* labels, int64_t* ptr, int64_t* eptr,
                      const cgnn_csr_out_t* csr, cgnn_stream_t stream);

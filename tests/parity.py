@@ -245,3 +245,43 @@ def check_trainer(kind, device):
                        # +-lr steps, so the value is a random walk in the reference too and never affects outputs
         if v.dtype.is_floating_point:
             helpers.assert_close(v, final[k], f"final {k}", tol=1e-4)
+
+
+def check_lean_collate(device, kind="gcn"):
+    """SubjectStore.collate(prepare_for=...) is LEAN: nothing but what the layer kernels read is written; the reference
+    fields and the CSR arrays appear on first access, bit for bit what a full collate writes; a forward-only batch
+    (backward=False) still trains - the missing half of the structure is built on demand."""
+    from connectome_gnn.graph import ConnectomeBatch, SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import CrossEntropyLoss
+    graphs = generate_dataset(num_subjects=6, num_regions=84, seed=41) + generate_dataset(num_subjects=2, num_regions=30, seed=42)
+    store = SubjectStore(pack_graphs(graphs), device)
+    ids = np.array([7, 0, 3, 3, 5, 1])
+    full = store.collate(ids)
+    lean = store.collate(ids, prepare_for=kind)
+    fwd_only = store.collate(ids, prepare_for=kind, backward=False)
+    peek = lambda b, f: object.__getattribute__(b, f)
+    for b in (lean, fwd_only):
+        assert all(peek(b, f) is None for f in ConnectomeBatch._LAZY) and not b.csr.is_full()
+        assert all(b.csr.peek(f) is None for f in b.csr._ARRAYS)
+    assert lean.csr.agg[kind][1] is not None and fwd_only.csr.agg[kind][1] is None
+    torch.manual_seed(0)
+    cls = GCNConnectome if kind == "gcn" else GraphSAGEConnectome
+    m = cls(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.0).to(device)
+    grads = []
+    for b in (full, lean, fwd_only):
+        m.zero_grad()
+        m.train()
+        CrossEntropyLoss()(m(b), b.labels).backward()
+        grads.append(torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone())
+        for bn in m.batch_norms:
+            bn.reset_running_stats()
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+    if torch.device(device).type == "cuda":   # (the simulator has no tensor-core kernels: its generic ones ask for the arrays)
+        assert not lean.csr.is_full(), "a training step on a lean batch must not need the CSR arrays"
+    for f in ("node_features", "edge_index", "edge_weight", "batch", "labels", "ptr"):
+        assert torch.equal(getattr(lean, f), getattr(full, f)), f
+    assert lean.csr.is_full()
+    for f in lean.csr._ARRAYS + ("graph_meta", "eptr"):
+        assert torch.equal(getattr(lean.csr, f), getattr(full.csr, f)), f

@@ -177,3 +177,8 @@ def test_ws_engine_dropout_matches_generic_kernels(on_emu):
         finally:
             on_emu.lib.cgnn_set_option(1, 1)
     assert float((outs[0] - outs[1]).abs().max()) <= 1e-5 * float(outs[1].abs().max())
+
+
+def test_lean_collate(on_emu):
+    # hidden 64: the GCN hidden layers run on the warp-specialised engine, which never reads the CSR arrays
+    parity.check_lean_collate("cpu", "gcn")

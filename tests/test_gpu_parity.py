@@ -442,6 +442,11 @@ def test_pair_store_collates_identically():
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_lean_collate(kind):
+    parity.check_lean_collate(DEV, kind)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_collate_emits_the_same_aggregation_structure(kind):
     """`prepare_for` (blobs written by the collate kernel) and the lazy `cgnn_build_agg` path feed the layer kernels
     identical structure: forward outputs and backward gradients are bit-identical."""

@@ -28,17 +28,17 @@ for p_drop in (0.0, 0.3):
     act = Act(scale, shift, True, p_drop, 1234, 1, 0)
     res = {}
     for on in (1, 0):
-        eng.lib.cgnn_set_option(5, on)
+        eng.lib.cgnn_set_option(1, on)
         z, stats, _ = eng.layer_fwd("gcn", t_in, act, W, bias, batch.csr, batch.ptr, B, want_stats=True)
         torch.cuda.synchronize()
         res[on] = (z.clone(), stats.clone())
-    eng.lib.cgnn_set_option(5, 1)
+    eng.lib.cgnn_set_option(1, 1)
     dz = float((res[1][0] - res[0][0]).abs().max() / res[0][0].abs().max())
     ds = float((res[1][1] - res[0][1]).abs().max() / res[0][1].abs().max())
     print(f"p_drop {p_drop}: z max-norm rel diff {dz:.3e}, stats rel diff {ds:.3e}, count {float(res[1][1][0])} vs {float(res[0][1][0])}", flush=True)
 act = Act(scale, shift, True, 0.3, 1234, 1, 0)
 for on in (1, 0):
-    eng.lib.cgnn_set_option(5, on)
+    eng.lib.cgnn_set_option(1, on)
     for want in (True, False):
         for _ in range(3):
             eng.layer_fwd("gcn", t_in, act, W, bias, batch.csr, batch.ptr, B, want_stats=want)
@@ -51,4 +51,4 @@ for on in (1, 0):
         ms = e0.elapsed_time(e1) / 10
         gb = (8 * rows * 64 + 4 * (rows + 1) + 8 * 8 * rows + 4 * rows) / 1e9
         print(f"engine={on} stats={want}: {ms*1e3:.1f} us per layer call ({B} x {N}-node), {gb/ms*1e3:.0f} GB/s algorithmic", flush=True)
-eng.lib.cgnn_set_option(5, 1)
+eng.lib.cgnn_set_option(1, 1)
