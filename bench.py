@@ -250,7 +250,7 @@ def run_b200(a):
         kind, mode = name.split("_")
         tr = trainers[kind]
         ids = torch.randperm(a.batch, generator=order_gen).numpy()
-        batch = st.collate(ids, prepare_for=kind, **meta)
+        batch = st.collate(ids, prepare_for=kind, backward=(mode == "train"), **meta)
         if mode == "train":
             tr.model.train()
             return tr.train_step(batch)
