@@ -29,10 +29,7 @@ struct BuildAggArgs {
 __global__ void __launch_bounds__(256) k_build_agg(BuildAggArgs p) {
   CGNN_SMEM_DECL;
   __shared__ int s_tot[2][8];
-  __shared__ int s_bk[8 * kAggBuckets];
   int* s_pos = reinterpret_cast<int*>(cgnn_smem);   // [2][max_nodes] padded record counts -> exclusive positions
-  int* s_len = s_pos + 2 * p.max_nodes;             // [2][max_nodes] padded record counts
-  int* s_slot = s_len + 2 * p.max_nodes;            // [2][max_nodes] descriptor position of every row (ascending length)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long g = blockIdx.x;
   const int4 m = reinterpret_cast<const int4*>(p.meta)[g];
@@ -50,7 +47,6 @@ __global__ void __launch_bounds__(256) k_build_agg(BuildAggArgs p) {
     for (int i = lo; i < hi; ++i) {
       const int c = (rp[nb + i + 1] - rp[nb + i] + self + 1) & ~1;
       s_pos[dir * p.max_nodes + i] = c;
-      s_len[dir * p.max_nodes + i] = c;
       sum += c;
     }
     int inc = sum;
@@ -66,7 +62,6 @@ __global__ void __launch_bounds__(256) k_build_agg(BuildAggArgs p) {
     for (int i = lo; i < hi; ++i) { const int c = s_pos[dir * p.max_nodes + i]; s_pos[dir * p.max_nodes + i] = run; run += c; }
   }
   __syncthreads();
-  for (int dir = 0; dir < 2; ++dir) agg_rank_rows(s_len + dir * p.max_nodes, n, s_slot + dir * p.max_nodes, s_bk);
   for (int i = tid; i < n; i += blockDim.x) p.row_graph[nb + i] = (int32_t)g;
   for (int dir = 0; dir < 2; ++dir) {
     const int32_t* rp = dir == 0 ? p.in_rowptr : p.out_rowptr;
@@ -89,7 +84,7 @@ __global__ void __launch_bounds__(256) k_build_agg(BuildAggArgs p) {
       if (self) { const float d = p.dinv[nb + i]; rec[pos++] = make_int2(self_x, __float_as_int(__fmul_rn(d, d))); }
       if (pos & 1) rec[pos++] = make_int2(self_x, 0);
       const float aux = p.kind == AGG_SAGE ? p.wsum[nb + i] : p.dinv[nb + i];
-      desc[s_slot[dir * p.max_nodes + i]] = make_int4(begin, pos, __float_as_int(aux), i);
+      desc[i] = make_int4(begin, pos, __float_as_int(aux), i);
     }
   }
 }
@@ -196,8 +191,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
       int row;
       float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f), rpre = dpre;
       if (MODE == GATHER_SAGE_BWD) {   // the row's direct gradient and stored input: loads fly during the gather
-        const int slotp = i0 + (tid & 31) / LPR;              // descriptor slot -> the row it stands for
-        const int rowp = slotp < n ? s_desc[slotp].w : n;
+        const int rowp = i0 + (tid & 31) / LPR;
         if (rowp < n && live_quad) {
           dpre = rt::ld_quad<VEC>(p.direct, nb + rowp, C, c0);
           if (p.want_prev) rpre = rt::ld_quad<VEC>(p.t_raw, nb + rowp, C, c0);
@@ -328,7 +322,7 @@ int launch_build_agg(const cgnn_csr_t* csr, int32_t kind, int64_t num_graphs, in
   a.dinv = csr->dinv; a.wsum = csr->wsum; a.meta = csr->graph_meta;
   a.kind = kind; a.max_nodes = max_nodes < 1 ? 1 : max_nodes; a.skip_edge_cap = skip_edge_cap;
   a.agg_in = agg_in; a.agg_out = agg_out; a.row_graph = row_graph;
-  const size_t smem = (size_t)6 * a.max_nodes * sizeof(int) + 16;
+  const size_t smem = (size_t)2 * a.max_nodes * sizeof(int) + 16;
   const DeviceInfo dev = device_info();
   if (smem > (size_t)dev.smem_optin) return CGNN_ERR_TILE_TOO_LARGE;
   auto kfn = k_build_agg;

@@ -6,9 +6,9 @@
 //   row descriptor  int4 {rec_begin, rec_end, aux bits, row}        one broadcast load per row
 //   record pair     int4 {nbr0, w0 bits, nbr1, w1 bits}             one broadcast load per two edges
 // Rows are padded to an even number of records (zero weight), GCN rows end with their self-loop record.
-// Descriptors are stored in ascending order of (padded) record count, ties by row index - descriptor k says which row
-// it stands for - so that the rows a warp walks in lock step have the same length (no padding to the longest row of
-// the group).  agg_rank_rows() is the one ordering both builders (collate.cu, agg.cu) use.
+// Descriptor k stands for row k (its fourth word repeats k).  Measured on B200 and dropped: descriptors sorted by record
+// count, so that rows walked in lock step have equal lengths - the ranking cost the collate kernel 17 % of its time and the
+// gathers did not get faster (352 us per layer either way).
 // The neighbour word of the by-destination blob (agg_in) is stored as agg_rec_x(nbr) = the byte offset of the
 // neighbour's row in a 256-byte-pitch tile with its XOR-swizzle key (row & 7) in the 16-byte-chunk bits: the
 // warp-specialised forward kernels (engine.cu) turn it into a shared-memory address with one XOR.  Everybody else
@@ -19,58 +19,6 @@
 namespace cgnn {
 
 enum { AGG_GCN = 0, AGG_SAGE = 1 };
-
-// Position of every row in ascending-length order (stable): whole CTA, warp w owns a contiguous range of rows.
-//   len[i]  padded record count of row i (even)        slot[i]  <- its position
-//   bk      [(blockDim.x / 32) * 64] ints of shared scratch
-constexpr int kAggBuckets = 64;
-__device__ __forceinline__ void agg_rank_rows(const int* len, int n, int* slot, int* bk) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  for (int i = tid; i < nw * kAggBuckets; i += blockDim.x) bk[i] = 0;
-  __syncthreads();
-  const int per = (((n + nw - 1) / nw) + 31) & ~31;
-  const int lo = min(warp * per, n), hi = min(lo + per, n);
-  int* mine = bk + warp * kAggBuckets;
-  for (int i0 = lo; i0 < hi; i0 += 32) {          // rank inside the warp's range: earlier rows of a bucket first
-    const int i = i0 + lane;
-    const bool live = i < hi;
-    const int b = live ? min(len[i] >> 1, kAggBuckets - 1) : -1 - lane;
-    const unsigned peers = __match_any_sync(kFull, b);
-    const int rank = __popc(peers & ((1u << lane) - 1u));
-    int old = 0;
-    if (live) old = mine[b];
-    __syncwarp();
-    if (live && rank == 0) mine[b] = old + __popc(peers);
-    __syncwarp();
-    if (live) slot[i] = old + rank;
-  }
-  __syncthreads();
-  if (warp == 0) {                                  // counts -> exclusive offsets over (bucket, warp), bucket-major
-    static_assert(kAggBuckets == 64, "two buckets per lane");
-    int t0 = 0, t1 = 0;
-    for (int w = 0; w < nw; ++w) { t0 += bk[w * kAggBuckets + lane]; t1 += bk[w * kAggBuckets + 32 + lane]; }
-    int i0 = t0, i1 = t1;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v0 = __shfl_up_sync(kFull, i0, o), v1 = __shfl_up_sync(kFull, i1, o);
-      if (lane >= o) { i0 += v0; i1 += v1; }
-    }
-    int run0 = i0 - t0, run1 = __shfl_sync(kFull, i0, 31) + i1 - t1;
-    for (int w = 0; w < nw; ++w) {
-      int t = bk[w * kAggBuckets + lane];
-      bk[w * kAggBuckets + lane] = run0;
-      run0 += t;
-      t = bk[w * kAggBuckets + 32 + lane];
-      bk[w * kAggBuckets + 32 + lane] = run1;
-      run1 += t;
-    }
-  }
-  __syncthreads();
-  for (int i0 = lo; i0 < hi; i0 += 32) {
-    const int i = i0 + lane;
-    if (i < hi) slot[i] += mine[min(len[i] >> 1, kAggBuckets - 1)];
-  }
-  __syncthreads();
-}
 
 static inline __host__ __device__ int agg_rec_x(int nbr) { return (nbr << 8) | ((nbr & 7) << 4); }
 static inline __host__ __device__ int agg_rec_row(int x) { return x >> 8; }
@@ -138,11 +86,10 @@ static __device__ __forceinline__ bool agg_gather_group(const int4* __restrict__
                                                         const float4* __restrict__ tile4, int i0, int n, float4& acc, float& aux,
                                                         int& row) {
   const int lane = threadIdx.x & 31, cl = lane % LPR;
-  const int slot = i0 + lane / LPR;                  // descriptors are sorted by length: slot k stands for row d.w
-  const bool valid = slot < n;
+  row = i0 + lane / LPR;
+  const bool valid = row < n;
   int4 d = make_int4(0, 0, 0, 0);
-  if (valid) d = s_desc[slot];
-  row = d.w;
+  if (valid) d = s_desc[row];
   const int len = d.y - d.x;
   int lmin = len, lmax = len;
 #pragma unroll

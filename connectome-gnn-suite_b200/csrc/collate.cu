@@ -125,7 +125,6 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
   constexpr int kNW = NT / 32;
   CGNN_SMEM_DECL;
   __shared__ int s_warp[32];
-  __shared__ int s_bk[kNW * kAggBuckets];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long g = blockIdx.x;
   const long long nb = p.ptr[g], eb = p.eptr[g];
@@ -329,14 +328,12 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
       const int self = p.csr.agg_kind == AGG_GCN ? 1 : 0;
       const int ndir = p.csr.agg_out ? 2 : 1;           // inference batches ask for the by-destination blob only
       int* pos = cnt;                                   // [2][n] padded record counts -> first record of every row
-      int* slot = cnt + 2 * n;                          // [2][n] descriptor position of every row (ascending length)
       for (int idx = tid; idx < ndir * n; idx += NT) {
         const int dd = idx >= n ? 1 : 0, i = idx - dd * n;
         const int* ce = dd == 0 ? cur_in : cur_out;
         pos[idx] = ((ce[i] - (i ? ce[i - 1] : 0)) + self + 1) & ~1;
       }
       __syncthreads();
-      for (int dd = 0; dd < ndir; ++dd) agg_rank_rows(pos + dd * n, n, slot + dd * n, s_bk);
       for (int dd = 0; dd < ndir; ++dd) block_excl_scan(pos + dd * n, n, s_warp);
       for (int i = tid; i < n; i += NT) p.csr.row_graph[nb + i] = (int32_t)g;
       for (int idx = tid; idx < ndir * n; idx += NT) {
@@ -360,7 +357,7 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
         if (self) { const float dv = s_dinv[i]; rec[at++] = make_int2(self_x, __float_as_int(__fmul_rn(dv, dv))); }
         if (at & 1) rec[at++] = make_int2(self_x, 0);
         const float aux = p.csr.agg_kind == AGG_SAGE ? s_wsum[i] : s_dinv[i];
-        reinterpret_cast<int4*>(blob)[slot[idx]] = make_int4(begin, at, __float_as_int(aux), i);
+        reinterpret_cast<int4*>(blob)[i] = make_int4(begin, at, __float_as_int(aux), i);
       }
     }
     if (lean) return;

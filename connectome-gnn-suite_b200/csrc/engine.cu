@@ -340,13 +340,12 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
         int j = 0;
         while (j + 1 < nsub && gi >= tab[8 + 8 * (j + 1) + 4]) ++j;
         const int* e = tab + 8 + 8 * j;
-        const int n = e[2], slot = 2 * (gi - e[4]) + half;     // descriptors are sorted by length: slot k stands for row d.w
-        const bool valid = slot < n;
+        const int n = e[2], i = 2 * (gi - e[4]) + half;
+        const bool valid = i < n;
         const int4* desc = reinterpret_cast<const int4*>(blob + e[3]);
         const int4* rec2 = reinterpret_cast<const int4*>(blob + e[3] + 4 * n);
         int4 d = make_int4(0, 0, 0, 0);
-        if (valid) d = desc[slot];
-        const int i = d.w;
+        if (valid) d = desc[i];
         const int len = d.y - d.x;
         const int lmin = min(len, __shfl_xor_sync(kFull, len, 16)), lmax = max(len, __shfl_xor_sync(kFull, len, 16));
         const unsigned char* pbase = s_p + (size_t)e[1] * 256;

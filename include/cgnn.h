@@ -88,8 +88,7 @@ typedef struct {
    * layer entry points then run their generic kernels).  One 16-byte aligned blob per subject and direction, at
    * word offset 8*first_row + 2*(first_edge rounded up to even) + 4*subject inside the buffer:
    *   [rows x int4 {rec_begin, rec_end, aux bits, row}] [records int2 {neighbour, weight bits}]
-   * Descriptors are sorted by ascending record count (ties by row; `row` says which row a descriptor stands for) so
-   * that rows walked in lock step have equal lengths.  Every row's record list is padded to an even length with
+   * Descriptor k stands for row k.  Every row's record list is padded to an even length with
    * zero-weight records; agg_kind 0 (GCN) carries the normalised weights w^ and ends every row with the self-loop
    * record {row, dinv^2} (reference models.py:98-100 puts self-loops last); agg_kind 1 (GraphSAGE) carries w with
    * aux = w_sum by destination, and w / (w_sum[dst] + 1e-8) by source (the adjoint of models.py:146-149).
