@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ActT, BnBwdT, CsrT, StoreT
+from ._lib import ActT, BnBwdT, CsrT, EvalLayerT, StoreT
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -217,6 +217,34 @@ class Engine:
         keep: list = []
         self._call_csr(f"cgnn_{kind}_layer_fwd", csr, build)
         return z, stats, agg
+
+    # -- K9 -------------------------------------------------------------------------------------
+    def eval_fused(self, kind: str, x, layers, head, csr, ptr, num_graphs: int, want_logits: bool = True):
+        """The whole eval-mode network in one kernel.  ``layers`` = [(W, bias, gamma, beta, running_mean, running_var,
+        eps), ...], ``head`` = (W0, b0, W1, b1).  Returns (emb, logits), or None when the shape is not covered (the
+        caller then runs the per-layer entry points)."""
+        rows, F = x.shape
+        H = layers[0][0].shape[0]
+        W0, b0, W1, b1 = head
+        M, K = W0.shape[0], W1.shape[0]
+        if kind != "gcn" or num_graphs == 0 or rows == 0:
+            return None
+        self.ensure_agg(csr, kind, num_graphs, rows, csr.num_edges, need_out=False)
+        arr = (EvalLayerT * len(layers))()
+        for i, (W, b, g, be, rm, rv, eps) in enumerate(layers):
+            arr[i] = EvalLayerT(_p(W), _p(b), _p(g), _p(be), _p(rm), _p(rv), float(eps))
+        emb = self.empty((num_graphs, H))
+        logits = self.empty((num_graphs, K)) if want_logits else None
+        cs = self.csr_struct(csr, kind)
+        try:
+            self._call("cgnn_eval_fused_fwd", Engine.KINDS[kind], _p(x), F, arr, len(layers), H, _p(W0), _p(b0), _p(W1), _p(b1),
+                       M, K, C.byref(cs), _p(ptr), num_graphs, rows, csr.max_nodes, csr.max_edges, _p(emb), _p(logits),
+                       _p(self.workspace), self.workspace_bytes, self.stream())
+        except _lib.CgnnError as e:
+            if e.status == _lib.ERR_UNSUPPORTED:
+                return None
+            raise
+        return emb, logits
 
     def project_tf32x3(self, X, W):
         """P = X W^T on the tensor cores (3xTF32, fp32-grade)."""

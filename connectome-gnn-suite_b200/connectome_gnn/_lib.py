@@ -45,6 +45,12 @@ class BnBwdT(C.Structure):
     ]
 
 
+class EvalLayerT(C.Structure):
+    """``cgnn_eval_layer_t``"""
+    _fields_ = [("W", C.c_void_p), ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("eps", C.c_float)]
+
+
 class StoreT(C.Structure):
     """``cgnn_store_t``"""
     _fields_ = [
@@ -74,6 +80,8 @@ PROTOTYPES = {
                                      _p, _sz, _p]),
     "cgnn_sage_layer_fwd": (C.c_int, [_p, _P(ActT), _p, _p, _P(CsrT), _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p,
                                       _p, _p, _sz, _p]),
+    "cgnn_eval_fused_fwd": (C.c_int, [_i32, _p, _i32, _P(EvalLayerT), _i32, _i32, _p, _p, _p, _p, _i32, _i32, _P(CsrT), _p,
+                                      _i64, _i64, _i32, _i32, _p, _p, _p, _sz, _p]),
     "cgnn_project_tf32x3": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p]),
     "cgnn_bn_merge_stats": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "cgnn_bn_finalize": (C.c_int, [_p, _p, _p, _i32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -101,6 +109,7 @@ class CgnnError(RuntimeError):
 
 
 ERR_NEED_CSR = 5   # a lean batch met a code path that reads the CSR arrays
+ERR_UNSUPPORTED = 6   # cgnn_eval_fused_fwd does not cover the shape
 
 
 def bind(path: str) -> C.CDLL:

@@ -261,6 +261,7 @@ class _ConnectomeClassifier(nn.Module):
             nn.Linear(hidden_dim // 2, num_classes),
         )
         self.process_group = None   # torch.distributed group for SyncBN statistics (None = default)
+        self.fused_eval = True      # inference runs cgnn_eval_fused_fwd where it applies (False: always layer by layer)
 
     # -- plumbing --------------------------------------------------------------------------
     def _ready(self, batch: ConnectomeBatch) -> ConnectomeBatch:
@@ -286,15 +287,42 @@ class _ConnectomeClassifier(nn.Module):
             params += [*conv.tensors(), bn.weight, bn.bias]
         return _EncodeFn.apply(cfg, batch.node_features, *params)
 
+    def _fused_eval(self, batch: ConnectomeBatch, want_logits: bool):
+        """Inference fast path (``cgnn_eval_fused_fwd``): eval mode, no autograd graph wanted - the whole network, readout
+        and head in ONE kernel, activations never leave the SM.  None when not applicable / not covered."""
+        if not self.fused_eval or self.training or (torch.is_grad_enabled() and (batch.node_features.requires_grad or
+                                                          any(p.requires_grad for p in self.parameters()))):
+            return None
+        layers = []
+        for conv, bn in zip(self.convs, self.batch_norms):
+            W, b = conv.tensors()
+            if bn.running_mean is None or bn.running_var is None:
+                return None
+            layers.append((W.detach().contiguous(), b.detach().contiguous(),
+                           None if bn.weight is None else bn.weight.detach().contiguous(),
+                           None if bn.bias is None else bn.bias.detach().contiguous(),
+                           bn.running_mean.contiguous(), bn.running_var.contiguous(), bn.eps))
+        fc0, fc1 = self.classifier[0], self.classifier[3]
+        head = tuple(t.detach().contiguous() for t in (fc0.weight, fc0.bias, fc1.weight, fc1.bias))
+        eng = _engine.engine_for(batch.node_features)
+        return eng.eval_fused(self.kind, batch.node_features.contiguous(), layers, head, batch.csr, batch.ptr,
+                              batch.num_graphs, want_logits)
+
     # -- public API ------------------------------------------------------------------------
     def encode(self, batch: ConnectomeBatch) -> torch.Tensor:
         """Graph-level embeddings ``[B, hidden_dim]``."""
         batch = self._ready(batch)
+        fused = self._fused_eval(batch, want_logits=False)
+        if fused is not None:
+            return fused[0]
         return self._encode(batch, self._cfg(batch))
 
     def forward(self, batch: ConnectomeBatch) -> torch.Tensor:
         """Class logits ``[B, num_classes]``."""
         batch = self._ready(batch)
+        fused = self._fused_eval(batch, want_logits=True)
+        if fused is not None:
+            return fused[1]
         cfg = self._cfg(batch)
         emb = self._encode(batch, cfg)
         fc0, fc1 = self.classifier[0], self.classifier[3]

@@ -20,25 +20,10 @@
 //                               lanes, records two at a time; write z (coalesced), BatchNorm statistics
 //
 // Only t_in, the records and z cross HBM.  The same sources run on the test-only simulator (ws.cuh).
-#include "agg.cuh"
-#include "ws.cuh"
+#include "engine.cuh"
 
 namespace cgnn {
 namespace eng {
-
-constexpr int kC = 64;                    // channels in and out
-constexpr int kTR = 128;                  // rows per tile (MMA M)
-constexpr int kMaxTiles = 3;              // tiles per unit
-constexpr int kMaxUnitRows = kTR * kMaxTiles;
-constexpr int kMaxSub = 16;               // subjects per unit
-constexpr int kStageBytes = kTR * 128;    // one box: 128 rows x 32 channels
-constexpr int kNS = 2;                    // staging slots (slot = channel half)
-constexpr int kWarpTile = 0, kWarpMma = 1, kWarpAlloc = 2, kWarpBlob = 3;
-constexpr int kConvWarp0 = 4, kConvWarps = 8, kGathWarp0 = 12, kGathWarps = 16;
-constexpr int kNT = 32 * (kGathWarp0 + kGathWarps);
-constexpr int kGathThreads = 32 * kGathWarps;
-constexpr uint32_t kColAHi = 0, kColALo = 64, kColD = 128, kTmemCols = 512;
-constexpr int kTabInts = 8 + 8 * kMaxSub;   // header + per-subject records of the unit table
 
 struct Args {
   Act act;
@@ -50,52 +35,8 @@ struct Args {
   int nblob;               // 1 or 2 blob buffers
   float* z; double* partials;
   int o_stage, o_p, o_blob, o_const, o_tab;   // byte offsets from the 1024-aligned base (W operands at 0)
+  __host__ __device__ UnitSrc src() const { return UnitSrc{meta, B, spu, blob_cap_bytes}; }
 };
-
-struct Barriers {
-  uint64_t stage_full[kNS], stage_free[kNS];
-  uint64_t a_full[2], a_free[2];
-  uint64_t d_full[kMaxTiles], d_free[kMaxTiles];
-  uint64_t blob_full[2], blob_free[2];
-};
-
-// geometry of unit u, from the per-subject records {first row, rows, first edge, edges}
-struct Unit {
-  long long g0; int nsub;
-  long long row0; int rows, tiles;
-  long long blob_word0; int blob_bytes;
-};
-__device__ __forceinline__ Unit unit_geom(const Args& p, long long u) {
-  Unit r;
-  r.g0 = u * p.spu;
-  long long g1 = r.g0 + p.spu;
-  if (g1 > p.B) g1 = p.B;
-  r.nsub = (int)(g1 - r.g0);
-  const int4* meta = reinterpret_cast<const int4*>(p.meta);
-  const int4 m0 = meta[r.g0], m1 = meta[g1 - 1];
-  r.row0 = m0.x;
-  r.rows = m1.x + m1.y - m0.x;
-  if (r.rows > kMaxUnitRows) r.rows = kMaxUnitRows;       // host contract; never index past the tiles
-  r.tiles = (r.rows + kTR - 1) / kTR;
-  r.blob_word0 = agg_base_words(m0.x, m0.z, r.g0);
-  const long long end = agg_base_words(m1.x, m1.z, g1 - 1) + ((agg_copy_words(m1.y, m1.w) + 3) & ~3);
-  long long bytes = (end - r.blob_word0) * 4;
-  if (bytes > p.blob_cap_bytes) bytes = p.blob_cap_bytes;
-  r.blob_bytes = (int)bytes;
-  return r;
-}
-
-// keep bits of channel quad `quad` at a row (same stream as common.cuh::drop_keep)
-__device__ __forceinline__ uint32_t keep4(const Act& a, uint32_t row_hash, int quad) {
-  const uint32_t w0 = fmix32(row_hash + (uint32_t)quad * 0x632BE5ABu + a.k1), w1 = drop_second_word(w0);
-  return ((w0 & 0xffffu) >= a.thresh ? 1u : 0u) | ((w0 >> 16) >= a.thresh ? 2u : 0u) | ((w1 & 0xffffu) >= a.thresh ? 4u : 0u) |
-         ((w1 >> 16) >= a.thresh ? 8u : 0u);
-}
-
-// byte offset of 16-byte chunk c (0..15) of row `prow` of the P tile; `key` = the row's index inside its subject
-__device__ __forceinline__ uint32_t p_chunk_offset(int prow, int key, int c) {
-  return (uint32_t)(prow * 256 + ((((c ^ key) & 7) | (c & 8)) << 4));
-}
 
 __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ ws::TensorMap tmap, Args p) {
 #ifdef CGNN_EMU
@@ -153,7 +94,7 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
     if (lane == 0) {
       uint32_t tcount = 0;     // tiles issued so far: slot h of tile k is in its k-th use
       for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
-        const Unit un = unit_geom(p, u);
+        const Unit un = unit_geom(p.src(), u);
         for (int t = 0; t < un.tiles; ++t, ++tcount)
           for (int h = 0; h < 2; ++h) {
             ws::mbar_wait_relaxed(&bars.stage_free[h], (tcount & 1u) ^ 1u);
@@ -167,7 +108,7 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
     if (lane == 0) {
       uint32_t ucount = 0;
       for (long long u = blockIdx.x; u < p.units; u += gridDim.x, ++ucount) {
-        const Unit un = unit_geom(p, u);
+        const Unit un = unit_geom(p.src(), u);
         const uint32_t b = ucount % (uint32_t)p.nblob, use = ucount / (uint32_t)p.nblob;
         ws::mbar_wait_relaxed(&bars.blob_free[b], (use & 1u) ^ 1u);
         ws::mbar_arrive_expect_tx(&bars.blob_full[b], (uint32_t)un.blob_bytes);
@@ -181,7 +122,7 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
       const uint64_t b_hi = ws::smem_desc_sw128(ws::smem_u32(w_hi)), b_lo = ws::smem_desc_sw128(ws::smem_u32(w_lo));
       uint32_t tcount = 0, uses[kMaxTiles] = {0, 0, 0};
       for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
-        const Unit un = unit_geom(p, u);
+        const Unit un = unit_geom(p.src(), u);
         for (int t = 0; t < un.tiles; ++t, ++tcount) {
           ws::mbar_wait_relaxed(&bars.d_free[t], (uses[t] & 1u) ^ 1u);     // the gather warps have drained this slot's previous tile
           ++uses[t];
@@ -211,7 +152,7 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
     const bool affine = p.act.scale != nullptr;
     uint32_t tcount = 0;
     for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
-      const Unit un = unit_geom(p, u);
+      const Unit un = unit_geom(p.src(), u);
       for (int t = 0; t < un.tiles; ++t, ++tcount) {
         ws::mbar_wait_relaxed(&bars.stage_full[h], tcount & 1u);
         float4 v[8];
@@ -276,7 +217,7 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
     // unit table: header {rows, nsub, groups, tiles, row0 lo, row0 hi, -, -}, then per subject
     // {first row in the tiles, first row in P (8-aligned), rows, blob word offset, first flat pair index, -, -, -}
     auto build_table = [&](long long u, int* tab) {
-      const Unit un = unit_geom(p, u);
+      const Unit un = unit_geom(p.src(), u);
       const int4* meta = reinterpret_cast<const int4*>(p.meta);
       int4 m = make_int4(0, 0, 0, 0);
       if (lane < un.nsub) m = meta[un.g0 + lane];

@@ -123,6 +123,7 @@ const char* cgnn_status_string(int status) {
     case CGNN_ERR_WORKSPACE: return "workspace too small";
     case CGNN_ERR_CUDA: return "CUDA runtime error";
     case CGNN_ERR_NEED_CSR: return "lean batch: this code path needs the CSR arrays";
+    case CGNN_ERR_UNSUPPORTED: return "shape not covered by the fused entry point";
     default: return "unknown status";
   }
 }

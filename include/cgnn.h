@@ -37,8 +37,9 @@ typedef enum {
   CGNN_ERR_TILE_TOO_LARGE = 2,  /* one subject's [N_g, C] fp32 tile (or W) exceeds shared memory */
   CGNN_ERR_WORKSPACE = 3,       /* workspace too small: call cgnn_workspace_bytes()          */
   CGNN_ERR_CUDA = 4,            /* a CUDA runtime call failed: see cgnn_last_cuda_error()     */
-  CGNN_ERR_NEED_CSR = 5         /* a lean batch (blobs only) met a code path that reads the CSR arrays: materialise
+  CGNN_ERR_NEED_CSR = 5,        /* a lean batch (blobs only) met a code path that reads the CSR arrays: materialise
                                  * them (full cgnn_collate_csr / cgnn_csr_from_coo) and call again                */
+  CGNN_ERR_UNSUPPORTED = 6      /* cgnn_eval_fused_fwd: shape not covered - use the per-layer entry points         */
 } cgnn_status;
 
 const char* cgnn_status_string(int status);
@@ -222,6 +223,29 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
                         const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
                         int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, double* bn_stats,
                         float* agg, void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
+
+/* ---- K9: the whole eval-mode network in one kernel (reference train.py:56-68 forward; models.py:203-216 with
+ * BatchNorm1d in eval mode and dropout off).  A unit - one subject, or several small ones - goes through all layers,
+ * the mean-pool readout (models.py:57-59) and the MLP head (models.py:196-201) without its activations leaving the SM:
+ * per subject HBM sees 4 N F bytes of node features, the packed in-edge records of csr->agg_in and the outputs.
+ * kind 0 = GCN (hidden width 64, 2..4 layers, F <= 8, subjects of <= 384 nodes); anything else returns
+ * CGNN_ERR_UNSUPPORTED and the caller runs the per-layer entry points.  emb [B, H] and / or logits [B, K] (either may be
+ * NULL).  Results agree with the per-layer path to fp32 round-off and do not depend on how subjects are batched.
+ * workspace: (L - 1) * 32768 + 1024 L bytes, 16-byte aligned. */
+typedef struct {
+  const float* W;             /* GCN [H, d_in] (layer 0: d_in = num_features) */
+  const float* bias;          /* [H] */
+  const float* gamma;         /* BatchNorm1d after the layer: weight, bias, running_mean, running_var [H], eps */
+  const float* beta;
+  const float* running_mean;
+  const float* running_var;
+  float eps;
+} cgnn_eval_layer_t;
+int cgnn_eval_fused_fwd(int32_t kind, const float* x, int32_t num_features, const cgnn_eval_layer_t* layers,
+                        int32_t num_layers, int32_t H, const float* W0, const float* b0, const float* W1, const float* b1,
+                        int32_t M, int32_t K, const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
+                        int32_t max_nodes, int32_t max_edges, float* emb, float* logits, void* workspace,
+                        size_t workspace_bytes, cgnn_stream_t stream);
 
 /* ---- K10: the dense contraction on tensor cores ---------------------------------------------
  * P[rows, N] = X[rows, K] W[N, K]^T (reference models.py:111 `self.linear(x)`), fp32-grade: three TF32

@@ -285,3 +285,45 @@ def check_lean_collate(device, kind="gcn"):
     assert lean.csr.is_full()
     for f in lean.csr._ARRAYS + ("graph_meta", "eptr"):
         assert torch.equal(getattr(lean.csr, f), getattr(full.csr, f)), f
+
+
+def check_fused_eval(device, layers=3, sizes=(84, 84, 360, 30, 84, 57, 84, 84, 130)):
+    """cgnn_eval_fused_fwd (the whole eval-mode network in one kernel) against the layer-by-layer path: logits and
+    embeddings within 1e-6 max-norm relative, and bit-identical for every subject however the batch is split."""
+    from connectome_gnn import _lib
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome
+    from connectome_gnn.synthetic import generate_connectome
+    graphs = [generate_connectome(num_regions=n, seed=100 + s) for s, n in enumerate(sizes)]
+    store = SubjectStore(pack_graphs(graphs), device)
+    torch.manual_seed(3)
+    m = GCNConnectome(in_channels=5, hidden_dim=64, num_classes=2, num_layers=layers, dropout=0.3).to(device)
+    with torch.no_grad():                       # non-trivial BatchNorm statistics
+        for bn in m.batch_norms:
+            bn.running_mean.normal_(0.0, 0.05)
+            bn.running_var.uniform_(0.8, 1.2)
+            bn.weight.normal_(1.0, 0.1)
+            bn.bias.normal_(0.0, 0.1)
+    m.eval()
+    ids = np.arange(len(graphs))
+    lib = _lib.load() if torch.device(device).type == "cuda" else None
+    with torch.no_grad():
+        batch = store.collate(ids, prepare_for="gcn", backward=False)
+        before = lib.cgnn_kernel_launches() if lib else 0
+        fused_logits, fused_emb = m(batch), m.encode(batch)
+        if lib:   # two launches per call: the weight / affine preparation and the fused kernel
+            assert lib.cgnn_kernel_launches() - before == 4
+        m.fused_eval = False
+        ref_logits, ref_emb = m(store.collate(ids, prepare_for="gcn")), m.encode(store.collate(ids, prepare_for="gcn"))
+        m.fused_eval = True
+        helpers.assert_close(fused_logits, ref_logits, "fused eval logits vs layer by layer", tol=1e-6)
+        helpers.assert_close(fused_emb, ref_emb, "fused eval embeddings vs layer by layer", tol=1e-6)
+        # any split, any order: every subject's logits are the same bits
+        n_s = len(ids)
+        for part in (ids[::-1].copy(), ids[: n_s // 2], ids[n_s // 2:], np.array([2]), np.array([n_s - 1, 2, n_s // 2])):
+            out = m(store.collate(part, prepare_for="gcn", backward=False))
+            assert torch.equal(out, fused_logits[torch.from_numpy(part).to(out.device)]), part
+    # a call that wants gradients takes the differentiable path
+    m.zero_grad()
+    m(store.collate(ids, prepare_for="gcn")).sum().backward()
+    assert all(p.grad is not None for p in m.parameters())

@@ -182,3 +182,9 @@ def test_ws_engine_dropout_matches_generic_kernels(on_emu):
 def test_lean_collate(on_emu):
     # hidden 64: the GCN hidden layers run on the warp-specialised engine, which never reads the CSR arrays
     parity.check_lean_collate("cpu", "gcn")
+
+
+@pytest.mark.parametrize("layers", [2, 3, 4])
+def test_fused_eval(on_emu, layers):
+    """K9 on the simulator: ring / weight-reload / readout protocol for 2, 3 and 4 layers, mixed subject sizes."""
+    parity.check_fused_eval("cpu", layers, sizes=(84, 30, 130, 57, 84, 200))

@@ -439,6 +439,11 @@ def test_pair_store_collates_identically():
     assert torch.equal(c.edge_index, d.edge_index) and torch.equal(c.csr.in_wn, d.csr.in_wn)
 
 
+@pytest.mark.parametrize("layers", [2, 3, 4])
+def test_fused_eval(layers):
+    parity.check_fused_eval(DEV, layers)
+
+
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_lean_collate(kind):
     parity.check_lean_collate(DEV, kind)
