@@ -435,9 +435,10 @@ int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, 
   off = (off + 15) & ~(size_t)15;
   a.o_blob = (int)off;
   const size_t tail = (size_t)3 * kC * 4 + (size_t)2 * kTabInts * 4 + 32;
+  const size_t limit = (size_t)dev.smem_optin - kStaticSmem;       // the kernel's static shared memory counts too
   int nblob = 2;
-  if (off + 2 * blob_cap + tail + 1024 > (size_t)dev.smem_optin) nblob = 1;
-  if (off + (size_t)nblob * blob_cap + tail + 1024 > (size_t)dev.smem_optin) return -1;
+  if (off + 2 * blob_cap + tail + 1024 > limit) nblob = 1;
+  if (off + (size_t)nblob * blob_cap + tail + 1024 > limit) return -1;
   a.nblob = nblob;
   a.blob_cap_bytes = (int)blob_cap;
   off += (size_t)nblob * blob_cap;

@@ -20,6 +20,7 @@ constexpr int kNT = 32 * (kGathWarp0 + kGathWarps);
 constexpr int kGathThreads = 32 * kGathWarps;
 constexpr uint32_t kColAHi = 0, kColALo = 64, kColD = 128, kTmemCols = 512;
 constexpr int kTabInts = 8 + 8 * kMaxSub;   // header + per-subject records of the unit table
+constexpr size_t kStaticSmem = 1024;        // barriers + tensor-memory address, rounded up by the alignment of the dynamic part
 
 
 struct Barriers {

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_eval_fused(Args p) {
   float* s_x = reinterpret_cast<float*>(base + p.o_x);          // [unit rows][8]
   float* s_pool = reinterpret_cast<float*>(base + p.o_pool);    // [subjects][16 warps][64]
   float* s_b1 = reinterpret_cast<float*>(base + p.o_const);     // [64]
-  float* s_w1 = s_b1 + kC;                                      // [64][8]
+  float* s_w1 = s_b1 + kC;                                      // [8][64]: W1 transposed (input channel major)
   float* s_hb = s_w1 + kC * kFeat;                              // [L - 1][64]
   float* s_aff = s_hb + (kMaxLayers - 1) * kC;                  // [L][2][64]
   float* s_head = reinterpret_cast<float*>(base + p.o_head);    // W0 [M][64], b0 [M], Wc [K][M], bc [K], then [16 warps][64 + M]
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_eval_fused(Args p) {
     ws::fence_mbar_init();
   }
   for (int c = tid; c < kC; c += kNT) s_b1[c] = p.b1 ? p.b1[c] : 0.0f;
-  for (int i = tid; i < kC * kFeat; i += kNT) { const int c = i >> 3, k = i & 7; s_w1[i] = k < p.F ? p.W1[c * p.F + k] : 0.0f; }
+  for (int i = tid; i < kC * kFeat; i += kNT) { const int k = i >> 6, c = i & 63; s_w1[i] = k < p.F ? p.W1[c * p.F + k] : 0.0f; }
   for (int i = tid; i < NH * kC; i += kNT) s_hb[i] = p.hbias[i];
   for (int i = tid; i < L * 2 * kC; i += kNT) s_aff[i] = p.affine[i];
   if (p.logits) {
@@ -312,8 +312,30 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_eval_fused(Args p) {
             __syncwarp();
             if (lane == 0) ws::mbar_arrive(&bars.d_free[t]);
           }
-          ws::named_sync(1, kGathThreads);          // P is complete
+        } else {
+          // ---- first layer: P = x W1^T with plain FMAs (F <= 8 input channels), written like a drained tile ------------
+          // (reference models.py:111 projects first as well; the gather below is the one every layer shares)
+          float4 wq[kFeat];
+#pragma unroll
+          for (int k = 0; k < kFeat; ++k) wq[k] = *reinterpret_cast<const float4*>(s_w1 + k * kC + 4 * cl);
+          for (int j = 0; j < nsub; ++j) {
+            const int* e = tab + 8 + 8 * j;
+            const int n = e[2];
+            for (int i = 2 * gw + half; i < n; i += 2 * kGathWarps) {
+              const float* xr = s_x + (size_t)(e[0] + i) * kFeat;
+              const float4 xa = *reinterpret_cast<const float4*>(xr), xb = *reinterpret_cast<const float4*>(xr + 4);
+              const float xv[kFeat] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int k = 0; k < kFeat; ++k) {
+                o.x = fmaf(xv[k], wq[k].x, o.x); o.y = fmaf(xv[k], wq[k].y, o.y);
+                o.z = fmaf(xv[k], wq[k].z, o.z); o.w = fmaf(xv[k], wq[k].w, o.w);
+              }
+              *reinterpret_cast<float4*>(s_p + p_chunk_offset(e[1] + i, i, cl)) = o;
+            }
+          }
         }
+        ws::named_sync(1, kGathThreads);            // P is complete
         const float4 bq = l == 0 ? b1q : *reinterpret_cast<const float4*>(s_hb + (l - 1) * kC + 4 * cl);
         const float4 scq = *reinterpret_cast<const float4*>(s_aff + (2 * l) * kC + 4 * cl);
         const float4 shq = *reinterpret_cast<const float4*>(s_aff + (2 * l + 1) * kC + 4 * cl);
@@ -345,35 +367,7 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_eval_fused(Args p) {
             const int lmax = max(len, __shfl_xor_sync(kFull, len, 16));
             const int4* rp = rec2 + (d.x >> 1);
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (l == 0) {
-              float ax[kFeat];
-#pragma unroll
-              for (int k = 0; k < kFeat; ++k) ax[k] = 0.0f;
-              const float* xb = s_x + (size_t)e[0] * kFeat;
-#pragma unroll 1
-              for (int k = 0; k < lmax; k += 2, ++rp) {
-                int4 r = make_int4(0, 0, 0, 0);
-                if (k < len) r = *rp;
-                const float* x0 = xb + (size_t)agg_rec_row(r.x) * kFeat;
-                const float* x1 = xb + (size_t)agg_rec_row(r.z) * kFeat;
-                const float4 u0 = *reinterpret_cast<const float4*>(x0), u1 = *reinterpret_cast<const float4*>(x0 + 4);
-                const float4 v0 = *reinterpret_cast<const float4*>(x1), v1 = *reinterpret_cast<const float4*>(x1 + 4);
-                const float w0 = __int_as_float(r.y), w1 = __int_as_float(r.w);
-                ax[0] = fmaf(u0.x, w0, ax[0]); ax[1] = fmaf(u0.y, w0, ax[1]); ax[2] = fmaf(u0.z, w0, ax[2]); ax[3] = fmaf(u0.w, w0, ax[3]);
-                ax[4] = fmaf(u1.x, w0, ax[4]); ax[5] = fmaf(u1.y, w0, ax[5]); ax[6] = fmaf(u1.z, w0, ax[6]); ax[7] = fmaf(u1.w, w0, ax[7]);
-                ax[0] = fmaf(v0.x, w1, ax[0]); ax[1] = fmaf(v0.y, w1, ax[1]); ax[2] = fmaf(v0.z, w1, ax[2]); ax[3] = fmaf(v0.w, w1, ax[3]);
-                ax[4] = fmaf(v1.x, w1, ax[4]); ax[5] = fmaf(v1.y, w1, ax[5]); ax[6] = fmaf(v1.z, w1, ax[6]); ax[7] = fmaf(v1.w, w1, ax[7]);
-              }
-              float z[4] = {0.f, 0.f, 0.f, 0.f};      // z[jj] = sum_k a[k] W1[4 cl + jj][k]
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const float4 wa = *reinterpret_cast<const float4*>(s_w1 + (4 * cl + jj) * kFeat);
-                const float4 wb = *reinterpret_cast<const float4*>(s_w1 + (4 * cl + jj) * kFeat + 4);
-                z[jj] = fmaf(ax[0], wa.x, z[jj]); z[jj] = fmaf(ax[1], wa.y, z[jj]); z[jj] = fmaf(ax[2], wa.z, z[jj]); z[jj] = fmaf(ax[3], wa.w, z[jj]);
-                z[jj] = fmaf(ax[4], wb.x, z[jj]); z[jj] = fmaf(ax[5], wb.y, z[jj]); z[jj] = fmaf(ax[6], wb.z, z[jj]); z[jj] = fmaf(ax[7], wb.w, z[jj]);
-              }
-              a = make_float4(z[0], z[1], z[2], z[3]);
-            } else {
+            {
               const int lmin = min(len, __shfl_xor_sync(kFull, len, 16));
               const unsigned char* pbase = s_p + (size_t)e[1] * 256;
               int k = 0;
@@ -445,7 +439,7 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_eval_fused(Args p) {
       // ---- mean-pool readout and MLP head: one warp per subject ------------------------------------------------------
       {
         const float* w0 = s_head; const float* b0 = w0 + M * kC; const float* wc = b0 + M; const float* bc = wc + K * M;
-        float* my = s_head + M * kC + M + K * M + K + (size_t)gw * (kC + kHeadMaxM);    // [64] emb, [M] hidden
+        float* my = s_head + M * kC + M + K * M + K + (size_t)gw * (kC + M);    // [64] emb, [M] hidden
         for (int j = gw; j < nsub; j += kGathWarps) {
           const float inv = 1.0f / ((float)tab[8 + 8 * j + 2] + 1e-8f);          // reference models.py:40-47: sum / (count + 1e-8)
           for (int c = lane; c < kC; c += 32) {
@@ -533,14 +527,15 @@ int launch_eval_fused(int kind, const float* x, int F, const cgnn_eval_layer_t* 
     off = (off + 15) & ~(size_t)15;
     a.o_pool = (int)off; off += (size_t)spu * kGathWarps * kC * 4;
     a.o_const = (int)off; off += (size_t)(kC + kC * kFeat + (kMaxLayers - 1) * kC + kMaxLayers * 2 * kC) * 4;
-    a.o_head = (int)off; off += (size_t)(M * kC + M + K * M + K + kGathWarps * (kC + kHeadMaxM)) * 4;
+    a.o_head = (int)off; off += (size_t)(M * kC + M + K * M + K + kGathWarps * (kC + M)) * 4;
     off = (off + 15) & ~(size_t)15;
     a.o_tab = (int)off; off += (size_t)2 * kTabInts * 4;
     off = (off + 15) & ~(size_t)15;
     a.o_blob = (int)off;
+    const size_t limit = (size_t)dev.smem_optin - kStaticSmem;     // the kernel's static shared memory counts too
     int nblob = 2;
-    if (off + 2 * blob_cap + 1024 > (size_t)dev.smem_optin) nblob = 1;
-    if (off + (size_t)nblob * blob_cap + 1024 > (size_t)dev.smem_optin) continue;
+    if (off + 2 * blob_cap + 1024 > limit) nblob = 1;
+    if (off + (size_t)nblob * blob_cap + 1024 > limit) continue;
     a.nblob = nblob; a.blob_cap_bytes = (int)blob_cap;
     smem = off + (size_t)nblob * blob_cap + 1024;
     break;

@@ -88,19 +88,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { tc::mbar_wait(bar, parity); }
-// for roles that are ahead of the critical path most of the time (producers, converters, the MMA issuer): sleep
-// between polls so that the spinning does not take issue slots from the gather warps
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-  while (!done) {
-    __nanosleep(100);
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-  }
-}
+// (a poll loop with __nanosleep between the try_waits was measured in the fused eval kernel: 400 M of its 680 M warp
+// instructions were the sleeping loop and every hand-over gained its latency; the plain try_wait suspends in hardware)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { tc::mbar_wait(bar, parity); }
 __device__ __forceinline__ void fence_proxy_async() { tc::fence_proxy_async(); }
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
