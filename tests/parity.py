@@ -305,6 +305,7 @@ def check_fused_eval(device, layers=3, sizes=(84, 84, 360, 30, 84, 57, 84, 84, 1
             bn.weight.normal_(1.0, 0.1)
             bn.bias.normal_(0.0, 0.1)
     m.eval()
+    m.fused_eval = True
     ids = np.arange(len(graphs))
     lib = _lib.load() if torch.device(device).type == "cuda" else None
     with torch.no_grad():
