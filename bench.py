@@ -177,26 +177,96 @@ def cpu_legs(a, graphs, steps, warmup, device=None, sample_size=None):
     return len(a.legs) * len(sample) / step_s, {leg: len(sample) / s for leg, s in leg_s.items()}, step_s
 
 
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+PKG_DIR = os.path.join(ROOT, "connectome-gnn-suite_b200")
+
+
+def reference_legs(a, steps, warmup):
+    """Times the UNMODIFIED reference (oracle/_ref, copied from /root/reference by oracle/make_ref.py): its own
+    generate_dataset, ConnectomeDataLoader, GCNConnectome / GraphSAGEConnectome and Trainer.train_epoch / evaluate on the
+    host cores, one batch of `cpu_sample` subjects per leg and step.  Only called in a process that has not imported
+    this repo's package (the two share the name `connectome_gnn`)."""
+    sys.path[:] = [q for q in sys.path if os.path.abspath(q or ".") != PKG_DIR]
+    sys.path.insert(0, REF_DIR)
+    import connectome_gnn as ref
+    assert os.path.abspath(ref.__file__).startswith(REF_DIR), ref.__file__
+    graphs = ref.generate_dataset(num_subjects=a.cpu_sample, num_regions=a.regions, k=8, beta=0.15, trait_idx=0, seed=42)
+    torch.manual_seed(0)
+    trainers = {}
+    for kind, cls in (("gcn", ref.GCNConnectome), ("sage", ref.GraphSAGEConnectome)):
+        model = cls(in_channels=5, hidden_dim=a.hidden, num_classes=2, num_layers=a.layers, dropout=a.dropout)
+        trainers[kind] = ref.Trainer(model, torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4), device="cpu")
+    train_loader = ref.ConnectomeDataLoader(graphs, batch_size=len(graphs), shuffle=True)
+    eval_loader = ref.ConnectomeDataLoader(graphs, batch_size=len(graphs), shuffle=False)
+
+    def run(leg):
+        kind, mode = leg.split("_")
+        if mode == "train":
+            trainers[kind].train_epoch(train_loader)
+        else:
+            trainers[kind].evaluate(eval_loader)
+
+    per_leg = {leg: [] for leg in a.legs}
+    for it in range(warmup + steps):
+        for leg in a.legs:
+            t0 = time.perf_counter()
+            run(leg)
+            if it >= warmup:
+                per_leg[leg].append(time.perf_counter() - t0)
+    leg_s = {leg: float(np.mean(v)) for leg, v in per_leg.items()}
+    step_s = sum(leg_s.values())
+    return len(a.legs) * len(graphs) / step_s, {leg: len(graphs) / s_ for leg, s_ in leg_s.items()}, step_s
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return   # the CPU arm runs once per box
-    from connectome_gnn.synthetic import generate_dataset
-    graphs = generate_dataset(num_subjects=a.cpu_sample, num_regions=a.regions, seed=42)
+    # every host core, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     steps, warmup = max(1, a.steps), max(0, a.warmup)
-    value, legs, step_s = cpu_legs(a, graphs, steps, warmup)
-    cores = torch.get_num_threads()
-    sample = f"{a.cpu_sample} subjects per leg per step ({steps} steps after {warmup} warm-up), same shapes as the GPU arm"
+    if os.path.isdir(os.path.join(REF_DIR, "connectome_gnn")):
+        value, legs, step_s = reference_legs(a, steps, warmup)
+        kind = "reference"
+        what = "unmodified reference (oracle/_ref): Trainer.train_epoch / evaluate, one batch per leg"
+    else:   # the copy did not travel: the oracle port (same ATen op sequence, pinned to the reference bit for bit)
+        from connectome_gnn.synthetic import generate_dataset
+        graphs = generate_dataset(num_subjects=a.cpu_sample, num_regions=a.regions, seed=42)
+        value, legs, step_s = cpu_legs(a, graphs, steps, warmup)
+        kind = "port"
+        what = "oracle/port.py (the reference copy oracle/_ref is absent)"
+    sample = (f"{a.cpu_sample} subjects per leg per step ({steps} steps after {warmup} warm-up), same shapes as the GPU arm; "
+              f"graphs/s on the CPU does not depend on the batch size (BASELINE.md section 2); {what}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": a.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1), "legs": legs,
-        "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def reference_subprocess(a, steps=2, warmup=1):
+    """cpu_baseline leg of the sm_100a arm: the reference arm in a process of its own (this one has the B200 package
+    imported under the same module name), all host cores, bounded sample."""
+    import subprocess
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "LOCAL_RANK",
+                                                             "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup),
+           "--regions", str(a.regions), "--hidden", str(a.hidden), "--layers", str(a.layers), "--dropout", str(a.dropout),
+           "--cpu-sample", str(a.cpu_sample), "--legs", ",".join(a.legs)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    if out.returncode != 0 or not lines:
+        raise RuntimeError("reference arm failed: " + out.stderr[-300:])
+    line = json.loads(lines[-1])
+    cpu = line["cpu_baseline"]
+    cpu["legs"] = line["legs"]
+    return cpu
 
 
 # ---------------------------------------------------------------------------------------------
@@ -339,17 +409,27 @@ def run_b200(a):
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, cl, s = cpu_legs(a, pool, steps=2, warmup=1)
-        cpu = {"value": v, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port", "legs": cl,
-               "sample": f"{a.cpu_sample} subjects per leg per step (2 steps after 1 warm-up) of the same shapes",
-               "host_cpus": os.cpu_count()}
+        cpu = reference_subprocess(a, steps=2, warmup=1)
         try:     # the reference's op sequence as PyTorch eager kernels on this GPU (informational second baseline)
             n_eager = min(a.eager_sample, len(pool))
             ve, cle, _ = cpu_legs(a, pool, steps=2, warmup=1, device=dev, sample_size=n_eager)
             cpu["eager_cuda"] = {"value": ve, "unit": "graphs/s", "legs": cle,
                                  "sample": f"{n_eager} subjects per leg per step, host collate + .to(device) as the reference Trainer does"}
+            cpu["eager_cuda"]["step_only"] = eager_step_only(a, graphs, dev)
         except Exception as exc:   # never fail the bench line over the informational leg
-            cpu["eager_cuda"] = {"unavailable": repr(exc)[:200]}
+            cpu.setdefault("eager_cuda", {})["unavailable"] = repr(exc)[:200]
+
+    extra = {}
+    try:
+        extra["configs"] = extra_configs(a, world, rank, dev, lib)
+    except Exception as exc:
+        extra["configs"] = {"unavailable": repr(exc)[:300]}
+    dp = None
+    if world > 1:
+        try:
+            dp = dp_parity(a, world, rank, dev, pool)
+        except Exception as exc:
+            dp = {"unavailable": repr(exc)[:300]}
 
     if rank == 0:
         line = {
@@ -357,11 +437,189 @@ def run_b200(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": f"synthetic ({a.pool} unique generated subjects tiled to {a.batch}, generated in {gen_s:.1f}s)",
             "config": workload_config(a, world), "legs": legs, "clocks": clocks.summary(), "e2e": e2e,
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
         }
+        if dp is not None:
+            line["dp_parity"] = dp
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def eager_step_only(a, graphs, dev, subjects=2048):
+    """The reference's op sequence as PyTorch eager kernels on the GPU WITHOUT the host collate: the batch is collated and
+    moved once, then train steps (zero_grad, forward, loss, backward, Adam) and eval forwards are timed with CUDA events -
+    the bar SURVEY 2.1 names for the B200 (the eager path's own host-side collate caps it near 25 k graphs/s)."""
+    import torch.nn.functional as F
+    from oracle import port
+    n = min(subjects, len(graphs))
+    batch = port.collate(graphs[:n])
+    batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+    out = {"subjects": n}
+    for kind in ("gcn", "sage"):
+        torch.manual_seed(0)
+        mod = port.Module(kind, port.init_params(kind, 5, a.hidden, 2, a.layers), dropout=a.dropout).to(dev)
+        opt = torch.optim.Adam(mod.parameters(), lr=1e-3, weight_decay=1e-4)
+
+        def train():
+            mod.train()
+            opt.zero_grad()
+            F.cross_entropy(mod(batch), batch["labels"]).backward()
+            opt.step()
+
+        def infer():
+            mod.eval()
+            with torch.no_grad():
+                mod(batch)
+
+        for name, fn in (("train", train), ("infer", infer)):
+            fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            out[f"{kind}_{name}_graphs_per_s"] = n / (e0.elapsed_time(e1) / 3e3)
+        del mod, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_configs(a, world, rank, dev, lib):
+    """The other BASELINE configs that fit this run, so that the driver's record carries them:
+    configs[0] / [1]: batch 16, 84-node subjects, hidden 64 - device time of one training step and one inference step
+    (collate included) for both models; configs[4] (only under --gpus 8): GCN, hidden 256, 8192 subjects per GPU, SyncBN."""
+    import torch.distributed as dist
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import Trainer
+    out = {}
+    if rank == 0:
+        graphs = generate_dataset(num_subjects=16, num_regions=84, seed=42)
+        store = SubjectStore(pack_graphs(graphs), dev)
+        ids = np.arange(16)
+        rec = {}
+        for kind, cls in (("gcn", GCNConnectome), ("sage", GraphSAGEConnectome)):
+            torch.manual_seed(0)
+            model = cls(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.3).to(dev)
+            model.process_group = False     # single-process semantics even under torchrun (no collectives: rank 0 only)
+            tr = Trainer(model, torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True), device=dev)
+            tr.distributed = False
+
+            def train():
+                tr.model.train()
+                return tr.train_step(store.collate(ids, prepare_for=kind))
+
+            def infer():
+                tr.model.eval()
+                return tr.eval_step(store.collate(ids, prepare_for=kind, backward=False))[0]
+
+            for name, fn in (("train", train), ("infer", infer)):
+                for _ in range(10):
+                    fn()
+                torch.cuda.synchronize()
+                l0 = lib.cgnn_kernel_launches()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                e0.record()
+                for _ in range(50):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                wall = (time.perf_counter() - t0) / 50
+                us = e0.elapsed_time(e1) / 50 * 1e3
+                rec[f"{kind}_{name}"] = {"us_per_step": us, "graphs_per_s": 16 / (us * 1e-6), "host_us_per_step": wall * 1e6,
+                                         "cgnn_launches_per_step": (lib.cgnn_kernel_launches() - l0) / 50}
+        out["configs[0],[1]: batch 16, 84-node, hidden 64 (collate + step, device time)"] = rec
+    if world == 8:
+        graphs = generate_dataset(num_subjects=64, num_regions=360, seed=42)
+        per = 8192
+        store = SubjectStore(pack_graphs((graphs * (per // 64 + 1))[:per]), dev)
+        torch.manual_seed(1234)
+        model = GCNConnectome(in_channels=5, hidden_dim=256, num_classes=2, num_layers=3, dropout=0.3).to(dev)
+        tr = Trainer(model, torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True), device=dev)
+        meta = dict(row_base=rank * per * 360, graph_base=rank * per, global_num_graphs=per * world, global_num_nodes=per * world * 360)
+        ids = np.arange(per)
+
+        def step():
+            tr.model.train()
+            return tr.train_step(store.collate(ids, prepare_for="gcn", **meta))
+
+        for _ in range(2):
+            step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            step()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / 4], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        gps = per * world / (float(ms) / 1e3)
+        b = bytes_per_graph(360, 256, 3)["train"]
+        out["configs[4]: DP GCN, SyncBN, batch 65536, 360-node, hidden 256, 8 GPUs"] = {
+            "ms_per_step": float(ms), "graphs_per_s": gps, "roofline_frac": gps * b / 1e9 / (8 * 6545.6)}
+        del store, model, tr
+        torch.cuda.empty_cache()
+    return out
+
+
+def dp_parity(a, world, rank, dev, pool, per_rank=48):
+    """Numerical parity of the real NCCL path: one data-parallel training step (SyncBN statistics + their backward sums +
+    the flat gradient all-reduce, dropout 0) against the same global batch run by rank 0 alone.  Max-norm relative
+    differences of the loss, rank 0's logits and all gradients; the bar is 1e-5."""
+    import torch.distributed as dist
+    from connectome_gnn import models as models_mod
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.train import CrossEntropyLoss, Trainer
+    n_all = per_rank * world
+    graphs = (pool * (n_all // len(pool) + 1))[:n_all]
+    store = SubjectStore(pack_graphs(graphs), dev)
+    nodes = a.regions
+    out = {}
+    for kind, cls in (("gcn", GCNConnectome), ("sage", GraphSAGEConnectome)):
+        res = {}
+        for mode in ("dp", "single"):
+            if mode == "single" and rank != 0:
+                continue
+            torch.manual_seed(77)
+            model = cls(in_channels=5, hidden_dim=a.hidden, num_classes=2, num_layers=a.layers, dropout=0.0).to(dev).train()
+            loss_fn = CrossEntropyLoss()
+            if mode == "dp":
+                ids = np.arange(rank * per_rank, (rank + 1) * per_rank)
+                batch = store.collate(ids, prepare_for=kind, row_base=rank * per_rank * nodes, graph_base=rank * per_rank,
+                                      global_num_graphs=n_all, global_num_nodes=n_all * nodes)
+                logits = model(batch)
+                loss = loss_fn(logits, batch.labels, n_all)
+                loss.backward()
+                Trainer(model, torch.optim.SGD(model.parameters(), lr=0.0), device=dev)._sync_gradients()
+                total = loss.detach().clone()
+                dist.all_reduce(total)
+            else:
+                model.process_group = False          # no collectives: the whole batch in this process
+                batch = store.collate(np.arange(n_all), prepare_for=kind)
+                full = model(batch)
+                total = loss_fn(full, batch.labels, n_all)
+                total.backward()
+                logits, total = full[:per_rank], total.detach()
+            res[mode] = (float(total), logits.detach().clone(), torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone())
+        if rank == 0:
+            rel = lambda x, y: float((x.double() - y.double()).abs().max() / y.double().abs().max().clamp_min(1e-30))
+            out[kind] = {"loss": abs(res["dp"][0] - res["single"][0]) / max(abs(res["single"][0]), 1e-30),
+                         "logits": rel(res["dp"][1], res["single"][1]), "grads": rel(res["dp"][2], res["single"][2])}
+    if rank == 0:
+        worst = max(v for d in out.values() for v in d.values())
+        out["max"] = worst
+        out["ok"] = bool(worst <= 1e-5)
+        out["what"] = f"one DP train step over NCCL ({world} ranks x {per_rank} subjects, dropout 0) vs the same global batch on rank 0 alone"
+    dist.barrier()
+    return out
 
 
 def profile_calls(a, eng, step_fn, peak, peak_src):

@@ -43,7 +43,11 @@ FUSED_EVAL_MAX_ROWS = 2 * 148 * 384   # two units per SM: below this the per-lay
 # ---------------------------------------------------------------------------
 
 def _world(group=None) -> int:
+    """Ranks that share BatchNorm statistics; ``group=False`` (``model.process_group = False``) = this process alone,
+    whatever torch.distributed says (single-process semantics under a multi-process launcher)."""
     import torch.distributed as dist
+    if group is False:
+        return 1
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group)
     return 1
@@ -262,7 +266,7 @@ class _ConnectomeClassifier(nn.Module):
             nn.Dropout(dropout),
             nn.Linear(hidden_dim // 2, num_classes),
         )
-        self.process_group = None   # torch.distributed group for SyncBN statistics (None = default)
+        self.process_group = None   # torch.distributed group for SyncBN statistics (None = default, False = no collectives)
         # Inference path: "auto" runs cgnn_eval_fused_fwd (whole network in one kernel, two launches) when the batch is small
         # enough to be launch-latency bound - at most FUSED_EVAL_MAX_ROWS nodes - and layer by layer otherwise: a unit's
         # layers are serial inside the fused kernel, while the per-layer kernels overlap the phases of different units

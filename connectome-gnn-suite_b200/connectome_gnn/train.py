@@ -84,11 +84,15 @@ class Trainer:
         self.optimizer = optimizer
         self.device = dev
         self.loss_fn = CrossEntropyLoss()
+        self.distributed = True              # False: no collectives even when torch.distributed is initialised
+
+    def _world(self) -> int:
+        return _dist_world() if self.distributed else 1
 
     # -- data-parallel plumbing ------------------------------------------------------------
     def _sync_gradients(self) -> None:
         """One flat all-reduce(sum) of every parameter gradient (loss was pre-scaled by 1/B_global)."""
-        if _dist_world() == 1:
+        if self._world() == 1:
             return
         import torch.distributed as dist
         params = [p for p in self.model.parameters() if p.requires_grad]
@@ -141,7 +145,7 @@ class Trainer:
         for batch in loader:
             losses.append(self.train_step(batch))
             sizes.append(batch.global_num_graphs if batch.global_num_graphs is not None else batch.num_graphs)
-        if _dist_world() > 1 and losses:
+        if self._world() > 1 and losses:
             import torch.distributed as dist
             stacked = torch.stack(losses)
             dist.all_reduce(stacked)          # per-rank partial sums of nll / B_global -> global mean
@@ -162,7 +166,7 @@ class Trainer:
             losses.append(loss)
             corrects.append(correct_count)
             sizes.append(batch.global_num_graphs if batch.global_num_graphs is not None else batch.num_graphs)
-        if _dist_world() > 1 and losses:
+        if self._world() > 1 and losses:
             import torch.distributed as dist
             stacked = torch.stack([torch.stack(losses).double(), torch.stack(corrects).double()])
             dist.all_reduce(stacked)
