@@ -81,17 +81,22 @@ def test_collate_full_size_is_the_stable_sort_with_sequential_sums(dataset):
             first[s] = g
 
 
-@pytest.mark.parametrize("kind", ["gcn", "sage"])
-def test_eval_logits_do_not_depend_on_the_batch_split(dataset, kind):
+@pytest.mark.parametrize("kind,fused", [("gcn", False), ("gcn", True), ("sage", False)])
+def test_eval_logits_do_not_depend_on_the_batch_split(dataset, kind, fused):
+    """Bit for bit, on either inference path (layer by layer / the fused kernel; the default "auto" picks one of the two by
+    batch size, and the two agree to 1e-6 - tests/parity.py::check_fused_eval - not to the bit)."""
     pool, graphs, store = dataset
     model = _model(kind)
     model.eval()
+    model.fused_eval = fused
     ids = np.random.default_rng(2).permutation(BATCH)
     with torch.no_grad():
         full = model(store.collate(ids, prepare_for=kind))
         parts = torch.cat([model(store.collate(ids[lo:hi])) for lo, hi in ((0, 1000), (1000, 1001), (1001, BATCH))])
     assert torch.isfinite(full).all()
-    assert torch.equal(full, parts), "eval-mode logits changed with the batch split"
+    diff = (full - parts).abs().max(dim=1).values
+    assert torch.equal(full, parts), ("eval-mode logits changed with the batch split", float(diff.max()),
+                                      diff.nonzero().flatten()[:8].tolist())
     sub = torch.from_numpy(ids % UNIQUE).to(DEV)
     rep = torch.zeros(UNIQUE, 2, device=DEV).index_copy_(0, sub, full)      # one copy per unique subject
     assert torch.equal(rep[sub], full), "identical subjects produced different logits"

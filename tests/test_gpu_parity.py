@@ -446,6 +446,50 @@ def test_pair_store_collates_identically():
     assert torch.equal(c.edge_index, d.edge_index) and torch.equal(c.csr.in_wn, d.csr.in_wn)
 
 
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_no_reads_of_unwritten_memory(kind):
+    """The allocator's free blocks are filled with zeros, NaN and huge values between runs (torch.empty then hands the
+    kernels exactly that garbage): inference on both paths, lean and full batches, and a training step give the same
+    bits every time - nothing reads a buffer before it is written (compute-sanitizer's initcheck is closed on this pool)."""
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import CrossEntropyLoss
+    store = SubjectStore(pack_graphs(generate_dataset(num_subjects=12, num_regions=360, seed=42)), DEV)
+
+    def poison(value):
+        blocks = [torch.full((n,), value, device=DEV) for n in (1 << 25, 1 << 23, 1 << 21, 1 << 19, 1 << 17, 1 << 15, 1 << 13) for _ in range(3)]
+        torch.cuda.synchronize()
+        del blocks
+
+    torch.manual_seed(0)
+    cls = GCNConnectome if kind == "gcn" else GraphSAGEConnectome
+    m = cls(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.0).to(DEV)
+    for fused in (False, True):
+        m.eval()
+        m.fused_eval = fused
+        outs = []
+        for value in (0.0, float("nan"), 3e38):
+            poison(value)
+            with torch.no_grad():
+                outs.append(torch.cat([m(store.collate(np.arange(12), prepare_for=kind)), m(store.collate(np.array([5]))),
+                                       m(store.collate(np.arange(3, 9), prepare_for=kind, backward=False))]).clone())
+        assert torch.isfinite(torch.stack(outs)).all()
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (kind, fused)
+    m.train()
+    grads = []
+    for value in (0.0, float("nan"), 3e38):
+        poison(value)
+        m.zero_grad()
+        for bn in m.batch_norms:
+            bn.reset_running_stats()
+        batch = store.collate(np.arange(12), prepare_for=kind)
+        CrossEntropyLoss()(m(batch), batch.labels).backward()
+        grads.append(torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone())
+    assert torch.isfinite(torch.stack(grads)).all()
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2]), kind
+
+
 @pytest.mark.parametrize("layers", [2, 3, 4])
 def test_fused_eval(layers):
     parity.check_fused_eval(DEV, layers)
