@@ -81,7 +81,7 @@ def batch_fields(batch) -> dict:
     return out
 
 
-def model_case(kind: str, batch, hidden: int, layers: int, tag: str, per_layer: bool = True) -> dict:
+def model_case(kind: str, batch, hidden: int, layers: int, tag: str, per_layer: bool = True, eval_grad: bool = True) -> dict:
     """Seeded reference model: initial weights, eval outputs, one train-mode forward/backward with
     dropout disabled (masks from the CPU generator cannot be reproduced on a GPU)."""
     torch.manual_seed(0)
@@ -111,6 +111,8 @@ def model_case(kind: str, batch, hidden: int, layers: int, tag: str, per_layer: 
     for k, v in model.state_dict().items():
         if "running" in k or "num_batches" in k:
             out[f"{tag}.train.after.{k}"] = v.clone().numpy()
+    if not eval_grad:
+        return out
     # gradient of sum(logits) in eval mode (BatchNorm with running statistics), cf. tests/test_models.py:32-40
     model.zero_grad()
     model.eval()
@@ -180,6 +182,28 @@ def main() -> None:
         "c1.labels": batch.labels.tolist(), "c1.deg": h16(torch.from_numpy(arrays["deg"])),
         "c1.wsum": h16(torch.from_numpy(arrays["wsum"])),
     }
+
+    # -- C3: 6 x 360-node subjects, hidden 64 (the shape of BASELINE.json configs[2]) ------------------
+    graphs = generate_dataset(num_subjects=6, num_regions=360, k=8, beta=0.15, trait_idx=0, seed=42)
+    batch = collate_graphs(graphs)
+    arrays = {**pack(graphs), **structure(batch)}
+    del arrays["w_norm"]
+    arrays["batch.ptr"] = batch.ptr.numpy()
+    arrays["batch.labels"] = batch.labels.numpy()
+    for kind in MODELS:
+        arrays.update(model_case(kind, batch, hidden=64, layers=3, tag=kind, per_layer=False))
+    save("ref_c3.npz", arrays)
+
+    # -- C5: 2 x 360-node subjects, hidden 256 (the layer shape of BASELINE.json configs[4]) ------------
+    graphs = graphs[:2]
+    batch = collate_graphs(graphs)
+    arrays = {**pack(graphs), **structure(batch)}
+    del arrays["w_norm"]
+    arrays["batch.ptr"] = batch.ptr.numpy()
+    arrays["batch.labels"] = batch.labels.numpy()
+    for kind in MODELS:
+        arrays.update(model_case(kind, batch, hidden=256, layers=3, tag=kind, per_layer=False, eval_grad=False))
+    save("ref_c5.npz", arrays)
 
     # -- ragged / degenerate inputs --------------------------------------------------------------
     graphs = ragged_graphs()

@@ -23,15 +23,17 @@ def _native_library_loaded():
     assert any("libcgnn.so" in line for line in open("/proc/self/maps")), "libcgnn.so is not mapped"
 
 
-@pytest.mark.parametrize("fixture", ["ref_small.npz", "ref_ragged.npz", "ref_c1.npz"])
+@pytest.mark.parametrize("fixture", ["ref_small.npz", "ref_ragged.npz", "ref_c1.npz", "ref_c3.npz", "ref_c5.npz"])
 def test_collate_bit_exact(fixture):
     parity.check_collate(helpers.golden(fixture), DEV)
 
 
-@pytest.mark.parametrize("fixture", ["ref_small.npz", "ref_ragged.npz", "ref_c1.npz"])
+@pytest.mark.parametrize("fixture", ["ref_small.npz", "ref_ragged.npz", "ref_c1.npz", "ref_c3.npz", "ref_c5.npz"])
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_model_parity(fixture, kind):
-    parity.check_model(helpers.golden(fixture), kind, DEV)
+    """Against fixtures made from the UNMODIFIED reference (tests/golden/make_golden.py), up to 360-node subjects at
+    hidden 64 and 256; every gradient tensor of the small fixtures within 1e-5 (parity.FIXTURE_TOL)."""
+    parity.check_model(helpers.golden(fixture), kind, DEV, tol=parity.FIXTURE_TOL[fixture])
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])

@@ -22,7 +22,7 @@ from oracle import port
 
 META = json.load(open(os.path.join(helpers.GOLDEN, "ref_meta.json")))
 SAME_BUILD = torch.__version__ == META["made_with"]["torch"]
-FIXTURES = ["ref_small.npz", "ref_ragged.npz", "ref_c1.npz"]
+FIXTURES = ["ref_small.npz", "ref_ragged.npz", "ref_c1.npz", "ref_c3.npz", "ref_c5.npz"]
 
 
 @pytest.fixture(autouse=True)
