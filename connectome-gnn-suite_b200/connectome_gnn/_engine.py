@@ -36,10 +36,11 @@ class Act:
     seed: int = 0
     site: int = 0
     row_base: int = 0
+    salt: Optional[torch.Tensor] = None    # device words folded into the mask stream (graphed steps), see cgnn_act_t
 
     def struct(self) -> ActT:
         return ActT(_p(self.scale), _p(self.shift), int(self.relu), float(self.p_drop),
-                    int(self.seed) & 0xFFFFFFFFFFFFFFFF, int(self.site) & 0xFFFFFFFF, int(self.row_base))
+                    int(self.seed) & 0xFFFFFFFFFFFFFFFF, int(self.site) & 0xFFFFFFFF, int(self.row_base), _p(self.salt))
 
 
 @dataclass
@@ -282,13 +283,21 @@ class Engine:
         self._call("cgnn_pool_fwd", _p(t_in), C.byref(a), _p(ptr), num_graphs, rows, C_, _p(emb), self.stream())
         return emb
 
-    def head_fwd(self, emb, W0, b0, W1, b1, p_drop: float, seed: int, graph_base: int):
+    def head_fwd(self, emb, W0, b0, W1, b1, p_drop: float, seed: int, graph_base: int, salt=None):
         B, C_ = emb.shape
         M, K = W0.shape[0], W1.shape[0]
         hidden, logits = self.empty((B, M)), self.empty((B, K))
         self._call("cgnn_head_fwd", _p(emb), _p(W0), _p(b0), _p(W1), _p(b1), B, C_, M, K, float(p_drop),
-                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(graph_base), _p(hidden), _p(logits), self.stream())
+                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(graph_base), _p(salt), _p(hidden), _p(logits), self.stream())
         return hidden, logits
+
+    # -- the step after backward -----------------------------------------------------------------
+    def step_tick(self, state: torch.Tensor) -> None:
+        self._call("cgnn_step_tick", _p(state), self.stream())
+
+    def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, state) -> None:
+        self._call("cgnn_adam_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr), float(beta1),
+                   float(beta2), float(eps), float(weight_decay), _p(state), self.stream())
 
     def ce_fwd(self, logits, labels, inv_count: float):
         B, K = logits.shape
@@ -304,32 +313,34 @@ class Engine:
         self._call("cgnn_ce_bwd", _p(logits), _p(labels), B, K, float(inv_count), _p(gout), _p(d), self.stream())
         return d
 
-    def head_bwd(self, emb, hidden, dlogits, W0, W1, p_drop: float):
+    def head_bwd(self, emb, hidden, dlogits, W0, W1, p_drop: float, out=None):
         B, C_ = emb.shape
         M, K = W0.shape[0], W1.shape[0]
         demb = self.empty((B, C_))
-        dW0, db0, dW1, db1 = self.empty((M, C_)), self.empty(M), self.empty((K, M)), self.empty(K)
+        dW0, db0, dW1, db1 = out if out is not None else (self.empty((M, C_)), self.empty(M), self.empty((K, M)), self.empty(K))
         self._call("cgnn_head_bwd", _p(emb), _p(hidden), _p(dlogits), _p(W0), _p(W1), B, C_, M, K, float(p_drop),
                    _p(demb), _p(dW0), _p(db0), _p(dW1), _p(db1), _p(self.workspace), self.workspace_bytes,
                    self.stream())
         return demb, dW0, db0, dW1, db1
 
-    def bn_bwd_sums(self, z, act: Act, mean, rstd, du, demb, ptr, num_graphs: int):
+    def bn_bwd_sums(self, z, act: Act, mean, rstd, du, demb, ptr, num_graphs: int, out=None):
         rows, C_ = z.shape
-        sums = self.empty((2, C_))
+        sums = out if out is not None else self.empty((2, C_))
         a = act.struct()
         self._call("cgnn_bn_bwd_sums", _p(z), C.byref(a), _p(mean), _p(rstd), _p(du), _p(demb), _p(ptr),
                    num_graphs, rows, C_, _p(sums), _p(self.workspace), self.workspace_bytes, self.stream())
         return sums
 
     def layer_bwd(self, kind: str, du, demb, z, act_out: Act, bn: Optional[BnBwd], t_in, act_in: Act, W, csr, ptr,
-                  num_graphs: int, need_du: bool, prev_mean, prev_rstd, agg=None):
+                  num_graphs: int, need_du: bool, prev_mean, prev_rstd, agg=None, out=None, prev_out=None):
+        """``out`` = (dW, db) and ``prev_out`` = the [2, d_in] BatchNorm-backward sums of the layer below, preallocated
+        (views of a flat gradient buffer), or None."""
         rows, d_in = t_in.shape
         H = z.shape[1]
-        dW, db = self.empty(W.shape), self.empty(H)
+        dW, db = out if out is not None else (self.empty(W.shape), self.empty(H))
         du_in = self.empty((rows, d_in)) if need_du else None
         want_prev = need_du and prev_mean is not None
-        prev_sums = self.empty((2, d_in)) if want_prev else None
+        prev_sums = (prev_out if prev_out is not None else self.empty((2, d_in))) if want_prev else None
         self.ensure_agg(csr, kind, num_graphs, rows, csr.num_edges, need_out=True)
         ao, ai = act_out.struct(), act_in.struct()
         bs = bn.struct() if bn is not None else None

@@ -14,7 +14,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcgnn.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_f32p = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 c_ptr = C.c_void_p
@@ -33,7 +33,7 @@ class ActT(C.Structure):
     """``cgnn_act_t``"""
     _fields_ = [
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int32), ("p_drop", C.c_float),
-        ("seed", C.c_uint64), ("site", C.c_uint32), ("row_base", C.c_int64),
+        ("seed", C.c_uint64), ("site", C.c_uint32), ("row_base", C.c_int64), ("salt", C.c_void_p),
     ]
 
 
@@ -87,7 +87,9 @@ PROTOTYPES = {
     "cgnn_bn_finalize": (C.c_int, [_p, _p, _p, _i32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "cgnn_bn_eval_affine": (C.c_int, [_p, _p, _p, _p, _i32, _f32, _p, _p, _p, _p, _p]),
     "cgnn_pool_fwd": (C.c_int, [_p, _P(ActT), _p, _i64, _i64, _i32, _p, _p]),
-    "cgnn_head_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _f32, _u64, _i64, _p, _p, _p]),
+    "cgnn_head_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _f32, _u64, _i64, _p, _p, _p, _p]),
+    "cgnn_step_tick": (C.c_int, [_p, _p]),
+    "cgnn_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _p, _p]),
     "cgnn_ce_fwd": (C.c_int, [_p, _p, _i64, _i32, _f32, _p, _p, _p, _p]),
     "cgnn_ce_bwd": (C.c_int, [_p, _p, _i64, _i32, _f32, _p, _p, _p]),
     "cgnn_head_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _f32, _p, _p, _p, _p, _p, _p, _sz,

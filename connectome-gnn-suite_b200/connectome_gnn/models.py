@@ -125,7 +125,7 @@ class _EncodeFn(torch.autograd.Function):
                 scale, shift, mean, rstd = eng.bn_eval_affine(gamma, beta, bn.running_mean, bn.running_var, bn.eps)
             saved.append((t, act, z, W, scale, mean, rstd, agg))
             t = z
-            act = Act(scale, shift, relu_after_bn, p_eff, seed, l, batch.row_base)
+            act = Act(scale, shift, relu_after_bn, p_eff, seed, l, batch.row_base, cfg.get("salt") if p_eff > 0.0 else None)
         emb = eng.pool_fwd(t, act, ptr, B)
 
         ctx.cfg, ctx.saved, ctx.final_act = cfg, saved, act
@@ -144,26 +144,40 @@ class _EncodeFn(torch.autograd.Function):
         demb = demb.contiguous()
 
         grads: list = [None] * (4 * L)
+        # With a flat gradient buffer (Trainer.enable_fused_step) the kernels write every parameter gradient straight into its
+        # slice - the BatchNorm pair [d beta; d gamma] is the [2, C] block of backward sums itself - and autograd receives
+        # fresh views of those slices: no per-parameter copy, one all-reduce, one optimizer kernel.
+        flat = cfg.get("flat")
+        layer_params = cfg.get("layer_params")        # [(W, b, gamma, beta)] Parameter objects per layer (flat mode)
+        bn_block = (lambda l: flat.bn_block(layer_params[l][3], layer_params[l][2])) if flat is not None else (lambda l: None)
         # BatchNorm backward sums of the top layer come from a standalone pass over z_L
         t_in, act_in, z, W, scale, mean, rstd, agg = saved[-1]
         act_out = ctx.final_act
-        sums = eng.bn_bwd_sums(z, act_out, mean, rstd, None, demb, ptr, B)
+        sums = eng.bn_bwd_sums(z, act_out, mean, rstd, None, demb, ptr, B, out=bn_block(L - 1))
         sums = _sum_across_ranks(sums, group)
         du, pooled, dx = None, demb, None
+        share = 1.0 / _world(group)
         for l in range(L - 1, -1, -1):
             t_in, act_in, z, W, scale, mean, rstd, agg = saved[l]
             need_du = l > 0 or ctx.x_needs_grad
             prev_mean = saved[l - 1][5] if l > 0 else None
             prev_rstd = saved[l - 1][6] if l > 0 else None
             bn = BnBwd(scale, mean, rstd, sums, count, training)
+            out = (flat.view(layer_params[l][0]), flat.view(layer_params[l][1])) if flat is not None else None
             dW, db, du_in, prev_sums = eng.layer_bwd(kind, du, pooled, z, act_out, bn, t_in, act_in, W, csr, ptr, B,
-                                                     need_du, prev_mean, prev_rstd, agg)
-            grads[4 * l + 0], grads[4 * l + 1] = dW, db
+                                                     need_du, prev_mean, prev_rstd, agg, out=out,
+                                                     prev_out=bn_block(l - 1) if l > 0 else None)
             # d gamma = sum dy*xhat, d beta = sum dy.  Under data parallelism `sums` is already the global sum while
             # every other gradient is this rank's share and Trainer adds the ranks up: hand out 1/world of it.
-            share = 1.0 / _world(group)
-            grads[4 * l + 2] = sums[1] if share == 1.0 else sums[1] * share
-            grads[4 * l + 3] = sums[0] if share == 1.0 else sums[0] * share
+            if flat is not None:
+                if share != 1.0:
+                    sums.mul_(share)          # in place, after the kernels that read the sums have been enqueued
+                grads[4 * l + 0], grads[4 * l + 1] = flat.view(layer_params[l][0]), flat.view(layer_params[l][1])
+                grads[4 * l + 2], grads[4 * l + 3] = flat.view(layer_params[l][2]), flat.view(layer_params[l][3])
+            else:
+                grads[4 * l + 0], grads[4 * l + 1] = dW, db
+                grads[4 * l + 2] = sums[1] if share == 1.0 else sums[1] * share
+                grads[4 * l + 3] = sums[0] if share == 1.0 else sums[0] * share
             sums = _sum_across_ranks(prev_sums, group)
             du, pooled, act_out = du_in, None, act_in
             if l == 0:
@@ -179,7 +193,8 @@ class _HeadFn(torch.autograd.Function):
         eng = cfg["engine"]
         emb, W0, b0, W1, b1 = (q.contiguous() for q in (emb, W0, b0, W1, b1))
         p_eff = cfg["dropout"] if cfg["training"] else 0.0
-        hidden, logits = eng.head_fwd(emb, W0, b0, W1, b1, p_eff, cfg["seed"], cfg["graph_base"])
+        hidden, logits = eng.head_fwd(emb, W0, b0, W1, b1, p_eff, cfg["seed"], cfg["graph_base"],
+                                      cfg.get("salt") if p_eff > 0.0 else None)
         ctx.cfg, ctx.p_eff = cfg, p_eff
         ctx.save_for_backward(emb, hidden, W0, W1)
         return logits
@@ -187,7 +202,11 @@ class _HeadFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         emb, hidden, W0, W1 = ctx.saved_tensors
-        demb, dW0, db0, dW1, db1 = ctx.cfg["engine"].head_bwd(emb, hidden, dlogits.contiguous(), W0, W1, ctx.p_eff)
+        flat, hp = ctx.cfg.get("flat"), ctx.cfg.get("head_params")
+        out = tuple(flat.view(q) for q in hp) if flat is not None else None
+        demb, dW0, db0, dW1, db1 = ctx.cfg["engine"].head_bwd(emb, hidden, dlogits.contiguous(), W0, W1, ctx.p_eff, out=out)
+        if flat is not None:
+            dW0, db0, dW1, db1 = (flat.view(q) for q in hp)       # fresh views: autograd adopts them as .grad without a copy
         return None, demb, dW0, db0, dW1, db1
 
 
@@ -272,6 +291,9 @@ class _ConnectomeClassifier(nn.Module):
         # layers are serial inside the fused kernel, while the per-layer kernels overlap the phases of different units
         # (measured on B200, 4096 x 360-node subjects: 1.29 ms fused, 0.91 ms layer by layer).  True / False force one.
         self.fused_eval = "auto"
+        self._salt = None           # device dropout salt of a CUDA-graphed step (Trainer.capture), else None
+        self._graph_seed = 0
+        self._flat = None           # flat parameter / gradient buffers (Trainer.enable_fused_step), else None
 
     # -- plumbing --------------------------------------------------------------------------
     def _ready(self, batch: ConnectomeBatch) -> ConnectomeBatch:
@@ -287,9 +309,16 @@ class _ConnectomeClassifier(nn.Module):
     def _cfg(self, batch: ConnectomeBatch) -> dict:
         training = self.training
         need_seed = training and self.dropout > 0.0
-        return dict(engine=_engine.engine_for(batch.node_features), batch=batch, kind=self.kind, training=training,
-                    dropout=float(self.dropout), seed=_draw_seed(batch.node_features.device) if need_seed else 0,
-                    bns=list(self.batch_norms), group=self.process_group, graph_base=batch.graph_base)
+        cfg = dict(engine=_engine.engine_for(batch.node_features), batch=batch, kind=self.kind, training=training,
+                   dropout=float(self.dropout), bns=list(self.batch_norms), group=self.process_group,
+                   graph_base=batch.graph_base, salt=self._salt, flat=self._flat)
+        # a graphed step keeps its dropout stream on the device (salt words refreshed inside the graph): the host seed is fixed
+        cfg["seed"] = (self._graph_seed if self._salt is not None else _draw_seed(batch.node_features.device)) if need_seed else 0
+        if self._flat is not None:
+            cfg["layer_params"] = [(*conv.tensors(), bn.weight, bn.bias) for conv, bn in zip(self.convs, self.batch_norms)]
+            fc0, fc1 = self.classifier[0], self.classifier[3]
+            cfg["head_params"] = (fc0.weight, fc0.bias, fc1.weight, fc1.bias)
+        return cfg
 
     def _encode(self, batch: ConnectomeBatch, cfg: dict) -> torch.Tensor:
         params = []

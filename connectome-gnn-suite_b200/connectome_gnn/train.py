@@ -24,7 +24,7 @@ import torch.nn as nn
 
 from . import _engine
 
-__all__ = ["Trainer", "CrossEntropyLoss"]
+__all__ = ["Trainer", "CrossEntropyLoss", "FlatParams", "GraphedStep"]
 
 
 class _CrossEntropyFn(torch.autograd.Function):
@@ -68,6 +68,100 @@ class CrossEntropyLoss(nn.CrossEntropyLoss):
         return loss
 
 
+class FlatParams:
+    """One flat fp32 buffer for all trainable parameters of a classifier and one for their gradients.
+
+    Every ``nn.Parameter`` keeps its identity (an optimizer built earlier stays valid) but its storage becomes a slice of
+    ``self.param``; backward kernels write each gradient straight into the matching slice of ``self.grad`` and hand
+    autograd a fresh view of it, so ``param.grad`` aliases the flat buffer without a copy.  The gradient all-reduce of a
+    data-parallel step is then ONE collective over ``self.grad`` and the fused Adam update ONE kernel.
+    Layout: per layer W, b, then the BatchNorm pair as [beta; gamma] (that [2, C] block is exactly the block of backward
+    sums the kernels produce: sum dy, sum dy*xhat), then the head."""
+
+    def __init__(self, model: nn.Module):
+        order = []
+        for conv, bn in zip(model.convs, model.batch_norms):
+            order += [*conv.tensors(), bn.bias, bn.weight]
+        fc0, fc1 = model.classifier[0], model.classifier[3]
+        order += [fc0.weight, fc0.bias, fc1.weight, fc1.bias]
+        seen = {id(q) for q in order}
+        order += [q for q in model.parameters() if id(q) not in seen]
+        total = sum(q.numel() for q in order)
+        dev = order[0].device
+        self.param = torch.empty(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.slots, off = {}, 0
+        for q in order:
+            n = q.numel()
+            self.param[off:off + n].copy_(q.detach().reshape(-1))
+            q.data = self.param[off:off + n].view(q.shape)
+            self.slots[id(q)] = (off, n, tuple(q.shape))
+            off += n
+        self.params = order
+
+    def view(self, q: torch.Tensor) -> torch.Tensor:
+        """A NEW view of q's gradient slice (autograd adopts a tensor as ``.grad`` only if nobody else holds it)."""
+        off, n, shape = self.slots[id(q)]
+        return self.grad[off:off + n].view(shape)
+
+    def bn_block(self, beta: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+        off, n, _ = self.slots[id(beta)]
+        assert self.slots[id(gamma)][0] == off + n
+        return self.grad[off:off + 2 * n].view(2, n)
+
+
+class GraphedStep:
+    """A training or evaluation step of fixed shape captured as ONE CUDA graph: subject gather + collate, forward, loss,
+    backward, gradient hand-over and the fused Adam update replay with a single launch (SURVEY 7 hard part f: at batch 16
+    the ~35 kernels and their host-side launches ARE the step).  ``__call__(ids)`` copies the subject indices into the
+    graph's input buffer and replays; it returns the loss (and the correct count for evaluation) as device scalars that the
+    next replay overwrites."""
+
+    def __init__(self, trainer: "Trainer", store, batch_size: int, kind: str, train: bool):
+        import numpy as np
+        self.trainer, self.train = trainer, train
+        dev = trainer.device
+        n0, e0 = int(store.node_ptr_host[1] - store.node_ptr_host[0]), int(store.edge_ptr_host[1] - store.edge_ptr_host[0])
+        if not (np.all(np.diff(store.node_ptr_host) == n0) and np.all(np.diff(store.edge_ptr_host) == e0)):
+            raise ValueError("a graphed step needs subjects of one size (the shapes of a captured launch are fixed)")
+        if not bool(store.has_label.all()):
+            raise ValueError("a graphed step needs every subject labelled")
+        self.batch_size = batch_size
+        self.ids_host = torch.zeros(batch_size, dtype=torch.int64).pin_memory()
+        self.ids_dev = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        ids0 = np.arange(batch_size, dtype=np.int64) % len(store)
+
+        def body():
+            batch = store.collate(ids0, ids_device=self.ids_dev, prepare_for=kind, backward=train)
+            if train:
+                return trainer.train_step(batch), None
+            return trainer.eval_step(batch)
+
+        model = trainer.model
+        model.train(train)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # warm-up outside the capture: lazy initialisation, allocator pools
+            for _ in range(3):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.correct = body()
+
+    def __call__(self, ids):
+        import numpy as np
+        ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+        if ids.size != self.batch_size:
+            raise ValueError(f"this step was captured for {self.batch_size} subjects, got {ids.size}")
+        self.ids_host.copy_(torch.from_numpy(ids))
+        self.ids_dev.copy_(self.ids_host, non_blocking=True)
+        self.trainer.model.train(self.train)
+        self.graph.replay()
+        return (self.loss if self.train else (self.loss, self.correct))
+
+
 def _dist_world() -> int:
     import torch.distributed as dist
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -85,6 +179,48 @@ class Trainer:
         self.device = dev
         self.loss_fn = CrossEntropyLoss()
         self.distributed = True              # False: no collectives even when torch.distributed is initialised
+        self.flat = None                     # FlatParams after enable_fused_step()
+        self._adam = None                    # (exp_avg, exp_avg_sq, state, hyper-parameters) of the fused update
+
+    # -- opt-in: flat buffers, one-kernel Adam, device-side step state -------------------------
+    def enable_fused_step(self, seed: int | None = None) -> "Trainer":
+        """Flat parameter / gradient buffers (``FlatParams``), and - when the optimizer is a plain ``torch.optim.Adam``
+        with one parameter group - its update as ONE kernel over the flat buffers (``cgnn_adam_step``: the arithmetic of
+        torch's Adam op for op) with the step counter and the dropout salt in a device state block, which is what lets
+        ``capture`` replay whole steps as CUDA graphs.  Any other optimizer keeps working on the flat views."""
+        if self.flat is not None:
+            return self
+        self.flat = FlatParams(self.model)
+        self.model._flat = self.flat
+        opt = self.optimizer
+        plain = (type(opt) is torch.optim.Adam and len(opt.param_groups) == 1 and not opt.param_groups[0].get("amsgrad", False)
+                 and not opt.param_groups[0].get("maximize", False) and len(opt.state) == 0 and
+                 {id(q) for q in opt.param_groups[0]["params"]} == {id(q) for q in self.flat.params})
+        eng = _engine.engine_for(self.flat.param)
+        state = torch.zeros(4, dtype=torch.int64, device=self.device)      # cgnn_step_tick's block: step, seed, salt, spare
+        state[1] = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
+        self._state = state
+        if plain:
+            g = opt.param_groups[0]
+            self._adam = dict(m=torch.zeros_like(self.flat.param), v=torch.zeros_like(self.flat.param), lr=g["lr"],
+                              b1=g["betas"][0], b2=g["betas"][1], eps=g["eps"], wd=g["weight_decay"], eng=eng)
+        return self
+
+    def _fused_optimizer_step(self) -> None:
+        a = self._adam
+        a["eng"].adam_step(self.flat.param, self.flat.grad, a["m"], a["v"], a["lr"], a["b1"], a["b2"], a["eps"], a["wd"], self._state)
+
+    def capture(self, store, batch_size: int, prepare_for: str, train: bool = True) -> GraphedStep:
+        """Capture ``train_step`` (or ``eval_step``) on batches of ``batch_size`` subjects of ``store`` as one CUDA graph.
+        Training needs ``enable_fused_step()`` with a plain Adam (the update has to live on the device); the dropout masks
+        of the replays come from the device salt, refreshed inside the graph."""
+        if train:
+            self.enable_fused_step()
+            if self._adam is None:
+                raise ValueError("a graphed training step needs a plain torch.optim.Adam (single group) to fuse")
+            salt = self._state[2:3].view(torch.int32)         # the two 32-bit salt words cgnn_step_tick refreshes
+            self.model._salt, self.model._graph_seed = salt, int(self._state[1].item())
+        return GraphedStep(self, store, batch_size, prepare_for, train)
 
     def _world(self) -> int:
         return _dist_world() if self.distributed else 1
@@ -95,6 +231,9 @@ class Trainer:
         if self._world() == 1:
             return
         import torch.distributed as dist
+        if self.flat is not None:          # the gradients already live in one buffer: one collective, nothing to copy
+            dist.all_reduce(self.flat.grad)
+            return
         params = [p for p in self.model.parameters() if p.requires_grad]
         for p in params:
             if p.grad is None:   # a rank with an empty slice still joins the collective
@@ -120,12 +259,19 @@ class Trainer:
         Returns this rank's share of the global mean loss as a device scalar (no host sync)."""
         batch = batch.to(self.device)
         global_b = batch.global_num_graphs if batch.global_num_graphs is not None else batch.num_graphs
-        self.optimizer.zero_grad()
+        if self.flat is not None:
+            _engine.engine_for(self.flat.param).step_tick(self._state)      # step counter + this step's dropout salt
+            if batch.num_graphs == 0:
+                self.flat.grad.zero_()      # an empty slice of a data-parallel batch contributes nothing
+        self.optimizer.zero_grad()          # set_to_none: autograd then ADOPTS the gradient views instead of adding to them
         logits = self.model(batch)
         loss = self.loss_fn(logits, batch.labels, global_b)
         loss.backward()
         self._sync_gradients()
-        self.optimizer.step()
+        if self._adam is not None:
+            self._fused_optimizer_step()
+        else:
+            self.optimizer.step()
         return loss.detach()
 
     @torch.no_grad()

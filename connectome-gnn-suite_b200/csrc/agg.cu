@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256) k_build_agg(BuildAggArgs p) {
 // tile on the way into shared memory; then 32 / LPR rows per warp are gathered with float4 lanes from shared memory.
 template <int MODE, int LPR, bool VEC>
 __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
+  act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
   CGNN_SMEM_DECL;
   constexpr int RP = kThreads / LPR;    // tile rows per load pass
   constexpr int RPW = 32 / LPR;         // rows per warp in the gather

@@ -73,12 +73,13 @@ struct Act {
   uint32_t thresh;    // keep when 16 random bits >= thresh; thresh = round(p * 65536)
   float keep_scale;   // 1 / (1 - p)
   long long row_base;
+  const uint32_t* salt;   // optional device words {s0, s1} folded into the stream key at kernel start (act_salt)
 };
 
 static inline Act make_act(const cgnn_act_t* a) {
   Act r;
   r.scale = nullptr; r.shift = nullptr; r.relu = 0; r.drop = 0;
-  r.k0 = r.k1 = 0; r.thresh = 0; r.keep_scale = 1.0f; r.row_base = 0;
+  r.k0 = r.k1 = 0; r.thresh = 0; r.keep_scale = 1.0f; r.row_base = 0; r.salt = nullptr;
   if (!a) return r;
   r.scale = a->scale;
   r.shift = a->shift;
@@ -91,8 +92,19 @@ static inline Act make_act(const cgnn_act_t* a) {
     r.keep_scale = 1.0f / (1.0f - a->p_drop);
     r.k0 = (uint32_t)(a->seed & 0xffffffffu) ^ (a->site * 0x9E3779B9u);
     r.k1 = (uint32_t)(a->seed >> 32) + a->site * 0x85EBCA6Bu + 0x27D4EB2Fu;
+    r.salt = a->salt;
   }
   return r;
+}
+
+// Dropout streams of CUDA-graph replays: the host-side seed is baked into a captured launch, so a graphed training step
+// keeps two salt words on the device (refreshed by cgnn_step_tick inside the graph) and every kernel folds them into
+// its stream key before anything else.  No salt (eager mode): the stream is a function of the host seed alone.
+__device__ __forceinline__ void act_salt(Act& a) {
+  if (a.drop && a.salt != nullptr) {
+    a.k0 ^= a.salt[0];
+    a.k1 += a.salt[1];
+  }
 }
 
 __device__ __forceinline__ uint32_t fmix32(uint32_t h) {

@@ -39,6 +39,7 @@ struct Args {
 };
 
 __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ ws::TensorMap tmap, Args p) {
+  act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
 #ifdef CGNN_EMU
   CGNN_SMEM_DECL;
   unsigned char* smem_raw = cgnn_smem;

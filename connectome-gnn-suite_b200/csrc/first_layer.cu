@@ -92,6 +92,7 @@ __device__ __forceinline__ void stage_subject(const FirstArgs& p, const int4& m,
 // QH = H / 4 output-channel quads; thread = (quad tid % QH, rows tid / QH + i * NT / QH); NT threads per CTA, two CTAs per SM
 template <int SAGE, int QH, int NT, int KX>
 __global__ void __launch_bounds__(NT, 2) k_first_fwd(FirstArgs p) {
+  act_salt(p.act_in); act_salt(p.act_out);   // device-side dropout salt (CUDA-graph replays)
   CGNN_SMEM_DECL;
   constexpr int RS = NT / QH, H = 4 * QH, KK = SAGE ? 2 * KX : KX;
   float4* s_x = reinterpret_cast<float4*>(cgnn_smem);                 // [max_nodes][2]
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(NT, 2) k_first_fwd(FirstArgs p) {
 
 template <int SAGE, int QH, int NT, int KX>
 __global__ void __launch_bounds__(NT, 2) k_first_bwd(FirstArgs p) {
+  act_salt(p.act_in); act_salt(p.act_out);   // device-side dropout salt (CUDA-graph replays)
   CGNN_SMEM_DECL;
   constexpr int RS = NT / QH, H = 4 * QH, KK = SAGE ? 2 * KX : KX;
   float4* s_x = reinterpret_cast<float4*>(cgnn_smem);

@@ -30,6 +30,7 @@ struct GcnFwdArgs {
 // The first chunk of the NEXT subject is already in flight during the aggregation.
 template <int HC>
 __global__ void __launch_bounds__(kThreads) k_gcn_fwd(GcnFwdArgs p) {
+  act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
   CGNN_SMEM_DECL;
   float* sm = reinterpret_cast<float*>(cgnn_smem);
   float* s_wt = sm + p.o_wt;        // [K4][H4]  W transposed, zero padded
@@ -204,6 +205,7 @@ __device__ __forceinline__ float gcn_dz(const GcnBwdArgs& p, const float* s_co, 
 
 template <int HC, int MAXT>
 __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
+  act_salt(p.act_out); act_salt(p.act_in);   // device-side dropout salt (CUDA-graph replays)
   CGNN_SMEM_DECL;
   float* sm = reinterpret_cast<float*>(cgnn_smem);
   float* s_w = sm + p.o_w;      // [H4][K4] natural layout, zero padded

@@ -76,6 +76,7 @@ struct SageFwdGemmArgs {
 // maps with 16-byte loads; otherwise one element-wise map over the padded K (first layer, C = 5).
 template <int KB, int HB, bool WIDE, int NT>
 __global__ void __launch_bounds__(NT, 1) k_sage_fwd_gemm(SageFwdGemmArgs p) {
+  act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
   constexpr int KP = 32 * KB, H = 32 * HB, TR = kRows;
   constexpr int A_HALF = KB * TR * 128, B_HALF = KB * H * 128;
   constexpr int QC = WIDE ? KP / 8 : KP / 4;           // quads per row of one loaded tensor (wide) / of the padded K
@@ -332,6 +333,7 @@ struct GcnBwdGemmArgs {
 // HB = H / 32, KB = padded Kin / 32.  WIDE: Kin is a multiple of 32 and t_in / du_in are 16-byte aligned.
 template <int HB, int KB, bool WIDE>
 __global__ void __launch_bounds__(kThreads, 1) k_gcn_bwd_gemm(GcnBwdGemmArgs p) {
+  act_salt(p.act_in);   // device-side dropout salt (CUDA-graph replays)
   constexpr int H = 32 * HB, KP = 32 * KB, TR = kRows;
   constexpr int Q1 = H / 4, Q2 = KP / 4;
   using M1 = rt::QuadMap<Q1, TR>;     // dP quads
@@ -599,6 +601,7 @@ struct SageBwdGemmArgs {
 // tensor memory as 128-byte coalesced stores without a staging pass.
 template <int HB, int CB, bool WIDE>
 __global__ void __launch_bounds__(kThreads, 1) k_sage_bwd_gemm(SageBwdGemmArgs p) {
+  act_salt(p.act_out); act_salt(p.act_in);   // device-side dropout salt (CUDA-graph replays)
   constexpr int H = 32 * HB, TR = 64, MP = 128;
   constexpr int QH = H / 4;
   using MHq = rt::QuadMap<QH, TR>;                      // z / du / dz quads

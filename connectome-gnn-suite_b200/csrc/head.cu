@@ -21,6 +21,7 @@ struct PoolArgs {
 
 template <int CC>
 __global__ void __launch_bounds__(kThreads) k_pool_fwd(PoolArgs p) {
+  act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
   CGNN_SMEM_DECL;
   float* sm = reinterpret_cast<float*>(cgnn_smem);
   const int C = p.C, C4 = p.C4;
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(kThreads) k_pool_fwd(PoolArgs p) {
 // independent 16-byte loads in flight per thread, two CTAs of 512 threads per SM.
 template <int Q>
 __global__ void __launch_bounds__(kThreads, 2) k_pool_fwd_quad(PoolArgs p) {
+  act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
   __shared__ float4 s_red[kThreads];
   constexpr int RS = kThreads / Q;
   const int tid = threadIdx.x, q = tid % Q, r = tid / Q;
@@ -113,6 +115,7 @@ struct HeadArgs {
 };
 
 __global__ void __launch_bounds__(kThreads) k_head_fwd(HeadArgs p) {
+  act_salt(p.drop);   // device-side dropout salt (CUDA-graph replays)
   __shared__ float s_hid[kWarps][kHeadMaxM];
   __shared__ float s_emb[kWarps][kHeadMaxC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -310,7 +313,7 @@ int cgnn_pool_fwd(const float* t_in, const cgnn_act_t* act, const int64_t* ptr, 
 
 int cgnn_head_fwd(const float* emb, const float* W0, const float* b0, const float* W1, const float* b1,
                   int64_t num_graphs, int32_t C, int32_t M, int32_t K, float p_drop, uint64_t seed,
-                  int64_t graph_base, float* hidden, float* logits, cgnn_stream_t stream_) {
+                  int64_t graph_base, const uint32_t* salt, float* hidden, float* logits, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (num_graphs < 0 || C <= 0 || M <= 0 || K <= 0) return CGNN_ERR_INVALID_ARG;
   if (num_graphs == 0) return CGNN_OK;
@@ -319,7 +322,7 @@ int cgnn_head_fwd(const float* emb, const float* W0, const float* b0, const floa
   HeadArgs a;
   a.emb = emb; a.W0 = W0; a.b0 = b0; a.W1 = W1; a.b1 = b1; a.B = num_graphs; a.C = C; a.M = M; a.K = K;
   cgnn_act_t d{};
-  d.p_drop = p_drop; d.seed = seed; d.site = kHeadSite; d.row_base = graph_base;
+  d.p_drop = p_drop; d.seed = seed; d.site = kHeadSite; d.row_base = graph_base; d.salt = salt;
   a.drop = make_act(&d);
   a.hidden = hidden; a.logits = logits;
   auto kfn = k_head_fwd;

@@ -56,6 +56,7 @@ struct BnSumsArgs {
 // s1 = sum dy, s2 = sum dy * xhat with dy = d act(z) * du.  Warp per row, lanes over channels.
 template <int CC>
 __global__ void __launch_bounds__(kThreads) k_bn_bwd_sums(BnSumsArgs p) {
+  act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
   CGNN_SMEM_DECL;
   float* sm = reinterpret_cast<float*>(cgnn_smem);
   const int C = p.C, C4 = p.C4;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(kThreads) k_bn_bwd_sums(BnSumsArgs p) {
 // Channel-quad edition of k_bn_bwd_sums (C = 32 / 64 / 128 / 256, 16-byte aligned rows).
 template <int Q>
 __global__ void __launch_bounds__(kThreads, 2) k_bn_bwd_sums_quad(BnSumsArgs p) {
+  act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
   __shared__ float4 s_red[2 * kThreads];
   constexpr int RS = kThreads / Q;
   const int tid = threadIdx.x, q = tid % Q, r = tid / Q;

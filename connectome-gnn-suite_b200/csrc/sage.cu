@@ -61,6 +61,7 @@ struct SageFwdArgs {
 
 template <int CC>
 __global__ void __launch_bounds__(kThreads) k_sage_fwd(SageFwdArgs p) {
+  act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
   CGNN_SMEM_DECL;
   float* sm = reinterpret_cast<float*>(cgnn_smem);
   float* s_wt = sm + p.o_wt;        // [2*K4][H4]
@@ -209,6 +210,7 @@ __device__ __forceinline__ float sage_dq(const SageBwdArgs& p, const float* s_co
 
 template <int CC, int MAXT>
 __global__ void __launch_bounds__(kThreads) k_sage_bwd_a(SageBwdArgs p) {
+  act_salt(p.act_out); act_salt(p.act_in);   // device-side dropout salt (CUDA-graph replays)
   CGNN_SMEM_DECL;
   float* sm = reinterpret_cast<float*>(cgnn_smem);
   float* s_w = sm + p.o_w;      // [H4][2*K4] natural layout
@@ -423,6 +425,7 @@ struct SageBwdBArgs {
 // du_in[j] = direct[j] + sum_{e: src=j} w_e * nbr[dst(e)]   (nbr already divided by wsum+1e-8)
 template <int CC>
 __global__ void __launch_bounds__(kThreads) k_sage_bwd_b(SageBwdBArgs p) {
+  act_salt(p.act_in);   // device-side dropout salt (CUDA-graph replays)
   CGNN_SMEM_DECL;
   float* sm = reinterpret_cast<float*>(cgnn_smem);
   float* s_g = sm + p.o_g;      // [max_nodes][K4]

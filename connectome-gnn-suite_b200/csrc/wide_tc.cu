@@ -264,6 +264,7 @@ struct WideXtyArgs {
 };
 
 __global__ void __launch_bounds__(kThreads, 1) k_wide_xty(WideXtyArgs p) {
+  act_salt(p.act_in);   // device-side dropout salt (CUDA-graph replays)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t mbar[X_STAGES];
   __shared__ uint32_t tmem_base_s;
@@ -411,6 +412,7 @@ struct WideDzArgs {
 };
 
 __global__ void __launch_bounds__(kThreads, 2) k_wide_dz(WideDzArgs p) {
+  act_salt(p.act_out);   // device-side dropout salt (CUDA-graph replays)
   __shared__ float4 s_red[kThreads];
   const int tid = threadIdx.x, q = tid & 63, r = tid >> 6;
   rt::ChanQuad cq;

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGNN_ABI_VERSION 6
+#define CGNN_ABI_VERSION 7
 
 typedef void* cgnn_stream_t; /* cudaStream_t */
 
@@ -118,6 +118,8 @@ typedef struct {
   uint64_t seed;
   uint32_t site;       /* which dropout site of the network (layer index)  */
   int64_t  row_base;   /* global row id of local row 0 (rank offset under data parallelism) */
+  const uint32_t* salt; /* NULL, or two DEVICE words folded into the mask stream at kernel start: a CUDA-graphed step keeps
+                         * them in its state block (cgnn_step_tick) so that every replay draws new masks */
 } cgnn_act_t;
 
 /* BatchNorm1d backward coefficients of one layer (reference: autograd of models.py:208/260):
@@ -283,7 +285,7 @@ int cgnn_pool_fwd(const float* t_in, const cgnn_act_t* act, const int64_t* ptr, 
  * post-ReLU, post-dropout activations (kept for backward). */
 int cgnn_head_fwd(const float* emb, const float* W0, const float* b0, const float* W1, const float* b1,
                   int64_t num_graphs, int32_t C, int32_t M, int32_t K, float p_drop, uint64_t seed,
-                  int64_t graph_base, float* hidden, float* logits, cgnn_stream_t stream);
+                  int64_t graph_base, const uint32_t* salt, float* hidden, float* logits, cgnn_stream_t stream);
 
 /* Cross entropy over graphs: loss_sum[0] = sum_g nll_g * inv_count (inv_count = 1/B_global gives
  * nn.CrossEntropyLoss()'s mean), correct[0] = #argmax == label (int64), nll [B] per graph.
@@ -345,6 +347,18 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
                         float* dW, float* dbias, float* du_in,
                         const float* prev_mean, const float* prev_rstd, float* prev_sums,
                         float* scratch, void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
+
+/* ---- the step after backward (reference train.py:51) -----------------------------------------
+ * A training step that is replayed as a CUDA graph cannot take anything that changes from step to step as a launch
+ * argument, so the step counter and the dropout salt live in a device state block of four uint64:
+ *   [0] steps taken   [1] seed (set once by the host)   [2] = the two 32-bit salt words cgnn_act_t.salt points at   [3] spare
+ * cgnn_step_tick: [0] += 1 and new salt words from (seed, step) - the first node of a graphed step.
+ * cgnn_adam_step: torch.optim.Adam's update (weight decay added to the gradient, bias-corrected first / second moments)
+ * over a FLAT parameter buffer of n floats, its flat gradient and moment buffers; the step number is read from state[0].
+ * Same arithmetic, op for op in fp32, as torch's single-tensor implementation. */
+int cgnn_step_tick(uint64_t* state, cgnn_stream_t stream);
+int cgnn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, const uint64_t* state, cgnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -344,3 +344,141 @@ def check_fused_eval(device, layers=3, sizes=(84, 84, 360, 30, 84, 57, 84, 84, 1
     m.zero_grad()
     m(store.collate(ids, prepare_for="gcn")).sum().backward()
     assert all(p.grad is not None for p in m.parameters())
+
+
+def check_fused_step(device, kind="gcn", steps=4):
+    """Trainer.enable_fused_step(): flat parameter / gradient buffers + cgnn_adam_step against the plain Trainer with
+    torch.optim.Adam on the same batches (dropout 0): identical losses, parameters equal to fp32 round-off of the update."""
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import Trainer
+    graphs = generate_dataset(num_subjects=24, num_regions=30, seed=9)
+    store = SubjectStore(pack_graphs(graphs), device)
+    cls = GCNConnectome if kind == "gcn" else GraphSAGEConnectome
+    runs = {}
+    for fused in (False, True):
+        torch.manual_seed(5)
+        model = cls(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.0).to(device)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-2, weight_decay=1e-3, foreach=False)
+        tr = Trainer(model, opt, device=device)
+        if fused:
+            tr.enable_fused_step()
+            assert tr._adam is not None and all(p.data_ptr() >= tr.flat.param.data_ptr() for p in model.parameters())
+        losses = []
+        for s in range(steps):
+            model.train()
+            ids = (np.arange(8) * 3 + s) % 24
+            losses.append(float(tr.train_step(store.collate(ids, prepare_for=kind))))
+        if fused:     # the gradients live in the flat buffer: param.grad aliases it
+            for p in model.parameters():
+                off, n, _ = tr.flat.slots[id(p)]
+                assert p.grad is not None and p.grad.data_ptr() == tr.flat.grad.data_ptr() + 4 * off
+        runs[fused] = (losses, {k: v.detach().clone() for k, v in model.state_dict().items()})
+    assert runs[True][0][0] == runs[False][0][0], "first-step loss must be identical (same kernels, same weights)"
+    for a, b in zip(runs[True][0], runs[False][0]):
+        assert abs(a - b) <= 2e-6 * max(abs(b), 1.0), (runs[True][0], runs[False][0])
+    for k, v in runs[False][1].items():
+        # GCN conv biases feed BatchNorm: their gradient is pure round-off (SURVEY 2.2) and Adam normalises round-off to
+        # full-size steps, so they are not comparable between two summation orders - and do not influence the output
+        noise_driven = kind == "gcn" and ((k.startswith("convs.") and k.endswith(".bias")) or k.endswith("running_mean"))
+        if v.dtype.is_floating_point and not noise_driven:     # (running_mean absorbs the conv bias)
+            helpers.assert_close(runs[True][1][k], v, f"after {steps} fused steps: {k}", tol=2e-5)
+
+
+def check_adam_kernel(device):
+    """cgnn_adam_step against torch.optim.Adam (single-tensor implementation) on the same gradient sequence."""
+    from connectome_gnn import _engine
+    eng = _engine.engine_for(torch.zeros(1, device=device)) if torch.device(device).type == "cuda" else helpers.emu_engine()
+    g = torch.Generator().manual_seed(3)
+    n = 5000
+    w0 = torch.randn(n, generator=g)
+    p_ref = torch.nn.Parameter(w0.clone().to(device))
+    opt = torch.optim.Adam([p_ref], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, foreach=False)
+    w, m, v = w0.clone().to(device), torch.zeros(n, device=device), torch.zeros(n, device=device)
+    state = torch.zeros(4, dtype=torch.int64, device=device)
+    worst, equal = 0.0, 0
+    for step in range(6):
+        grad = (torch.randn(n, generator=g) * (0.5 ** step)).to(device)
+        p_ref.grad = grad.clone()
+        opt.step()
+        eng.step_tick(state)
+        eng.adam_step(w, grad, m, v, 3e-3, 0.9, 0.999, 1e-8, 1e-4, state)
+        assert int(state[0]) == step + 1
+        worst = max(worst, helpers.max_rel(w, p_ref.detach()))
+        equal += int(torch.equal(w, p_ref.detach()))
+    assert worst <= 1e-6, worst          # one fp32 ulp of the update at most
+    return worst, equal
+
+
+def check_graphed_step(kind="gcn", batch=16, regions=84):
+    """Trainer.capture(): one CUDA graph per step.  With dropout off the replays reproduce the eager fused step bit for
+    bit (same kernels, same order); with dropout on every replay draws new masks from the device salt; evaluation replays
+    equal the eager evaluation.  Returns (train us per step, eval us per step) measured with CUDA events."""
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import Trainer
+    dev = "cuda"
+    graphs = generate_dataset(num_subjects=3 * batch, num_regions=regions, seed=21)
+    store = SubjectStore(pack_graphs(graphs), dev)
+    cls = GCNConnectome if kind == "gcn" else GraphSAGEConnectome
+    id_seq = [(np.arange(batch) * 3 + s) % len(graphs) for s in range(6)]
+
+    def make(dropout):
+        torch.manual_seed(11)
+        model = cls(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=dropout).to(dev)
+        return Trainer(model, torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4), device=dev)
+
+    eager = make(0.0).enable_fused_step(seed=1)
+    ref_losses = []
+    for ids in id_seq:
+        eager.model.train()
+        ref_losses.append(float(eager.train_step(store.collate(ids, prepare_for=kind))))
+    graphed = make(0.0)
+    graphed.enable_fused_step(seed=1)
+    step = graphed.capture(store, batch, kind, train=True)
+    # the capture's warm-up steps trained the model: start both from the same weights again
+    fresh = make(0.0)
+    with torch.no_grad():
+        for p, q in zip(graphed.model.parameters(), fresh.model.parameters()):
+            p.copy_(q)
+        for (_, b1), (_, b2) in zip(graphed.model.named_buffers(), fresh.model.named_buffers()):
+            b1.copy_(b2)
+        graphed._adam["m"].zero_(); graphed._adam["v"].zero_(); graphed._state[0] = 0
+    got = [float(step(ids)) for ids in id_seq]
+    assert got == ref_losses, (got, ref_losses)
+    for p, q in zip(graphed.model.parameters(), eager.model.parameters()):
+        assert torch.equal(p, q)
+    # dropout: new masks on every replay
+    drop = make(0.3)
+    dstep = drop.capture(store, batch, kind, train=True)
+    with torch.no_grad():
+        saved = [p.detach().clone() for p in drop.model.parameters()]
+    l1 = float(dstep(id_seq[0]))
+    with torch.no_grad():
+        for p, q in zip(drop.model.parameters(), saved):
+            p.copy_(q)
+    l2 = float(dstep(id_seq[0]))
+    assert np.isfinite(l1) and np.isfinite(l2) and l1 != l2, (l1, l2)
+    # evaluation replays
+    estep = graphed.capture(store, batch, kind, train=False)
+    graphed.model.eval()
+    for ids in id_seq[:3]:
+        loss_g, corr_g = estep(ids)
+        lg, cg = float(loss_g), int(corr_g)
+        loss_e, corr_e = graphed.eval_step(store.collate(ids, prepare_for=kind, backward=False))
+        assert lg == float(loss_e) and cg == int(corr_e)
+    # device time per replay
+    out = []
+    for fn in (lambda: step(id_seq[0]), lambda: estep(id_seq[0])):
+        for _ in range(5):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1) / 50 * 1e3)
+    return tuple(out)

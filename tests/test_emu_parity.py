@@ -188,3 +188,12 @@ def test_lean_collate(on_emu):
 def test_fused_eval(on_emu, layers):
     """K9 on the simulator: ring / weight-reload / readout protocol for 2, 3 and 4 layers, mixed subject sizes."""
     parity.check_fused_eval("cpu", layers, sizes=(84, 30, 130, 57, 84, 200))
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_fused_step_flat_buffers(on_emu, kind):
+    parity.check_fused_step("cpu", kind, steps=3)
+
+
+def test_adam_kernel(on_emu):
+    parity.check_adam_kernel("cpu")

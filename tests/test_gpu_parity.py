@@ -492,6 +492,23 @@ def test_no_reads_of_unwritten_memory(kind):
     assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2]), kind
 
 
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_fused_step_flat_buffers(kind):
+    parity.check_fused_step(DEV, kind)
+
+
+def test_adam_kernel_matches_torch_adam():
+    worst, equal = parity.check_adam_kernel(DEV)
+    print(f"cgnn_adam_step vs torch.optim.Adam: max-norm relative difference {worst:.2e}, bit-identical after {equal} of 6 steps")
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_graphed_step(kind):
+    """BASELINE configs[0] / [1] shape (batch 16, 84-node subjects, hidden 64) as CUDA graphs."""
+    train_us, eval_us = parity.check_graphed_step(kind, batch=16, regions=84)
+    print(f"{kind}: graphed train step {train_us:.0f} us, graphed eval step {eval_us:.0f} us (batch 16, 84 nodes, collate included)")
+
+
 @pytest.mark.parametrize("layers", [2, 3, 4])
 def test_fused_eval(layers):
     parity.check_fused_eval(DEV, layers)
