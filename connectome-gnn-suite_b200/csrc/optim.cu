@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) k_adam(AdamArgs p) {
   const double step = (double)p.state[0];
   const double bc1 = 1.0 - pow((double)p.beta1, step), bc2 = 1.0 - pow((double)p.beta2, step);
   const float step_size = (float)((double)p.lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  const float inv_bc2_sqrt = 1.0f / (float)sqrt(bc2);     // ATen divides a tensor by a host scalar as a multiplication by its reciprocal
   const float w1 = (float)(1.0 - (double)p.beta1), w2 = (float)(1.0 - (double)p.beta2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     const float w = p.param[i];
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_adam(AdamArgs p) {
     float m = p.exp_avg[i], v = p.exp_avg_sq[i];
     m = fmaf(w1, g - m, m);                                               // exp_avg.lerp_(grad, 1 - beta1)
     v = fmaf(__fmul_rn(w2, g), g, __fmul_rn(v, p.beta2));                 // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), p.eps);  // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+    const float denom = __fadd_rn(__fmul_rn(sqrtf(v), inv_bc2_sqrt), p.eps);   // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
     p.param[i] = fmaf(-step_size, __fdiv_rn(m, denom), w);                // param.addcdiv_(exp_avg, denom, value=-step_size)
     p.exp_avg[i] = m;
     p.exp_avg_sq[i] = v;
