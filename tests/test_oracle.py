@@ -104,7 +104,7 @@ def test_models_match_reference(fixture, kind):
     scale = max(float(np.abs(a[f"{kind}.train.grad.{k}"]).max()) for k in grads)
     for k, g in grads.items():
         zero_by_construction = kind == "gcn" and k.startswith("convs.") and k.endswith(".bias")
-        _same(g, a[f"{kind}.train.grad.{k}"], f"grad {k}", noise_atol=5e-6 * scale if zero_by_construction else 0.0,   # pure round-off, not run-to-run deterministic at 8 threads
+        _same(g, a[f"{kind}.train.grad.{k}"], f"grad {k}", noise_atol=5e-6 * scale if zero_by_construction else 0.0,   # pure round-off, not deterministic at 8 threads
               grad=True)
     for k in p:
         if "running" in k or "num_batches" in k:
@@ -260,4 +260,4 @@ print(json.dumps(out))
         for k, g in grads.items():
             zero_by_construction = kind == "gcn" and k.startswith("convs.") and k.endswith(".bias")
             _same(g, np.array(ref[kind]["grads"][k], dtype=np.float32), f"live grad {k}",
-                  noise_atol=5e-6 * scale if zero_by_construction else 0.0,   # pure round-off, not run-to-run deterministic at 8 threads grad=True)
+                  noise_atol=5e-6 * scale if zero_by_construction else 0.0, grad=True)
