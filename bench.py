@@ -532,6 +532,22 @@ def extra_configs(a, world, rank, dev, lib):
                 us = e0.elapsed_time(e1) / 50 * 1e3
                 rec[f"{kind}_{name}"] = {"us_per_step": us, "graphs_per_s": 16 / (us * 1e-6), "host_us_per_step": wall * 1e6,
                                          "cgnn_launches_per_step": (lib.cgnn_kernel_launches() - l0) / 50}
+            # the same two steps replayed as CUDA graphs (Trainer.capture: flat buffers, fused Adam, device-side dropout salt)
+            for name, train in (("train", True), ("infer", False)):
+                step = tr.capture(store, 16, kind, train=train)
+                for _ in range(10):
+                    step(ids)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                e0.record()
+                for _ in range(100):
+                    step(ids)
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) / 100 * 1e3
+                rec[f"{kind}_{name}_graphed"] = {"us_per_step": us, "graphs_per_s": 16 / (us * 1e-6),
+                                                 "host_us_per_step": (time.perf_counter() - t0) / 100 * 1e6}
         out["configs[0],[1]: batch 16, 84-node, hidden 64 (collate + step, device time)"] = rec
     if world == 8:
         graphs = generate_dataset(num_subjects=64, num_regions=360, seed=42)
