@@ -288,6 +288,7 @@ def run_b200(a):
         raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_to_gpu_numa_node(local)     # before any pinned allocation: first touch puts the arenas on that node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -312,8 +313,10 @@ def run_b200(a):
     trainers = {}
     for kind, cls in (("gcn", GCNConnectome), ("sage", GraphSAGEConnectome)):
         model = cls(in_channels=5, hidden_dim=a.hidden, num_classes=2, num_layers=a.layers, dropout=a.dropout).to(dev)
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
-        trainers[kind] = Trainer(model, opt, device=dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+        # flat parameter / gradient buffers: the Adam update is one kernel and the data-parallel gradient exchange one
+        # all-reduce over the flat buffer (no per-parameter cat / copy)
+        trainers[kind] = Trainer(model, opt, device=dev).enable_fused_step()
     order_gen = torch.Generator().manual_seed(99 + rank)
 
     def leg(name, st):
@@ -401,9 +404,13 @@ def run_b200(a):
             step_e2e()
         e2e_steps = max(2, min(a.steps, 5))
         ms_e = timed(step_e2e, e2e_steps)
+        # what the host link gives this rank when nothing else runs: one arena upload alone, timed on the copy stream
+        h2d_gbs = measure_h2d(streaming, pinned, h2d_bytes)
         e2e = {"value": graphs_per_step * e2e_steps / (ms_e / 1e3), "unit": "graphs/s",
                "h2d_bytes_per_step": int(h2d_bytes * len(a.legs)), "d2h_bytes_per_step": 4 * len(a.legs),
                "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
+               "h2d_gbs_per_rank_alone": h2d_gbs, "h2d_gbs_per_rank_in_step": h2d_bytes * len(a.legs) / (ms_e / e2e_steps / 1e3) / 1e9,
+               "cpu_affinity": affinity,
                "path": "pinned host arena (compact pair store: " + ("one entry per undirected edge" if packed_c.get("edge_pairs") else "one entry per directed edge") + ") -> StreamingStore (H2D on a copy stream, double-buffered) -> collate -> Trainer.train_step/eval_step -> the step's four losses read back to the host"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------------
@@ -636,6 +643,41 @@ def dp_parity(a, world, rank, dev, pool, per_rank=48):
         out["what"] = f"one DP train step over NCCL ({world} ranks x {per_rank} subjects, dropout 0) vs the same global batch on rank 0 alone"
     dist.barrier()
     return out
+
+
+def pin_to_gpu_numa_node(index):
+    """Bind this process (and with it every pinned host allocation it first touches) to the CPUs NVML reports as local to
+    GPU `index`: eight ranks pulling their batches through one socket's memory controller was the end-to-end limiter at
+    N = 8.  Returns a short description for the record; a box that exposes no topology is left alone."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1 and 64 * i + b < ncpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed and len(allowed) < ncpu:
+            os.sched_setaffinity(0, allowed)
+            return {"cpus": f"{allowed[0]}-{allowed[-1]}", "count": len(allowed), "of": ncpu}
+        return {"cpus": "all", "count": len(os.sched_getaffinity(0)), "of": ncpu, "note": "GPU is local to every CPU the box exposes"}
+    except Exception as exc:
+        return {"cpus": "unchanged", "note": repr(exc)[:120]}
+
+
+def measure_h2d(streaming, pinned, nbytes, reps=3):
+    arena = streaming._arenas[0]
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(streaming.stream):
+            e0.record()
+            arena.reload(pinned, streaming.stream)
+            e1.record()
+        torch.cuda.synchronize()
+        best = max(best, nbytes / (e0.elapsed_time(e1) / 1e3) / 1e9)
+    return best
 
 
 def profile_calls(a, eng, step_fn, peak, peak_src):

@@ -308,6 +308,26 @@ class SubjectStore:
                               self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), self.label.data_ptr(),
                               self.num_features, self.edge_pairs)
 
+    def _upload_ids(self, ids_np: np.ndarray) -> torch.Tensor:
+        """Subject indices to the device through a small ring of PINNED staging buffers (a pageable source makes the copy
+        synchronous and bounces it through the driver's own staging area)."""
+        n = int(ids_np.size)
+        if self.device.type != "cuda":       # test-only simulator engine: host pointers
+            return torch.from_numpy(ids_np).to(self.device)
+        ring = getattr(self, "_ids_ring", None)
+        if ring is None or ring[0][0].numel() < n:
+            ring = self._ids_ring = [[torch.empty(max(n, 1), dtype=torch.int64).pin_memory(), None] for _ in range(4)]
+            self._ids_next = 0
+        slot = ring[self._ids_next % len(ring)]
+        self._ids_next += 1
+        if slot[1] is not None:
+            slot[1].synchronize()            # the copy that last used this buffer (four collates ago) has long finished
+        slot[0][:n].copy_(torch.from_numpy(ids_np))
+        out = slot[0][:n].to(self.device, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(self.device))
+        return out
+
     def release(self) -> None:
         """Mark the work enqueued so far on the current stream as the last use of this arena's contents: a later
         ``reload`` on another stream waits for it on the device, so the host never has to synchronise."""
@@ -369,7 +389,7 @@ class SubjectStore:
         labelled = self.has_label[ids_np]
         all_labelled = bool(labelled.all()) and ids_np.size > 0
         if ids_device is None:
-            ids_device = torch.from_numpy(ids_np).to(self.device, non_blocking=True)
+            ids_device = self._upload_ids(ids_np)
         ready = getattr(self, "_ready", None)
         if ready is not None:      # an upload enqueued on another stream (reload): order this stream after it
             torch.cuda.current_stream(self.device).wait_event(ready)
