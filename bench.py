@@ -292,6 +292,8 @@ def run_b200(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    if os.environ.get("BENCH_PAGEABLE_IDS"):      # A/B switch of the harness only: subject indices from pageable memory
+        SubjectStore._upload_ids = lambda self, ids_np: torch.from_numpy(ids_np).to(self.device, non_blocking=True)
 
     # ---- synthetic inputs: a pool of unique reference-identical subjects, tiled to the batch -------------
     t0 = time.time()
@@ -514,6 +516,11 @@ def extra_configs(a, world, rank, dev, lib):
             model.process_group = False     # single-process semantics even under torchrun (no collectives: rank 0 only)
             tr = Trainer(model, torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True), device=dev)
             tr.distributed = False
+            torch.manual_seed(0)
+            gmodel = cls(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.3).to(dev)
+            gmodel.process_group = False
+            gtr = Trainer(gmodel, torch.optim.Adam(gmodel.parameters(), lr=1e-3, weight_decay=1e-4), device=dev)
+            gtr.distributed = False
 
             def train():
                 tr.model.train()
@@ -541,7 +548,7 @@ def extra_configs(a, world, rank, dev, lib):
                                          "cgnn_launches_per_step": (lib.cgnn_kernel_launches() - l0) / 50}
             # the same two steps replayed as CUDA graphs (Trainer.capture: flat buffers, fused Adam, device-side dropout salt)
             for name, train in (("train", True), ("infer", False)):
-                step = tr.capture(store, 16, kind, train=train)
+                step = gtr.capture(store, 16, kind, train=train)
                 for _ in range(10):
                     step(ids)
                 torch.cuda.synchronize()
