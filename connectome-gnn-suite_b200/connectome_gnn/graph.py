@@ -443,21 +443,25 @@ class StreamingStore:
     last kernel that reads a set has been enqueued (or synchronise with the host): ``prefetch`` into that arena then
     waits for it on the device."""
 
-    def __init__(self, packed: dict, device=None):
+    def __init__(self, packed: dict, device=None, depth: int = 2):
         self.device = torch.device(device) if device is not None else _engine.default_device()
         self.stream = torch.cuda.Stream(device=self.device)
-        self._arenas = [SubjectStore(packed, self.device), SubjectStore(packed, self.device)]
+        # `depth` device arenas: uploads run up to depth - 1 sets ahead of the set being processed (depth 3 gives every
+        # upload two processing steps of slack - short inference steps no longer wait for the host link)
+        self._arenas = [SubjectStore(packed, self.device) for _ in range(max(2, int(depth)))]
         torch.cuda.current_stream(self.device).synchronize()
         self._filled, self._taken = 0, 0
 
     def prefetch(self, packed: dict) -> None:
-        self._arenas[self._filled % 2].reload(packed, self.stream)
+        if self._filled - self._taken >= len(self._arenas):
+            raise RuntimeError("StreamingStore.prefetch(): every arena holds a set that has not been taken yet")
+        self._arenas[self._filled % len(self._arenas)].reload(packed, self.stream)
         self._filled += 1
 
     def next(self) -> SubjectStore:
         if self._taken >= self._filled:
             raise RuntimeError("StreamingStore.next() without a matching prefetch()")
-        store = self._arenas[self._taken % 2]
+        store = self._arenas[self._taken % len(self._arenas)]
         self._taken += 1
         return store
 
