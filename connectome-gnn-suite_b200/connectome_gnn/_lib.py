@@ -73,6 +73,7 @@ PROTOTYPES = {
     "cgnn_set_option": (C.c_int, [_i32, _i32]),
     "cgnn_collate_csr": (C.c_int, [_P(StoreT), _p, _i64, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p,
                                    _P(CsrT), _p]),
+    "cgnn_fetch_ids": (C.c_int, [_p, _i64, _p, _p]),
     "cgnn_csr_from_coo": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i32, _p, _P(CsrT), _p]),
     "cgnn_agg_words": (_sz, [_i64, _i64, _i64]),
     "cgnn_build_agg": (C.c_int, [_P(CsrT), _i32, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),

@@ -309,8 +309,7 @@ class SubjectStore:
                               self.num_features, self.edge_pairs)
 
     def _upload_ids(self, ids_np: np.ndarray) -> torch.Tensor:
-        """Subject indices to the device through a small ring of PINNED staging buffers (a pageable source makes the copy
-        synchronous and bounces it through the driver's own staging area)."""
+        """Subject indices to the device through a small ring of PINNED staging buffers, fetched by a kernel."""
         n = int(ids_np.size)
         if self.device.type != "cuda":       # test-only simulator engine: host pointers
             return torch.from_numpy(ids_np).to(self.device)
@@ -323,7 +322,11 @@ class SubjectStore:
         if slot[1] is not None:
             slot[1].synchronize()            # the copy that last used this buffer (four collates ago) has long finished
         slot[0][:n].copy_(torch.from_numpy(ids_np))
-        out = slot[0][:n].to(self.device, non_blocking=True)
+        # a kernel reads the pinned buffer over the bus (cgnn_fetch_ids): a DMA of these few KB would wait on the copy
+        # engine behind a StreamingStore upload of tens of MB
+        eng = _engine.engine_for(self.x)
+        out = torch.empty(n, dtype=torch.int64, device=self.device)
+        eng._call("cgnn_fetch_ids", slot[0].data_ptr(), n, out.data_ptr(), eng.stream())
         slot[1] = torch.cuda.Event()
         slot[1].record(torch.cuda.current_stream(self.device))
         return out

@@ -58,6 +58,15 @@ __global__ void __launch_bounds__(1024) k_scan_ptrs(const long long* __restrict_
   }
 }
 
+// Subject indices from PINNED HOST memory (dereferenced over the bus: pinned allocations are mapped into the device's
+// address space) into a device buffer.  A cudaMemcpyAsync of these few KB would queue behind whatever the host-to-device
+// copy engine is doing - with dataset arenas streaming in (StreamingStore) that is a 77 MB upload per step leg, and the
+// compute stream would wait for it; a kernel read does not touch the copy engine.
+__global__ void __launch_bounds__(256) k_fetch_ids(const long long* __restrict__ host_ids, long long n, long long* __restrict__ ids) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] = host_ids[i];
+}
+
 // Edge ranges of an already collated COO batch: edges are grouped by subject, so
 // eptr[g] = first edge whose source id is >= ptr[g].
 __global__ void __launch_bounds__(256) k_edge_ranges(const long long* __restrict__ src, long long E,
@@ -515,6 +524,16 @@ int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int6
   a.ptr = (const long long*)ptr; a.eptr = (const long long*)eptr;
   a.csr = *csr;
   return collate_launch(a, true, max_nodes, max_edges, stream);
+}
+
+int cgnn_fetch_ids(const int64_t* pinned_host_ids, int64_t n, int64_t* ids, cgnn_stream_t stream_) {
+  if (n < 0 || (n > 0 && (!pinned_host_ids || !ids))) return CGNN_ERR_INVALID_ARG;
+  if (n == 0) return CGNN_OK;
+  auto kfn = k_fetch_ids;
+  CGNN_LAUNCH(kfn, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_, (const long long*)pinned_host_ids, (long long)n,
+              (long long*)ids);
+  CGNN_CHECK_LAUNCH();
+  return CGNN_OK;
 }
 
 int cgnn_csr_from_coo(const int64_t* edge_index, const float* edge_weight, const int64_t* ptr,

@@ -189,6 +189,10 @@ int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int6
                      int64_t* batch, int64_t* labels, int64_t* ptr, int64_t* eptr,
                      const cgnn_csr_out_t* csr, cgnn_stream_t stream);
 
+/* ids[i] = pinned_host_ids[i]: brings the subject indices of a batch from PINNED (device-mapped) host memory into a
+ * device buffer with a kernel instead of a DMA, so that they never queue behind a dataset upload on the copy engine. */
+int cgnn_fetch_ids(const int64_t* pinned_host_ids, int64_t n, int64_t* ids, cgnn_stream_t stream);
+
 /* Same CSR, from an already collated batch (COO with global ids, grouped by subject as
  * collate_graphs emits it).  Used for ConnectomeBatch objects built by hand / moved from
  * the host.  eptr [B+1] is an output. */
