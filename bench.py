@@ -292,8 +292,6 @@ def run_b200(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    if os.environ.get("BENCH_PAGEABLE_IDS"):      # A/B switch of the harness only: subject indices from pageable memory
-        SubjectStore._upload_ids = lambda self, ids_np: torch.from_numpy(ids_np).to(self.device, non_blocking=True)
 
     # ---- synthetic inputs: a pool of unique reference-identical subjects, tiled to the batch -------------
     t0 = time.time()

@@ -429,7 +429,7 @@ class SubjectStore:
 
 
 class StreamingStore:
-    """Subjects that live in (pinned) host memory and visit the GPU one packed set at a time: two device arenas, the
+    """Subjects that live in (pinned) host memory and visit the GPU one packed set at a time: ``depth`` device arenas, the
     upload of set k+1 runs on a side stream while set k is being collated and processed (pinned-host
     staging for datasets that do not stay resident).  Usage::
 
