@@ -355,17 +355,24 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, trace=None):
+        """Device time of ``steps`` calls (CUDA events on the launching stream, barrier + synchronize on both sides, max
+        over ranks).  ``trace`` receives this rank's per-step device and host milliseconds (diagnostic only)."""
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        host = [time.perf_counter()]
+        marks[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            marks[i + 1].record()
+            host.append(time.perf_counter())
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        ms = torch.tensor([marks[0].elapsed_time(marks[-1])], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if trace is not None:
+            trace["device_ms"] = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(steps)]
+            trace["host_enqueue_ms"] = [round((host[i + 1] - host[i]) * 1e3, 3) for i in range(steps)]
         return float(ms)
 
     warm = max(a.warmup, 3)
@@ -373,7 +380,8 @@ def run_b200(a):
         step_resident()
     launches0 = lib.cgnn_kernel_launches()
     with ClockSampler(local) as clocks:
-        ms = timed(step_resident, a.steps)
+        trace = {}
+        ms = timed(step_resident, a.steps, trace)
     launches = lib.cgnn_kernel_launches() - launches0
     graphs_per_step = len(a.legs) * a.batch * world
     value = graphs_per_step * a.steps / (ms / 1e3)
@@ -404,14 +412,15 @@ def run_b200(a):
         for _ in range(2):
             step_e2e()
         e2e_steps = max(2, min(a.steps, 5))
-        ms_e = timed(step_e2e, e2e_steps)
+        trace_e = {}
+        ms_e = timed(step_e2e, e2e_steps, trace_e)
         # what the host link gives this rank when nothing else runs: one arena upload alone, timed on the copy stream
         h2d_gbs = measure_h2d(streaming, pinned, h2d_bytes)
         e2e = {"value": graphs_per_step * e2e_steps / (ms_e / 1e3), "unit": "graphs/s",
                "h2d_bytes_per_step": int(h2d_bytes * len(a.legs)), "d2h_bytes_per_step": 4 * len(a.legs),
                "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
                "h2d_gbs_per_rank_alone": h2d_gbs, "h2d_gbs_per_rank_in_step": h2d_bytes * len(a.legs) / (ms_e / e2e_steps / 1e3) / 1e9,
-               "cpu_affinity": affinity,
+               "cpu_affinity": affinity, "per_step": trace_e,
                "path": "pinned host arena (compact pair store: " + ("one entry per undirected edge" if packed_c.get("edge_pairs") else "one entry per directed edge") + ") -> StreamingStore (H2D on a copy stream, double-buffered) -> collate -> Trainer.train_step/eval_step -> the step's four losses read back to the host"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------------
@@ -445,7 +454,7 @@ def run_b200(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": f"synthetic ({a.pool} unique generated subjects tiled to {a.batch}, generated in {gen_s:.1f}s)",
             "config": workload_config(a, world), "legs": legs, "clocks": clocks.summary(), "e2e": e2e,
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+            "per_step": trace, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
         }
         if dp is not None:
             line["dp_parity"] = dp

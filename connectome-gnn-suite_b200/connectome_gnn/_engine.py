@@ -62,6 +62,17 @@ class BnBwd:
         return BnBwdT(_p(self.scale), _p(self.mean), _p(self.rstd), s1, s2, float(self.count), int(self.train))
 
 
+_EVAL_ARRAYS: dict = {}
+
+
+def _eval_layer_array(n: int):
+    """ctypes array types are created per ``T * n`` expression and each one sits in a reference cycle: keep one per n."""
+    t = _EVAL_ARRAYS.get(n)
+    if t is None:
+        t = _EVAL_ARRAYS[n] = EvalLayerT * n
+    return t
+
+
 class Engine:
     """Binds a loaded ABI library to one device: workspace, stream lookup, call wrappers."""
 
@@ -231,7 +242,7 @@ class Engine:
         if kind != "gcn" or num_graphs == 0 or rows == 0:
             return None
         self.ensure_agg(csr, kind, num_graphs, rows, csr.num_edges, need_out=False)
-        arr = (EvalLayerT * len(layers))()
+        arr = _eval_layer_array(len(layers))()
         for i, (W, b, g, be, rm, rv, eps) in enumerate(layers):
             arr[i] = EvalLayerT(_p(W), _p(b), _p(g), _p(be), _p(rm), _p(rv), float(eps))
         emb = self.empty((num_graphs, H))

@@ -77,6 +77,20 @@ class ConnectomeGraph:
 # Batch
 # ---------------------------------------------------------------------------
 
+class _FullCollate:
+    """What a lean batch and its lean CSR share to fill themselves in: the store and the subject indices, and - once
+    somebody asked - the full batch collated from them.  Holds no reference to the lean objects (no cycle)."""
+    __slots__ = ("store", "ids_np", "ids_device", "full")
+
+    def __init__(self, store, ids_np, ids_device):
+        self.store, self.ids_np, self.ids_device, self.full = store, ids_np, ids_device, None
+
+    def get(self):
+        if self.full is None:
+            self.full = self.store.collate(self.ids_np, ids_device=self.ids_device)
+        return self.full
+
+
 class BatchCSR:
     """Device CSR of a batch (``cgnn_csr_t``): by-destination and by-source rows in stable COO
     order, raw and GCN-normalised weights, D^ / d^-1/2 / w_sum.  See include/cgnn.h.
@@ -101,7 +115,7 @@ class BatchCSR:
         self.max_edges = max_edges       # most edges in one subject
         self.agg = agg                   # model family -> (agg_in, agg_out | None, row_graph) packed blobs
         self.num_edges = int(num_edges) if num_edges is not None else (int(in_col.shape[0]) if in_col is not None else 0)
-        self._fill = fill                # callable returning a full BatchCSR of the same batch (lean instances)
+        self._fill = fill                # lean instances: _FullCollate of the same subjects (holds no reference back)
 
     def peek(self, name: str):
         """The array if it exists on the device, else None (never materialises)."""
@@ -117,7 +131,7 @@ class BatchCSR:
         if not self.is_full():
             if self._fill is None:
                 raise RuntimeError("this BatchCSR has no CSR arrays and no way to build them")
-            self._fill()
+            self._adopt(self._fill.get().csr)
         return self
 
     def _adopt(self, full: "BatchCSR") -> None:
@@ -157,7 +171,9 @@ class ConnectomeBatch:
     global_num_graphs: Optional[int] = None
     global_num_nodes: Optional[int] = None
     # lean batches (SubjectStore.collate(prepare_for=...)): edge_index / edge_weight / batch are None until somebody
-    # reads them; `_fill` then collates the same subjects again with every reference field requested
+    # reads them; `_fill` (a _FullCollate, shared with the CSR) then collates the same subjects again with every
+    # reference field requested.  It must not refer back to the batch: a reference cycle would keep every batch (GBs of
+    # device memory) alive until the cyclic garbage collector happens to run
     _fill: Optional[object] = None
 
     _LAZY = ("edge_index", "edge_weight", "batch")
@@ -167,7 +183,10 @@ class ConnectomeBatch:
         if v is None and name in ConnectomeBatch._LAZY:
             fill = object.__getattribute__(self, "_fill")
             if fill is not None:
-                fill()
+                full = fill.get()
+                for k in ConnectomeBatch._LAZY:
+                    object.__setattr__(self, k, object.__getattribute__(full, k))
+                object.__setattr__(self, "_fill", None)
                 v = object.__getattribute__(self, name)
         return v
 
@@ -415,16 +434,9 @@ class SubjectStore:
             out["node_features"], out["edge_index"], out["edge_weight"], out["batch"], labels, out["ptr"],
             bcsr, row_base, graph_base, global_num_graphs, global_num_nodes)
         if out["edge_index"] is None:          # lean: the missing fields are one full collate of the same subjects away
-            def fill(batch=batch, bcsr=bcsr, ids_np=ids_np, ids_device=ids_device):
-                if object.__getattribute__(batch, "_fill") is None:
-                    return
-                full = self.collate(ids_np, ids_device=ids_device)
-                for k in ConnectomeBatch._LAZY:
-                    object.__setattr__(batch, k, object.__getattribute__(full, k))
-                bcsr._adopt(full.csr)
-                object.__setattr__(batch, "_fill", None)
-            object.__setattr__(batch, "_fill", fill)
-            bcsr._fill = fill
+            src = _FullCollate(self, ids_np, ids_device)
+            object.__setattr__(batch, "_fill", src)
+            bcsr._fill = src
         return batch
 
 

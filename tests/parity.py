@@ -482,3 +482,40 @@ def check_graphed_step(kind="gcn", batch=16, regions=84):
         torch.cuda.synchronize()
         out.append(e0.elapsed_time(e1) / 50 * 1e3)
     return tuple(out)
+
+
+def check_batches_die_by_refcount(device, kind="gcn", num_regions=30):
+    """A step leaves no reference cycle behind: every batch (and with it GBs of device memory at bench sizes) is freed
+    when its last reference goes, not whenever the cyclic garbage collector next runs - with cycles the caching allocator
+    keeps asking the driver for new segments in the middle of timed steps."""
+    import gc
+    import weakref
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import Trainer
+    graphs = generate_dataset(num_subjects=8, num_regions=num_regions, seed=9)
+    store = SubjectStore(pack_graphs(graphs), device)
+    cls = GCNConnectome if kind == "gcn" else GraphSAGEConnectome
+    model = cls(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.3).to(device)
+    tr = Trainer(model, torch.optim.Adam(model.parameters(), lr=1e-2), device=device).enable_fused_step()
+    ids = np.arange(8)
+    for mode in ("train", "eval", "untouched"):
+        for rep in range(2):
+            if rep == 1:
+                gc.collect()
+                gc.disable()
+            try:
+                b = store.collate(ids, prepare_for=kind, backward=(mode == "train"))
+                alive = [weakref.ref(b.csr), weakref.ref(b.node_features)]
+                if mode == "train":
+                    model.train()
+                    tr.train_step(b)
+                elif mode == "eval":
+                    model.eval()
+                    tr.eval_step(b)
+                del b
+                if rep == 1:
+                    assert all(r() is None for r in alive), f"{kind} {mode}: the batch survived its last reference (cycle)"
+            finally:
+                gc.enable()

@@ -184,6 +184,11 @@ def test_lean_collate(on_emu):
     parity.check_lean_collate("cpu", "gcn")
 
 
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_batches_die_by_refcount(on_emu, kind):
+    parity.check_batches_die_by_refcount("cpu", kind)
+
+
 @pytest.mark.parametrize("layers", [2, 3, 4])
 def test_fused_eval(on_emu, layers):
     """K9 on the simulator: ring / weight-reload / readout protocol for 2, 3 and 4 layers, mixed subject sizes."""

@@ -520,6 +520,11 @@ def test_lean_collate(kind):
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_batches_die_by_refcount(kind):
+    parity.check_batches_die_by_refcount(DEV, kind, num_regions=120)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_collate_emits_the_same_aggregation_structure(kind):
     """`prepare_for` (blobs written by the collate kernel) and the lazy `cgnn_build_agg` path feed the layer kernels
     identical structure: forward outputs and backward gradients are bit-identical."""
