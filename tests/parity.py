@@ -298,9 +298,9 @@ def check_lean_collate(device, kind="gcn"):
         assert not lean.csr.is_full(), "a training step on a lean batch must not need the CSR arrays"
     for f in ("node_features", "edge_index", "edge_weight", "batch", "labels", "ptr"):
         assert torch.equal(getattr(lean, f), getattr(full, f)), f
-    assert lean.csr.is_full()
-    for f in lean.csr._ARRAYS + ("graph_meta", "eptr"):
+    for f in lean.csr._ARRAYS + ("graph_meta", "eptr"):      # first read adopts the arrays of the same full collate
         assert torch.equal(getattr(lean.csr, f), getattr(full.csr, f)), f
+    assert lean.csr.is_full()
 
 
 def check_fused_eval(device, layers=3, sizes=(84, 84, 360, 30, 84, 57, 84, 84, 130)):
