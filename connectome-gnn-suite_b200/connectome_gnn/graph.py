@@ -248,14 +248,16 @@ def _is_pair_list(ei: torch.Tensor, w: torch.Tensor, n_edges: np.ndarray) -> boo
     return bool(torch.equal(a[0], b[1]) and torch.equal(a[1], b[0]) and torch.equal(w[0::2], w[1::2]))
 
 
-def pack_graphs(graphs: Sequence[ConnectomeGraph], compact: bool = False, pairs: bool = False) -> dict:
+def pack_graphs(graphs: Sequence[ConnectomeGraph], compact: Optional[bool] = None, pairs: Optional[bool] = None) -> dict:
     """Host packing of a list of subjects into arena arrays (pure indexing, no arithmetic).
 
     Returns CPU tensors: ``x [sum N, F]`` f32, ``src/dst [sum E]`` int32 subject-local ids,
     ``w [sum E]`` f32, ``node_ptr/edge_ptr [S+1]`` int64, ``label [S]`` int64 (0 where absent)
     and ``has_label [S]`` bool.  ``compact`` packs both endpoints into one int32; ``pairs`` (with ``compact``)
     additionally stores one entry per undirected edge when every subject's list allows it (``edge_pairs`` = 1 in the
-    result, else 0 and the plain compact form).  Raises ``ValueError`` on ragged feature widths or edge
+    result, else 0 and the plain compact form).  Both default to "when possible" (``None``): subjects under 65536 nodes,
+    lists made of adjacent reversed pairs - the smallest arena, and the collate kernel then sorts once for both
+    directions; pass ``False`` for the plain forms.  Raises ``ValueError`` on ragged feature widths or edge
     endpoints outside ``[0, N_s)`` - the kernels index shared-memory tiles with them."""
     if len(graphs) == 0:
         raise ValueError("cannot pack an empty list of ConnectomeGraph")
@@ -283,6 +285,10 @@ def pack_graphs(graphs: Sequence[ConnectomeGraph], compact: bool = False, pairs:
         vals = torch.stack([cpu(g.label).reshape(()).to(torch.int64) for g in graphs if g.label is not None])
         label[torch.from_numpy(np.nonzero(has_label)[0])] = vals
     edge_pairs = 0
+    if compact is None:
+        compact = not (n_nodes.size and int(n_nodes.max()) > 65535)
+    if pairs is None:
+        pairs = bool(compact)
     if compact:
         # both endpoints of an edge in one int32 (src | dst << 16): 4 bytes less per edge over PCIe
         if n_nodes.size and int(n_nodes.max()) > 65535:

@@ -417,6 +417,180 @@ __global__ void __launch_bounds__(NT) k_collate_graph(CollateArgs p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Lean collate of a PAIR store (one stored entry per undirected edge; entry k stands for the directed edges 2k = u -> v
+// and 2k + 1 = v -> u of equal weight).  Every node then meets the same partners, in the same order and with the same
+// weights, in its by-destination list as in its by-source list (pair k contributes exactly one half-edge to either
+// list of each endpoint, and the lists are ordered by k), so ONE stable counting sort of the 2 * pairs half-edges by
+// owner serves both aggregation blobs, the weighted degree D^ and w_sum; the general kernel above sorts twice.  The
+// records are then written edge-parallel (consecutive threads, consecutive records) instead of row by row.  Bit for bit
+// the blobs of k_collate_graph (tests: lean vs full collate).  NT / 32 warps = NT / 32 chunks of the half-edge list.
+template <int NT>
+__global__ void __launch_bounds__(NT) k_collate_pairs(CollateArgs p) {
+  constexpr int kNW = NT / 32;
+  CGNN_SMEM_DECL;
+  __shared__ int s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long g = blockIdx.x;
+  const long long nb = p.ptr[g], eb = p.eptr[g];
+  const int n = (int)(p.ptr[g + 1] - nb);
+  const int m = (int)(p.eptr[g + 1] - eb);       // directed edges = half-edges
+  if (tid == 0) reinterpret_cast<int4*>(p.csr.graph_meta)[g] = make_int4((int)nb, n, (int)eb, m);
+  if (n > p.max_nodes || m > p.edge_cap) return;  // host contract violated: never index past the shared arrays
+
+  int* start = reinterpret_cast<int*>(cgnn_smem);          // [n] packed counts -> first sorted slot (low 16 bits) | first record (high)
+  float* s_dinv = reinterpret_cast<float*>(start + n);     // [n]
+  float* s_wsum = s_dinv + n;                              // [n]
+  int* cnt = reinterpret_cast<int*>(s_wsum + n);           // [kNW][n] per-chunk counts -> cursors
+  uint32_t* pk = reinterpret_cast<uint32_t*>(cnt + kNW * n);   // [m] sorted half-edges: owner | partner << 16
+  float* cw = reinterpret_cast<float*>(pk + m);                // [m]
+  uint32_t* raw_pk = reinterpret_cast<uint32_t*>(cw + m);      // [m / 2] stored pairs: u | v << 16
+  float* raw_w = reinterpret_cast<float*>(raw_pk + (m >> 1));  // [m / 2]
+
+  const long long sid = p.ids[g];
+  const long long sn = p.store.node_ptr[sid], so = p.store.edge_ptr[sid] >> 1;
+  const int32_t* lsrc = p.store.src + so;
+  const float* lw = p.store.w + so;
+  const int np = m >> 1;
+  {
+    const int F = p.store.num_features;
+    const float* sx = p.store.x + sn * F;
+    float* dx = p.x + nb * F;
+    for (int i0 = tid; i0 < n * F; i0 += 4 * NT) {     // four loads in flight per thread
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = i0 + u * NT < n * F ? sx[i0 + u * NT] : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * NT < n * F) dx[i0 + u * NT] = v[u];
+    }
+    if (p.batch)
+      for (int i = tid; i < n; i += NT) p.batch[nb + i] = g;
+    if (tid == 0 && p.labels && p.store.label) p.labels[g] = p.store.label[sid];
+  }
+  for (int k0 = tid; k0 < np; k0 += 3 * NT) {          // three pairs in flight per thread
+    uint32_t v[3]; float w[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) { v[u] = 0u; w[u] = 0.0f; if (k0 + u * NT < np) { v[u] = (uint32_t)lsrc[k0 + u * NT]; w[u] = lw[k0 + u * NT]; } }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      if (k0 + u * NT >= np) continue;
+      // endpoints outside the subject: a zero-weight self edge on node 0 (as k_collate_graph does, edge by edge)
+      if ((v[u] & 0xffffu) >= (uint32_t)n || (v[u] >> 16) >= (uint32_t)n) { v[u] = 0u; w[u] = 0.0f; }
+      raw_pk[k0 + u * NT] = v[u];
+      raw_w[k0 + u * NT] = w[u];
+    }
+  }
+  for (int i = tid; i < kNW * n; i += NT) cnt[i] = 0;
+  __syncthreads();
+
+  // half-edge h: owner = (h & 1 ? v : u), partner = the other endpoint of pair h >> 1
+  const int clen = (((m + kNW - 1) / kNW) + 31) & ~31;
+  const int h_lo = min(warp * clen, m), h_hi = min(h_lo + clen, m);
+  int* my_cnt = cnt + (size_t)warp * n;
+  for (int h = h_lo + lane; h < h_hi; h += 32) {
+    const uint32_t v = raw_pk[h >> 1];
+    atomicAdd(&my_cnt[(h & 1) ? (v >> 16) : (v & 0xffffu)], 1);
+  }
+  __syncthreads();
+  const int self = p.csr.agg_kind == AGG_GCN ? 1 : 0;
+  for (int i = tid; i < n; i += NT) {
+    int t = 0;
+    for (int c = 0; c < kNW; ++c) t += cnt[(size_t)c * n + i];
+    start[i] = t | (((t + self + 1) & ~1) << 16);     // both totals stay below 2^16 (the lists fit in shared memory)
+  }
+  __syncthreads();
+  block_excl_scan(start, n, s_warp);
+  for (int i = tid; i < n; i += NT) {
+    int run = start[i] & 0xffff;
+    for (int c = 0; c < kNW; ++c) {
+      int* q = &cnt[(size_t)c * n + i];
+      const int t = *q;
+      *q = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  for (int h0 = h_lo; h0 < h_hi; h0 += 32) {
+    const int h = h0 + lane;
+    const bool live = h < h_hi;
+    uint32_t v = 0u; float w = 0.0f;
+    if (live) { v = raw_pk[h >> 1]; w = raw_w[h >> 1]; }
+    if (h & 1) v = (v >> 16) | (v << 16);             // owner in the low half
+    const int key = live ? (int)(v & 0xffffu) : -1 - lane;
+    const unsigned peers = __match_any_sync(kFull, key);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int at = 0;
+    if (live) at = my_cnt[key];
+    __syncwarp();
+    if (live) {
+      pk[at + rank] = v;
+      cw[at + rank] = w;
+      if (rank == 0) my_cnt[key] = at + __popc(peers);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // D^ (by-source sum, self-loop weight 1 last) and w_sum (by-destination sum): the same sequence here
+  for (int i = tid; i < n; i += NT) {
+    const int q0 = start[i] & 0xffff, q1 = i + 1 < n ? (start[i + 1] & 0xffff) : m;
+    float s = 0.0f;
+    for (int q = q0; q < q1; ++q) s = __fadd_rn(s, cw[q]);
+    const float deg = __fadd_rn(s, 1.0f);
+    s_dinv[i] = (float)(1.0 / sqrt((double)__fadd_rn(deg, 1e-8f)));
+    s_wsum[i] = s;
+    p.csr.row_graph[nb + i] = (int32_t)g;
+  }
+  __syncthreads();
+
+  const bool gcn = p.csr.agg_kind == AGG_GCN;
+  int32_t* blob_in = p.csr.agg_in + agg_base_words(nb, eb, g);
+  int32_t* blob_out = p.csr.agg_out ? p.csr.agg_out + agg_base_words(nb, eb, g) : nullptr;
+  int2* rec_in = reinterpret_cast<int2*>(blob_in + 4 * (long long)n);
+  int2* rec_out = blob_out ? reinterpret_cast<int2*>(blob_out + 4 * (long long)n) : nullptr;
+  for (int q = tid; q < m; q += NT) {
+    const uint32_t v = pk[q];
+    const int i = (int)(v & 0xffffu), j = (int)(v >> 16);
+    const float w = cw[q];
+    const int st = start[i];
+    const int at = ((unsigned)st >> 16) + (q - (st & 0xffff));
+    const float di = s_dinv[i], dj = s_dinv[j];
+    // row i as destination, j the source:  (dinv[src] * w) * dinv[dst]   (reference models.py:108 evaluation order)
+    rec_in[at] = make_int2(agg_rec_x(j), __float_as_int(gcn ? __fmul_rn(__fmul_rn(dj, w), di) : w));
+    // row i as source, j the destination; GraphSAGE: the adjoint of the weighted mean
+    if (rec_out) rec_out[at] = make_int2(j, __float_as_int(gcn ? __fmul_rn(__fmul_rn(di, w), dj) : w / (s_wsum[j] + 1e-8f)));
+  }
+  for (int i = tid; i < n; i += NT) {
+    const int st = start[i];
+    const int q0 = st & 0xffff, q1 = i + 1 < n ? (start[i + 1] & 0xffff) : m;
+    const int begin = (int)((unsigned)st >> 16);
+    int at = begin + (q1 - q0);
+    const int at0 = at;
+    const float dv = s_dinv[i];
+    const int self_w = __float_as_int(__fmul_rn(dv, dv));
+    int end = at;
+    if (self) ++end;
+    const bool pad = end & 1;
+    if (pad) ++end;
+    {
+      int a2 = at0;
+      if (self) rec_in[a2++] = make_int2(agg_rec_x(i), self_w);
+      if (pad) rec_in[a2++] = make_int2(agg_rec_x(i), 0);
+    }
+    if (rec_out) {
+      int a2 = at0;
+      if (self) rec_out[a2++] = make_int2(i, self_w);
+      if (pad) rec_out[a2++] = make_int2(i, 0);
+    }
+    const float aux = gcn ? dv : s_wsum[i];
+    reinterpret_cast<int4*>(blob_in)[i] = make_int4(begin, end, __float_as_int(aux), i);
+    if (blob_out) reinterpret_cast<int4*>(blob_out)[i] = make_int4(begin, end, __float_as_int(aux), i);
+    (void)at;
+  }
+}
+
 }  // namespace cgnn
 
 using namespace cgnn;
@@ -462,6 +636,27 @@ static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, int ma
   }
   a.max_nodes = max_nodes;
   if (a.B <= 0) return CGNN_OK;
+  // pair store + lean batch: one sort serves both blobs (k_collate_pairs); four CTAs per SM at the 360-node shape
+  if (from_store && lean && a.store.edge_pairs && max_edges >= 0 && (max_edges & 1) == 0 && a.csr.agg_kind >= 0 && max_nodes <= 65535) {
+    const int ntp = (max_nodes <= 128 && a.total_edges / a.B <= 2048) ? 128 : 256;
+    const size_t smem_p = (size_t)max_nodes * (12 + 4 * (ntp / 32)) + (size_t)max_edges * 12 + 16;
+    if (smem_p <= (size_t)dev.smem_optin) {
+      const int cap = a.edge_cap;
+      a.edge_cap = max_edges;
+      if (ntp == 128) {
+        auto kfn = k_collate_pairs<128>;
+        if (smem_p > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+        CGNN_LAUNCH(kfn, (unsigned)a.B, 128, smem_p, stream, a);
+      } else {
+        auto kfn = k_collate_pairs<256>;
+        if (smem_p > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+        CGNN_LAUNCH(kfn, (unsigned)a.B, 256, smem_p, stream, a);
+      }
+      CGNN_CHECK_LAUNCH();
+      (void)cap;
+      return CGNN_OK;
+    }
+  }
 #define CGNN_COLLATE(FS_, NT_)                                                                              \
   {                                                                                                         \
     auto kfn = k_collate_graph<FS_, NT_>;                                                                   \

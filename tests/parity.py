@@ -263,7 +263,7 @@ def check_trainer(kind, device):
             helpers.assert_close(v, final[k], f"final {k}", tol=1e-4)
 
 
-def check_lean_collate(device, kind="gcn"):
+def check_lean_collate(device, kind="gcn", compact=None):
     """SubjectStore.collate(prepare_for=...) is LEAN: nothing but what the layer kernels read is written; the reference
     fields and the CSR arrays appear on first access, bit for bit what a full collate writes; a forward-only batch
     (backward=False) still trains - the missing half of the structure is built on demand."""
@@ -272,7 +272,7 @@ def check_lean_collate(device, kind="gcn"):
     from connectome_gnn.synthetic import generate_dataset
     from connectome_gnn.train import CrossEntropyLoss
     graphs = generate_dataset(num_subjects=6, num_regions=84, seed=41) + generate_dataset(num_subjects=2, num_regions=30, seed=42)
-    store = SubjectStore(pack_graphs(graphs), device)
+    store = SubjectStore(pack_graphs(graphs, compact=compact), device)
     ids = np.array([7, 0, 3, 3, 5, 1])
     full = store.collate(ids)
     lean = store.collate(ids, prepare_for=kind)
@@ -519,3 +519,48 @@ def check_batches_die_by_refcount(device, kind="gcn", num_regions=30):
                     assert all(r() is None for r in alive), f"{kind} {mode}: the batch survived its last reference (cycle)"
             finally:
                 gc.enable()
+
+
+def _blob_words(blob, meta, g):
+    """The defined words of subject g's aggregation blob: descriptors, then every row's records [begin, end)."""
+    nb, n, eb, m = (int(v) for v in meta[g])
+    base = 8 * nb + 2 * (eb + (eb & 1)) + 4 * g
+    desc = blob[base:base + 4 * n].reshape(n, 4)
+    out = [desc.reshape(-1)]
+    rec = blob[base + 4 * n:]
+    for i in range(n):
+        b, e = int(desc[i, 0]), int(desc[i, 1])
+        out.append(rec[2 * b:2 * e])
+    return torch.cat(out)
+
+
+def check_pair_collate(device, sizes=(30, 84, 57, 130), with_bad_edge=True):
+    """k_collate_pairs (pair store, lean batch: one sort for both blobs) writes bit for bit the blobs, row_graph and
+    graph_meta the general collate kernel writes for the same subjects - also with an out-of-range endpoint in the store."""
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.synthetic import generate_dataset
+    graphs = []
+    for k, n in enumerate(sizes):
+        graphs += generate_dataset(num_subjects=2, num_regions=n, seed=100 + k)
+    packed = pack_graphs(graphs)
+    assert packed["edge_pairs"] == 1, "the synthetic generator emits adjacent reversed pairs: pack_graphs must detect them"
+    if with_bad_edge:       # endpoint beyond the subject: both kernels turn the edge into a zero-weight self edge on node 0
+        packed["src"] = packed["src"].clone()
+        packed["src"][5] = int(packed["src"][5]) | (0x7fff << 16)
+    store = SubjectStore(packed, device)
+    ids = np.array([3, 0, 7, 7, 2, 5, 1])
+    for kind in ("gcn", "sage"):
+        for backward in (True, False):
+            lean = store.collate(ids, prepare_for=kind, backward=backward)
+            full = store.collate(ids, prepare_for=kind, lean=False, backward=backward)
+            assert not lean.csr.is_full() and full.csr.is_full()
+            meta = full.csr.graph_meta.cpu()
+            assert torch.equal(lean.csr.graph_meta.cpu(), meta)
+            assert torch.equal(lean.node_features, full.node_features) and torch.equal(lean.labels, full.labels)
+            la, fa = lean.csr.agg[kind], full.csr.agg[kind]
+            assert torch.equal(la[2], fa[2]), "row_graph"
+            assert (la[1] is None) == (not backward)
+            for d in range(2 if backward else 1):
+                lb, fb = la[d].cpu(), fa[d].cpu()
+                for g in range(len(ids)):
+                    assert torch.equal(_blob_words(lb, meta, g), _blob_words(fb, meta, g)), (kind, backward, d, g)

@@ -179,9 +179,14 @@ def test_ws_engine_dropout_matches_generic_kernels(on_emu):
     assert float((outs[0] - outs[1]).abs().max()) <= 1e-5 * float(outs[1].abs().max())
 
 
-def test_lean_collate(on_emu):
+@pytest.mark.parametrize("compact", [None, False])      # pair store (k_collate_pairs) / plain store (k_collate_graph)
+def test_lean_collate(on_emu, compact):
     # hidden 64: the GCN hidden layers run on the warp-specialised engine, which never reads the CSR arrays
-    parity.check_lean_collate("cpu", "gcn")
+    parity.check_lean_collate("cpu", "gcn", compact)
+
+
+def test_pair_collate_bit_exact(on_emu):
+    parity.check_pair_collate("cpu")
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])

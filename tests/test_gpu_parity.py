@@ -514,9 +514,15 @@ def test_fused_eval(layers):
     parity.check_fused_eval(DEV, layers)
 
 
+@pytest.mark.parametrize("compact", [None, False])      # pair store (k_collate_pairs) / plain store (k_collate_graph)
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
-def test_lean_collate(kind):
-    parity.check_lean_collate(DEV, kind)
+def test_lean_collate(kind, compact):
+    parity.check_lean_collate(DEV, kind, compact)
+
+
+@pytest.mark.parametrize("sizes", [(30, 84, 57, 130), (360, 200, 360, 84)])
+def test_pair_collate_bit_exact(sizes):
+    parity.check_pair_collate(DEV, sizes)
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])

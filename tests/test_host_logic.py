@@ -29,11 +29,14 @@ def test_connectome_graph_helpers():
 def test_pack_graphs_layout_and_validation():
     from connectome_gnn.graph import pack_graphs
     graphs = [_graph(5, 7, seed=1), _graph(9, 0, seed=2, label=None), _graph(4, 12, seed=3, label=1)]
-    p = pack_graphs(graphs)
+    p = pack_graphs(graphs, compact=False)
     assert p["node_ptr"].tolist() == [0, 5, 14, 18] and p["edge_ptr"].tolist() == [0, 7, 7, 19]
     assert p["src"].dtype == torch.int32 and p["x"].shape == (18, 3) and p["num_features"] == 3
     assert p["has_label"].tolist() == [True, False, True] and p["label"].tolist() == [0, 0, 1]
     assert torch.equal(p["src"][7:].long(), graphs[2].edge_index[0])
+    c = pack_graphs(graphs)      # default: the smallest form the lists allow - compact words; these random lists are not pair lists
+    assert c["edge_pairs"] == 0 and c["dst"].numel() == 0
+    assert torch.equal(c["src"][7:].long() & 0xffff, graphs[2].edge_index[0]) and torch.equal((c["src"][7:].long() >> 16) & 0xffff, graphs[2].edge_index[1])
     bad = _graph(5, 7, seed=4)
     bad.edge_index[1, 3] = 5
     with pytest.raises(ValueError, match="outside its subject"):
