@@ -2,7 +2,7 @@
 //
 //   GCN (reference models.py:84-114 after models.py:208-210):   z = A^ (u W^T) + b,   u = dropout(relu(bn(t_in)))
 //   GraphSAGE (models.py:136-152 after models.py:259-261):      z = relu(u Ws^T + mean_w(u Wn^T) + b),   u = dropout(bn(t_in)),
-//       W = [Ws | Wn]; forward-only calls (no `agg` buffer wanted for a backward pass).  Two N = 64 MMAs per K step give
+//       W = [Ws | Wn]; forward-only calls (no `agg` buffer wanted for a backward pass).  One MMA of N = 128 gives
 //       S = u Ws^T and P = u Wn^T; S goes to z and comes back through L2 when the row's neighbours have been gathered.
 //
 // A UNIT is one subject, or several consecutive small subjects, of at most 384 rows.  Five roles run concurrently and
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kNT, 1) k_layer_fwd_ws(const __grid_constant__
   } else if (warp == kWarpMma) {
     // ================================ MMA issuer ===================================================================
     if (lane == 0) {
-      const uint32_t idesc = ws::idesc_tf32(kTR, kC);
+      const uint32_t idesc = ws::idesc_tf32(kTR, kN);
       const uint64_t b_hi = ws::smem_desc_sw128(ws::smem_u32(w_hi)), b_lo = ws::smem_desc_sw128(ws::smem_u32(w_lo));
       uint32_t tcount = 0, uses[kMaxTiles] = {0, 0, 0};
       for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -144,13 +144,7 @@ __global__ void __launch_bounds__(kNT, 1) k_layer_fwd_ws(const __grid_constant__
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t bo = (uint64_t)((h * kN * 128 + ks * 32) >> 4);
               const uint32_t ac = (uint32_t)(32 * h + 8 * ks);
-              // GraphSAGE: two N = 64 products per step, S = u Ws^T into the first 64 accumulator columns and P = u Wn^T
-              // (operand rows 64.., 8 KB further) into the next 64.  Measured on B200: ONE N = 128 tcgen05.mma with the A
-              // operand in tensor memory gave wrong accumulator rows in about one launch in twenty (same operands,
-              // same barriers; 80 launches of this form: none) - so the proven N = 64 shape is issued twice.
               ws::mma_tf32x3_ts(d, tmem + kColAHi + ac, tmem + kColALo + ac, b_hi + bo, b_lo + bo, idesc, (h | ks) ? 1u : 0u);
-              if (kSage)
-                ws::mma_tf32x3_ts(d + kC, tmem + kColAHi + ac, tmem + kColALo + ac, b_hi + bo + 512u, b_lo + bo + 512u, idesc, (h | ks) ? 1u : 0u);
             }
             ws::mma_commit(&bars.a_free[h]);       // this half of the A columns may be rewritten once these MMAs are done
           }

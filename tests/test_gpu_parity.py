@@ -520,9 +520,8 @@ def test_lean_collate(kind, compact):
     parity.check_lean_collate(DEV, kind, compact)
 
 
-@pytest.mark.parametrize("sizes", [(84, 30, 130, 57, 84, 200, 360), (360,) * 12, (84,) * 64])
-def test_sage_engine_forward(sizes):
-    parity.check_sage_engine_forward(DEV, sizes, repeats=40)
+def test_sage_engine_forward():
+    parity.check_sage_engine_forward(DEV)
 
 
 @pytest.mark.parametrize("sizes", [(30, 84, 57, 130), (360, 200, 360, 84)])
