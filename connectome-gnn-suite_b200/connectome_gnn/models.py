@@ -110,7 +110,7 @@ class _EncodeFn(torch.autograd.Function):
 
         t, act = x.contiguous(), Act()
         saved = []
-        will_backward = cfg.get("will_backward", True)
+        will_backward = any(ctx.needs_input_grad)       # False under torch.no_grad() / with every input frozen
         for l, bn in enumerate(cfg["bns"]):
             W, b, gamma, beta = (q.contiguous() for q in params[4 * l: 4 * l + 4])
             z, stats, agg = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, want_stats=training, need_agg=will_backward)
@@ -325,9 +325,6 @@ class _ConnectomeClassifier(nn.Module):
         params = []
         for conv, bn in zip(self.convs, self.batch_norms):
             params += [*conv.tensors(), bn.weight, bn.bias]
-        # decided here: inside Function.forward grad mode is always off.  False under torch.no_grad() / with everything frozen
-        cfg["will_backward"] = torch.is_grad_enabled() and (batch.node_features.requires_grad or
-                                                            any(q is not None and q.requires_grad for q in params))
         return _EncodeFn.apply(cfg, batch.node_features, *params)
 
     def _fused_eval(self, batch: ConnectomeBatch, want_logits: bool):
