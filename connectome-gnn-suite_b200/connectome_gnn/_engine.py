@@ -205,11 +205,8 @@ class Engine:
         return csr, eptr
 
     # -- K1 / K2 ------------------------------------------------------------------------------
-    def layer_fwd(self, kind: str, t_in, act: Act, W, bias, csr, ptr, num_graphs: int, want_stats: bool,
-                  need_agg: bool = True):
-        """Returns (z, stats, agg): ``agg`` is GraphSAGE's aggregated neighbourhood [rows, d_in] (kept for backward).
-        ``need_agg`` = False (nobody will call the backward): hidden 64 -> 64 GraphSAGE layers then run on the
-        warp-specialised engine, which projects before it aggregates and never forms ``agg`` (returned as None)."""
+    def layer_fwd(self, kind: str, t_in, act: Act, W, bias, csr, ptr, num_graphs: int, want_stats: bool):
+        """Returns (z, stats, agg): ``agg`` is GraphSAGE's aggregated neighbourhood [rows, d_in] (kept for backward)."""
         rows, d_in = t_in.shape
         H = W.shape[0]
         if W.shape[1] != (2 * d_in if kind == "sage" else d_in):
@@ -218,8 +215,7 @@ class Engine:
         stats = self.empty(1 + 2 * H, torch.float64) if want_stats else None
         self.ensure_agg(csr, kind, num_graphs, rows, csr.num_edges, need_out=False)
         a = act.struct()
-        engine_shape = d_in == 64 and H == 64 and 1 <= csr.max_nodes <= 384
-        agg = self.empty((rows, d_in)) if kind == "sage" and (need_agg or not engine_shape) else None
+        agg = self.empty((rows, d_in)) if kind == "sage" else None
 
         def build():
             cs = self.csr_struct(csr, kind)

@@ -110,10 +110,9 @@ class _EncodeFn(torch.autograd.Function):
 
         t, act = x.contiguous(), Act()
         saved = []
-        will_backward = any(ctx.needs_input_grad)       # False under torch.no_grad() / with every input frozen
         for l, bn in enumerate(cfg["bns"]):
             W, b, gamma, beta = (q.contiguous() for q in params[4 * l: 4 * l + 4])
-            z, stats, agg = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, want_stats=training, need_agg=will_backward)
+            z, stats, agg = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, want_stats=training)
             if training:
                 stats = _merge_stats_across_ranks(eng, stats, W.shape[0], cfg["group"])
                 if bn.momentum is None:    # torch: cumulative moving average, factor 1 / num_batches_tracked (after increment)

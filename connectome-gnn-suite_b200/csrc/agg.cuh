@@ -156,9 +156,8 @@ struct GatherArgs {
 // agg.cu: one gather kernel; CGNN_OK when launched (grid in *grid_out: the caller reduces `partials` over it),
 // -1 when the shape is not covered.
 int launch_gather(int mode, GatherArgs& a, int* grid_out, cudaStream_t stream);
-// engine.cu: warp-specialised hidden-layer forward (64 -> 64 channels; kind = AGG_GCN, or AGG_SAGE for forward-only
-// calls; also built for the simulator)
-int launch_layer_fwd_ws(int kind, const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+// engine.cu: warp-specialised hidden-layer forward (64 -> 64 channels; also built for the simulator)
+int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
                       int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
                       double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream);
 #ifndef CGNN_EMU

@@ -1,9 +1,6 @@
 // engine.cu - warp-specialised hidden-layer forward (64 -> 64 channels), one persistent CTA per SM.
 //
 //   GCN (reference models.py:84-114 after models.py:208-210):   z = A^ (u W^T) + b,   u = dropout(relu(bn(t_in)))
-//   GraphSAGE (models.py:136-152 after models.py:259-261):      z = relu(u Ws^T + mean_w(u Wn^T) + b),   u = dropout(bn(t_in)),
-//       W = [Ws | Wn]; forward-only calls (no `agg` buffer wanted for a backward pass).  One MMA of N = 128 gives
-//       S = u Ws^T and P = u Wn^T; S goes to z and comes back through L2 when the row's neighbours have been gathered.
 //
 // A UNIT is one subject, or several consecutive small subjects, of at most 384 rows.  Five roles run concurrently and
 // hand tiles to each other through mbarriers, so the HBM stream, the tensor core and the shared-memory gather of
@@ -41,10 +38,7 @@ struct Args {
   __host__ __device__ UnitSrc src() const { return UnitSrc{meta, B, spu, blob_cap_bytes}; }
 };
 
-template <int KIND>
-__global__ void __launch_bounds__(kNT, 1) k_layer_fwd_ws(const __grid_constant__ ws::TensorMap tmap, Args p) {
-  constexpr bool kSage = KIND == AGG_SAGE;
-  constexpr int kN = kSage ? 2 * kC : kC;       // MMA N = accumulator columns per tile: [S | P] or P
+__global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ ws::TensorMap tmap, Args p) {
   act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
 #ifdef CGNN_EMU
   CGNN_SMEM_DECL;
@@ -55,8 +49,8 @@ __global__ void __launch_bounds__(kNT, 1) k_layer_fwd_ws(const __grid_constant__
   __shared__ Barriers bars;
   __shared__ uint32_t tmem_base_s;
   unsigned char* base = ws::smem_align1024(smem_raw);
-  unsigned char* w_hi = base;                           // [2 K blocks][kN rows][128 B]
-  unsigned char* w_lo = base + 2 * kN * 128;
+  unsigned char* w_hi = base;                           // [2 K blocks][64 rows][128 B]
+  unsigned char* w_lo = base + 2 * kC * 128;
   unsigned char* s_stage = base + p.o_stage;
   unsigned char* s_p = base + p.o_p;
   unsigned char* s_blob = base + p.o_blob;
@@ -76,14 +70,12 @@ __global__ void __launch_bounds__(kNT, 1) k_layer_fwd_ws(const __grid_constant__
     ws::fence_mbar_init();
   }
   if (warp == kWarpTile && lane == 0) ws::prefetch_tensor_map(&tmap);
-  // W -> K-major operand, row n = accumulator column, hi / lo parts.  GCN: W [64 out][64 in].  GraphSAGE: W [64 out][128] =
-  // [Ws | Wn]: rows 0..63 = Ws (the S columns), rows 64..127 = Wn (the P columns)
-  for (int idx = tid; idx < kN * (kC / 4); idx += kNT) {
+  // W [64 out][64 in] -> K-major operand rows n = output channel, hi / lo parts
+  for (int idx = tid; idx < kC * (kC / 4); idx += kNT) {
     const int n = idx / (kC / 4), k = (idx - n * (kC / 4)) * 4;
-    const float* src = kSage ? p.W + (n & (kC - 1)) * 2 * kC + (n >= kC ? kC : 0) + k : p.W + n * kC + k;
-    const float4 v = *reinterpret_cast<const float4*>(src);
+    const float4 v = *reinterpret_cast<const float4*>(p.W + n * kC + k);
     const float4 h = make_float4(ws::tf32_hi(v.x), ws::tf32_hi(v.y), ws::tf32_hi(v.z), ws::tf32_hi(v.w));
-    const uint32_t off = ws::kmajor_offset(n, k, kN);
+    const uint32_t off = ws::kmajor_offset(n, k, kC);
     *reinterpret_cast<float4*>(w_hi + off) = h;
     *reinterpret_cast<float4*>(w_lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
   }
@@ -127,7 +119,7 @@ __global__ void __launch_bounds__(kNT, 1) k_layer_fwd_ws(const __grid_constant__
   } else if (warp == kWarpMma) {
     // ================================ MMA issuer ===================================================================
     if (lane == 0) {
-      const uint32_t idesc = ws::idesc_tf32(kTR, kN);
+      const uint32_t idesc = ws::idesc_tf32(kTR, kC);
       const uint64_t b_hi = ws::smem_desc_sw128(ws::smem_u32(w_hi)), b_lo = ws::smem_desc_sw128(ws::smem_u32(w_lo));
       uint32_t tcount = 0, uses[kMaxTiles] = {0, 0, 0};
       for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -135,14 +127,14 @@ __global__ void __launch_bounds__(kNT, 1) k_layer_fwd_ws(const __grid_constant__
         for (int t = 0; t < un.tiles; ++t, ++tcount) {
           ws::mbar_wait_relaxed(&bars.d_free[t], (uses[t] & 1u) ^ 1u);     // the gather warps have drained this slot's previous tile
           ++uses[t];
-          const uint32_t d = tmem + kColD + (uint32_t)(kN * t);
+          const uint32_t d = tmem + kColD + (uint32_t)(kC * t);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             ws::mbar_wait_relaxed(&bars.a_full[h], tcount & 1u);
             ws::fence_after_sync();
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t bo = (uint64_t)((h * kN * 128 + ks * 32) >> 4);
+              const uint64_t bo = (uint64_t)((h * kC * 128 + ks * 32) >> 4);
               const uint32_t ac = (uint32_t)(32 * h + 8 * ks);
               ws::mma_tf32x3_ts(d, tmem + kColAHi + ac, tmem + kColALo + ac, b_hi + bo, b_lo + bo, idesc, (h | ks) ? 1u : 0u);
             }
@@ -263,18 +255,9 @@ __global__ void __launch_bounds__(kNT, 1) k_layer_fwd_ws(const __grid_constant__
         ++uses[t];
         ws::fence_after_sync();
         float v[16];
-        const int drow = t * kTR + 32 * q + lane;
-        if (kSage) {       // S = u Ws^T: parked in z (L2), picked up again by whoever gathers the row
-          ws::tmem_ld<16>(tmem + ((uint32_t)(32 * q) << 16) + kColD + (uint32_t)(kN * t + 16 * cg), v);
-          ws::tmem_ld_wait();
-          if (drow < rows) {
-            float4* zr = reinterpret_cast<float4*>(p.z + (row0 + drow) * kC + 16 * cg);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) zr[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-          }
-        }
-        ws::tmem_ld<16>(tmem + ((uint32_t)(32 * q) << 16) + kColD + (uint32_t)(kN * t + (kSage ? kC : 0) + 16 * cg), v);
+        ws::tmem_ld<16>(tmem + ((uint32_t)(32 * q) << 16) + kColD + (uint32_t)(kC * t + 16 * cg), v);
         ws::tmem_ld_wait();
+        const int drow = t * kTR + 32 * q + lane;
         if (drow < rows) {
           int j = 0;
           while (j + 1 < nsub && drow >= tab[8 + 8 * (j + 1)]) ++j;
@@ -309,8 +292,6 @@ __global__ void __launch_bounds__(kNT, 1) k_layer_fwd_ws(const __grid_constant__
         const int lmin = min(len, __shfl_xor_sync(kFull, len, 16)), lmax = max(len, __shfl_xor_sync(kFull, len, 16));
         const unsigned char* pbase = s_p + (size_t)e[1] * 256;
         const int4* rp = rec2 + (d.x >> 1);
-        float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);      // GraphSAGE: the row's own term, in flight during the gather
-        if (kSage && valid) sv = *reinterpret_cast<const float4*>(p.z + (row0 + e[0] + i) * kC + 4 * cl);
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         int k = 0;
 #pragma unroll 1
@@ -335,13 +316,7 @@ __global__ void __launch_bounds__(kNT, 1) k_layer_fwd_ws(const __grid_constant__
           fma_quad(a, v1, __int_as_float(r.w));
         }
         if (!valid) continue;
-        if (kSage) {       // weighted mean of the projected neighbours (models.py:149), own term, bias, ReLU (models.py:152)
-          const float inv = 1.0f / (__int_as_float(d.z) + 1e-8f);
-          a.x = fmaxf(fmaf(a.x, inv, sv.x) + bias4.x, 0.0f); a.y = fmaxf(fmaf(a.y, inv, sv.y) + bias4.y, 0.0f);
-          a.z = fmaxf(fmaf(a.z, inv, sv.z) + bias4.z, 0.0f); a.w = fmaxf(fmaf(a.w, inv, sv.w) + bias4.w, 0.0f);
-        } else {
-          a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-        }
+        a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
         *reinterpret_cast<float4*>(p.z + (row0 + e[0] + i) * kC + 4 * cl) = a;
         if (want_stats) {
           if (cnt == 0) sh = a;
@@ -433,12 +408,11 @@ int make_tensor_map(TensorMap* m, const float* base, long long rows, int cols, i
 #endif
 
 // Returns CGNN_OK when launched (grid in *grid_out: the caller merges `partials`), -1 when the shape is not covered.
-int launch_layer_fwd_ws(int kind, const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
                       int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
                       double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream) {
   using namespace eng;
-  if (!csr->agg_in || csr->agg_kind != kind || (kind != AGG_GCN && kind != AGG_SAGE)) return -1;
-  const int kN = kind == AGG_SAGE ? 2 * kC : kC;
+  if (!csr->agg_in || csr->agg_kind != AGG_GCN) return -1;
   if (d_in != kC || H != kC) return -1;
   if (max_nodes < 1 || max_nodes > kMaxUnitRows) return -1;
   if ((((uintptr_t)t_in) & 15u) != 0 || (((uintptr_t)z) & 15u) != 0 || (((uintptr_t)W) & 15u) != 0) return -1;
@@ -455,7 +429,7 @@ int launch_layer_fwd_ws(int kind, const float* t_in, const cgnn_act_t* act, cons
   // P rows: every subject starts at a multiple of 8
   const int p_rows = spu * ((max_nodes + 7) & ~7);
   const size_t blob_cap = (size_t)(((long long)spu * (agg_copy_words(max_nodes, max_edges) + 8) + 3) & ~3ll) * 4;
-  size_t off = (size_t)4 * kN * 128;                      // W hi / lo
+  size_t off = (size_t)4 * kC * 128;                      // W hi / lo
   a.o_stage = (int)off; off += (size_t)kNS * kStageBytes;
   a.o_p = (int)off; off += (size_t)p_rows * 256;
   if (off < (size_t)a.o_p + (size_t)kGathThreads * 9 * 4) off = (size_t)a.o_p + (size_t)kGathThreads * 9 * 4;
@@ -482,15 +456,9 @@ int launch_layer_fwd_ws(int kind, const float* t_in, const cgnn_act_t* act, cons
   *grid_out = (int)grid;
   ws::TensorMap tmap;
   if (ws::make_tensor_map(&tmap, t_in, rows, kC, kTR) != CGNN_OK) return -1;
-  if (kind == AGG_SAGE) {
-    auto kfn = k_layer_fwd_ws<AGG_SAGE>;
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    CGNN_LAUNCH(kfn, (unsigned)grid, kNT, smem, stream, tmap, a);
-  } else {
-    auto kfn = k_layer_fwd_ws<AGG_GCN>;
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    CGNN_LAUNCH(kfn, (unsigned)grid, kNT, smem, stream, tmap, a);
-  }
+  auto kfn = k_gcn_fwd_ws;
+  cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  CGNN_LAUNCH(kfn, (unsigned)grid, kNT, smem, stream, tmap, a);
   CGNN_CHECK_LAUNCH();
   return CGNN_OK;
 }

@@ -509,7 +509,7 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
   if (bn_stats && (!workspace || workspace_bytes < (size_t)(1 + 2 * H) * sizeof(double))) return CGNN_ERR_WORKSPACE;
   if (tensor_cores_enabled()) {   // warp-specialised hidden layer (TMA + tensor memory); also runs on the simulator
     int ws_grid = 0;
-    const int rc = launch_layer_fwd_ws(AGG_GCN, t_in, act, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, z,
+    const int rc = launch_gcn_fwd_ws(t_in, act, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, z,
                                      bn_stats ? (double*)workspace : nullptr, &ws_grid, workspace_bytes, stream);
     if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, ws_grid, H, bn_stats, stream) : CGNN_OK;
     if (rc > 0) return rc;

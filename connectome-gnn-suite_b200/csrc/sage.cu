@@ -538,14 +538,6 @@ int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W
   if (!t_in || !W || !csr || !csr->graph_meta || !(arrays_fwd || lean) || !ptr || !z) return CGNN_ERR_INVALID_ARG;
   if (d_in % 4 == 0 && !aligned16(t_in)) return CGNN_ERR_INVALID_ARG;
   if (bn_stats && (!workspace || workspace_bytes < (size_t)(1 + 2 * H) * sizeof(double))) return CGNN_ERR_WORKSPACE;
-  // Forward-only hidden layer (no `agg` wanted for a backward pass): the warp-specialised engine, projection first
-  if (tensor_cores_enabled() && !agg) {
-    int ws_grid = 0;
-    const int rc = launch_layer_fwd_ws(AGG_SAGE, t_in, act, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, z,
-                                       bn_stats ? (double*)workspace : nullptr, &ws_grid, workspace_bytes, stream);
-    if (rc == CGNN_OK) return bn_stats ? launch_stats_merge((const double*)workspace, ws_grid, H, bn_stats, stream) : CGNN_OK;
-    if (rc > 0) return rc;
-  }
 #ifndef CGNN_EMU
   // Narrow first layer: gather + projection in one kernel, no tensor cores.
   if (tensor_cores_enabled() && agg && d_in <= 8) {

@@ -564,40 +564,3 @@ def check_pair_collate(device, sizes=(30, 84, 57, 130), with_bad_edge=True):
                 lb, fb = la[d].cpu(), fa[d].cpu()
                 for g in range(len(ids)):
                     assert torch.equal(_blob_words(lb, meta, g), _blob_words(fb, meta, g)), (kind, backward, d, g)
-
-
-def check_sage_engine_forward(device, sizes=(84, 30, 130, 57, 84, 200, 360), hidden=64):
-    """GraphSAGE forward-only calls (torch.no_grad: nobody needs `agg`) run the hidden layers on the warp-specialised
-    engine, projection first; with gradients enabled the same model takes the gather + contraction kernels that keep
-    `agg` for the backward pass.  Both must agree to 1e-5 max-norm relative - in eval mode, and in train mode with
-    dropout (same seed -> same masks) including the BatchNorm running statistics they leave behind."""
-    from connectome_gnn.graph import SubjectStore, pack_graphs
-    from connectome_gnn.models import GraphSAGEConnectome
-    from connectome_gnn.synthetic import generate_connectome
-    graphs = [generate_connectome(num_regions=n, seed=300 + k) for k, n in enumerate(sizes)]
-    store = SubjectStore(pack_graphs(graphs), device)
-    ids = np.arange(len(sizes))
-    torch.manual_seed(11)
-    m = GraphSAGEConnectome(in_channels=5, hidden_dim=hidden, num_classes=2, num_layers=3, dropout=0.3).to(device)
-    with torch.no_grad():      # non-trivial BatchNorm state
-        for bn in m.batch_norms:
-            bn.running_mean.uniform_(-0.2, 0.2)
-            bn.running_var.uniform_(0.5, 1.5)
-            bn.weight.uniform_(0.5, 1.5)
-            bn.bias.uniform_(-0.3, 0.3)
-    state = {k: v.clone() for k, v in m.state_dict().items()}
-    outs = {}
-    for mode in ("eval", "train"):
-        for grad in (False, True):
-            m.load_state_dict(state)
-            m.train(mode == "train")
-            b = store.collate(ids, prepare_for="sage", backward=grad)
-            torch.manual_seed(77)
-            with torch.set_grad_enabled(grad):
-                out = m(b)
-            outs[mode, grad] = (out.detach().clone(), [bn.running_mean.clone() for bn in m.batch_norms],
-                                [bn.running_var.clone() for bn in m.batch_norms])
-        a, r = outs[mode, False], outs[mode, True]
-        helpers.assert_close(a[0], r[0], f"sage engine forward ({mode}) logits", tol=1e-5)
-        for x, y in zip(a[1] + a[2], r[1] + r[2]):
-            helpers.assert_close(x, y, f"sage engine forward ({mode}) running stats", tol=1e-5)

@@ -185,10 +185,6 @@ def test_lean_collate(on_emu, compact):
     parity.check_lean_collate("cpu", "gcn", compact)
 
 
-def test_sage_engine_forward(on_emu):
-    parity.check_sage_engine_forward("cpu", sizes=(84, 30, 130, 57, 200))
-
-
 def test_pair_collate_bit_exact(on_emu):
     parity.check_pair_collate("cpu")
 

@@ -520,10 +520,6 @@ def test_lean_collate(kind, compact):
     parity.check_lean_collate(DEV, kind, compact)
 
 
-def test_sage_engine_forward():
-    parity.check_sage_engine_forward(DEV)
-
-
 @pytest.mark.parametrize("sizes", [(30, 84, 57, 130), (360, 200, 360, 84)])
 def test_pair_collate_bit_exact(sizes):
     parity.check_pair_collate(DEV, sizes)
