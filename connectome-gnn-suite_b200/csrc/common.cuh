@@ -296,6 +296,16 @@ __device__ __forceinline__ void cta_write_stats(const float* s_cnt, const float*
 // fixed order): maps a zero-padded [rows, ld] partial onto a dense output (out_ld <= 0 -> cols).
 int launch_reduce_partials(const float* partials, int G, int stride, int rows, int cols, int ld,
                            float* out, cudaStream_t stream, int out_ld = 0);
+// Several of them in one launch: q.add(...) per reduction, then q.flush() (returns the first error).
+constexpr int kReduceMaxSegs = 4;
+struct ReduceSeg { const float* partials; float* out; int G, stride, rows, cols, ld, out_ld, first_block; };
+struct ReduceBatch { ReduceSeg seg[kReduceMaxSegs]; int n; };
+struct ReduceQueue {
+  ReduceBatch b; int blocks; int status; cudaStream_t stream;
+  explicit ReduceQueue(cudaStream_t s) : blocks(0), status(0), stream(s) { b.n = 0; }
+  void add(const float* partials, int G, int stride, int rows, int cols, int ld, float* out, int out_ld = 0);
+  int flush();
+};
 int launch_stats_merge(const double* parts, int parts_n, int C, double* stats, cudaStream_t stream);
 
 // Process-wide switch (cgnn_set_option): 1 = eligible shapes run on the tcgen05 kernels (default),

@@ -604,9 +604,10 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
     if (rc0 > 0) return rc0;
     if (rc0 == CGNN_OK) {
       const int stride = H * d_in + H;
-      int rc1 = launch_reduce_partials((const float*)workspace, g0, stride, H, d_in, d_in, dW, stream);
-      if (rc1) return rc1;
-      return launch_reduce_partials((const float*)workspace + H * d_in, g0, stride, 1, H, H, dbias, stream);
+      ReduceQueue rq(stream);
+      rq.add((const float*)workspace, g0, stride, H, d_in, d_in, dW);
+      rq.add((const float*)workspace + H * d_in, g0, stride, 1, H, H, dbias);
+      return rq.flush();
     }
   }
   // Wide layers (H = d_in = 256): gather + K-looped contractions (wide_tc.cu).
@@ -642,12 +643,11 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
                                  parts_b, part_stride, H * d_in, &g2, workspace_bytes - region_a, stream);
         if (rc > 0) return rc;
         if (rc == CGNN_OK) {
-          rc = launch_reduce_partials((const float*)workspace, g1, H, 1, H, H, dbias, stream);
-          if (rc) return rc;
-          rc = launch_reduce_partials(parts_b, g2, part_stride, H, d_in, d_in, dW, stream);
-          if (rc) return rc;
-          if (prev_sums) rc = launch_reduce_partials(parts_b + H * d_in, g2, part_stride, 2, d_in, d_in, prev_sums, stream);
-          return rc;
+          ReduceQueue rq(stream);
+          rq.add((const float*)workspace, g1, H, 1, H, H, dbias);
+          rq.add(parts_b, g2, part_stride, H, d_in, d_in, dW);
+          if (prev_sums) rq.add(parts_b + H * d_in, g2, part_stride, 2, d_in, d_in, prev_sums);
+          return rq.flush();
         }
       }
     }
@@ -708,15 +708,11 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
   else { if (maxt == 1) CGNN_GCN_BWD(4, 1) else if (maxt == 2) CGNN_GCN_BWD(4, 2) else CGNN_GCN_BWD(4, 4) }
 #undef CGNN_GCN_BWD
   CGNN_CHECK_LAUNCH();
-  int rc = launch_reduce_partials(a.partials + a.o_pdw, grid, a.part_stride, H, d_in, a.K4, dW, stream);
-  if (rc) return rc;
-  rc = launch_reduce_partials(a.partials + a.o_pdb, grid, a.part_stride, 1, H, a.H4, dbias, stream);
-  if (rc) return rc;
-  if (prev_sums) {
-    rc = launch_reduce_partials(a.partials + a.o_pprev, grid, a.part_stride, 2, d_in, a.K4, prev_sums, stream);
-    if (rc) return rc;
-  }
-  return CGNN_OK;
+  ReduceQueue rq(stream);
+  rq.add(a.partials + a.o_pdw, grid, a.part_stride, H, d_in, a.K4, dW);
+  rq.add(a.partials + a.o_pdb, grid, a.part_stride, 1, H, a.H4, dbias);
+  if (prev_sums) rq.add(a.partials + a.o_pprev, grid, a.part_stride, 2, d_in, a.K4, prev_sums);
+  return rq.flush();
 }
 
 }  // extern "C"

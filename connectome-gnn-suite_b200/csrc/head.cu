@@ -143,12 +143,14 @@ __global__ void __launch_bounds__(kThreads) k_head_fwd(HeadArgs p) {
 }
 
 // ---- cross entropy --------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ce_fwd(const float* __restrict__ logits, const long long* __restrict__ labels,
-                                                long long B, int K, float inv_count, float* __restrict__ nll,
-                                                float* __restrict__ loss, long long* __restrict__ correct) {
-  __shared__ double s_loss[256];
-  __shared__ long long s_corr[256];
-  const int tid = threadIdx.x;
+// One CTA (the loss is one number; fixed summation order): 1024 threads, a warp-shuffle tree per warp, then warp 0 over
+// the 32 warp sums - doubles, the same order every launch.
+__global__ void __launch_bounds__(1024) k_ce_fwd(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                 long long B, int K, float inv_count, float* __restrict__ nll,
+                                                 float* __restrict__ loss, long long* __restrict__ correct) {
+  __shared__ double s_loss[32];
+  __shared__ long long s_corr[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double acc = 0.0;
   long long corr = 0;
   for (long long g = tid; g < B; g += blockDim.x) {
@@ -167,14 +169,24 @@ __global__ void __launch_bounds__(256) k_ce_fwd(const float* __restrict__ logits
     acc += (double)v;
     corr += (ok && arg == (int)y) ? 1 : 0;
   }
-  s_loss[tid] = acc;
-  s_corr[tid] = corr;
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_down_sync(kFull, acc, o);
+    corr += __shfl_down_sync(kFull, corr, o);
+  }
+  if (lane == 0) { s_loss[warp] = acc; s_corr[warp] = corr; }
   __syncthreads();
-  if (tid == 0) {
-    double s = 0.0; long long c = 0;
-    for (int i = 0; i < (int)blockDim.x; ++i) { s += s_loss[i]; c += s_corr[i]; }
-    if (loss) loss[0] = (float)(s * (double)inv_count);
-    if (correct) correct[0] = c;
+  if (warp == 0) {
+    const int nw = (int)(blockDim.x >> 5);
+    double s = lane < nw ? s_loss[lane] : 0.0;
+    long long c = lane < nw ? s_corr[lane] : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_down_sync(kFull, s, o);
+      c += __shfl_down_sync(kFull, c, o);
+    }
+    if (lane == 0) {
+      if (loss) loss[0] = (float)(s * (double)inv_count);
+      if (correct) correct[0] = c;
+    }
   }
 }
 
@@ -337,8 +349,8 @@ int cgnn_ce_fwd(const float* logits, const int64_t* labels, int64_t num_graphs, 
   if (num_graphs < 0 || K <= 0) return CGNN_ERR_INVALID_ARG;
   if (num_graphs > 0 && (!logits || !labels)) return CGNN_ERR_INVALID_ARG;
   auto kfn = k_ce_fwd;
-  CGNN_LAUNCH(kfn, 1, 256, 0, stream, logits, (const long long*)labels, (long long)num_graphs, (int)K, inv_count,
-              nll, loss, (long long*)correct);
+  CGNN_LAUNCH(kfn, 1, num_graphs > 256 ? 1024 : 256, 0, stream, logits, (const long long*)labels, (long long)num_graphs, (int)K,
+              inv_count, nll, loss, (long long*)correct);
   CGNN_CHECK_LAUNCH();
   return CGNN_OK;
 }
@@ -398,13 +410,12 @@ int cgnn_head_bwd(const float* emb, const float* hidden, const float* dlogits, c
   if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   CGNN_LAUNCH(kfn, grid, kThreads, smem, stream, a);
   CGNN_CHECK_LAUNCH();
-  int rc = launch_reduce_partials(a.partials + a.o_dw0, grid, a.part_stride, M, C, C, dW0, stream);
-  if (rc) return rc;
-  rc = launch_reduce_partials(a.partials + a.o_db0, grid, a.part_stride, 1, M, M, db0, stream);
-  if (rc) return rc;
-  rc = launch_reduce_partials(a.partials + a.o_dw1, grid, a.part_stride, K, M, M, dW1, stream);
-  if (rc) return rc;
-  return launch_reduce_partials(a.partials + a.o_db1, grid, a.part_stride, 1, K, K, db1, stream);
+  ReduceQueue rq(stream);
+  rq.add(a.partials + a.o_dw0, grid, a.part_stride, M, C, C, dW0);
+  rq.add(a.partials + a.o_db0, grid, a.part_stride, 1, M, M, db0);
+  rq.add(a.partials + a.o_dw1, grid, a.part_stride, K, M, M, dW1);
+  rq.add(a.partials + a.o_db1, grid, a.part_stride, 1, K, K, db1);
+  return rq.flush();
 }
 
 }  // extern "C"

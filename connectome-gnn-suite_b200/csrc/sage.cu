@@ -657,9 +657,10 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
     if (rc0 > 0) return rc0;
     if (rc0 == CGNN_OK) {
       const int stride = H * 2 * d_in + H;
-      int rc1 = launch_reduce_partials((const float*)workspace, g0, stride, H, 2 * d_in, 2 * d_in, dW, stream);
-      if (rc1) return rc1;
-      return launch_reduce_partials((const float*)workspace + H * 2 * d_in, g0, stride, 1, H, H, dbias, stream);
+      ReduceQueue rq(stream);
+      rq.add((const float*)workspace, g0, stride, H, 2 * d_in, 2 * d_in, dW);
+      rq.add((const float*)workspace + H * 2 * d_in, g0, stride, 1, H, H, dbias);
+      return rq.flush();
     }
   }
   // Wide layers (H = d_in = 256): dz pass, K-looped contractions, transposed gather (wide_tc.cu; scratch = 3 x [rows, 256]).
@@ -684,11 +685,10 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
                                     direct, nbr, (float*)workspace, part_stride, H * 2 * d_in, &g1, region_a, stream);
       if (rc > 0) return rc;
       if (rc == CGNN_OK) {
-        rc = launch_reduce_partials((const float*)workspace, g1, part_stride, H, 2 * d_in, 2 * d_in, dW, stream);
-        if (rc) return rc;
-        rc = launch_reduce_partials((const float*)workspace + H * 2 * d_in, g1, part_stride, 1, H, H, dbias, stream);
-        if (rc) return rc;
-        if (!du_in) return CGNN_OK;
+        ReduceQueue rq(stream);
+        rq.add((const float*)workspace, g1, part_stride, H, 2 * d_in, 2 * d_in, dW);
+        rq.add((const float*)workspace + H * 2 * d_in, g1, part_stride, 1, H, H, dbias);
+        if (!du_in) return rq.flush();
         GatherArgs ga{};
         ga.meta = csr->graph_meta; ga.B = num_graphs; ga.blob = csr->agg_out;
         ga.C = d_in; ga.max_nodes = max_nodes; ga.max_edges = max_edges;
@@ -698,8 +698,8 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
         ga.partials = (float*)((char*)workspace + region_a); ga.part_stride = 2 * d_in;
         rc = launch_gather(GATHER_SAGE_BWD, ga, &g2, stream);
         if (rc != CGNN_OK) return rc > 0 ? rc : CGNN_ERR_TILE_TOO_LARGE;
-        if (prev_sums) return launch_reduce_partials(ga.partials, g2, 2 * d_in, 2, d_in, d_in, prev_sums, stream);
-        return CGNN_OK;
+        if (prev_sums) rq.add(ga.partials, g2, 2 * d_in, 2, d_in, d_in, prev_sums);     // all three after the gather: one launch
+        return rq.flush();
       }
     }
   }
@@ -760,13 +760,15 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
 #undef CGNN_SAGE_BWD
   CGNN_CHECK_LAUNCH();
   // dW = [dW_self | dW_neigh]: the two halves sit K4 apart in the padded partial, d_in apart in dW
-  int rc = launch_reduce_partials(a.partials + a.o_pdw, grid, a.part_stride, H, d_in, 2 * a.K4, dW, stream, 2 * d_in);
-  if (rc) return rc;
-  rc = launch_reduce_partials(a.partials + a.o_pdw + a.K4, grid, a.part_stride, H, d_in, 2 * a.K4, dW + d_in, stream,
-                              2 * d_in);
-  if (rc) return rc;
-  rc = launch_reduce_partials(a.partials + a.o_pdb, grid, a.part_stride, 1, H, a.H4, dbias, stream);
-  if (rc) return rc;
+  int rc = CGNN_OK;
+  {
+    ReduceQueue rq(stream);
+    rq.add(a.partials + a.o_pdw, grid, a.part_stride, H, d_in, 2 * a.K4, dW, 2 * d_in);
+    rq.add(a.partials + a.o_pdw + a.K4, grid, a.part_stride, H, d_in, 2 * a.K4, dW + d_in, 2 * d_in);
+    rq.add(a.partials + a.o_pdb, grid, a.part_stride, 1, H, a.H4, dbias);
+    rc = rq.flush();
+    if (rc) return rc;
+  }
   if (!du_in) return CGNN_OK;
 
   // kernel B: transposed neighbour aggregation

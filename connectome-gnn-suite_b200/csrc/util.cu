@@ -32,42 +32,60 @@ DeviceInfo device_info() {
 
 // out[r*out_ld + c] = sum_g partials[g*stride + r*ld + c]; fp64, fixed order: a CTA owns 32 consecutive outputs
 // (128-byte coalesced loads), its 8 warps sum one eighth of the records each, warp 0 adds the eight slices in order.
+// Up to four such reductions (the weight, bias and BatchNorm-sum partials of one backward call) share ONE launch: the
+// segments are laid end to end over the grid.  Every output is summed exactly as a launch of its own would.
 constexpr int kReduceSlices = 8;
-__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partials, int G, int stride,
-                                                         int rows, int cols, int ld, float* __restrict__ out,
-                                                         int out_ld) {
+__global__ void __launch_bounds__(256) k_reduce_partials(ReduceBatch b) {
   __shared__ double s_part[kReduceSlices][32];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + lane;
-  const bool live = i < rows * cols;
+  int sg = 0;
+  while (sg + 1 < b.n && (int)blockIdx.x >= b.seg[sg + 1].first_block) ++sg;
+  const ReduceSeg q = b.seg[sg];
+  const int i = ((int)blockIdx.x - q.first_block) * 32 + lane;
+  const bool live = i < q.rows * q.cols;
   double s = 0.0;
   int r = 0, c = 0;
   if (live) {
-    r = i / cols; c = i - r * cols;
-    const float* p = partials + (size_t)r * ld + c;
-    const int per = (G + kReduceSlices - 1) / kReduceSlices;
-    const int g0 = slice * per, g1 = (g0 + per < G) ? g0 + per : G;
+    r = i / q.cols; c = i - r * q.cols;
+    const float* p = q.partials + (size_t)r * q.ld + c;
+    const int per = (q.G + kReduceSlices - 1) / kReduceSlices;
+    const int g0 = slice * per, g1 = (g0 + per < q.G) ? g0 + per : q.G;
 #pragma unroll 4
-    for (int g = g0; g < g1; ++g) s += (double)p[(size_t)g * stride];
+    for (int g = g0; g < g1; ++g) s += (double)p[(size_t)g * q.stride];
   }
   s_part[slice][lane] = s;
   __syncthreads();
   if (slice == 0 && live) {
     double t = 0.0;
     for (int k = 0; k < kReduceSlices; ++k) t += s_part[k][lane];
-    out[(size_t)r * out_ld + c] = (float)t;
+    q.out[(size_t)r * q.out_ld + c] = (float)t;
   }
+}
+
+void ReduceQueue::add(const float* partials, int G, int stride, int rows, int cols, int ld, float* out, int out_ld) {
+  if (rows * cols <= 0) return;
+  if (b.n == kReduceMaxSegs) { const int rc = flush(); if (rc && !status) status = rc; }
+  ReduceSeg& q = b.seg[b.n++];
+  q.partials = partials; q.G = G; q.stride = stride; q.rows = rows; q.cols = cols; q.ld = ld; q.out = out;
+  q.out_ld = out_ld > 0 ? out_ld : cols;
+  q.first_block = blocks;
+  blocks += (rows * cols + 31) / 32;
+}
+
+int ReduceQueue::flush() {
+  if (b.n == 0) return status;
+  auto kfn = k_reduce_partials;
+  CGNN_LAUNCH(kfn, (unsigned)blocks, 256, 0, stream, b);
+  b.n = 0; blocks = 0;
+  CGNN_CHECK_LAUNCH();
+  return status;
 }
 
 int launch_reduce_partials(const float* partials, int G, int stride, int rows, int cols, int ld, float* out,
                            cudaStream_t stream, int out_ld) {
-  if (out_ld <= 0) out_ld = cols;
-  int n = rows * cols;
-  if (n <= 0) return CGNN_OK;
-  auto kfn = k_reduce_partials;
-  CGNN_LAUNCH(kfn, (n + 31) / 32, 256, 0, stream, partials, G, stride, rows, cols, ld, out, out_ld);
-  CGNN_CHECK_LAUNCH();
-  return CGNN_OK;
+  ReduceQueue q(stream);
+  q.add(partials, G, stride, rows, cols, ld, out, out_ld);
+  return q.flush();
 }
 
 // One warp per channel: merge `parts` records {count, mean[C], M2[C]} (doubles) exactly:
