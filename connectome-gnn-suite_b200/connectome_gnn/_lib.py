@@ -14,7 +14,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcgnn.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_f32p = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 c_ptr = C.c_void_p
@@ -74,6 +74,8 @@ PROTOTYPES = {
     "cgnn_collate_csr": (C.c_int, [_P(StoreT), _p, _i64, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p,
                                    _P(CsrT), _p]),
     "cgnn_fetch_ids": (C.c_int, [_p, _i64, _p, _p]),
+    "cgnn_ingest_threshold": (C.c_int, [_p, _i64, _i32, C.c_float, _p, _p, _p]),
+    "cgnn_ingest_emit": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "cgnn_csr_from_coo": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i32, _p, _P(CsrT), _p]),
     "cgnn_agg_words": (_sz, [_i64, _i64, _i64]),
     "cgnn_build_agg": (C.c_int, [_P(CsrT), _i32, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGNN_ABI_VERSION 7
+#define CGNN_ABI_VERSION 8
 
 typedef void* cgnn_stream_t; /* cudaStream_t */
 
@@ -188,6 +188,19 @@ int cgnn_collate_csr(const cgnn_store_t* store, const int64_t* subject_ids, int6
                      float* node_features, int64_t* edge_index, float* edge_weight,
                      int64_t* batch, int64_t* labels, int64_t* ptr, int64_t* eptr,
                      const cgnn_csr_out_t* csr, cgnn_stream_t stream);
+
+/* Dense connectivity matrices -> thresholded subjects (reference README.md:145-179, `hcp_matrix_to_graph`: keep the
+ * entries above the matrix's own q-quantile, list every kept (i, j) in row-major order as i -> j and then again as
+ * j -> i, feature = weighted row sum / its maximum).  matrices [S, N, N] f32.
+ *   cgnn_ingest_threshold: threshold[s] = torch.quantile(A_s.flatten(), q) (linear interpolation, fp32 rank arithmetic),
+ *                          selected[s] = number of entries with A > threshold and A > 0.
+ *   cgnn_ingest_emit:      edge_ptr [S+1] = prefix sums of 2 * selected (the caller's scan); writes subject-local
+ *                          src / dst / weight [edge_ptr[S]] and node_features [S * N, 1].
+ * Edges and weights are bit-exact against the recipe (with `A_thresh[src, dst]` for its `A_thresh[src]`). */
+int cgnn_ingest_threshold(const float* matrices, int64_t num_subjects, int32_t N, float q, float* threshold, int32_t* selected,
+                          cgnn_stream_t stream);
+int cgnn_ingest_emit(const float* matrices, int64_t num_subjects, int32_t N, const float* threshold, const int64_t* edge_ptr,
+                     int32_t* src, int32_t* dst, float* weight, float* node_features, cgnn_stream_t stream);
 
 /* ids[i] = pinned_host_ids[i]: brings the subject indices of a batch from PINNED (device-mapped) host memory into a
  * device buffer with a kernel instead of a DMA, so that they never queue behind a dataset upload on the copy engine. */
