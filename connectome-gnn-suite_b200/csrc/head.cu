@@ -142,6 +142,57 @@ __global__ void __launch_bounds__(kThreads) k_head_fwd(HeadArgs p) {
   }
 }
 
+// Small heads (C <= 128, M <= 64, K <= 8 - the reference's 64 -> 32 -> 2): the weights are staged once per CTA (W0
+// transposed, so that lane = hidden unit reads consecutive words), every warp then walks graphs: the pooled row is
+// broadcast from shared memory, 64 FMAs per lane and hidden unit, no shuffle in the first layer.
+constexpr int kHeadSmallC = 128, kHeadSmallM = 64, kHeadSmallK = 8, kHeadSmallWarps = 8;
+__global__ void __launch_bounds__(32 * kHeadSmallWarps) k_head_fwd_small(HeadArgs p) {
+  act_salt(p.drop);   // device-side dropout salt (CUDA-graph replays)
+  CGNN_SMEM_DECL;
+  const int C = p.C, M = p.M, K = p.K, MP = M + 1;
+  float* s_w0t = reinterpret_cast<float*>(cgnn_smem);       // [C][M + 1]
+  float* s_w1 = s_w0t + C * MP;                             // [K][M]
+  float* s_b0 = s_w1 + K * M;                               // [M]
+  float* s_b1 = s_b0 + M;                                   // [K]
+  float* s_emb = s_b1 + K;                                  // [warps][C]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < M * C; i += blockDim.x) { const int m = i / C, c = i - m * C; s_w0t[c * MP + m] = p.W0[i]; }
+  for (int i = tid; i < K * M; i += blockDim.x) s_w1[i] = p.W1[i];
+  for (int i = tid; i < M; i += blockDim.x) s_b0[i] = p.b0[i];
+  for (int i = tid; i < K; i += blockDim.x) s_b1[i] = p.b1[i];
+  __syncthreads();
+  float* my_emb = s_emb + warp * C;
+  const int m0 = lane, m1 = lane + 32;
+  for (long long g = (long long)blockIdx.x * kHeadSmallWarps + warp; g < p.B; g += (long long)gridDim.x * kHeadSmallWarps) {
+    for (int c = lane; c < C; c += 32) my_emb[c] = p.emb[g * C + c];
+    __syncwarp();
+    float h0 = 0.0f, h1 = 0.0f;
+    if (m1 < M) {
+      for (int c = 0; c < C; ++c) { const float e = my_emb[c]; h0 = fmaf(s_w0t[c * MP + m0], e, h0); h1 = fmaf(s_w0t[c * MP + m1], e, h1); }
+    } else if (m0 < M) {
+      for (int c = 0; c < C; ++c) h0 = fmaf(s_w0t[c * MP + m0], my_emb[c], h0);
+    }
+    const uint32_t rh = p.drop.drop ? drop_row_hash(p.drop, p.drop.row_base + g) : 0u;
+    if (m0 < M) {
+      h0 = fmaxf(h0 + s_b0[m0], 0.0f);
+      if (p.drop.drop) h0 = drop_keep(p.drop, rh, m0) ? h0 * p.drop.keep_scale : 0.0f;
+      p.hidden[g * M + m0] = h0;
+    } else h0 = 0.0f;
+    if (m1 < M) {
+      h1 = fmaxf(h1 + s_b0[m1], 0.0f);
+      if (p.drop.drop) h1 = drop_keep(p.drop, rh, m1) ? h1 * p.drop.keep_scale : 0.0f;
+      p.hidden[g * M + m1] = h1;
+    } else h1 = 0.0f;
+    for (int k = 0; k < K; ++k) {
+      float part = m0 < M ? s_w1[k * M + m0] * h0 : 0.0f;
+      if (m1 < M) part = fmaf(s_w1[k * M + m1], h1, part);
+      const float v = warp_sum(part) + s_b1[k];
+      if (lane == 0) p.logits[g * K + k] = v;
+    }
+    __syncwarp();       // my_emb is rewritten for the next graph
+  }
+}
+
 // ---- cross entropy --------------------------------------------------------------------------
 // One CTA (the loss is one number; fixed summation order): 1024 threads, a warp-shuffle tree per warp, then warp 0 over
 // the 32 warp sums - doubles, the same order every launch.
@@ -337,6 +388,19 @@ int cgnn_head_fwd(const float* emb, const float* W0, const float* b0, const floa
   d.p_drop = p_drop; d.seed = seed; d.site = kHeadSite; d.row_base = graph_base; d.salt = salt;
   a.drop = make_act(&d);
   a.hidden = hidden; a.logits = logits;
+  if (C <= kHeadSmallC && M <= kHeadSmallM && K <= kHeadSmallK) {
+    const size_t smem = (size_t)(C * (M + 1) + K * M + M + K + kHeadSmallWarps * C) * sizeof(float);
+    long long grid = (num_graphs + kHeadSmallWarps - 1) / kHeadSmallWarps;
+    const long long cap = 4ll * device_info().sm_count;        // persistent: the weights are staged once per CTA
+    if (grid > cap) grid = cap;
+    auto kfs = k_head_fwd_small;
+#ifndef CGNN_EMU
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    CGNN_LAUNCH(kfs, (unsigned)grid, 32 * kHeadSmallWarps, smem, stream, a);
+    CGNN_CHECK_LAUNCH();
+    return CGNN_OK;
+  }
   auto kfn = k_head_fwd;
   CGNN_LAUNCH(kfn, (unsigned)((num_graphs + kWarps - 1) / kWarps), kThreads, 0, stream, a);
   CGNN_CHECK_LAUNCH();
