@@ -52,6 +52,7 @@ class BnBwd:
     sums: Optional[torch.Tensor]   # [2, C]: sum dy, sum dy*xhat (global batch)
     count: float
     train: bool
+    sums64: Optional[torch.Tensor] = None   # the same in float64: what the kernels read when given (see cgnn_bn_bwd_t)
 
     def struct(self) -> BnBwdT:
         s1 = s2 = None
@@ -59,7 +60,7 @@ class BnBwd:
             c = self.scale.shape[0]
             base = self.sums.data_ptr()
             s1, s2 = base, base + 4 * c
-        return BnBwdT(_p(self.scale), _p(self.mean), _p(self.rstd), s1, s2, float(self.count), int(self.train))
+        return BnBwdT(_p(self.scale), _p(self.mean), _p(self.rstd), s1, s2, float(self.count), int(self.train), _p(self.sums64))
 
 
 _EVAL_ARRAYS: dict = {}
@@ -337,10 +338,11 @@ class Engine:
     def bn_bwd_sums(self, z, act: Act, mean, rstd, du, demb, ptr, num_graphs: int, out=None):
         rows, C_ = z.shape
         sums = out if out is not None else self.empty((2, C_))
+        sums64 = self.empty((2, C_), torch.float64)
         a = act.struct()
         self._call("cgnn_bn_bwd_sums", _p(z), C.byref(a), _p(mean), _p(rstd), _p(du), _p(demb), _p(ptr),
-                   num_graphs, rows, C_, _p(sums), _p(self.workspace), self.workspace_bytes, self.stream())
-        return sums
+                   num_graphs, rows, C_, _p(sums), _p(sums64), _p(self.workspace), self.workspace_bytes, self.stream())
+        return sums, sums64
 
     def layer_bwd(self, kind: str, du, demb, z, act_out: Act, bn: Optional[BnBwd], t_in, act_in: Act, W, csr, ptr,
                   num_graphs: int, need_du: bool, prev_mean, prev_rstd, agg=None, out=None, prev_out=None):
@@ -352,6 +354,7 @@ class Engine:
         du_in = self.empty((rows, d_in)) if need_du else None
         want_prev = need_du and prev_mean is not None
         prev_sums = (prev_out if prev_out is not None else self.empty((2, d_in))) if want_prev else None
+        prev_sums64 = self.empty((2, d_in), torch.float64) if want_prev else None
         self.ensure_agg(csr, kind, num_graphs, rows, csr.num_edges, need_out=True)
         ao, ai = act_out.struct(), act_in.struct()
         bs = bn.struct() if bn is not None else None
@@ -368,12 +371,12 @@ class Engine:
             args += [C.byref(ai), _p(W), C.byref(cs), _p(ptr), num_graphs, rows, d_in, H, csr.max_nodes, csr.max_edges,
                      _p(dW), _p(db),
                      _p(du_in), _p(prev_mean) if want_prev else None, _p(prev_rstd) if want_prev else None,
-                     _p(prev_sums)]
+                     _p(prev_sums), _p(prev_sums64)]
             return args + [_p(scratch), _p(self.workspace), self.workspace_bytes, self.stream()]
 
         keep: list = []
         self._call_csr(f"cgnn_{kind}_layer_bwd", csr, build)
-        return dW, db, du_in, prev_sums
+        return dW, db, du_in, prev_sums, prev_sums64
 
 
 _ENGINES: dict = {}

@@ -14,7 +14,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcgnn.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 c_f32p = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 c_ptr = C.c_void_p
@@ -41,7 +41,7 @@ class BnBwdT(C.Structure):
     """``cgnn_bn_bwd_t``"""
     _fields_ = [
         ("scale", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p), ("s1", C.c_void_p),
-        ("s2", C.c_void_p), ("count", C.c_double), ("train", C.c_int32),
+        ("s2", C.c_void_p), ("count", C.c_double), ("train", C.c_int32), ("sums64", C.c_void_p),
     ]
 
 
@@ -97,11 +97,11 @@ PROTOTYPES = {
     "cgnn_ce_bwd": (C.c_int, [_p, _p, _i64, _i32, _f32, _p, _p, _p]),
     "cgnn_head_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _f32, _p, _p, _p, _p, _p, _p, _sz,
                                 _p]),
-    "cgnn_bn_bwd_sums": (C.c_int, [_p, _P(ActT), _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _sz, _p]),
+    "cgnn_bn_bwd_sums": (C.c_int, [_p, _P(ActT), _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
     "cgnn_gcn_layer_bwd": (C.c_int, [_p, _p, _p, _P(ActT), _P(BnBwdT), _p, _P(ActT), _p, _P(CsrT), _p, _i64, _i64,
-                                     _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+                                     _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "cgnn_sage_layer_bwd": (C.c_int, [_p, _p, _p, _P(ActT), _P(BnBwdT), _p, _p, _P(ActT), _p, _P(CsrT), _p, _i64,
-                                      _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+                                      _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 

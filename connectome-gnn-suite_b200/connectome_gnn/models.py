@@ -64,16 +64,15 @@ def _merge_stats_across_ranks(eng, stats: torch.Tensor, channels: int, group=Non
     return eng.bn_merge_stats(flat.view(world, stats.numel()), channels)
 
 
-def _sum_across_ranks(t: Optional[torch.Tensor], group=None) -> Optional[torch.Tensor]:
-    """SyncBN backward: the [sum dy, sum dy x^] records of all ranks, added in float64 on the wire.  BatchNorm's backward
-    subtracts these means from every row (heavy cancellation), so the seven extra fp32 roundings of a ring sum over eight
-    ranks showed up as 1.8e-5 in the gradients against the single-process batch; a few hundred bytes per layer."""
-    if t is not None and _world(group) > 1:
+def _sum_across_ranks(sums: Optional[torch.Tensor], sums64: Optional[torch.Tensor], group=None):
+    """SyncBN backward: the [sum dy, sum dy x^] records of all ranks added up - the float64 record (the one the kernels
+    read: BatchNorm's backward subtracts these means from every row, so the sums are carried unrounded from the reduction
+    kernel to their consumer, also across ranks) and from it the fp32 copy that becomes d beta / d gamma."""
+    if sums64 is not None and _world(group) > 1:
         import torch.distributed as dist
-        wide = t.to(torch.float64)
-        dist.all_reduce(wide, group=group)
-        t.copy_(wide)
-    return t
+        dist.all_reduce(sums64, group=group)
+        sums.copy_(sums64)
+    return sums, sums64
 
 
 def _draw_seed(device=None) -> int:
@@ -158,8 +157,8 @@ class _EncodeFn(torch.autograd.Function):
         # BatchNorm backward sums of the top layer come from a standalone pass over z_L
         t_in, act_in, z, W, scale, mean, rstd, agg = saved[-1]
         act_out = ctx.final_act
-        sums = eng.bn_bwd_sums(z, act_out, mean, rstd, None, demb, ptr, B, out=bn_block(L - 1))
-        sums = _sum_across_ranks(sums, group)
+        sums, sums64 = eng.bn_bwd_sums(z, act_out, mean, rstd, None, demb, ptr, B, out=bn_block(L - 1))
+        sums, sums64 = _sum_across_ranks(sums, sums64, group)
         du, pooled, dx = None, demb, None
         share = 1.0 / _world(group)
         for l in range(L - 1, -1, -1):
@@ -167,9 +166,9 @@ class _EncodeFn(torch.autograd.Function):
             need_du = l > 0 or ctx.x_needs_grad
             prev_mean = saved[l - 1][5] if l > 0 else None
             prev_rstd = saved[l - 1][6] if l > 0 else None
-            bn = BnBwd(scale, mean, rstd, sums, count, training)
+            bn = BnBwd(scale, mean, rstd, sums, count, training, sums64)
             out = (flat.view(layer_params[l][0]), flat.view(layer_params[l][1])) if flat is not None else None
-            dW, db, du_in, prev_sums = eng.layer_bwd(kind, du, pooled, z, act_out, bn, t_in, act_in, W, csr, ptr, B,
+            dW, db, du_in, prev_sums, prev_sums64 = eng.layer_bwd(kind, du, pooled, z, act_out, bn, t_in, act_in, W, csr, ptr, B,
                                                      need_du, prev_mean, prev_rstd, agg, out=out,
                                                      prev_out=bn_block(l - 1) if l > 0 else None)
             # d gamma = sum dy*xhat, d beta = sum dy.  Under data parallelism `sums` is already the global sum while
@@ -183,7 +182,7 @@ class _EncodeFn(torch.autograd.Function):
                 grads[4 * l + 0], grads[4 * l + 1] = dW, db
                 grads[4 * l + 2] = sums[1] if share == 1.0 else sums[1] * share
                 grads[4 * l + 3] = sums[0] if share == 1.0 else sums[0] * share
-            sums = _sum_across_ranks(prev_sums, group)
+            sums, sums64 = _sum_across_ranks(prev_sums, prev_sums64, group)
             du, pooled, act_out = du_in, None, act_in
             if l == 0:
                 dx = du_in

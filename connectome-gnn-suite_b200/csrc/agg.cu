@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gather(GatherArgs p) {
   rt::chan_quad_init(cq, p.act, c0, C);
   const rt::RowKey rk = rt::row_key(p.act);
   rt::BnBwdDev bn;
-  bn.scale = p.bn_scale; bn.mean = p.bn_mean; bn.rstd = p.bn_rstd; bn.s1 = p.bn_s1; bn.s2 = p.bn_s2;
+  bn.scale = p.bn_scale; bn.mean = p.bn_mean; bn.rstd = p.bn_rstd; bn.s1 = p.bn_s1; bn.s2 = p.bn_s2; bn.sums64 = p.bn_sums64;
   bn.inv_count = p.inv_count; bn.train = p.bn_train; bn.has = p.has_bn;
   rt::BnQuad bq;
   if (MODE == GATHER_GCN_BWD) rt::bn_quad_init(bq, bn, c0, C);

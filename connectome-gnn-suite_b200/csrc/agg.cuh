@@ -141,7 +141,7 @@ struct GatherArgs {
   const float* src;        // SAGE_FWD / GCN_FWD: t_in   GCN_BWD: z   SAGE_BWD: d_agg
   Act act;                 // SAGE_FWD: act on load   GCN_BWD: act_out (its backward)   SAGE_BWD: act_in (for the sums)
   const float* du; const float* demb;                                    // GCN_BWD upstream
-  const float* bn_scale; const float* bn_mean; const float* bn_rstd; const float* bn_s1; const float* bn_s2;
+  const float* bn_scale; const float* bn_mean; const float* bn_rstd; const float* bn_s1; const float* bn_s2; const double* bn_sums64;
   float inv_count; int bn_train, has_bn;
   // SAGE_BWD
   const float* direct;     // d_u [rows, C]
@@ -194,12 +194,12 @@ int launch_sage_fwd_wide(const float* t_in, const cgnn_act_t* act, float* agg, c
 int launch_sage_bwd_wide(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out, const cgnn_bn_bwd_t* bn,
                          const float* t_in, const float* agg, const cgnn_act_t* act_in, const float* W, const cgnn_csr_t* csr,
                          int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* dW,
-                         float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
+                         float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, double* prev_sums64, float* scratch,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_gcn_bwd_wide(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out, const cgnn_bn_bwd_t* bn,
                         const float* t_in, const cgnn_act_t* act_in, const float* W, const cgnn_csr_t* csr, const int64_t* ptr,
                         int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
-                        float* dW, float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums,
+                        float* dW, float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, double* prev_sums64,
                         float* scratch, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 #endif
 // agg.cu: blob builder; subjects with <= skip_edge_cap edges (and < 65536 rows) are skipped (built by the collate kernel)

@@ -295,15 +295,16 @@ __device__ __forceinline__ void cta_write_stats(const float* s_cnt, const float*
 // out[r*out_ld + c] = sum_g partials[g*stride + r*ld + c] for r < rows, c < cols (fp64 accumulation,
 // fixed order): maps a zero-padded [rows, ld] partial onto a dense output (out_ld <= 0 -> cols).
 int launch_reduce_partials(const float* partials, int G, int stride, int rows, int cols, int ld,
-                           float* out, cudaStream_t stream, int out_ld = 0);
+                           float* out, cudaStream_t stream, int out_ld = 0, double* out64 = nullptr);
 // Several of them in one launch: q.add(...) per reduction, then q.flush() (returns the first error).
 constexpr int kReduceMaxSegs = 4;
-struct ReduceSeg { const float* partials; float* out; int G, stride, rows, cols, ld, out_ld, first_block; };
+struct ReduceSeg { const float* partials; float* out; double* out64; int G, stride, rows, cols, ld, out_ld, first_block; };
 struct ReduceBatch { ReduceSeg seg[kReduceMaxSegs]; int n; };
 struct ReduceQueue {
   ReduceBatch b; int blocks; int status; cudaStream_t stream;
   explicit ReduceQueue(cudaStream_t s) : blocks(0), status(0), stream(s) { b.n = 0; }
-  void add(const float* partials, int G, int stride, int rows, int cols, int ld, float* out, int out_ld = 0);
+  // out64 (optional): the same sums unrounded, dense [rows, cols]
+  void add(const float* partials, int G, int stride, int rows, int cols, int ld, float* out, int out_ld = 0, double* out64 = nullptr);
   int flush();
 };
 int launch_stats_merge(const double* parts, int parts_n, int C, double* stats, cudaStream_t stream);

@@ -361,7 +361,7 @@ int launch_first_bwd(int kind, const float* du, const float* demb, const float* 
   a.du = du; a.demb = demb; a.zin = z; a.act_out = make_act(act_out); a.agg_in = agg;
   a.bn.has = bn ? 1 : 0;
   a.bn.scale = bn ? bn->scale : nullptr; a.bn.mean = bn ? bn->mean : nullptr; a.bn.rstd = bn ? bn->rstd : nullptr;
-  a.bn.s1 = bn ? bn->s1 : nullptr; a.bn.s2 = bn ? bn->s2 : nullptr;
+  a.bn.s1 = bn ? bn->s1 : nullptr; a.bn.s2 = bn ? bn->s2 : nullptr; a.bn.sums64 = bn ? bn->sums64 : nullptr;
   a.bn.train = bn ? bn->train : 0;
   a.bn.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
   const int K2 = kind == AGG_SAGE ? 2 * d_in : d_in;

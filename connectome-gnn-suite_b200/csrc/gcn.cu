@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kThreads) k_gcn_fwd(GcnFwdArgs p) {
 // ------------------------------------------------------------------------------------------
 struct GcnBwdArgs {
   const float* du; const float* demb; const float* z; Act act_out;
-  const float* bn_scale; const float* bn_mean; const float* bn_rstd; const float* bn_s1; const float* bn_s2;
+  const float* bn_scale; const float* bn_mean; const float* bn_rstd; const float* bn_s1; const float* bn_s2; const double* bn_sums64;
   float inv_count; int bn_train; int has_bn;
   const float* t_in; Act act_in; const float* W;
   const int32_t* out_rowptr; const int32_t* out_col; const float* out_wn; const float* dinv;
@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(kThreads) k_gcn_bwd(GcnBwdArgs p) {
     s_co[CO_BSC * H4 + c] = ok ? p.bn_scale[c] : (c < H ? 1.0f : 0.0f);
     s_co[CO_MEAN * H4 + c] = ok ? p.bn_mean[c] : 0.0f;
     s_co[CO_RSTD * H4 + c] = ok ? p.bn_rstd[c] : 0.0f;
-    s_co[CO_S1N * H4 + c] = (ok && p.bn_train) ? p.bn_s1[c] * p.inv_count : 0.0f;
-    s_co[CO_S2N * H4 + c] = (ok && p.bn_train) ? p.bn_s2[c] * p.inv_count : 0.0f;
+    s_co[CO_S1N * H4 + c] = (ok && p.bn_train) ? (p.bn_sums64 ? (float)(p.bn_sums64[c] * (double)p.inv_count) : p.bn_s1[c] * p.inv_count) : 0.0f;
+    s_co[CO_S2N * H4 + c] = (ok && p.bn_train) ? (p.bn_sums64 ? (float)(p.bn_sums64[H + c] * (double)p.inv_count) : p.bn_s2[c] * p.inv_count) : 0.0f;
   }
   stage_affine(p.act_in, K, K4, s_ci + CI_SCALE * K4, s_ci + CI_SHIFT * K4);
   for (int c = tid; c < K4; c += kThreads) {
@@ -580,7 +580,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
                        const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in, const float* W,
                        const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
                        int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* dW, float* dbias,
-                       float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
+                       float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, double* prev_sums64, float* scratch,
                        void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (max_edges < 0) return CGNN_ERR_INVALID_ARG;
@@ -589,6 +589,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
     cudaMemsetAsync(dW, 0, (size_t)H * d_in * sizeof(float), stream);
     cudaMemsetAsync(dbias, 0, (size_t)H * sizeof(float), stream);
     if (prev_sums) cudaMemsetAsync(prev_sums, 0, (size_t)2 * d_in * sizeof(float), stream);
+    if (prev_sums64) cudaMemsetAsync(prev_sums64, 0, (size_t)2 * d_in * sizeof(double), stream);
     return CGNN_OK;
   }
   if ((du == nullptr) == (demb == nullptr)) return CGNN_ERR_INVALID_ARG;
@@ -613,7 +614,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
   // Wide layers (H = d_in = 256): gather + K-looped contractions (wide_tc.cu).
   if (tensor_cores_enabled() && wide_shape(d_in, H)) {
     const int rcw = launch_gcn_bwd_wide(du, demb, z, act_out, bn, t_in, act_in, W, csr, ptr, num_graphs, rows, d_in, H, max_nodes,
-                                        max_edges, dW, dbias, du_in, prev_mean, prev_rstd, prev_sums, scratch, workspace,
+                                        max_edges, dW, dbias, du_in, prev_mean, prev_rstd, prev_sums, prev_sums64, scratch, workspace,
                                         workspace_bytes, stream);
     if (rcw >= 0) return rcw;
   }
@@ -630,7 +631,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
       ga.src = z; ga.act = make_act(act_out); ga.du = du; ga.demb = demb;
       ga.has_bn = bn ? 1 : 0;
       ga.bn_scale = bn ? bn->scale : nullptr; ga.bn_mean = bn ? bn->mean : nullptr; ga.bn_rstd = bn ? bn->rstd : nullptr;
-      ga.bn_s1 = bn ? bn->s1 : nullptr; ga.bn_s2 = bn ? bn->s2 : nullptr;
+      ga.bn_s1 = bn ? bn->s1 : nullptr; ga.bn_s2 = bn ? bn->s2 : nullptr; ga.bn_sums64 = bn ? bn->sums64 : nullptr;
       ga.bn_train = bn ? bn->train : 0;
       ga.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
       ga.out = scratch; ga.partials = (float*)workspace; ga.part_stride = H;
@@ -646,7 +647,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
           ReduceQueue rq(stream);
           rq.add((const float*)workspace, g1, H, 1, H, H, dbias);
           rq.add(parts_b, g2, part_stride, H, d_in, d_in, dW);
-          if (prev_sums) rq.add(parts_b + H * d_in, g2, part_stride, 2, d_in, d_in, prev_sums);
+          if (prev_sums) rq.add(parts_b + H * d_in, g2, part_stride, 2, d_in, d_in, prev_sums, 0, prev_sums64);
           return rq.flush();
         }
       }
@@ -659,7 +660,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
   a.du = du; a.demb = demb; a.z = z; a.act_out = make_act(act_out);
   a.has_bn = bn ? 1 : 0;
   a.bn_scale = bn ? bn->scale : nullptr; a.bn_mean = bn ? bn->mean : nullptr; a.bn_rstd = bn ? bn->rstd : nullptr;
-  a.bn_s1 = bn ? bn->s1 : nullptr; a.bn_s2 = bn ? bn->s2 : nullptr;
+  a.bn_s1 = bn ? bn->s1 : nullptr; a.bn_s2 = bn ? bn->s2 : nullptr; a.bn_sums64 = bn ? bn->sums64 : nullptr;
   a.bn_train = bn ? bn->train : 0;
   a.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
   a.t_in = t_in; a.act_in = make_act(act_in); a.W = W;
@@ -711,7 +712,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
   ReduceQueue rq(stream);
   rq.add(a.partials + a.o_pdw, grid, a.part_stride, H, d_in, a.K4, dW);
   rq.add(a.partials + a.o_pdb, grid, a.part_stride, 1, H, a.H4, dbias);
-  if (prev_sums) rq.add(a.partials + a.o_pprev, grid, a.part_stride, 2, d_in, a.K4, prev_sums);
+  if (prev_sums) rq.add(a.partials + a.o_pprev, grid, a.part_stride, 2, d_in, a.K4, prev_sums, 0, prev_sums64);
   return rq.flush();
 }
 

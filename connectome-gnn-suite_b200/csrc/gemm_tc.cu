@@ -861,7 +861,7 @@ int launch_sage_bwd_gemm(const float* du, const float* demb, const int32_t* row_
   a.z = z; a.act_out = make_act(act_out);
   a.bn.has = bn ? 1 : 0;
   a.bn.scale = bn ? bn->scale : nullptr; a.bn.mean = bn ? bn->mean : nullptr; a.bn.rstd = bn ? bn->rstd : nullptr;
-  a.bn.s1 = bn ? bn->s1 : nullptr; a.bn.s2 = bn ? bn->s2 : nullptr;
+  a.bn.s1 = bn ? bn->s1 : nullptr; a.bn.s2 = bn ? bn->s2 : nullptr; a.bn.sums64 = bn ? bn->sums64 : nullptr;
   a.bn.train = bn ? bn->train : 0;
   a.bn.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
   a.t_in = t_in; a.agg = agg; a.act_in = make_act(act_in); a.W = W;

@@ -206,11 +206,12 @@ int cgnn_bn_eval_affine(const float* gamma, const float* beta, const float* runn
 
 int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, const float* rstd, const float* du,
                      const float* demb, const int64_t* ptr, int64_t num_graphs, int64_t rows, int32_t C,
-                     float* sums, void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
+                     float* sums, double* sums64, void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!sums || C <= 0 || num_graphs < 0 || rows < 0) return CGNN_ERR_INVALID_ARG;
   if (num_graphs == 0 || rows == 0) {
     cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(float), stream);
+    if (sums64) cudaMemsetAsync(sums64, 0, (size_t)2 * C * sizeof(double), stream);
     return CGNN_OK;
   }
   if ((du == nullptr) == (demb == nullptr)) return CGNN_ERR_INVALID_ARG;
@@ -237,7 +238,7 @@ int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, c
     else if (C == 128) { auto kfn = k_bn_bwd_sums_quad<32>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
     else { auto kfn = k_bn_bwd_sums_quad<64>; CGNN_LAUNCH(kfn, (unsigned)g2, kThreads, 0, stream, a); }
     CGNN_CHECK_LAUNCH();
-    return launch_reduce_partials(a.partials, (int)g2, 2 * a.C4, 2, C, a.C4, sums, stream);
+    return launch_reduce_partials(a.partials, (int)g2, 2 * a.C4, 2, C, a.C4, sums, stream, 0, sums64);
   }
 #endif
   const int cc = pick_hc(a.C4);
@@ -249,7 +250,7 @@ int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, c
   if (cc == 1) CGNN_BN_SUMS(1) else if (cc == 2) CGNN_BN_SUMS(2) else if (cc == 4) CGNN_BN_SUMS(4) else CGNN_BN_SUMS(8)
 #undef CGNN_BN_SUMS
   CGNN_CHECK_LAUNCH();
-  return launch_reduce_partials(a.partials, grid, 2 * a.C4, 2, C, a.C4, sums, stream);
+  return launch_reduce_partials(a.partials, grid, 2 * a.C4, 2, C, a.C4, sums, stream, 0, sums64);
 }
 
 }  // extern "C"

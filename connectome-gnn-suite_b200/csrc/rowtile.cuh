@@ -129,7 +129,12 @@ struct BnQuad {
 struct BnBwdDev {
   const float* scale; const float* mean; const float* rstd; const float* s1; const float* s2;
   float inv_count; int train, has;
+  const double* sums64;     // [2, C] in double, read instead of s1 / s2 when given
 };
+// sum / count of channel c: from the double record when there is one
+__device__ __forceinline__ float bn_sum_over_count(const float* s, const double* s64, int c, float inv_count) {
+  return s64 ? (float)(s64[c] * (double)inv_count) : s[c] * inv_count;
+}
 __device__ __forceinline__ void bn_quad_init(BnQuad& b, const BnBwdDev& bn, int c0, int C) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -137,8 +142,8 @@ __device__ __forceinline__ void bn_quad_init(BnQuad& b, const BnBwdDev& bn, int 
     b.bsc[j] = ok ? bn.scale[c0 + j] : 1.0f;
     b.mean[j] = ok ? bn.mean[c0 + j] : 0.0f;
     b.rstd[j] = ok ? bn.rstd[c0 + j] : 0.0f;
-    b.s1n[j] = (ok && bn.train) ? bn.s1[c0 + j] * bn.inv_count : 0.0f;
-    b.s2n[j] = (ok && bn.train) ? bn.s2[c0 + j] * bn.inv_count : 0.0f;
+    b.s1n[j] = (ok && bn.train) ? bn_sum_over_count(bn.s1, bn.sums64, c0 + j, bn.inv_count) : 0.0f;
+    b.s2n[j] = (ok && bn.train) ? bn_sum_over_count(bn.s2, bn.sums64 ? bn.sums64 + C : nullptr, c0 + j, bn.inv_count) : 0.0f;
   }
 }
 __device__ __forceinline__ float4 bn_bwd4(const BnBwdDev& bn, const BnQuad& b, float4 t, float4 dy) {

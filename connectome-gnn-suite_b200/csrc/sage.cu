@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads) k_sage_fwd(SageFwdArgs p) {
 // ------------------------------------------------------------------------------------------
 struct SageBwdArgs {
   const float* du; const float* demb; const float* z; Act act_out;
-  const float* bn_scale; const float* bn_mean; const float* bn_rstd; const float* bn_s1; const float* bn_s2;
+  const float* bn_scale; const float* bn_mean; const float* bn_rstd; const float* bn_s1; const float* bn_s2; const double* bn_sums64;
   float inv_count; int bn_train; int has_bn;
   const float* t_in; Act act_in; const float* W;
   const int32_t* in_rowptr; const int32_t* in_col; const float* in_w; const float* wsum;
@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(kThreads) k_sage_bwd_a(SageBwdArgs p) {
     s_co[SO_BSC * H4 + c] = ok ? p.bn_scale[c] : (c < H ? 1.0f : 0.0f);
     s_co[SO_MEAN * H4 + c] = ok ? p.bn_mean[c] : 0.0f;
     s_co[SO_RSTD * H4 + c] = ok ? p.bn_rstd[c] : 0.0f;
-    s_co[SO_S1N * H4 + c] = (ok && p.bn_train) ? p.bn_s1[c] * p.inv_count : 0.0f;
-    s_co[SO_S2N * H4 + c] = (ok && p.bn_train) ? p.bn_s2[c] * p.inv_count : 0.0f;
+    s_co[SO_S1N * H4 + c] = (ok && p.bn_train) ? (p.bn_sums64 ? (float)(p.bn_sums64[c] * (double)p.inv_count) : p.bn_s1[c] * p.inv_count) : 0.0f;
+    s_co[SO_S2N * H4 + c] = (ok && p.bn_train) ? (p.bn_sums64 ? (float)(p.bn_sums64[H + c] * (double)p.inv_count) : p.bn_s2[c] * p.inv_count) : 0.0f;
   }
   stage_affine(p.act_in, K, K4, s_ci, s_ci + K4);
   __syncthreads();
@@ -627,7 +627,7 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
                         const cgnn_bn_bwd_t* bn, const float* t_in, const float* agg, const cgnn_act_t* act_in, const float* W,
                         const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
                         int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* dW, float* dbias,
-                        float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
+                        float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, double* prev_sums64, float* scratch,
                         void* workspace, size_t workspace_bytes, cgnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   (void)agg;
@@ -637,6 +637,7 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
     cudaMemsetAsync(dW, 0, (size_t)H * 2 * d_in * sizeof(float), stream);
     cudaMemsetAsync(dbias, 0, (size_t)H * sizeof(float), stream);
     if (prev_sums) cudaMemsetAsync(prev_sums, 0, (size_t)2 * d_in * sizeof(float), stream);
+    if (prev_sums64) cudaMemsetAsync(prev_sums64, 0, (size_t)2 * d_in * sizeof(double), stream);
     return CGNN_OK;
   }
   if ((du == nullptr) == (demb == nullptr)) return CGNN_ERR_INVALID_ARG;
@@ -666,7 +667,7 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
   // Wide layers (H = d_in = 256): dz pass, K-looped contractions, transposed gather (wide_tc.cu; scratch = 3 x [rows, 256]).
   if (tensor_cores_enabled() && wide_shape(d_in, H)) {
     const int rcw = launch_sage_bwd_wide(du, demb, z, act_out, bn, t_in, agg, act_in, W, csr, num_graphs, rows, d_in, H, max_nodes,
-                                         max_edges, dW, dbias, du_in, prev_mean, prev_rstd, prev_sums, scratch, workspace,
+                                         max_edges, dW, dbias, du_in, prev_mean, prev_rstd, prev_sums, prev_sums64, scratch, workspace,
                                          workspace_bytes, stream);
     if (rcw >= 0) return rcw;
   }
@@ -698,7 +699,7 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
         ga.partials = (float*)((char*)workspace + region_a); ga.part_stride = 2 * d_in;
         rc = launch_gather(GATHER_SAGE_BWD, ga, &g2, stream);
         if (rc != CGNN_OK) return rc > 0 ? rc : CGNN_ERR_TILE_TOO_LARGE;
-        if (prev_sums) rq.add(ga.partials, g2, 2 * d_in, 2, d_in, d_in, prev_sums);     // all three after the gather: one launch
+        if (prev_sums) rq.add(ga.partials, g2, 2 * d_in, 2, d_in, d_in, prev_sums, 0, prev_sums64);     // all three after the gather: one launch
         return rq.flush();
       }
     }
@@ -710,7 +711,7 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
   a.du = du; a.demb = demb; a.z = z; a.act_out = make_act(act_out);
   a.has_bn = bn ? 1 : 0;
   a.bn_scale = bn ? bn->scale : nullptr; a.bn_mean = bn ? bn->mean : nullptr; a.bn_rstd = bn ? bn->rstd : nullptr;
-  a.bn_s1 = bn ? bn->s1 : nullptr; a.bn_s2 = bn ? bn->s2 : nullptr;
+  a.bn_s1 = bn ? bn->s1 : nullptr; a.bn_s2 = bn ? bn->s2 : nullptr; a.bn_sums64 = bn ? bn->sums64 : nullptr;
   a.bn_train = bn ? bn->train : 0;
   a.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
   a.t_in = t_in; a.act_in = make_act(act_in); a.W = W;
@@ -806,7 +807,7 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
 #undef CGNN_SAGE_BWDB
   CGNN_CHECK_LAUNCH();
   if (prev_sums) {
-    rc = launch_reduce_partials(b.partials, grid_b, 2 * a.K4, 2, d_in, a.K4, prev_sums, stream);
+    rc = launch_reduce_partials(b.partials, grid_b, 2 * a.K4, 2, d_in, a.K4, prev_sums, stream, 0, prev_sums64);
     if (rc) return rc;
   }
   return CGNN_OK;

@@ -58,16 +58,18 @@ __global__ void __launch_bounds__(256) k_reduce_partials(ReduceBatch b) {
   if (slice == 0 && live) {
     double t = 0.0;
     for (int k = 0; k < kReduceSlices; ++k) t += s_part[k][lane];
-    q.out[(size_t)r * q.out_ld + c] = (float)t;
+    if (q.out) q.out[(size_t)r * q.out_ld + c] = (float)t;
+    if (q.out64) q.out64[(size_t)r * q.cols + c] = t;
   }
 }
 
-void ReduceQueue::add(const float* partials, int G, int stride, int rows, int cols, int ld, float* out, int out_ld) {
+void ReduceQueue::add(const float* partials, int G, int stride, int rows, int cols, int ld, float* out, int out_ld, double* out64) {
   if (rows * cols <= 0) return;
   if (b.n == kReduceMaxSegs) { const int rc = flush(); if (rc && !status) status = rc; }
   ReduceSeg& q = b.seg[b.n++];
   q.partials = partials; q.G = G; q.stride = stride; q.rows = rows; q.cols = cols; q.ld = ld; q.out = out;
   q.out_ld = out_ld > 0 ? out_ld : cols;
+  q.out64 = out64;
   q.first_block = blocks;
   blocks += (rows * cols + 31) / 32;
 }
@@ -82,9 +84,9 @@ int ReduceQueue::flush() {
 }
 
 int launch_reduce_partials(const float* partials, int G, int stride, int rows, int cols, int ld, float* out,
-                           cudaStream_t stream, int out_ld) {
+                           cudaStream_t stream, int out_ld, double* out64) {
   ReduceQueue q(stream);
-  q.add(partials, G, stride, rows, cols, ld, out, out_ld);
+  q.add(partials, G, stride, rows, cols, ld, out, out_ld, out64);
   return q.flush();
 }
 

@@ -554,7 +554,7 @@ int launch_gcn_fwd_wide(const float* t_in, const cgnn_act_t* act, const float* W
 int launch_gcn_bwd_wide(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out, const cgnn_bn_bwd_t* bn,
                         const float* t_in, const cgnn_act_t* act_in, const float* W, const cgnn_csr_t* csr, const int64_t* ptr,
                         int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
-                        float* dW, float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums,
+                        float* dW, float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, double* prev_sums64,
                         float* scratch, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (!wide_shape(d_in, H)) return -1;
   if (!scratch || !csr->agg_out || csr->agg_kind != AGG_GCN || !gather_supported(WN, max_nodes, max_edges)) return -1;
@@ -577,7 +577,7 @@ int launch_gcn_bwd_wide(const float* du, const float* demb, const float* z, cons
   ga.src = z; ga.act = make_act(act_out); ga.du = du; ga.demb = demb;
   ga.has_bn = bn ? 1 : 0;
   ga.bn_scale = bn ? bn->scale : nullptr; ga.bn_mean = bn ? bn->mean : nullptr; ga.bn_rstd = bn ? bn->rstd : nullptr;
-  ga.bn_s1 = bn ? bn->s1 : nullptr; ga.bn_s2 = bn ? bn->s2 : nullptr;
+  ga.bn_s1 = bn ? bn->s1 : nullptr; ga.bn_s2 = bn ? bn->s2 : nullptr; ga.bn_sums64 = bn ? bn->sums64 : nullptr;
   ga.bn_train = bn ? bn->train : 0;
   ga.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
   ga.out = scratch; ga.partials = (float*)workspace; ga.part_stride = WN;
@@ -598,7 +598,7 @@ int launch_gcn_bwd_wide(const float* du, const float* demb, const float* z, cons
   if (rc) return rc;
   rc = launch_reduce_partials(parts, g3, WN * WN, WN, WN, WN, dW, stream);
   if (rc) return rc;
-  if (fuse_prev) rc = launch_reduce_partials(prev_parts, g3, 2 * WN, 2, WN, WN, prev_sums, stream);
+  if (fuse_prev) rc = launch_reduce_partials(prev_parts, g3, 2 * WN, 2, WN, WN, prev_sums, stream, 0, prev_sums64);
   (void)ptr;
   return rc;
 }
@@ -632,7 +632,7 @@ int launch_sage_fwd_wide(const float* t_in, const cgnn_act_t* act, float* agg, c
 int launch_sage_bwd_wide(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out, const cgnn_bn_bwd_t* bn,
                          const float* t_in, const float* agg, const cgnn_act_t* act_in, const float* W, const cgnn_csr_t* csr,
                          int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* dW,
-                         float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, float* scratch,
+                         float* dbias, float* du_in, const float* prev_mean, const float* prev_rstd, float* prev_sums, double* prev_sums64, float* scratch,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (!wide_shape(d_in, H)) return -1;
   if (!scratch || !agg || !csr->agg_out || !csr->row_graph || csr->agg_kind != AGG_SAGE || !gather_supported(WN, max_nodes, max_edges))
@@ -656,7 +656,7 @@ int launch_sage_bwd_wide(const float* du, const float* demb, const float* z, con
   a.act_out = make_act(act_out);
   a.bn.has = bn ? 1 : 0;
   a.bn.scale = bn ? bn->scale : nullptr; a.bn.mean = bn ? bn->mean : nullptr; a.bn.rstd = bn ? bn->rstd : nullptr;
-  a.bn.s1 = bn ? bn->s1 : nullptr; a.bn.s2 = bn ? bn->s2 : nullptr;
+  a.bn.s1 = bn ? bn->s1 : nullptr; a.bn.s2 = bn ? bn->s2 : nullptr; a.bn.sums64 = bn ? bn->sums64 : nullptr;
   a.bn.train = bn ? bn->train : 0;
   a.bn.inv_count = (bn && bn->count > 0) ? (float)(1.0 / bn->count) : 0.0f;
   a.rows = rows; a.dz = dz; a.partials = (float*)workspace;
@@ -702,7 +702,7 @@ int launch_sage_bwd_wide(const float* du, const float* demb, const float* z, con
   rc = launch_gather(GATHER_SAGE_BWD, ga, &g4, stream);
   if (rc != CGNN_OK) return rc > 0 ? rc : CGNN_ERR_TILE_TOO_LARGE;
   if ((size_t)g4 * 2 * WN * sizeof(float) > region_a) return CGNN_ERR_WORKSPACE;
-  if (prev_sums) return launch_reduce_partials(ga.partials, g4, 2 * WN, 2, WN, WN, prev_sums, stream);
+  if (prev_sums) return launch_reduce_partials(ga.partials, g4, 2 * WN, 2, WN, WN, prev_sums, stream, 0, prev_sums64);
   return CGNN_OK;
 }
 #endif  // CGNN_EMU

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGNN_ABI_VERSION 8
+#define CGNN_ABI_VERSION 9
 
 typedef void* cgnn_stream_t; /* cudaStream_t */
 
@@ -134,6 +134,9 @@ typedef struct {
   const float* s2;     /* [C] */
   double  count;       /* rows of the global batch */
   int32_t train;       /* 1: batch statistics were used in forward */
+  const double* sums64; /* NULL, or [2, C] = the same s1, s2 in double (what cgnn_bn_bwd_sums / prev_sums64 wrote): read instead
+                         * of s1 / s2.  The backward subtracts s/count from every row (cancellation): with the sums carried in
+                         * double a data-parallel run and the single-process batch agree to fp32 round-off of the inputs */
 } cgnn_bn_bwd_t;
 
 /* ---- K0: collate (reference graph.py:143-167) ---------------------------------------- */
@@ -330,8 +333,8 @@ int cgnn_head_bwd(const float* emb, const float* hidden, const float* dlogits, c
  * itself is a ReLU output (SAGE) - it does not change the sums, only documents the caller. */
 int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, const float* rstd,
                      const float* du, const float* demb, const int64_t* ptr, int64_t num_graphs,
-                     int64_t rows, int32_t C, float* sums, void* workspace, size_t workspace_bytes,
-                     cgnn_stream_t stream);
+                     int64_t rows, int32_t C, float* sums, double* sums64, void* workspace, size_t workspace_bytes,
+                     cgnn_stream_t stream);   /* sums64 (optional): the same [2, C] in double */
 
 /* GCN layer backward (autograd of models.py:84-114 plus the BN/ReLU/dropout that follows).
  *   upstream: du [rows,H] or pooled demb [B,H] (exactly one non-NULL), w.r.t. act_out(z).
@@ -339,7 +342,7 @@ int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, c
  *   t_in [rows,d_in] this layer's stored input, act_in how it was transformed on load
  * Outputs: dW [H,d_in], dbias [H]; du_in [rows,d_in] = gradient w.r.t. act_in(t_in) (NULL for
  * the first layer); prev_sums [2*d_in] = BN backward sums of the previous layer computed
- * from du_in on the fly (NULL to skip; needs prev_mean/prev_rstd).
+ * from du_in on the fly (NULL to skip; needs prev_mean/prev_rstd), prev_sums64 [2*d_in] (optional) the same in double.
  * scratch [rows, H] fp32 (may be NULL) holds dP = A^^T dz between the gather kernel and the tensor-core
  * contraction; without it (or without the blobs of cgnn_build_agg) the generic kernel runs. */
 int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
@@ -347,7 +350,7 @@ int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const
                        const float* W, const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs,
                        int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
                        float* dW, float* dbias, float* du_in,
-                       const float* prev_mean, const float* prev_rstd, float* prev_sums,
+                       const float* prev_mean, const float* prev_rstd, float* prev_sums, double* prev_sums64,
                        float* scratch, void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
 
 /* GraphSAGE layer backward (autograd of models.py:136-152 plus the BN/dropout that follows).
@@ -362,7 +365,7 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
                         const float* W, const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs,
                         int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
                         float* dW, float* dbias, float* du_in,
-                        const float* prev_mean, const float* prev_rstd, float* prev_sums,
+                        const float* prev_mean, const float* prev_rstd, float* prev_sums, double* prev_sums64,
                         float* scratch, void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
 
 /* ---- the step after backward (reference train.py:51) -----------------------------------------

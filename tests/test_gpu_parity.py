@@ -378,6 +378,13 @@ def test_tensor_core_backward_matches_the_generic_kernels(kind, shape, top):
             eng.lib.cgnn_set_option(1, 1)
     for name, got, ref in zip(("dW", "dbias", "du_in", "prev_sums"), out[1], out[0]):
         helpers.assert_close(got, ref, f"{kind} bwd {name}: tensor-core vs generic", tol=5e-6)
+    # the float64 record of the sums: written next to the fp32 one, and read instead of it when handed in
+    for use_tc in (1, 0):
+        assert torch.equal(out[use_tc][4].float(), out[use_tc][3]), "prev_sums64 must round to prev_sums"
+    bn64 = BnBwd(act_out.scale, mean, rstd, torch.full_like(sums, float("nan")), float(rows), True, sums.double())
+    got64 = eng.layer_bwd(kind, du, demb, z, act_out, bn64, t_in, act_in, W, b.csr, b.ptr, B, True, pmean, prstd, agg)
+    for name, got, ref in zip(("dW", "dbias", "du_in", "prev_sums"), got64, out[1]):
+        helpers.assert_close(got, ref, f"{kind} bwd {name}: sums read from the float64 record", tol=1e-6)
 
 
 def test_streaming_store_matches_resident_store():

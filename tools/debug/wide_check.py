@@ -68,7 +68,7 @@ report("stats.M2", stats[1 + H:], ((z_ref - z_ref.mean(0)) ** 2).sum(0))
 act_out = Act(None, None, True, 0.0)
 du = rn(rows, H).to(DEV)
 pmean, prstd = (0.1 * rn(H)).to(DEV), (1 + 0.1 * rn(H)).abs().to(DEV)
-dW, db, du_in, prev = eng.layer_bwd("gcn", du, None, z, act_out, None, t_in, act_in, W, c, b.ptr, B, True, pmean, prstd)
+dW, db, du_in, prev, _ = eng.layer_bwd("gcn", du, None, z, act_out, None, t_in, act_in, W, c, b.ptr, B, True, pmean, prstd)
 torch.cuda.synchronize()
 dz = du.double() * (z.double() > 0)
 dP = A.T @ dz
