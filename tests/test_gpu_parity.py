@@ -615,3 +615,39 @@ def test_first_layer_kernels_match_the_generic_kernels(kind, shape, top):
             eng.lib.cgnn_set_option(1, 1)
     for name, got, ref in zip(("dW", "dbias"), out[1], out[0]):
         helpers.assert_close(got, ref, f"{kind} first layer bwd {name}", tol=5e-6)
+
+
+@pytest.mark.parametrize("kind,fused", [("gcn", "auto"), ("gcn", False), ("sage", False)])
+def test_same_launch_same_bits(kind, fused):
+    """Every forward path (warp-specialised engine, fused eval kernel, gather + contraction) and a training step's gradients
+    give the same bits launch after launch - the check that caught an intermittently wrong N = 128 tcgen05.mma."""
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome, GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_connectome
+    from connectome_gnn.train import CrossEntropyLoss
+    sizes = [360] * 6 + [84, 30, 130, 57, 200]
+    store = SubjectStore(pack_graphs([generate_connectome(num_regions=n, seed=300 + k) for k, n in enumerate(sizes)]), DEV)
+    ids = np.arange(len(sizes))
+    torch.manual_seed(0)
+    m = (GCNConnectome if kind == "gcn" else GraphSAGEConnectome)(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3,
+                                                                  dropout=0.25).to(DEV)
+    m.fused_eval = fused
+    m.eval()
+    first = None
+    for rep in range(24):
+        with torch.no_grad():
+            out = m(store.collate(ids, prepare_for=kind, backward=False))
+        first = out.clone() if first is None else first
+        assert torch.equal(out, first), f"{kind} eval forward changed at repeat {rep}"
+    m.train()
+    g0 = None
+    for rep in range(8):
+        m.zero_grad()
+        for bn in m.batch_norms:
+            bn.reset_running_stats()
+        torch.manual_seed(5)
+        b = store.collate(ids, prepare_for=kind)
+        CrossEntropyLoss()(m(b), b.labels).backward()
+        g = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+        g0 = g.clone() if g0 is None else g0
+        assert torch.equal(g, g0), f"{kind} training gradients changed at repeat {rep}"
