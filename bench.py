@@ -120,7 +120,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.nv is not None:
