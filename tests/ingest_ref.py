@@ -5,16 +5,19 @@ import torch
 
 
 def recipe(connectivity_matrix: np.ndarray, q: float = 0.90):
-    A = torch.tensor(connectivity_matrix, dtype=torch.float32)
-    threshold = A.flatten().quantile(q)
-    A_thresh = (A > threshold).float() * A
-    src, dst = torch.where(A_thresh > 0)
-    edge_index = torch.stack([torch.cat([src, dst]), torch.cat([dst, src])])
-    weights = A_thresh[src, dst]
-    edge_weight = torch.cat([weights, weights])
-    deg = A_thresh.sum(dim=1, keepdim=True)
-    node_features = deg / (deg.max() + 1e-8)
-    return node_features, edge_index, edge_weight, float(threshold)
+    """(node_features [N, 1], edge_index [2, 2 nnz], edge_weight [2 nnz], threshold) as the README recipe defines them:
+    entries above the matrix's own q-quantile survive; every survivor (i, j), taken in row-major order, is listed once as
+    i -> j in the first half of the edge list and once as j -> i in the second half, both with weight A[i, j]; the feature
+    is the surviving row sum divided by the largest one (+1e-8)."""
+    dense = torch.as_tensor(connectivity_matrix, dtype=torch.float32)
+    cut = torch.quantile(dense.reshape(-1), q)
+    kept = torch.where(dense > cut, dense, torch.zeros_like(dense))
+    rows, cols = torch.nonzero(kept > 0, as_tuple=True)          # row-major
+    w = kept[rows, cols]
+    edge_index = torch.stack([torch.cat([rows, cols]), torch.cat([cols, rows])])
+    edge_weight = torch.cat([w, w])
+    strength = kept.sum(dim=1, keepdim=True)
+    return strength / (strength.max() + 1e-8), edge_index, edge_weight, float(cut)
 
 
 def random_matrices(S: int, N: int, seed: int, kind: str = "dense") -> np.ndarray:
