@@ -431,7 +431,7 @@ def run_b200(a):
                "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
                "h2d_gbs_per_rank_alone": h2d_gbs, "h2d_gbs_per_rank_in_step": h2d_bytes * len(a.legs) / (ms_e / e2e_steps / 1e3) / 1e9,
                "cpu_affinity": affinity, "per_step": trace_e,
-               "path": "pinned host arena (compact pair store: " + ("one entry per undirected edge" if packed_c.get("edge_pairs") else "one entry per directed edge") + ") -> StreamingStore (H2D on a copy stream, double-buffered) -> collate -> Trainer.train_step/eval_step -> the step's four losses read back to the host"}
+               "path": "pinned host arena (compact pair store: " + ("one entry per undirected edge" if packed_c.get("edge_pairs") else "one entry per directed edge") + ") -> StreamingStore (H2D on a copy stream, three device arenas) -> collate -> Trainer.train_step/eval_step -> the step's four losses read back to the host"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------------
     cpu = None
