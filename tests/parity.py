@@ -564,3 +564,43 @@ def check_pair_collate(device, sizes=(30, 84, 57, 130), with_bad_edge=True):
                 lb, fb = la[d].cpu(), fa[d].cpu()
                 for g in range(len(ids)):
                     assert torch.equal(_blob_words(lb, meta, g), _blob_words(fb, meta, g)), (kind, backward, d, g)
+
+
+def check_pair_collate_fuzz(device, seed=0, rounds=6):
+    """Random undirected multigraphs - self-loop pairs, repeated pairs, isolated nodes, one-node and edgeless subjects,
+    ragged sizes - through the pair store: k_collate_pairs vs k_collate_graph blob for blob, and the lean batch's lazily
+    filled reference fields vs the full collate."""
+    from connectome_gnn.graph import ConnectomeGraph, SubjectStore, pack_graphs
+    rng = np.random.default_rng(seed)
+    for rnd in range(rounds):
+        graphs = []
+        for s in range(int(rng.integers(3, 9))):
+            n = int(rng.choice([1, 2, 5, 17, 40, 84, 130, 200]))
+            pairs = int(rng.integers(0, 4 * n + 1)) if n > 1 else int(rng.integers(0, 3))
+            u = rng.integers(0, n, pairs)
+            v = rng.integers(0, n, pairs)            # u == v happens: a self-loop pair; repeats happen: multi-edges
+            w = rng.random(pairs).astype(np.float32) + 0.05
+            ei = np.empty((2, 2 * pairs), dtype=np.int64)
+            ei[0, 0::2], ei[1, 0::2], ei[0, 1::2], ei[1, 1::2] = u, v, v, u
+            ew = np.repeat(w, 2)
+            graphs.append(ConnectomeGraph(torch.from_numpy(rng.normal(size=(n, 5)).astype(np.float32)), torch.from_numpy(ei),
+                                          torch.from_numpy(ew), torch.tensor(int(rng.integers(0, 2)))))
+        packed = pack_graphs(graphs)
+        if all(g.num_edges == 0 for g in graphs):
+            continue
+        assert packed["edge_pairs"] == 1
+        store = SubjectStore(packed, device)
+        ids = rng.permutation(len(graphs))
+        for kind in ("gcn", "sage"):
+            lean = store.collate(ids, prepare_for=kind)
+            full = store.collate(ids, prepare_for=kind, lean=False)
+            meta = full.csr.graph_meta.cpu()
+            assert torch.equal(lean.csr.graph_meta.cpu(), meta)
+            la, fa = lean.csr.agg[kind], full.csr.agg[kind]
+            assert torch.equal(la[2], fa[2])
+            for d in range(2):
+                lb, fb = la[d].cpu(), fa[d].cpu()
+                for g in range(len(ids)):
+                    assert torch.equal(_blob_words(lb, meta, g), _blob_words(fb, meta, g)), (rnd, kind, d, g)
+            for f in ("node_features", "edge_index", "edge_weight", "batch", "labels", "ptr"):
+                assert torch.equal(getattr(lean, f), getattr(full, f)), f

@@ -189,6 +189,10 @@ def test_pair_collate_bit_exact(on_emu):
     parity.check_pair_collate("cpu")
 
 
+def test_pair_collate_fuzz(on_emu):
+    parity.check_pair_collate_fuzz("cpu", seed=1, rounds=3)
+
+
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_batches_die_by_refcount(on_emu, kind):
     parity.check_batches_die_by_refcount("cpu", kind)

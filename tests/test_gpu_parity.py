@@ -532,6 +532,11 @@ def test_pair_collate_bit_exact(sizes):
     parity.check_pair_collate(DEV, sizes)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_pair_collate_fuzz(seed):
+    parity.check_pair_collate_fuzz(DEV, seed=seed, rounds=8)
+
+
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_batches_die_by_refcount(kind):
     parity.check_batches_die_by_refcount(DEV, kind, num_regions=120)
