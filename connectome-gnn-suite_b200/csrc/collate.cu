@@ -439,20 +439,29 @@ __global__ void __launch_bounds__(NT) k_collate_pairs(CollateArgs p) {
   if (tid == 0) reinterpret_cast<int4*>(p.csr.graph_meta)[g] = make_int4((int)nb, n, (int)eb, m);
   if (n > p.max_nodes || m > p.edge_cap) return;  // host contract violated: never index past the shared arrays
 
+  // 33 KB for a 360-node subject: six CTAs per SM - the kernel is a chain of short shared-memory phases, occupancy is
+  // what hides their latency.  The stored pairs are read from global memory twice (count, place: the second time from
+  // L1 / L2) instead of being staged, the per-chunk counters are 16 bits wide.
   int* start = reinterpret_cast<int*>(cgnn_smem);          // [n] packed counts -> first sorted slot (low 16 bits) | first record (high)
   float* s_dinv = reinterpret_cast<float*>(start + n);     // [n]
   float* s_wsum = s_dinv + n;                              // [n]
-  int* cnt = reinterpret_cast<int*>(s_wsum + n);           // [kNW][n] per-chunk counts -> cursors
-  uint32_t* pk = reinterpret_cast<uint32_t*>(cnt + kNW * n);   // [m] sorted half-edges: owner | partner << 16
-  float* cw = reinterpret_cast<float*>(pk + m);                // [m]
-  uint32_t* raw_pk = reinterpret_cast<uint32_t*>(cw + m);      // [m / 2] stored pairs: u | v << 16
-  float* raw_w = reinterpret_cast<float*>(raw_pk + (m >> 1));  // [m / 2]
+  uint32_t* pk = reinterpret_cast<uint32_t*>(s_wsum + n);  // [m] sorted half-edges: owner | partner << 16
+  float* cw = reinterpret_cast<float*>(pk + m);            // [m]
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(cw + m);     // [kNW][n] per-chunk counts -> cursors (all below 2^16)
+  uint32_t* cnt32 = reinterpret_cast<uint32_t*>(cnt);      // the same words, for the atomics
 
   const long long sid = p.ids[g];
   const long long sn = p.store.node_ptr[sid], so = p.store.edge_ptr[sid] >> 1;
   const int32_t* lsrc = p.store.src + so;
   const float* lw = p.store.w + so;
-  const int np = m >> 1;
+  // stored pair k: u | v << 16; endpoints outside the subject make it a zero-weight self edge on node 0 (as
+  // k_collate_graph does, edge by edge)
+  auto pair_at = [&](int k, float& w) -> uint32_t {
+    uint32_t v = (uint32_t)lsrc[k];
+    w = lw[k];
+    if ((v & 0xffffu) >= (uint32_t)n || (v >> 16) >= (uint32_t)n) { v = 0u; w = 0.0f; }
+    return v;
+  };
   {
     const int F = p.store.num_features;
     const float* sx = p.store.x + sn * F;
@@ -469,35 +478,25 @@ __global__ void __launch_bounds__(NT) k_collate_pairs(CollateArgs p) {
       for (int i = tid; i < n; i += NT) p.batch[nb + i] = g;
     if (tid == 0 && p.labels && p.store.label) p.labels[g] = p.store.label[sid];
   }
-  for (int k0 = tid; k0 < np; k0 += 3 * NT) {          // three pairs in flight per thread
-    uint32_t v[3]; float w[3];
-#pragma unroll
-    for (int u = 0; u < 3; ++u) { v[u] = 0u; w[u] = 0.0f; if (k0 + u * NT < np) { v[u] = (uint32_t)lsrc[k0 + u * NT]; w[u] = lw[k0 + u * NT]; } }
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      if (k0 + u * NT >= np) continue;
-      // endpoints outside the subject: a zero-weight self edge on node 0 (as k_collate_graph does, edge by edge)
-      if ((v[u] & 0xffffu) >= (uint32_t)n || (v[u] >> 16) >= (uint32_t)n) { v[u] = 0u; w[u] = 0.0f; }
-      raw_pk[k0 + u * NT] = v[u];
-      raw_w[k0 + u * NT] = w[u];
-    }
-  }
-  for (int i = tid; i < kNW * n; i += NT) cnt[i] = 0;
+  const int cnt_words = (kNW * n + 1) >> 1;
+  for (int i = tid; i < cnt_words; i += NT) cnt32[i] = 0u;
   __syncthreads();
 
   // half-edge h: owner = (h & 1 ? v : u), partner = the other endpoint of pair h >> 1
   const int clen = (((m + kNW - 1) / kNW) + 31) & ~31;
   const int h_lo = min(warp * clen, m), h_hi = min(h_lo + clen, m);
-  int* my_cnt = cnt + (size_t)warp * n;
+  const int my_base = warp * n;
   for (int h = h_lo + lane; h < h_hi; h += 32) {
-    const uint32_t v = raw_pk[h >> 1];
-    atomicAdd(&my_cnt[(h & 1) ? (v >> 16) : (v & 0xffffu)], 1);
+    float w;
+    const uint32_t v = pair_at(h >> 1, w);
+    const int idx = my_base + (int)((h & 1) ? (v >> 16) : (v & 0xffffu));
+    atomicAdd(&cnt32[idx >> 1], 1u << (16 * (idx & 1)));
   }
   __syncthreads();
   const int self = p.csr.agg_kind == AGG_GCN ? 1 : 0;
   for (int i = tid; i < n; i += NT) {
     int t = 0;
-    for (int c = 0; c < kNW; ++c) t += cnt[(size_t)c * n + i];
+    for (int c = 0; c < kNW; ++c) t += cnt[c * n + i];
     start[i] = t | (((t + self + 1) & ~1) << 16);     // both totals stay below 2^16 (the lists fit in shared memory)
   }
   __syncthreads();
@@ -505,18 +504,19 @@ __global__ void __launch_bounds__(NT) k_collate_pairs(CollateArgs p) {
   for (int i = tid; i < n; i += NT) {
     int run = start[i] & 0xffff;
     for (int c = 0; c < kNW; ++c) {
-      int* q = &cnt[(size_t)c * n + i];
+      uint16_t* q = &cnt[c * n + i];
       const int t = *q;
-      *q = run;
+      *q = (uint16_t)run;
       run += t;
     }
   }
   __syncthreads();
+  uint16_t* my_cnt = cnt + my_base;
   for (int h0 = h_lo; h0 < h_hi; h0 += 32) {
     const int h = h0 + lane;
     const bool live = h < h_hi;
     uint32_t v = 0u; float w = 0.0f;
-    if (live) { v = raw_pk[h >> 1]; w = raw_w[h >> 1]; }
+    if (live) v = pair_at(h >> 1, w);
     if (h & 1) v = (v >> 16) | (v << 16);             // owner in the low half
     const int key = live ? (int)(v & 0xffffu) : -1 - lane;
     const unsigned peers = __match_any_sync(kFull, key);
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(NT) k_collate_pairs(CollateArgs p) {
     if (live) {
       pk[at + rank] = v;
       cw[at + rank] = w;
-      if (rank == 0) my_cnt[key] = at + __popc(peers);
+      if (rank == 0) my_cnt[key] = (uint16_t)(at + __popc(peers));
     }
     __syncwarp();
   }
@@ -566,11 +566,10 @@ __global__ void __launch_bounds__(NT) k_collate_pairs(CollateArgs p) {
     const int st = start[i];
     const int q0 = st & 0xffff, q1 = i + 1 < n ? (start[i + 1] & 0xffff) : m;
     const int begin = (int)((unsigned)st >> 16);
-    int at = begin + (q1 - q0);
-    const int at0 = at;
+    const int at0 = begin + (q1 - q0);
     const float dv = s_dinv[i];
     const int self_w = __float_as_int(__fmul_rn(dv, dv));
-    int end = at;
+    int end = at0;
     if (self) ++end;
     const bool pad = end & 1;
     if (pad) ++end;
@@ -587,7 +586,6 @@ __global__ void __launch_bounds__(NT) k_collate_pairs(CollateArgs p) {
     const float aux = gcn ? dv : s_wsum[i];
     reinterpret_cast<int4*>(blob_in)[i] = make_int4(begin, end, __float_as_int(aux), i);
     if (blob_out) reinterpret_cast<int4*>(blob_out)[i] = make_int4(begin, end, __float_as_int(aux), i);
-    (void)at;
   }
 }
 
@@ -636,10 +634,10 @@ static int collate_launch(CollateArgs& a, bool from_store, int max_nodes, int ma
   }
   a.max_nodes = max_nodes;
   if (a.B <= 0) return CGNN_OK;
-  // pair store + lean batch: one sort serves both blobs (k_collate_pairs); four CTAs per SM at the 360-node shape
+  // pair store + lean batch: one sort serves both blobs (k_collate_pairs); six CTAs per SM at the 360-node shape
   if (from_store && lean && a.store.edge_pairs && max_edges >= 0 && (max_edges & 1) == 0 && a.csr.agg_kind >= 0 && max_nodes <= 65535) {
     const int ntp = (max_nodes <= 128 && a.total_edges / a.B <= 2048) ? 128 : 256;
-    const size_t smem_p = (size_t)max_nodes * (12 + 4 * (ntp / 32)) + (size_t)max_edges * 12 + 16;
+    const size_t smem_p = (size_t)max_nodes * (12 + 2 * (ntp / 32)) + (size_t)max_edges * 8 + 16;
     if (smem_p <= (size_t)dev.smem_optin) {
       const int cap = a.edge_cap;
       a.edge_cap = max_edges;
