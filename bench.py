@@ -243,7 +243,7 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": a.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1), "legs": legs,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a, max(1, a.gpus)), "legs": legs,
         "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
