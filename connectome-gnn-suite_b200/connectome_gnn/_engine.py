@@ -231,6 +231,28 @@ class Engine:
         self._call_csr(f"cgnn_{kind}_layer_fwd", csr, build)
         return z, stats, agg
 
+    def gcn_layer_fwd_pool(self, t_in, act: Act, W, bias, csr, ptr, num_graphs: int, act_out: Act):
+        """Eval-mode last GCN layer with its BatchNorm affine + ReLU and the mean-pool readout folded into the kernel:
+        returns emb [B, H], or None when the shape is not covered (the caller runs layer_fwd + pool_fwd)."""
+        rows, d_in = t_in.shape
+        H = W.shape[0]
+        if W.shape[1] != d_in:
+            raise RuntimeError(f"gcn layer: input has {d_in} channels but the weight is {tuple(W.shape)}")
+        if d_in != 64 or H != 64 or not (1 <= csr.max_nodes <= 384) or act_out.p_drop > 0.0:
+            return None
+        self.ensure_agg(csr, "gcn", num_graphs, rows, csr.num_edges, need_out=False)
+        emb = self.empty((num_graphs, H))
+        a, ao = act.struct(), act_out.struct()
+        cs = self.csr_struct(csr, "gcn")
+        try:
+            self._call("cgnn_gcn_layer_fwd_pool", _p(t_in), C.byref(a), _p(W), _p(bias), C.byref(cs), _p(ptr), num_graphs, rows,
+                       d_in, H, csr.max_nodes, csr.max_edges, C.byref(ao), _p(emb), self.stream())
+        except _lib.CgnnError as e:
+            if e.status == _lib.ERR_UNSUPPORTED:
+                return None
+            raise
+        return emb
+
     # -- K9 -------------------------------------------------------------------------------------
     def eval_fused(self, kind: str, x, layers, head, csr, ptr, num_graphs: int, want_logits: bool = True):
         """The whole eval-mode network in one kernel.  ``layers`` = [(W, bias, gamma, beta, running_mean, running_var,

@@ -114,8 +114,17 @@ class _EncodeFn(torch.autograd.Function):
 
         t, act = x.contiguous(), Act()
         saved = []
+        L = len(cfg["bns"])
         for l, bn in enumerate(cfg["bns"]):
             W, b, gamma, beta = (q.contiguous() for q in params[4 * l: 4 * l + 4])
+            if l == L - 1 and l > 0 and kind == "gcn" and not training and cfg.get("forward_only"):
+                # eval mode, nobody will call backward: the last layer folds its BatchNorm (running statistics), ReLU and
+                # the mean-pool readout into the layer kernel - z_L is never written
+                scale, shift, mean, rstd = eng.bn_eval_affine(gamma, beta, bn.running_mean, bn.running_var, bn.eps)
+                emb = eng.gcn_layer_fwd_pool(t, act, W, b, csr, ptr, B, Act(scale, shift, True, 0.0, 0, l, batch.row_base))
+                if emb is not None:
+                    ctx.cfg, ctx.saved, ctx.final_act, ctx.x_needs_grad = cfg, None, None, False
+                    return emb
             z, stats, agg = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, want_stats=training)
             if training:
                 stats = _merge_stats_across_ranks(eng, stats, W.shape[0], cfg["group"])
@@ -328,6 +337,10 @@ class _ConnectomeClassifier(nn.Module):
         params = []
         for conv, bn in zip(self.convs, self.batch_norms):
             params += [*conv.tensors(), bn.weight, bn.bias]
+        # decided here (inside Function.forward grad mode is always off): under torch.no_grad() / with everything frozen no
+        # backward can follow, and the forward may skip what only a backward pass would read
+        cfg["forward_only"] = not (torch.is_grad_enabled() and (batch.node_features.requires_grad or
+                                                                any(q is not None and q.requires_grad for q in params)))
         return _EncodeFn.apply(cfg, batch.node_features, *params)
 
     def _fused_eval(self, batch: ConnectomeBatch, want_logits: bool):

@@ -160,6 +160,10 @@ int launch_gather(int mode, GatherArgs& a, int* grid_out, cudaStream_t stream);
 int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
                       int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
                       double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream);
+// eval-mode last layer: BatchNorm affine + ReLU of the output and the mean-pool readout in the epilogue (emb instead of z)
+int launch_gcn_fwd_ws_pool(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+                           int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
+                           const cgnn_act_t* act_out, float* emb, cudaStream_t stream);
 #ifndef CGNN_EMU
 // gemm_tc.cu: tensor-core contractions; same return convention.
 int launch_sage_fwd_gemm(const float* t_in, const cgnn_act_t* act, const float* agg, const float* W, const float* bias,

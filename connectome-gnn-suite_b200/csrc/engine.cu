@@ -34,10 +34,13 @@ struct Args {
   int blob_cap_bytes;      // one blob buffer
   int nblob;               // 1 or 2 blob buffers
   float* z; double* partials;
-  int o_stage, o_p, o_blob, o_const, o_tab;   // byte offsets from the 1024-aligned base (W operands at 0)
+  // POOL variant (eval-mode last layer): emb[g] = mean_i relu2(z_i * scale2 + shift2); z itself is not written
+  const float* scale2; const float* shift2; int relu2; float* emb;
+  int o_stage, o_p, o_blob, o_const, o_tab, o_pool;   // byte offsets from the 1024-aligned base (W operands at 0)
   __host__ __device__ UnitSrc src() const { return UnitSrc{meta, B, spu, blob_cap_bytes}; }
 };
 
+template <bool POOL>
 __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ ws::TensorMap tmap, Args p) {
   act_salt(p.act);   // device-side dropout salt (CUDA-graph replays)
 #ifdef CGNN_EMU
@@ -207,6 +210,9 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
     const int cl = lane & 15, half = lane >> 4;                     // gather: channel quad, which row of the pair
     const uint32_t lane_const = (uint32_t)(((cl & 7) << 4) | ((cl & 8) << 4));
     const float4 bias4 = *reinterpret_cast<const float4*>(s_bias + 4 * cl);
+    float4 sc2 = make_float4(1.f, 1.f, 1.f, 1.f), sh2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (POOL && p.scale2) { sc2 = *reinterpret_cast<const float4*>(p.scale2 + 4 * cl); sh2 = *reinterpret_cast<const float4*>(p.shift2 + 4 * cl); }
+    float* s_pool = reinterpret_cast<float*>(base + p.o_pool);      // [subjects per unit][16 warps][64]
     const bool want_stats = p.partials != nullptr;
     // BatchNorm statistics of this thread's channel quad as shifted sums: s1 = sum (z - c), s2 = sum (z - c)^2 with
     // c = the thread's first value (no cancellation: |z - c| is of the order of the spread); turned into
@@ -240,6 +246,7 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
       if (lane == 0) {
         tab[0] = un.rows; tab[1] = un.nsub; tab[2] = groups; tab[3] = un.tiles;
         tab[4] = (int)(un.row0 & 0xffffffffll); tab[5] = (int)(un.row0 >> 32);
+        tab[6] = (int)un.g0;
       }
     };
     if (gw == 0 && (long long)blockIdx.x < p.units) build_table(blockIdx.x, s_tab);
@@ -278,9 +285,16 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
 
       // ---- gather: half a warp per row, pairs of rows in lock step -------------------------------------------------
       const int32_t* blob = reinterpret_cast<const int32_t*>(s_blob + (size_t)b * p.blob_cap_bytes);
-      for (int gi = gw; gi < groups; gi += kGathWarps) {
-        int j = 0;
-        while (j + 1 < nsub && gi >= tab[8 + 8 * (j + 1) + 4]) ++j;
+      // POOL: pair k of a subject always goes to warp k % 16, whatever else shares the unit - the subject's sum is then
+      // formed in the same order in every batch (eval logits are bit-identical under any batch split)
+      const int n_outer = POOL ? nsub : 1;
+      for (int jo = 0; jo < n_outer; ++jo) {
+      float4 pool = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int g_lo = POOL ? tab[8 + 8 * jo + 4] + gw : gw;
+      const int g_hi = POOL ? tab[8 + 8 * jo + 4] + ((tab[8 + 8 * jo + 2] + 1) >> 1) : groups;
+      for (int gi = g_lo; gi < g_hi; gi += kGathWarps) {
+        int j = POOL ? jo : 0;
+        if (!POOL) while (j + 1 < nsub && gi >= tab[8 + 8 * (j + 1) + 4]) ++j;
         const int* e = tab + 8 + 8 * j;
         const int n = e[2], i = 2 * (gi - e[4]) + half;
         const bool valid = i < n;
@@ -317,6 +331,12 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
         }
         if (!valid) continue;
         a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+        if (POOL) {       // the next BatchNorm (running statistics) + ReLU on the value, straight into the subject's sum
+          if (p.scale2) { a.x = fmaf(a.x, sc2.x, sh2.x); a.y = fmaf(a.y, sc2.y, sh2.y); a.z = fmaf(a.z, sc2.z, sh2.z); a.w = fmaf(a.w, sc2.w, sh2.w); }
+          if (p.relu2) { a.x = fmaxf(a.x, 0.0f); a.y = fmaxf(a.y, 0.0f); a.z = fmaxf(a.z, 0.0f); a.w = fmaxf(a.w, 0.0f); }
+          pool.x += a.x; pool.y += a.y; pool.z += a.z; pool.w += a.w;
+          continue;
+        }
         *reinterpret_cast<float4*>(p.z + (row0 + e[0] + i) * kC + 4 * cl) = a;
         if (want_stats) {
           if (cnt == 0) sh = a;
@@ -326,8 +346,26 @@ __global__ void __launch_bounds__(kNT, 1) k_gcn_fwd_ws(const __grid_constant__ w
           s2.x = fmaf(dv.x, dv.x, s2.x); s2.y = fmaf(dv.y, dv.y, s2.y); s2.z = fmaf(dv.z, dv.z, s2.z); s2.w = fmaf(dv.w, dv.w, s2.w);
         }
       }
+      if (POOL) {       // this warp's share of subject jo: even rows + odd rows, one slot per (subject, warp)
+        pool.x += __shfl_xor_sync(kFull, pool.x, 16); pool.y += __shfl_xor_sync(kFull, pool.y, 16);
+        pool.z += __shfl_xor_sync(kFull, pool.z, 16); pool.w += __shfl_xor_sync(kFull, pool.w, 16);
+        if (half == 0) *reinterpret_cast<float4*>(s_pool + ((size_t)jo * kGathWarps + gw) * kC + 4 * cl) = pool;
+      }
+      }
       __syncwarp();
       if (lane == 0) ws::mbar_arrive(&bars.blob_free[b]);     // this warp has read its last record of the unit
+      if (POOL) {
+        ws::named_sync(1, kGathThreads);          // every warp's partial sums are in place
+        const long long g0 = (long long)tab[6];
+        for (int j = gw; j < nsub; j += kGathWarps) {
+          // mean over the subject's rows (models.py:57-59)
+          for (int c = lane; c < kC; c += 32) {
+            float sum = 0.0f;
+            for (int w = 0; w < kGathWarps; ++w) sum += s_pool[((size_t)j * kGathWarps + w) * kC + c];
+            p.emb[(g0 + j) * kC + c] = sum / ((float)tab[8 + 8 * j + 2] + 1e-8f);
+          }
+        }
+      }
       ws::named_sync(1, kGathThreads);            // every warp is done with P: the next drain may overwrite it
     }
 
@@ -408,14 +446,20 @@ int make_tensor_map(TensorMap* m, const float* base, long long rows, int cols, i
 #endif
 
 // Returns CGNN_OK when launched (grid in *grid_out: the caller merges `partials`), -1 when the shape is not covered.
-int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
-                      int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
-                      double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream) {
+// emb != nullptr: the POOL variant - act_out (BatchNorm affine + ReLU of the layer's output, no dropout) and the mean-pool
+// readout are applied in the epilogue, emb [num_graphs, 64] is written instead of z.
+static int launch_ws(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+                     int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
+                     double* partials, const cgnn_act_t* act_out, float* emb, int* grid_out, size_t workspace_bytes,
+                     cudaStream_t stream) {
   using namespace eng;
   if (!csr->agg_in || csr->agg_kind != AGG_GCN) return -1;
   if (d_in != kC || H != kC) return -1;
   if (max_nodes < 1 || max_nodes > kMaxUnitRows) return -1;
-  if ((((uintptr_t)t_in) & 15u) != 0 || (((uintptr_t)z) & 15u) != 0 || (((uintptr_t)W) & 15u) != 0) return -1;
+  if ((((uintptr_t)t_in) & 15u) != 0 || (z && (((uintptr_t)z) & 15u) != 0) || (((uintptr_t)W) & 15u) != 0) return -1;
+  const bool pool = emb != nullptr;
+  if (pool && act_out && act_out->p_drop > 0.0f) return -1;       // eval mode only
+  if (pool && act_out && act_out->scale && ((((uintptr_t)act_out->scale) & 15u) != 0 || (((uintptr_t)act_out->shift) & 15u) != 0)) return -1;
   const DeviceInfo dev = device_info();
   Args a;
   a.act = make_act(act); a.W = W; a.bias = bias;
@@ -426,6 +470,10 @@ int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, 
   a.spu = spu;
   a.units = (num_graphs + spu - 1) / spu;
   a.z = z; a.partials = partials;
+  a.scale2 = (pool && act_out) ? act_out->scale : nullptr;
+  a.shift2 = (pool && act_out) ? act_out->shift : nullptr;
+  a.relu2 = (pool && act_out) ? act_out->relu : 0;
+  a.emb = emb;
   // P rows: every subject starts at a multiple of 8
   const int p_rows = spu * ((max_nodes + 7) & ~7);
   const size_t blob_cap = (size_t)(((long long)spu * (agg_copy_words(max_nodes, max_edges) + 8) + 3) & ~3ll) * 4;
@@ -435,7 +483,8 @@ int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, 
   if (off < (size_t)a.o_p + (size_t)kGathThreads * 9 * 4) off = (size_t)a.o_p + (size_t)kGathThreads * 9 * 4;
   off = (off + 15) & ~(size_t)15;
   a.o_blob = (int)off;
-  const size_t tail = (size_t)3 * kC * 4 + (size_t)2 * kTabInts * 4 + 32;
+  const size_t pool_bytes = pool ? (size_t)spu * kGathWarps * kC * 4 : 0;
+  const size_t tail = (size_t)3 * kC * 4 + (size_t)2 * kTabInts * 4 + 32 + pool_bytes;
   const size_t limit = (size_t)dev.smem_optin - kStaticSmem;       // the kernel's static shared memory counts too
   int nblob = 2;
   if (off + 2 * blob_cap + tail + 1024 > limit) nblob = 1;
@@ -445,6 +494,8 @@ int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, 
   off += (size_t)nblob * blob_cap;
   a.o_const = (int)off; off += (size_t)3 * kC * 4;
   a.o_tab = (int)off; off += (size_t)2 * kTabInts * 4;
+  off = (off + 15) & ~(size_t)15;
+  a.o_pool = (int)off; off += pool_bytes;
   const size_t smem = off + 1024;
   long long grid = dev.sm_count;
   if (grid > a.units) grid = a.units;
@@ -456,11 +507,32 @@ int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, 
   *grid_out = (int)grid;
   ws::TensorMap tmap;
   if (ws::make_tensor_map(&tmap, t_in, rows, kC, kTR) != CGNN_OK) return -1;
-  auto kfn = k_gcn_fwd_ws;
-  cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  CGNN_LAUNCH(kfn, (unsigned)grid, kNT, smem, stream, tmap, a);
+  if (pool) {
+    auto kfn = k_gcn_fwd_ws<true>;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CGNN_LAUNCH(kfn, (unsigned)grid, kNT, smem, stream, tmap, a);
+  } else {
+    auto kfn = k_gcn_fwd_ws<false>;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CGNN_LAUNCH(kfn, (unsigned)grid, kNT, smem, stream, tmap, a);
+  }
   CGNN_CHECK_LAUNCH();
   return CGNN_OK;
+}
+
+int launch_gcn_fwd_ws(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+                      int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z,
+                      double* partials, int* grid_out, size_t workspace_bytes, cudaStream_t stream) {
+  return launch_ws(t_in, act, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, z, partials, nullptr, nullptr, grid_out,
+                   workspace_bytes, stream);
+}
+
+int launch_gcn_fwd_ws_pool(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+                           int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
+                           const cgnn_act_t* act_out, float* emb, cudaStream_t stream) {
+  int grid = 0;
+  return launch_ws(t_in, act, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, nullptr, nullptr, act_out, emb, &grid, 0,
+                   stream);
 }
 
 }  // namespace cgnn

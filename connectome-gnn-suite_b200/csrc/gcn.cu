@@ -576,6 +576,20 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
   return CGNN_OK;
 }
 
+int cgnn_gcn_layer_fwd_pool(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias, const cgnn_csr_t* csr,
+                            const int64_t* ptr, int64_t num_graphs, int64_t rows, int32_t d_in, int32_t H, int32_t max_nodes,
+                            int32_t max_edges, const cgnn_act_t* act_out, float* emb, cgnn_stream_t stream_) {
+  (void)ptr;
+  if (num_graphs < 0 || rows < 0 || d_in <= 0 || H <= 0 || max_nodes < 0 || max_edges < 0) return CGNN_ERR_INVALID_ARG;
+  if (num_graphs == 0 || rows == 0) return CGNN_OK;
+  if (!t_in || !W || !csr || !csr->graph_meta || !csr->agg_in || !emb) return CGNN_ERR_INVALID_ARG;
+  if (!tensor_cores_enabled()) return CGNN_ERR_UNSUPPORTED;
+  const int rc = launch_gcn_fwd_ws_pool(t_in, act, W, bias, csr, num_graphs, rows, d_in, H, max_nodes, max_edges, act_out, emb,
+                                        (cudaStream_t)stream_);
+  if (rc == CGNN_OK) return CGNN_OK;
+  return rc > 0 ? rc : CGNN_ERR_UNSUPPORTED;
+}
+
 int cgnn_gcn_layer_bwd(const float* du, const float* demb, const float* z, const cgnn_act_t* act_out,
                        const cgnn_bn_bwd_t* bn, const float* t_in, const cgnn_act_t* act_in, const float* W,
                        const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,

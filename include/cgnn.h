@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGNN_ABI_VERSION 9
+#define CGNN_ABI_VERSION 10
 
 typedef void* cgnn_stream_t; /* cudaStream_t */
 
@@ -241,6 +241,16 @@ int cgnn_gcn_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W,
  * W [H, 2*d_in], b [H].  agg [rows, d_in] (may be NULL) receives the aggregated neighbourhood (every code path fills
  * it when given): with it and the blobs of cgnn_build_agg the layer runs as a gather kernel plus a tensor-core
  * contraction, and backward reuses it instead of gathering again. */
+/* GCN layer forward with the readout folded in (eval mode, last layer; reference models.py:208-211 in eval):
+ *   emb[g] = mean over the rows i of subject g of act_out(z_i),  z = A^ (act(t_in) W^T) + b
+ * act_out = the BatchNorm affine (running statistics) + ReLU of this layer's output, p_drop = 0.  z is not written.
+ * Hidden layers 64 -> 64 with the GCN blobs only; CGNN_ERR_UNSUPPORTED otherwise (the caller runs cgnn_gcn_layer_fwd +
+ * cgnn_pool_fwd).  A subject's sum is formed in the same order in every batch. */
+int cgnn_gcn_layer_fwd_pool(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
+                            const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
+                            int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges,
+                            const cgnn_act_t* act_out, float* emb, cgnn_stream_t stream);
+
 int cgnn_sage_layer_fwd(const float* t_in, const cgnn_act_t* act, const float* W, const float* bias,
                         const cgnn_csr_t* csr, const int64_t* ptr, int64_t num_graphs, int64_t rows,
                         int32_t d_in, int32_t H, int32_t max_nodes, int32_t max_edges, float* z, double* bn_stats,

@@ -604,3 +604,52 @@ def check_pair_collate_fuzz(device, seed=0, rounds=6):
                     assert torch.equal(_blob_words(lb, meta, g), _blob_words(fb, meta, g)), (rnd, kind, d, g)
             for f in ("node_features", "edge_index", "edge_weight", "batch", "labels", "ptr"):
                 assert torch.equal(getattr(lean, f), getattr(full, f)), f
+
+
+def check_pooled_last_layer(device, sizes=(84, 30, 130, 57, 84, 200, 360, 1, 2)):
+    """GCN in eval mode under torch.no_grad(): the last layer runs as cgnn_gcn_layer_fwd_pool (BatchNorm with running
+    statistics, ReLU and the mean-pool readout folded into the layer kernel, z_L never written).  Against the same model
+    with gradients enabled (layer kernel + cgnn_pool_fwd): embeddings and logits within 1e-6 max-norm relative; and the
+    embedding of a subject does not depend on what else is in the batch (bit for bit)."""
+    from connectome_gnn import _engine
+    from connectome_gnn.graph import SubjectStore, pack_graphs
+    from connectome_gnn.models import GCNConnectome
+    from connectome_gnn.synthetic import generate_connectome
+    graphs = [generate_connectome(num_regions=max(n, 10), seed=400 + k) for k, n in enumerate(sizes)]
+    store = SubjectStore(pack_graphs(graphs), device)
+    ids = np.arange(len(graphs))
+    torch.manual_seed(21)
+    m = GCNConnectome(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.4).to(device).eval()
+    m.fused_eval = False            # not the whole-network kernel: the layer path
+    with torch.no_grad():
+        for bn in m.batch_norms:
+            bn.running_mean.uniform_(-0.2, 0.2); bn.running_var.uniform_(0.5, 1.5)
+            bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.3, 0.3)
+    eng = _engine.engine_for(store.x)
+    calls = {"n": 0}
+    orig = eng.gcn_layer_fwd_pool
+
+    def counted(*a, **k):
+        out = orig(*a, **k)
+        calls["n"] += out is not None
+        return out
+    eng.gcn_layer_fwd_pool = counted
+    try:
+        with torch.no_grad():
+            emb_fused = m.encode(store.collate(ids, prepare_for="gcn", backward=False)).clone()
+            logits_fused = m(store.collate(ids, prepare_for="gcn", backward=False)).clone()
+            # every subject alone and in reverse order: same bits
+            rev = m.encode(store.collate(ids[::-1].copy(), prepare_for="gcn", backward=False))
+            assert torch.equal(rev.flip(0), emb_fused), "embedding depends on the position in the batch"
+            for g in (0, 3, 6):
+                alone = m.encode(store.collate(np.array([g]), prepare_for="gcn", backward=False))
+                assert torch.equal(alone[0], emb_fused[g]), f"subject {g}: embedding depends on the rest of the batch"
+        assert calls["n"] >= 3, "the pooled last-layer kernel was not taken"
+        before = calls["n"]
+        emb_ref = m.encode(store.collate(ids, prepare_for="gcn")).detach()       # gradients enabled: the unfused path
+        logits_ref = m(store.collate(ids, prepare_for="gcn")).detach()
+        assert calls["n"] == before, "the pooled kernel must not run when a backward pass can follow"
+    finally:
+        eng.gcn_layer_fwd_pool = orig
+    helpers.assert_close(emb_fused, emb_ref, "pooled last layer: embeddings", tol=1e-6)
+    helpers.assert_close(logits_fused, logits_ref, "pooled last layer: logits", tol=1e-6)

@@ -185,6 +185,10 @@ def test_lean_collate(on_emu, compact):
     parity.check_lean_collate("cpu", "gcn", compact)
 
 
+def test_pooled_last_layer(on_emu):
+    parity.check_pooled_last_layer("cpu", sizes=(84, 30, 130, 57, 200, 10, 12))
+
+
 def test_pair_collate_bit_exact(on_emu):
     parity.check_pair_collate("cpu")
 

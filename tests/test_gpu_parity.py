@@ -532,6 +532,10 @@ def test_pair_collate_bit_exact(sizes):
     parity.check_pair_collate(DEV, sizes)
 
 
+def test_pooled_last_layer():
+    parity.check_pooled_last_layer(DEV)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_pair_collate_fuzz(seed):
     parity.check_pair_collate_fuzz(DEV, seed=seed, rounds=8)
