@@ -466,6 +466,12 @@ static int launch_ws(const float* t_in, const cgnn_act_t* act, const float* W, c
   a.blob = csr->agg_in; a.meta = csr->graph_meta; a.B = num_graphs;
   int spu = kMaxUnitRows / max_nodes;
   if (spu > kMaxSub) spu = kMaxSub;
+  // small batches: fewer subjects per unit so that the units cover the SMs (16 x 84-node subjects: 16 CTAs of one tile each
+  // instead of 4 CTAs of three) - the launch is latency-bound there, not throughput-bound
+  {
+    const long long fill = (num_graphs + dev.sm_count - 1) / dev.sm_count;
+    if ((long long)spu > fill) spu = (int)fill;
+  }
   if (spu < 1) spu = 1;
   a.spu = spu;
   a.units = (num_graphs + spu - 1) / spu;

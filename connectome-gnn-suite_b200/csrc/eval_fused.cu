@@ -515,6 +515,10 @@ int launch_eval_fused(int kind, const float* x, int F, const cgnn_eval_layer_t* 
   a.emb = emb; a.logits = logits;
   int spu = kMaxUnitRows / max_nodes;
   if (spu > kMaxSub) spu = kMaxSub;
+  {   // small batches: fewer subjects per unit so that the units cover the SMs (the launch is latency-bound there)
+    const long long fill = (num_graphs + dev.sm_count - 1) / dev.sm_count;
+    if ((long long)spu > fill) spu = (int)(fill < 1 ? 1 : fill);
+  }
   size_t smem = 0;
   for (; spu >= 1; --spu) {         // the largest number of subjects per unit whose tiles, records and readout partials fit
     const int p_rows = spu * ((max_nodes + 7) & ~7);
