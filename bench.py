@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dp-parity-only", action="store_true", help="N > 1: print only the data-parallel parity record")
+    ap.add_argument("--no-peer-collectives", action="store_true",
+                    help="N > 1: SyncBN statistics through NCCL collectives instead of the peer-memory exchange kernel (A/B)")
     ap.add_argument("--dp-per-rank", type=int, default=48, help="subjects per rank in the data-parallel parity step")
     a = ap.parse_args()
     a.legs = tuple(x for x in a.legs.split(",") if x)
@@ -326,6 +328,7 @@ def run_b200(a):
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
         # flat parameter / gradient buffers: the Adam update is one kernel and the data-parallel gradient exchange one
         # all-reduce over the flat buffer (no per-parameter cat / copy)
+        model.peer_collectives = not a.no_peer_collectives
         trainers[kind] = Trainer(model, opt, device=dev).enable_fused_step()
     order_gen = torch.Generator().manual_seed(99 + rank)
 
@@ -587,6 +590,7 @@ def extra_configs(a, world, rank, dev, lib):
         store = SubjectStore(pack_graphs((graphs * (per // 64 + 1))[:per]), dev)
         torch.manual_seed(1234)
         model = GCNConnectome(in_channels=5, hidden_dim=256, num_classes=2, num_layers=3, dropout=0.3).to(dev)
+        model.peer_collectives = not a.no_peer_collectives
         tr = Trainer(model, torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True), device=dev)
         meta = dict(row_base=rank * per * 360, graph_base=rank * per, global_num_graphs=per * world, global_num_nodes=per * world * 360)
         ids = np.arange(per)
@@ -639,6 +643,7 @@ def dp_parity(a, world, rank, dev, pool, per_rank=None):
                 continue
             torch.manual_seed(77)
             model = cls(in_channels=5, hidden_dim=a.hidden, num_classes=2, num_layers=a.layers, dropout=0.0).to(dev).train()
+            model.peer_collectives = not a.no_peer_collectives
             loss_fn = CrossEntropyLoss()
             if mode == "dp":
                 ids = np.arange(rank * per_rank, (rank + 1) * per_rank)
@@ -689,7 +694,12 @@ def dp_parity(a, world, rank, dev, pool, per_rank=None):
         out["max"] = worst
         out["ok"] = bool(ok)
         out["bar"] = "loss, logits <= 1e-5; gradients <= max(1e-5, 4 x the difference between two orderings of the single-process batch)"
-        out["what"] = f"one DP train step over NCCL ({world} ranks x {per_rank} subjects, dropout 0) vs the same global batch on rank 0 alone"
+        from connectome_gnn import peers as peers_mod
+        px = [v for v in peers_mod._CACHE.values() if v is not None]
+        out["syncbn_transport"] = "peer memory (cgnn_peer_exchange)" if px else "NCCL collectives"
+        for v in px:
+            v.check()
+        out["what"] = f"one DP train step ({world} ranks x {per_rank} subjects, dropout 0; gradients over NCCL) vs the same global batch on rank 0 alone"
     dist.barrier()
     return out
 

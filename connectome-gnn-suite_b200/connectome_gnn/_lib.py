@@ -14,7 +14,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcgnn.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 c_f32p = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 c_ptr = C.c_void_p
@@ -82,6 +82,7 @@ PROTOTYPES = {
     "cgnn_gcn_layer_fwd": (C.c_int, [_p, _P(ActT), _p, _p, _P(CsrT), _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p,
                                      _p, _sz, _p]),
     "cgnn_gcn_layer_fwd_pool": (C.c_int, [_p, _P(ActT), _p, _p, _P(CsrT), _p, _i64, _i64, _i32, _i32, _i32, _i32, _P(ActT), _p, _p]),
+    "cgnn_peer_exchange": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, C.c_uint32, _i32, _p, _i32, _i32, _p, _p, _p]),
     "cgnn_sage_layer_fwd": (C.c_int, [_p, _P(ActT), _p, _p, _P(CsrT), _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p,
                                       _p, _p, _sz, _p]),
     "cgnn_eval_fused_fwd": (C.c_int, [_i32, _p, _i32, _P(EvalLayerT), _i32, _i32, _p, _p, _p, _p, _i32, _i32, _P(CsrT), _p,

@@ -53,24 +53,30 @@ def _world(group=None) -> int:
     return 1
 
 
-def _merge_stats_across_ranks(eng, stats: torch.Tensor, channels: int, group=None) -> torch.Tensor:
-    """SyncBN forward: gather every rank's {count, mean, M2} and merge them identically everywhere."""
+def _merge_stats_across_ranks(eng, stats: torch.Tensor, channels: int, group=None, peers=None, layer: int = 0) -> torch.Tensor:
+    """SyncBN forward: gather every rank's {count, mean, M2} and merge them identically everywhere - over NVLink peer
+    memory in one kernel when ``peers`` (a PeerExchange) is given, else NCCL all-gather + merge kernel."""
     world = _world(group)
     if world == 1:
         return stats
+    if peers is not None:
+        return peers.merge_stats(layer, stats, channels)
     import torch.distributed as dist
     flat = torch.empty(world * stats.numel(), dtype=stats.dtype, device=stats.device)   # 1-D: gloo insists on it
     dist.all_gather_into_tensor(flat, stats.contiguous().reshape(-1), group=group)
     return eng.bn_merge_stats(flat.view(world, stats.numel()), channels)
 
 
-def _sum_across_ranks(sums: Optional[torch.Tensor], sums64: Optional[torch.Tensor], group=None):
+def _sum_across_ranks(sums: Optional[torch.Tensor], sums64: Optional[torch.Tensor], group=None, peers=None, layer: int = 0):
     """SyncBN backward: the [sum dy, sum dy x^] records of all ranks added up - the float64 record (the one the kernels
     read: BatchNorm's backward subtracts these means from every row, so the sums are carried unrounded from the reduction
     kernel to their consumer, also across ranks) and from it the fp32 copy that becomes d beta / d gamma."""
     if sums64 is not None and _world(group) > 1:
-        import torch.distributed as dist
-        dist.all_reduce(sums64, group=group)
+        if peers is not None:
+            sums64 = peers.sum(layer, sums64)
+        else:
+            import torch.distributed as dist
+            dist.all_reduce(sums64, group=group)
         sums.copy_(sums64)
     return sums, sums64
 
@@ -127,7 +133,7 @@ class _EncodeFn(torch.autograd.Function):
                     return emb
             z, stats, agg = eng.layer_fwd(kind, t, act, W, b, csr, ptr, B, want_stats=training)
             if training:
-                stats = _merge_stats_across_ranks(eng, stats, W.shape[0], cfg["group"])
+                stats = _merge_stats_across_ranks(eng, stats, W.shape[0], cfg["group"], cfg.get("peers"), l)
                 if bn.momentum is None:    # torch: cumulative moving average, factor 1 / num_batches_tracked (after increment)
                     momentum = 1.0 / float(int(bn.num_batches_tracked) + 1)
                 else:
@@ -167,7 +173,7 @@ class _EncodeFn(torch.autograd.Function):
         t_in, act_in, z, W, scale, mean, rstd, agg = saved[-1]
         act_out = ctx.final_act
         sums, sums64 = eng.bn_bwd_sums(z, act_out, mean, rstd, None, demb, ptr, B, out=bn_block(L - 1))
-        sums, sums64 = _sum_across_ranks(sums, sums64, group)
+        sums, sums64 = _sum_across_ranks(sums, sums64, group, cfg.get("peers"), L - 1)
         du, pooled, dx = None, demb, None
         share = 1.0 / _world(group)
         for l in range(L - 1, -1, -1):
@@ -191,7 +197,7 @@ class _EncodeFn(torch.autograd.Function):
                 grads[4 * l + 0], grads[4 * l + 1] = dW, db
                 grads[4 * l + 2] = sums[1] if share == 1.0 else sums[1] * share
                 grads[4 * l + 3] = sums[0] if share == 1.0 else sums[0] * share
-            sums, sums64 = _sum_across_ranks(prev_sums, prev_sums64, group)
+            sums, sums64 = _sum_across_ranks(prev_sums, prev_sums64, group, cfg.get("peers"), l - 1)
             du, pooled, act_out = du_in, None, act_in
             if l == 0:
                 dx = du_in
@@ -325,6 +331,12 @@ class _ConnectomeClassifier(nn.Module):
         cfg = dict(engine=_engine.engine_for(batch.node_features), batch=batch, kind=self.kind, training=training,
                    dropout=float(self.dropout), bns=list(self.batch_norms), group=self.process_group,
                    graph_base=batch.graph_base, salt=self._salt, flat=self._flat)
+        # data parallel on an NVLink box: BatchNorm statistics and their backward sums travel through peer memory in one
+        # kernel per exchange (peers.py) instead of NCCL collectives; `model.peer_collectives = False` keeps NCCL
+        cfg["peers"] = None
+        if training and getattr(self, "peer_collectives", True) and _world(self.process_group) > 1:
+            from .peers import peer_exchange_for
+            cfg["peers"] = peer_exchange_for(self.process_group, batch.node_features.device)
         # a graphed step keeps its dropout stream on the device (salt words refreshed inside the graph): the host seed is fixed
         cfg["seed"] = (self._graph_seed if self._salt is not None else _draw_seed(batch.node_features.device)) if need_seed else 0
         if self._flat is not None:

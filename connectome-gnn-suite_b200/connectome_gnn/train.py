@@ -138,6 +138,9 @@ class GraphedStep:
             return trainer.eval_step(batch)
 
         model = trainer.model
+        # the peer-memory SyncBN exchange takes a sequence number as a launch argument: a replayed graph would repeat it.
+        # Captured data-parallel steps keep their BatchNorm exchanges on NCCL.
+        model.peer_collectives = False
         model.train(train)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

@@ -174,6 +174,90 @@ __global__ void __launch_bounds__(kThreads, 2) k_bn_bwd_sums_quad(BnSumsArgs p) 
 }
 #endif
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SyncBN exchange over peer memory (NVLink / NVSwitch): ONE kernel writes this rank's record straight into every peer's
+// symmetric buffer, raises a flag there, waits for the peers' flags in its own buffer and then merges the records in rank
+// order - identical on every rank.  It replaces an NCCL all-gather (or all-reduce) of a few hundred bytes plus the merge
+// kernel behind it: three of these per training step and model sit on the critical path between two layer kernels.
+//   symmetric buffer of a rank (doubles): [slots][world][rec_cap] records, then uint32 flags [slots][world]
+//   flag (slot, r) in rank q's buffer = the sequence number of the last record rank r delivered to q in that slot
+// A slot is written again only two uses later (the caller alternates two physical slots per logical one), by which time
+// every peer has consumed it: a rank can only be one exchange ahead of the slowest one.
+#ifndef CGNN_EMU
+struct PeerArgs {
+  const unsigned long long* bufs;   // [world] device pointers to the ranks' symmetric buffers
+  int rank, world, slot, slots, rec_cap, n, mode, C;
+  unsigned int seq;
+  const double* mine; double* out; int* error;
+};
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256) k_peer_exchange(PeerArgs p) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t rec0 = ((size_t)p.slot * p.world) * p.rec_cap;
+  const size_t flags_off = (size_t)p.slots * p.world * p.rec_cap;      // in doubles
+  for (int t = tid; t < p.n; t += blockDim.x) {
+    const double v = p.mine[t];
+    for (int r = 0; r < p.world; ++r) reinterpret_cast<double*>(p.bufs[r])[rec0 + (size_t)p.rank * p.rec_cap + t] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < p.world) {
+    unsigned int* peer_flags = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(p.bufs[tid]) + flags_off);
+    st_release_sys(peer_flags + (size_t)p.slot * p.world + p.rank, p.seq);
+    const unsigned int* my_flags = reinterpret_cast<const unsigned int*>(reinterpret_cast<const double*>(p.bufs[p.rank]) + flags_off);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(my_flags + (size_t)p.slot * p.world + tid) != p.seq) {
+      if (clock64() - t0 > 8000000000ll) { atomicExch(p.error, 1); break; }     // ~4 s: a peer died; do not hang the GPU
+    }
+  }
+  __syncthreads();
+  const double* recs = reinterpret_cast<const double*>(p.bufs[p.rank]) + rec0;
+  if (p.mode == 1) {                     // plain sum in rank order
+    for (int t = tid; t < p.n; t += blockDim.x) {
+      double s = 0.0;
+      for (int r = 0; r < p.world; ++r) s += recs[(size_t)r * p.rec_cap + t];
+      p.out[t] = s;
+    }
+    return;
+  }
+  // BatchNorm statistics {count, mean[C], M2[C]}: the exact merge of k_stats_merge, one warp per channel
+  const int C = p.C;
+  for (int c = warp; c < C; c += (int)(blockDim.x >> 5)) {
+    double n = 0.0, s = 0.0;
+    for (int r = lane; r < p.world; r += 32) {
+      const double nr = recs[(size_t)r * p.rec_cap];
+      n += nr;
+      s += nr * recs[(size_t)r * p.rec_cap + 1 + c];
+    }
+    n = warp_sum(n);
+    s = warp_sum(s);
+    const double mean = n > 0.0 ? s / n : 0.0;
+    double q = 0.0;
+    for (int r = lane; r < p.world; r += 32) {
+      const double nr = recs[(size_t)r * p.rec_cap];
+      if (nr > 0.0) {
+        const double d = recs[(size_t)r * p.rec_cap + 1 + c] - mean;
+        q += recs[(size_t)r * p.rec_cap + 1 + C + c] + nr * d * d;
+      }
+    }
+    q = warp_sum(q);
+    if (lane == 0) {
+      p.out[1 + c] = mean;
+      p.out[1 + C + c] = q;
+      if (c == 0) p.out[0] = n;
+    }
+  }
+}
+#endif
+
 }  // namespace cgnn
 
 using namespace cgnn;
@@ -251,6 +335,28 @@ int cgnn_bn_bwd_sums(const float* z, const cgnn_act_t* act, const float* mean, c
 #undef CGNN_BN_SUMS
   CGNN_CHECK_LAUNCH();
   return launch_reduce_partials(a.partials, grid, 2 * a.C4, 2, C, a.C4, sums, stream, 0, sums64);
+}
+
+int cgnn_peer_exchange(const uint64_t* peer_buffers, int32_t rank, int32_t world, int32_t slot, int32_t slots, int32_t rec_cap,
+                       uint32_t seq, int32_t mode, const double* mine, int32_t n, int32_t C, double* out, int32_t* error,
+                       cgnn_stream_t stream_) {
+#ifdef CGNN_EMU
+  (void)peer_buffers; (void)rank; (void)world; (void)slot; (void)slots; (void)rec_cap; (void)seq; (void)mode; (void)mine; (void)n;
+  (void)C; (void)out; (void)error; (void)stream_;
+  return CGNN_ERR_UNSUPPORTED;
+#else
+  if (!peer_buffers || !mine || !out || !error || world < 1 || world > 64 || rank < 0 || rank >= world || slot < 0 || slot >= slots ||
+      n < 1 || n > rec_cap || seq == 0 || (mode != 0 && mode != 1))
+    return CGNN_ERR_INVALID_ARG;
+  if (mode == 0 && n != 1 + 2 * C) return CGNN_ERR_INVALID_ARG;
+  PeerArgs a;
+  a.bufs = (const unsigned long long*)peer_buffers; a.rank = rank; a.world = world; a.slot = slot; a.slots = slots;
+  a.rec_cap = rec_cap; a.n = n; a.mode = mode; a.C = C; a.seq = seq; a.mine = mine; a.out = out; a.error = error;
+  auto kfn = k_peer_exchange;
+  CGNN_LAUNCH(kfn, 1, 256, 0, (cudaStream_t)stream_, a);
+  CGNN_CHECK_LAUNCH();
+  return CGNN_OK;
+#endif
 }
 
 }  // extern "C"

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGNN_ABI_VERSION 10
+#define CGNN_ABI_VERSION 11
 
 typedef void* cgnn_stream_t; /* cudaStream_t */
 
@@ -377,6 +377,19 @@ int cgnn_sage_layer_bwd(const float* du, const float* demb, const float* z, cons
                         float* dW, float* dbias, float* du_in,
                         const float* prev_mean, const float* prev_rstd, float* prev_sums, double* prev_sums64,
                         float* scratch, void* workspace, size_t workspace_bytes, cgnn_stream_t stream);
+
+/* SyncBN exchange over peer memory (one process per GPU of one NVLink / NVSwitch box): this rank's record of n doubles is
+ * written into every peer's symmetric buffer, flags are exchanged, and the world's records are merged in rank order - one
+ * kernel instead of an NCCL collective plus a merge kernel.  peer_buffers: DEVICE array of `world` pointers to the ranks'
+ * symmetric buffers (torch.distributed._symmetric_memory: handle.buffer_ptrs_dev), each
+ *   slots * world * rec_cap doubles of records followed by slots * world uint32 flags, zero-initialised once.
+ * seq: a number > 0 that grows by one with every use of `slot` on every rank; use two physical slots alternately for one
+ * logical exchange.  mode 0: records are BatchNorm statistics {count, mean[C], M2[C]} (n = 1 + 2C), out = their exact
+ * merge (as cgnn_bn_merge_stats); mode 1: out = the sum of the records.  *error is set to 1 if a peer's flag does not
+ * arrive within a few seconds (the kernel then returns instead of hanging the device). */
+int cgnn_peer_exchange(const uint64_t* peer_buffers, int32_t rank, int32_t world, int32_t slot, int32_t slots, int32_t rec_cap,
+                       uint32_t seq, int32_t mode, const double* mine, int32_t n, int32_t C, double* out, int32_t* error,
+                       cgnn_stream_t stream);
 
 /* ---- the step after backward (reference train.py:51) -----------------------------------------
  * A training step that is replayed as a CUDA graph cannot take anything that changes from step to step as a launch

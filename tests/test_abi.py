@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(product_lib):
     for name in declared_functions():
         assert hasattr(lib, name), f"{name} is declared in include/cgnn.h but not exported by libcgnn.so"
     lib.cgnn_abi_version.restype = ctypes.c_int
-    assert lib.cgnn_abi_version() == 10
+    assert lib.cgnn_abi_version() == 11
     lib.cgnn_status_string.restype = ctypes.c_char_p
     assert lib.cgnn_status_string(0) == b"ok" and b"shared memory" in lib.cgnn_status_string(2)
 
