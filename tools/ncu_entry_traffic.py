@@ -11,7 +11,7 @@ ENTRY = [("k_first_fwd<0", "cgnn_gcn_layer_fwd"), ("k_first_fwd<1", "cgnn_sage_l
          ("k_sage_bwd_gemm", "cgnn_sage_layer_bwd"), ("k_first_bwd<1", "cgnn_sage_layer_bwd"), ("k_collate", "cgnn_collate_csr"),
          ("k_pool_fwd", "cgnn_pool_fwd"), ("k_bn_bwd_sums", "cgnn_bn_bwd_sums"), ("k_head_fwd", "cgnn_head_fwd"), ("k_ce_fwd", "cgnn_ce_fwd")]
 CALLS = {"cgnn_gcn_layer_fwd": 6, "cgnn_sage_layer_fwd": 6, "cgnn_gcn_layer_bwd": 3, "cgnn_sage_layer_bwd": 3, "cgnn_collate_csr": 4,
-         "cgnn_pool_fwd": 4, "cgnn_bn_bwd_sums": 2, "cgnn_head_fwd": 4, "cgnn_ce_fwd": 4}
+         "cgnn_pool_fwd": 3, "cgnn_bn_bwd_sums": 2, "cgnn_head_fwd": 4, "cgnn_ce_fwd": 4}
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
 
 
