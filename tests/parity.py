@@ -653,3 +653,47 @@ def check_pooled_last_layer(device, sizes=(84, 30, 130, 57, 84, 200, 360, 1, 2))
         eng.gcn_layer_fwd_pool = orig
     helpers.assert_close(emb_fused, emb_ref, "pooled last layer: embeddings", tol=1e-6)
     helpers.assert_close(logits_fused, logits_ref, "pooled last layer: logits", tol=1e-6)
+
+
+def check_multi_subject_units(device, subjects=600, regions=84):
+    """Enough small subjects that the warp-specialised kernels pack several of them into one unit (on a GPU the units are
+    otherwise sized to cover the SMs): engine layers, the pooled last layer and the fused eval kernel against the generic
+    SIMT kernels, and a training step's gradients, to 1e-5 max-norm relative."""
+    from connectome_gnn import _engine
+    from connectome_gnn.graph import SubjectStore
+    from connectome_gnn.models import GCNConnectome
+    from connectome_gnn.synthetic_fast import generate_packed
+    from connectome_gnn.train import CrossEntropyLoss
+    store = SubjectStore(generate_packed(subjects, regions, seed=3, device=device if str(device) != "cpu" else "cpu"), device)
+    ids = np.arange(subjects)
+    eng = _engine.engine_for(store.x)
+    torch.manual_seed(4)
+    m = GCNConnectome(in_channels=5, hidden_dim=64, num_classes=2, num_layers=3, dropout=0.0).to(device)
+    with torch.no_grad():
+        for bn in m.batch_norms:
+            bn.running_mean.uniform_(-0.2, 0.2); bn.running_var.uniform_(0.5, 1.5)
+
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+
+    def run(tensor_cores: int, fused):
+        assert eng.lib.cgnn_set_option(1, tensor_cores) == 0
+        try:
+            m.load_state_dict(state)         # (the training step below moves the running statistics)
+            m.fused_eval = fused
+            m.eval()
+            with torch.no_grad():
+                logits = m(store.collate(ids, prepare_for="gcn", backward=False)).clone()
+            m.train()
+            m.zero_grad()
+            b = store.collate(ids, prepare_for="gcn")
+            CrossEntropyLoss()(m(b), b.labels).backward()
+            grads = torch.cat([p.grad.reshape(-1) for n, p in m.named_parameters() if not (n.startswith("convs.") and n.endswith(".bias"))])
+            return logits, grads.clone()
+        finally:
+            eng.lib.cgnn_set_option(1, 1)
+
+    ref_logits, ref_grads = run(0, False)               # generic SIMT kernels
+    for fused in (False, True):                         # engine + pooled last layer / whole-network kernel
+        logits, grads = run(1, fused)
+        helpers.assert_close(logits, ref_logits, f"multi-subject units (fused_eval={fused}): eval logits", tol=1e-5)
+        helpers.assert_close(grads, ref_grads, f"multi-subject units (fused_eval={fused}): gradients", tol=1e-5)

@@ -185,6 +185,10 @@ def test_lean_collate(on_emu, compact):
     parity.check_lean_collate("cpu", "gcn", compact)
 
 
+def test_multi_subject_units(on_emu):
+    parity.check_multi_subject_units("cpu", subjects=10, regions=30)
+
+
 def test_pooled_last_layer(on_emu):
     parity.check_pooled_last_layer("cpu", sizes=(84, 30, 130, 57, 200, 10, 12))
 

@@ -536,6 +536,10 @@ def test_pooled_last_layer():
     parity.check_pooled_last_layer(DEV)
 
 
+def test_multi_subject_units():
+    parity.check_multi_subject_units(DEV)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_pair_collate_fuzz(seed):
     parity.check_pair_collate_fuzz(DEV, seed=seed, rounds=8)
