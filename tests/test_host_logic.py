@@ -150,3 +150,20 @@ def test_generator_properties():
     stats = small_world_stats(ds[:5])
     assert stats["num_graphs"] == 5 and stats["mean_clustering"] >= 0 and stats["mean_avg_path_length"] > 1
     assert len(REGION_NAMES) == 83
+
+
+def test_peer_exchange_slot_schedule():
+    """PeerExchange alternates two physical slots per logical exchange and numbers the uses from 1 (a zeroed flag never
+    matches): the property the kernel's reuse argument rests on.  Pure host logic - no device, no process group."""
+    from connectome_gnn.peers import PeerExchange, _SLOTS
+    px = PeerExchange.__new__(PeerExchange)
+    px.seq = {}
+    seen = {}
+    for use in range(1, 7):
+        for logical in (0, 1, 5):
+            slot, seq = px._slot(logical)
+            assert seq == use and slot == 2 * logical + (use & 1) and 0 <= slot < _SLOTS
+            assert seen.get(logical) != slot, "two consecutive uses of one exchange must not share a physical slot"
+            seen[logical] = slot
+    with pytest.raises(RuntimeError):
+        px._slot(_SLOTS // 2)
