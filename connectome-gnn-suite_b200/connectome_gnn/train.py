@@ -287,8 +287,31 @@ class Trainer:
         return loss, self.loss_fn.last_correct
 
     # -- reference API -----------------------------------------------------------------------
+    def _lean(self, loader):
+        """The loader's batches are consumed right here, by this trainer's model: unless the caller chose otherwise, a
+        ``ConnectomeDataLoader`` then collates lean batches for that model family (only what its kernels read; the
+        reference fields stay available on access).  Returns a context manager that undoes the setting."""
+        import contextlib
+        kind = getattr(self.model, "kind", None)
+
+        @contextlib.contextmanager
+        def scope():
+            mine = kind in ("gcn", "sage") and hasattr(loader, "prepare_for") and getattr(loader, "prepare_for") is None
+            if mine:
+                loader.prepare_for = kind
+            try:
+                yield
+            finally:
+                if mine:
+                    loader.prepare_for = None
+        return scope()
+
     def train_epoch(self, loader) -> float:
         """One pass over ``loader`` with parameter updates; returns the mean loss (``train.py:41-54``)."""
+        with self._lean(loader):
+            return self._train_epoch(loader)
+
+    def _train_epoch(self, loader) -> float:
         self.model.train()
         losses, sizes = [], []
         for batch in loader:
@@ -308,6 +331,10 @@ class Trainer:
     @torch.no_grad()
     def evaluate(self, loader) -> dict:
         """Accuracy and mean loss over ``loader`` (``train.py:56-74``)."""
+        with self._lean(loader):
+            return self._evaluate(loader)
+
+    def _evaluate(self, loader) -> dict:
         self.model.eval()
         losses, corrects, sizes = [], [], []
         for batch in loader:

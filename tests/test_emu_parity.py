@@ -219,3 +219,35 @@ def test_fused_step_flat_buffers(on_emu, kind):
 
 def test_adam_kernel(on_emu):
     parity.check_adam_kernel("cpu")
+
+
+def test_trainer_asks_its_loader_for_lean_batches(on_emu):
+    """Trainer.train_epoch / evaluate consume the loader's batches themselves: a ConnectomeDataLoader without an explicit
+    prepare_for collates for the trainer's model family while it is being driven by the trainer, and is left as it was."""
+    from connectome_gnn.graph import ConnectomeDataLoader, SubjectStore
+    from connectome_gnn.models import GraphSAGEConnectome
+    from connectome_gnn.synthetic import generate_dataset
+    from connectome_gnn.train import Trainer
+    graphs = generate_dataset(num_subjects=12, num_regions=20, seed=3)
+    loader = ConnectomeDataLoader(graphs, batch_size=4, shuffle=False)
+    seen = []
+    orig = SubjectStore.collate
+
+    def spy(self, ids, *a, **k):
+        if "ids_device" not in k:                       # (a lean batch filling itself in calls collate again: not the loader)
+            seen.append(k.get("prepare_for"))
+        return orig(self, ids, *a, **k)
+    SubjectStore.collate = spy
+    try:
+        torch.manual_seed(0)
+        m = GraphSAGEConnectome(in_channels=5, hidden_dim=32, num_classes=2, num_layers=2, dropout=0.0)
+        tr = Trainer(m, torch.optim.SGD(m.parameters(), lr=0.01), device="cpu")
+        tr.train_epoch(loader)
+        tr.evaluate(loader)
+        assert seen and all(k == "sage" for k in seen[:6]), seen
+        assert loader.prepare_for is None
+        n = len(seen)
+        next(iter(loader))                              # outside the trainer: the caller's own setting (none)
+        assert seen[n] is None
+    finally:
+        SubjectStore.collate = orig
